@@ -1,0 +1,22 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import numpy as np
+
+from oracle.oracle import OracleEnvs
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_FILES = ("kat", "lockstep_fixed", "lockstep_random", "close_hits")
+INT_FIELDS = ("px", "py", "qx", "qy", "cd", "age", "valid")
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def oracle_from_golden(g):
+    n = g["actions"].shape[0]
+    o = OracleEnvs(n, g["positions"])
+    o.envs["prot"] = g["rotations"]
+    o.envs["np_pos"] = g["np_pos"]
+    return o
