@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the Skillshot hot path on B200 (driver contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): physics-only, 65,536 SkillshotGame envs per
+GPU, U(-1.2,1.2) float32 random actions, random starts, terminal +1/-1/0 reward,
+2,000-tick limit with auto-reset.  One bench "step" = TICKS ticks of all envs
+(TICKS * 65,536 env-steps per GPU), played by ss_env_step in launches of
+TICKS_PER_LAUNCH fused ticks.  The action stream of a step ([TICKS, E, 2, 2]
+float32 = 268 MB) is larger than the 126 MB L2, so every timed iteration streams
+it from HBM ("inputs larger than L2"); the 4 MB game state is L2-resident by
+design.
+
+  value     whole-job env-steps/s, actions resident in HBM, CUDA-event timed
+  e2e       the same through SkillshotEnvs.step_host: pinned HOST actions in,
+            reward/done/winner back to pinned HOST memory, copies inside the timing
+  roofline  HBM: algorithmic 202 B per env-step x env-steps per
+            launch / average launch time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the C oracle port (oracle/skillshot_oracle.c, OpenMP over envs)
+            on the host cores, on a bounded sample of the same workload
+
+--impl reference times that CPU port alone (the Python reference cannot travel
+to the GPU box) and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+ENVS_PER_GPU = 65536
+TICKS = 256                 # ticks per bench step
+TICKS_PER_LAUNCH = 32       # fused ticks per ss_env_step launch
+TICK_LIMIT = 2000           # SkillshotLearner.py:62
+ALGO_BYTES_PER_ENV_STEP = 202   # SURVEY.md 8(d), physics-only
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+WORKLOAD = "physics-only: 65,536 SkillshotGame envs per GPU, random actions, terminal reward, 2000-tick auto-reset"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("step_kernel_physics_bytes_per_launch")
+        except Exception:
+            pass
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------
+# CPU port (oracle) timing -- cpu_baseline leg and --impl reference arm
+# ---------------------------------------------------------------------------
+def cpu_port_run(n_envs: int, ticks: int, nthreads: int, seed: int = 0, envs=None, actions=None):
+    """Times `ticks` ticks of n_envs oracle envs; returns (seconds, envs, actions)."""
+    from oracle.oracle import OracleEnvs
+    rng = np.random.default_rng(seed)
+    if envs is None:
+        envs = OracleEnvs(n_envs, rng.integers(25, 225, size=(n_envs, 4)))
+    if actions is None:
+        actions = rng.uniform(-1.2, 1.2, size=(8, n_envs, 2, 2)).astype(np.float32)
+    t0 = time.perf_counter()
+    for t in range(ticks):
+        envs.step(actions[t % actions.shape[0]], want_obs=False, reward_mode=2, tick_limit=TICK_LIMIT,
+                  auto_reset=True, nthreads=nthreads)
+    return time.perf_counter() - t0, envs, actions
+
+
+def cpu_baseline(target_seconds: float = 4.0):
+    """Oracle port on all host cores, bounded sample (~10-30 s of CPU work)."""
+    from oracle.oracle import lib as olib
+    cores = int(olib().ss_oracle_max_threads())
+    dt, envs, actions = cpu_port_run(ENVS_PER_GPU, 4, cores)            # warm-up + calibration
+    ticks = int(max(8, min(4096, target_seconds / max(dt / 4, 1e-6))))
+    dt, _, _ = cpu_port_run(ENVS_PER_GPU, ticks, cores, envs=envs, actions=actions)
+    return {"value": ENVS_PER_GPU * ticks / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d envs x %d ticks (%.1f s wall, %d OpenMP threads) of the same workload, C port of the "
+                      "Python reference (oracle/skillshot_oracle.c)" % (ENVS_PER_GPU, ticks, dt, cores)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle.oracle import lib as olib
+    cores = int(olib().ss_oracle_max_threads())
+    ticks_per_step = 64
+    _, envs, actions = cpu_port_run(ENVS_PER_GPU, 2, cores)
+    for _ in range(args.warmup):
+        cpu_port_run(ENVS_PER_GPU, ticks_per_step, cores, envs=envs, actions=actions)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_run(ENVS_PER_GPU, ticks_per_step, cores, envs=envs, actions=actions)
+    dt = time.perf_counter() - t0
+    value = ENVS_PER_GPU * ticks_per_step * args.steps / dt
+    sample = "each step = %d envs x %d ticks of the workload on %d OpenMP threads" % (ENVS_PER_GPU, ticks_per_step, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs_per_gpu": ENVS_PER_GPU, "ticks_per_step": ticks_per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from skillshot_learning_b200 import SkillshotEnvs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the GPU arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    E, T, KF = ENVS_PER_GPU, args.ticks, args.ticks_per_launch
+    assert T % KF == 0
+    launches_per_step = T // KF
+    envs = SkillshotEnvs(E, device=dev, random_positions=True, seed=1234 + rank, reward_mode="terminal",
+                         tick_limit=TICK_LIMIT, auto_reset=True)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    actions = (torch.rand((T, E, 2, 2), device=dev, generator=gen) * 2.4 - 1.2).contiguous()
+
+    def device_step():
+        for c in range(launches_per_step):
+            envs.step(actions[c * KF:(c + 1) * KF], want_obs=False)
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        device_step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    envs.check_status()
+
+    # ---- end to end through the host-buffer API (e2e) ----
+    e2e_steps, e2e_s = max(3, min(args.steps, 20)), float("nan")
+    if not args.no_e2e:
+        host_actions = torch.empty((T, E, 2, 2), dtype=torch.float32, pin_memory=True)
+        host_actions.copy_(actions)
+        host_out = envs.alloc_host_outputs(T)
+        for _ in range(2):
+            envs.step_host(host_actions, host_out, ticks_per_launch=KF)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            envs.step_host(host_actions, host_out, ticks_per_launch=KF)   # synchronises before returning
+        barrier()
+        e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        total_env_steps = world * E * T * args.steps
+        value = total_env_steps / (ms * 1e-3)
+        launch_s = (ms * 1e-3) / (args.steps * launches_per_step)
+        achieved = ALGO_BYTES_PER_ENV_STEP * E * KF / launch_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "ticks_per_step": T, "ticks_per_launch": KF,
+                       "l2": "action stream per step (%.0f MB) exceeds the 126 MB L2; game state (4 MB) is L2-resident by design"
+                             % (T * E * 16 / 1e6)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(), "peak_source": peak_kind,
+                         "kernel": "step_kernel<OBS=false,SPEEDS=false>",
+                         "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                         "moved_bytes_per_env_step": 16 + 8 + 2 + 128.0 / KF,
+                         "launch_us": launch_s * 1e6},
+            "e2e": {"value": None if args.no_e2e else world * E * T * e2e_steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": T * E * 16, "d2h_bytes_per_step": T * E * 10},
+            "gpu_launches": args.steps * launches_per_step,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ticks", type=int, default=TICKS)
+    ap.add_argument("--ticks-per-launch", type=int, default=TICKS_PER_LAUNCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,140 @@
+/*
+ * skillshot_b200.h -- C ABI of libskillshot_b200.so (sm_100a).
+ *
+ * The reference (adrientremblay/Skillshot_Learning) has no FFI layer: its
+ * boundary is the Python object surface of SkillshotGame / Player / Projectile
+ * and SkillshotLearner.  The Python facade in skillshot_learning_b200/ keeps
+ * that surface and binds these entry points with ctypes; each entry point names
+ * the reference code it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch tensors in
+ *    the facade) unless the name ends in _host; the library never allocates or
+ *    frees caller memory and keeps no global state;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *    the call returns without synchronising;
+ *  - return value: 0 = success, SS_ERR_* (< 0) otherwise; nothing throws;
+ *  - player index p is 0 or 1 (reference ids 1 and 2).
+ */
+#ifndef SKILLSHOT_B200_H
+#define SKILLSHOT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_OK 0
+#define SS_ERR_INVALID_ARG (-1)
+#define SS_ERR_CUDA (-2)
+
+/* ---- game state in HBM --------------------------------------------------
+ * Structure of arrays, four 16-byte planes, plane k of env i at
+ * state + (k * n_envs + i) * 16:
+ *   plane 0  double2 { Player1.rotation, Player2.rotation }          (Player.py:21)
+ *   plane 1  double2 { P1.projectile.rotation, P2.projectile.rotation } (Projectile.py:14)
+ *   plane 2  int4    { player xy packed u8 (p1x | p1y<<8 | p2x<<16 | p2y<<24),
+ *                      projectile xy packed u8 (same order),
+ *                      P1.projectile.cooldown_current, P2...cooldown_current }
+ *   plane 3  int4    { P1.projectile.age, P2.projectile.age, SkillshotGame.ticks,
+ *                      flags: bit0/1 projectile.valid, bit2 game_live, bits 4-5 winner_id }
+ * 64 bytes per env (the reference-natural widths of SURVEY.md 8(d) are 88). */
+#define SS_STATE_BYTES_PER_ENV 64
+#define SS_NUM_FEATURES 18   /* per-player keys of get_state, SkillshotGame.py:145-162 */
+#define SS_NUM_OBS 12        /* prepare_states, SkillshotLearner.py:525-539 */
+
+/* reward_mode */
+#define SS_REWARD_NONE 0
+#define SS_REWARD_LOOKING 1   /* calculate_rewards_looking, SkillshotLearner.py:575-588 */
+#define SS_REWARD_TERMINAL 2  /* +1 / -1 / 0, readme.md:10 (no reference code) */
+#define SS_REWARD_SIMPLE 3    /* calculate_rewards_simple, SkillshotLearner.py:590-603 */
+
+/* reset_mode */
+#define SS_RESET_FIXED 0      /* P1 [50,50], P2 [200,200], SkillshotGame.py:17-18 */
+#define SS_RESET_RANDOM 1     /* uniform ints in [25,225), SkillshotGame.py:15; Philox4x32-10 */
+#define SS_RESET_GIVEN 2      /* caller-supplied positions */
+
+/* flags of ss_env_step */
+#define SS_STEP_OBS_EVERY_TICK 1  /* obs_out is [n_ticks][n][2][12] instead of last tick only */
+
+/* status bits OR-ed into *status by the kernels */
+#define SS_STATUS_NAN 1       /* where the reference raises ValueError: int(round(nan)), Player.py:63 */
+
+/* ops of ss_env_apply: the single-object methods of the reference */
+#define SS_OP_MOVE_DIRECTION_FLOAT 0  /* Player.move_direction_float(value), Player.py:57-68 */
+#define SS_OP_MOVE_LOOK_FLOAT 1       /* Player.move_look_float(value),     Player.py:33-39 */
+#define SS_OP_SHOOT 2                 /* Player.move_shoot_projectile(),    Player.py:78-89 */
+#define SS_OP_MOVE_FORWARDS 3         /* Player.move_forwards(),            Player.py:41-47 */
+#define SS_OP_MOVE_BACKWARDS 4        /* Player.move_backwards(),           Player.py:49-55 */
+#define SS_OP_LOOK_LEFT 5             /* Player.move_look_left(),           Player.py:27-28 */
+#define SS_OP_LOOK_RIGHT 6            /* Player.move_look_right(),          Player.py:30-31 */
+#define SS_OP_GAME_TICK 7             /* SkillshotGame.game_tick(),         SkillshotGame.py:115-122 */
+
+int ss_version(void);
+
+/* Bytes of `state` for n_envs games. */
+int64_t ss_state_bytes(int64_t n_envs);
+
+/* SkillshotGame.__init__ / game_reset (SkillshotGame.py:10-25, 168-169) for
+ * every env whose mask byte is non-zero (mask == NULL: all).
+ *   reset_mode SS_RESET_GIVEN reads positions int32 [n_envs][4] = p1x,p1y,p2x,p2y;
+ *   SS_RESET_RANDOM draws them from Philox4x32-10(key = seed, counter = (env, counter)). */
+int ss_env_reset(void *state, int64_t n_envs, const uint8_t *mask, int reset_mode,
+                 const int32_t *positions, uint64_t seed, uint64_t counter, void *stream);
+
+/* One or more ticks of the model_train inner loop for every env
+ * (SkillshotLearner.py:304-315): both players act from the pre-tick state --
+ * do_actions = move_direction_float, move_look_float, move_shoot_projectile
+ * (SkillshotLearner.py:206-213), P1 then P2 -- then SkillshotGame.game_tick
+ * (projectile advance, hit test, winner), then reward of the post-tick state
+ * and the 12-float observation of each player (get_state + prepare_states).
+ *
+ *   actions     float32 [n_ticks][n_envs][2][2]   (player, (move, look))
+ *   obs_out     float32 [n_envs][2][12] of the last tick (or [n_ticks]... with
+ *               SS_STEP_OBS_EVERY_TICK); NULL = not computed
+ *   reward_out  float32 [n_ticks][n_envs][2]; NULL or reward_mode 0 = not written
+ *   done_out    uint8   [n_ticks][n_envs]  1 when the game ended (hit) or
+ *               ticks >= tick_limit after the tick (tick_limit <= 0: no limit); NULL ok
+ *   winner_out  uint8   [n_ticks][n_envs]  winner_id after the tick (the id of the
+ *               player that was hit, SkillshotGame.py:77); NULL ok
+ *   auto_reset  non-zero: a done env is reset (reset_mode FIXED or RANDOM) after
+ *               its reward/done/winner are written; its obs is the post-reset one
+ *   speeds      NULL (reference constants) or per-env constants, two 16-byte planes:
+ *               plane 0 double2 {Player.speed_move, Player.speed_look},
+ *               plane 1 {double Projectile.speed_move, int64 cooldown_max}
+ *   status      NULL or uint32[1], SS_STATUS_* bits are OR-ed in
+ */
+int ss_env_step(void *state, int64_t n_envs, const float *actions, float *obs_out,
+                float *reward_out, uint8_t *done_out, uint8_t *winner_out,
+                int n_ticks, int reward_mode, int64_t tick_limit, int auto_reset,
+                int reset_mode, uint64_t seed, uint64_t counter, const void *speeds,
+                uint32_t *status, int flags, void *stream);
+
+/* SkillshotGame.get_state (SkillshotGame.py:136-166) + prepare_states
+ * (SkillshotLearner.py:512-543) in float64, formulas evaluated as written.
+ *   feat_out    float64 [n_envs][2][18] in the dict's key order, or NULL
+ *   obs_out     float64 [n_envs][2][12], or NULL
+ *   general_out int32   [n_envs][3] = game_live, ticks, game_winner, or NULL */
+int ss_env_features(const void *state, int64_t n_envs, double *feat_out, double *obs_out,
+                    int32_t *general_out, const void *speeds, void *stream);
+
+/* Unpack / pack `count` envs starting at `first` to natural-width arrays:
+ *   ints  int32 [count][17] = px1,px2, py1,py2, qx1,qx2, qy1,qy2, cd1,cd2,
+ *                             age1,age2, valid1,valid2, ticks, live, winner
+ *   rots  float64 [count][4] = prot1, prot2, qrot1, qrot2                     */
+#define SS_EXPORT_INTS 17
+int ss_env_export(const void *state, int64_t n_envs, int64_t first, int64_t count,
+                  int32_t *ints, double *rots, void *stream);
+int ss_env_import(void *state, int64_t n_envs, int64_t first, int64_t count,
+                  const int32_t *ints, const double *rots, void *stream);
+
+/* One reference method call on one env (the object-style surface used by
+ * skillshot_playable.py:51-64 and by do_actions). */
+int ss_env_apply(void *state, int64_t n_envs, int64_t env, int player, int op, double value,
+                 const void *speeds, uint32_t *status, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKILLSHOT_B200_H */

@@ -1,0 +1,64 @@
+"""ctypes binding of libskillshot_b200.so (the C ABI of include/skillshot_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing, importing this module
+raises.  Build it with `python -m skillshot_learning_b200.build`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libskillshot_b200.so")
+
+# constants of include/skillshot_b200.h
+STATE_BYTES_PER_ENV = 64
+NUM_FEATURES = 18
+NUM_OBS = 12
+EXPORT_INTS = 17
+REWARD_NONE, REWARD_LOOKING, REWARD_TERMINAL, REWARD_SIMPLE = 0, 1, 2, 3
+RESET_FIXED, RESET_RANDOM, RESET_GIVEN = 0, 1, 2
+STEP_OBS_EVERY_TICK = 1
+STATUS_NAN = 1
+(OP_MOVE_DIRECTION_FLOAT, OP_MOVE_LOOK_FLOAT, OP_SHOOT, OP_MOVE_FORWARDS, OP_MOVE_BACKWARDS,
+ OP_LOOK_LEFT, OP_LOOK_RIGHT, OP_GAME_TICK) = range(8)
+
+_vp, _i64, _i32, _u64, _f64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint64, ctypes.c_double
+
+# name -> (restype, argtypes); every symbol the header declares
+SIGNATURES = {
+    "ss_version": (_i32, []),
+    "ss_state_bytes": (_i64, [_i64]),
+    "ss_env_reset": (_i32, [_vp, _i64, _vp, _i32, _vp, _u64, _u64, _vp]),
+    "ss_env_step": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i32, _u64, _u64,
+                            _vp, _vp, _i32, _vp]),
+    "ss_env_features": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "ss_env_export": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "ss_env_import": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "ss_env_apply": (_i32, [_vp, _i64, _i64, _i32, _i32, _f64, _vp, _vp, _vp]),
+}
+
+
+class SkillshotLibraryError(RuntimeError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "skillshot_learning_b200: %s is missing -- build the CUDA library with "
+            "`python -m skillshot_learning_b200.build` (there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the library is stale
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise SkillshotLibraryError("%s failed with code %d (%s)" % (
+            what, rc, {-1: "invalid argument", -2: "CUDA error"}.get(rc, "unknown")))

@@ -1,0 +1,332 @@
+// ss_env.cu -- sm_100a kernels for the SkillshotGame hot path and their C ABI
+// (include/skillshot_b200.h).  Compiled with -fmad=false (see ss_env_core.cuh).
+//
+// Data layout: four 16-byte SoA planes per env (header).  One thread owns one
+// env: four coalesced 16-byte loads bring the whole game into registers, K ticks
+// are played there, four 16-byte stores put it back.  Per tick a thread reads one
+// float4 of actions and writes a float2 reward, two status bytes and (optionally)
+// the 2x12 float observation, which is staged through shared memory so that each
+// warp writes its 3 KB of observations as six fully coalesced 512-byte requests.
+// The step is HBM-bound by design: no tensor-core work here.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/skillshot_b200.h"
+#include "ss_env_core.cuh"
+
+namespace {
+
+using namespace ss;
+
+constexpr int kBlock = 64;             // 2 warps: fine-grained CTAs balance small grids over 148 SMs
+constexpr int kWarps = kBlock / 32;
+constexpr int kRowF4 = 7;              // 6 float4 of observation + 1 pad: conflict-free float4 smem rows
+
+struct StatePlanes {
+    double2 *rot;    // plane 0
+    double2 *qrot;   // plane 1
+    int4 *ia;        // plane 2
+    int4 *ib;        // plane 3
+};
+__host__ __device__ inline StatePlanes planes_of(void *state, int64_t n) {
+    char *b = (char *)state;
+    return StatePlanes{(double2 *)b, (double2 *)(b + 16 * n), (int4 *)(b + 32 * n), (int4 *)(b + 48 * n)};
+}
+
+__device__ __forceinline__ void load_env(const StatePlanes &s, int64_t i, Env &e) {
+    double2 r = s.rot[i], q = s.qrot[i];
+    int4 a = s.ia[i], b = s.ib[i];
+    unpack(e, r.x, r.y, q.x, q.y, Int4{a.x, a.y, a.z, a.w}, Int4{b.x, b.y, b.z, b.w});
+}
+__device__ __forceinline__ void store_env(const StatePlanes &s, int64_t i, const Env &e) {
+    Int4 a, b;
+    pack(e, a, b);
+    s.rot[i] = make_double2(e.prot[0], e.prot[1]);
+    s.qrot[i] = make_double2(e.qrot[0], e.qrot[1]);
+    s.ia[i] = make_int4(a.x, a.y, a.z, a.w);
+    s.ib[i] = make_int4(b.x, b.y, b.z, b.w);
+}
+__device__ __forceinline__ Speeds load_speeds(const void *speeds, int64_t n, int64_t i) {
+    const char *b = (const char *)speeds;
+    double2 a = ((const double2 *)b)[i];
+    const double *p1 = (const double *)(b + 16 * n) + 2 * i;
+    long long cm = ((const long long *)(b + 16 * n))[2 * i + 1];
+    return Speeds{a.x, a.y, p1[0], (int)cm};
+}
+
+struct StepArgs {
+    void *state;
+    int64_t n;
+    const float4 *actions;
+    float4 *obs_out;
+    float2 *reward_out;
+    uint8_t *done_out;
+    uint8_t *winner_out;
+    const void *speeds;
+    uint32_t *status;
+    TickParams P;
+    int n_ticks, obs_every_tick;
+};
+
+template <bool OBS, bool SPEEDS>
+__global__ void __launch_bounds__(kBlock) step_kernel(const StepArgs A) {
+    __shared__ float4 tile[OBS ? kWarps : 1][OBS ? 32 * kRowF4 : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t warp_base = i - lane;
+    const bool active = i < A.n;
+    const StatePlanes S = planes_of(A.state, A.n);
+
+    Env e;
+    Speeds k = default_speeds();
+    if (active) {
+        load_env(S, i, e);
+        if (SPEEDS) k = load_speeds(A.speeds, A.n, i);
+    } else {
+        reset_env(e, 50, 50, 200, 200);
+    }
+    uint32_t status = 0;
+    const bool write_reward = A.reward_out && A.P.reward_mode != SS_REWARD_NONE;
+
+    for (int t = 0; t < A.n_ticks; ++t) {
+        const int64_t row = (int64_t)t * A.n + i;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) a = __ldg(A.actions + row);
+        const bool want_obs = OBS && (A.obs_every_tick || t == A.n_ticks - 1);
+        float r[2], obs[OBS ? 2 * kNumObs : 1];
+        int done, winner;
+        tick_env<OBS>(e, a.x, a.y, a.z, a.w, k, A.P, (uint64_t)i, t, want_obs, status, r, done, winner, obs);
+        if (active) {
+            if (write_reward) A.reward_out[row] = make_float2(r[0], r[1]);
+            if (A.done_out) A.done_out[row] = (uint8_t)done;
+            if (A.winner_out) A.winner_out[row] = (uint8_t)winner;
+        }
+        if (OBS && want_obs) {
+            // stage the warp's 32 x 24 floats, then write them as 6 coalesced 512-byte requests
+            float4 *mine = &tile[warp][lane * kRowF4];
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                mine[j] = make_float4(obs[4 * j], obs[4 * j + 1], obs[4 * j + 2], obs[4 * j + 3]);
+            __syncwarp();
+            const int64_t tick_off = A.obs_every_tick ? (int64_t)t * A.n * 6 : 0;
+            float4 *dst = A.obs_out + tick_off + warp_base * 6;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                int idx = j * 32 + lane, rw = idx / 6, cl = idx - rw * 6;
+                if (warp_base + rw < A.n) dst[idx] = tile[warp][rw * kRowF4 + cl];
+            }
+            __syncwarp();
+        }
+    }
+    if (active) store_env(S, i, e);
+    if (status && A.status) atomicOr(A.status, status);
+}
+
+__global__ void reset_kernel(void *state, int64_t n, const uint8_t *mask, int reset_mode,
+                             const int32_t *positions, uint64_t seed, uint64_t counter) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (mask && !mask[i]) return;
+    Env e;
+    if (reset_mode == SS_RESET_GIVEN) {
+        const int4 p = ((const int4 *)positions)[i];
+        reset_env(e, p.x, p.y, p.z, p.w);
+    } else if (reset_mode == SS_RESET_RANDOM) {
+        reset_random(e, seed, (uint64_t)i, counter);
+    } else {
+        reset_env(e, 50, 50, 200, 200);
+    }
+    store_env(planes_of(state, n), i, e);
+}
+
+template <bool SPEEDS>
+__global__ void features_kernel(const void *state, int64_t n, double *feat_out, double *obs_out,
+                                int32_t *general_out, const void *speeds) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Env e;
+    load_env(planes_of((void *)state, n), i, e);
+    Speeds k = default_speeds();
+    if (SPEEDS) k = load_speeds(speeds, n, i);
+    if (general_out) {
+        general_out[i * 3 + 0] = e.live; general_out[i * 3 + 1] = e.ticks; general_out[i * 3 + 2] = e.winner;
+    }
+    if (feat_out) {
+        double f[kNumFeat];
+        features_of<0>(e, f);
+        for (int j = 0; j < kNumFeat; ++j) feat_out[(i * 2 + 0) * kNumFeat + j] = f[j];
+        features_of<1>(e, f);
+        for (int j = 0; j < kNumFeat; ++j) feat_out[(i * 2 + 1) * kNumFeat + j] = f[j];
+    }
+    if (obs_out) {
+        double o[kNumObs];
+        View v0 = view_of<0, false>(e), v1 = view_of<1, false>(e);
+        obs_of<0>(e, v0, k, o);
+        for (int j = 0; j < kNumObs; ++j) obs_out[(i * 2 + 0) * kNumObs + j] = o[j];
+        obs_of<1>(e, v1, k, o);
+        for (int j = 0; j < kNumObs; ++j) obs_out[(i * 2 + 1) * kNumObs + j] = o[j];
+    }
+}
+
+__global__ void export_kernel(const void *state, int64_t n, int64_t first, int64_t count,
+                              int32_t *ints, double *rots) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    Env e;
+    load_env(planes_of((void *)state, n), first + j, e);
+    int32_t *o = ints + j * SS_EXPORT_INTS;
+    o[0] = e.px[0]; o[1] = e.px[1]; o[2] = e.py[0]; o[3] = e.py[1];
+    o[4] = e.qx[0]; o[5] = e.qx[1]; o[6] = e.qy[0]; o[7] = e.qy[1];
+    o[8] = e.cd[0]; o[9] = e.cd[1]; o[10] = e.age[0]; o[11] = e.age[1];
+    o[12] = e.valid[0]; o[13] = e.valid[1]; o[14] = e.ticks; o[15] = e.live; o[16] = e.winner;
+    double *r = rots + j * 4;
+    r[0] = e.prot[0]; r[1] = e.prot[1]; r[2] = e.qrot[0]; r[3] = e.qrot[1];
+}
+
+__global__ void import_kernel(void *state, int64_t n, int64_t first, int64_t count,
+                              const int32_t *ints, const double *rots) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    Env e;
+    const int32_t *o = ints + j * SS_EXPORT_INTS;
+    e.px[0] = o[0] & 255; e.px[1] = o[1] & 255; e.py[0] = o[2] & 255; e.py[1] = o[3] & 255;
+    e.qx[0] = o[4] & 255; e.qx[1] = o[5] & 255; e.qy[0] = o[6] & 255; e.qy[1] = o[7] & 255;
+    e.cd[0] = o[8]; e.cd[1] = o[9]; e.age[0] = o[10]; e.age[1] = o[11];
+    e.valid[0] = o[12] != 0; e.valid[1] = o[13] != 0; e.ticks = o[14]; e.live = o[15] != 0; e.winner = o[16] & 3;
+    const double *r = rots + j * 4;
+    e.prot[0] = r[0]; e.prot[1] = r[1]; e.qrot[0] = r[2]; e.qrot[1] = r[3];
+    store_env(planes_of(state, n), first + j, e);
+}
+
+template <int P>
+__device__ void apply_player_op(Env &e, int op, double value, const Speeds &k, uint32_t &status) {
+    double s, c;
+    switch (op) {
+        case SS_OP_MOVE_DIRECTION_FLOAT:
+            sincos_d(e.prot[P], &s, &c);
+            move_direction_float<P>(e, value, s, c, k, status);
+            break;
+        case SS_OP_MOVE_LOOK_FLOAT: move_look_float<P>(e, value, k); break;
+        case SS_OP_SHOOT: move_shoot<P>(e, k); break;
+        // Player.move_forwards / move_backwards (Player.py:41-55) are
+        // pos -/+ sin(rot)*speed_move: the same IEEE values as
+        // move_direction_float(+1 / -1).
+        case SS_OP_MOVE_FORWARDS:
+            sincos_d(e.prot[P], &s, &c);
+            move_direction_float<P>(e, 1.0, s, c, k, status);
+            break;
+        case SS_OP_MOVE_BACKWARDS:
+            sincos_d(e.prot[P], &s, &c);
+            move_direction_float<P>(e, -1.0, s, c, k, status);
+            break;
+        case SS_OP_LOOK_LEFT: e.prot[P] = add(e.prot[P], k.speed_look); break;     // Player.py:28
+        case SS_OP_LOOK_RIGHT: e.prot[P] = sub(e.prot[P], k.speed_look); break;    // Player.py:31
+        default: break;
+    }
+}
+
+__global__ void apply_kernel(void *state, int64_t n, int64_t env, int player, int op, double value,
+                             const void *speeds, uint32_t *status_out) {
+    Env e;
+    const StatePlanes S = planes_of(state, n);
+    load_env(S, env, e);
+    Speeds k = speeds ? load_speeds(speeds, n, env) : default_speeds();
+    uint32_t status = 0;
+    if (op == SS_OP_GAME_TICK) {
+        if (e.live) {                                   // SkillshotGame.py:115-122
+            double s, c;
+            e.ticks += 1;
+            sincos_d(e.qrot[0], &s, &c); proj_tick<0>(e, s, c, k, status);
+            sincos_d(e.qrot[1], &s, &c); proj_tick<1>(e, s, c, k, status);
+            check_collision(e);
+        }
+    } else if (player == 0) {
+        apply_player_op<0>(e, op, value, k, status);
+    } else {
+        apply_player_op<1>(e, op, value, k, status);
+    }
+    store_env(S, env, e);
+    if (status && status_out) atomicOr(status_out, status);
+}
+
+inline int check_launch() { return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA; }
+inline unsigned blocks_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+}  // namespace
+
+extern "C" {
+
+int ss_version(void) { return 100; }
+
+int64_t ss_state_bytes(int64_t n_envs) { return n_envs * SS_STATE_BYTES_PER_ENV; }
+
+int ss_env_reset(void *state, int64_t n_envs, const uint8_t *mask, int reset_mode,
+                 const int32_t *positions, uint64_t seed, uint64_t counter, void *stream) {
+    if (!state || n_envs <= 0 || reset_mode < 0 || reset_mode > 2) return SS_ERR_INVALID_ARG;
+    if (reset_mode == SS_RESET_GIVEN && !positions) return SS_ERR_INVALID_ARG;
+    reset_kernel<<<blocks_for(n_envs, 256), 256, 0, (cudaStream_t)stream>>>(state, n_envs, mask, reset_mode,
+                                                                            positions, seed, counter);
+    return check_launch();
+}
+
+int ss_env_step(void *state, int64_t n_envs, const float *actions, float *obs_out,
+                float *reward_out, uint8_t *done_out, uint8_t *winner_out,
+                int n_ticks, int reward_mode, int64_t tick_limit, int auto_reset,
+                int reset_mode, uint64_t seed, uint64_t counter, const void *speeds,
+                uint32_t *status, int flags, void *stream) {
+    if (!state || !actions || n_envs <= 0 || n_ticks <= 0) return SS_ERR_INVALID_ARG;
+    if (reward_mode < 0 || reward_mode > 3) return SS_ERR_INVALID_ARG;
+    if (auto_reset && reset_mode != SS_RESET_FIXED && reset_mode != SS_RESET_RANDOM) return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)state | (uintptr_t)actions | (uintptr_t)obs_out) & 15) return SS_ERR_INVALID_ARG;
+    if ((uintptr_t)reward_out & 7) return SS_ERR_INVALID_ARG;
+    StepArgs A;
+    A.state = state; A.n = n_envs; A.actions = (const float4 *)actions; A.obs_out = (float4 *)obs_out;
+    A.reward_out = (float2 *)reward_out; A.done_out = done_out; A.winner_out = winner_out;
+    A.speeds = speeds; A.status = status;
+    A.P.seed = seed; A.P.counter = counter; A.P.tick_limit = tick_limit;
+    A.P.reward_mode = reward_mode; A.P.auto_reset = auto_reset ? 1 : 0; A.P.reset_mode = reset_mode;
+    A.n_ticks = n_ticks; A.obs_every_tick = (flags & SS_STEP_OBS_EVERY_TICK) ? 1 : 0;
+    const dim3 grid(blocks_for(n_envs, kBlock)), block(kBlock);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (obs_out) {
+        if (speeds) step_kernel<true, true><<<grid, block, 0, st>>>(A);
+        else step_kernel<true, false><<<grid, block, 0, st>>>(A);
+    } else {
+        if (speeds) step_kernel<false, true><<<grid, block, 0, st>>>(A);
+        else step_kernel<false, false><<<grid, block, 0, st>>>(A);
+    }
+    return check_launch();
+}
+
+int ss_env_features(const void *state, int64_t n_envs, double *feat_out, double *obs_out,
+                    int32_t *general_out, const void *speeds, void *stream) {
+    if (!state || n_envs <= 0) return SS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (speeds) features_kernel<true><<<blocks_for(n_envs, 128), 128, 0, st>>>(state, n_envs, feat_out, obs_out, general_out, speeds);
+    else features_kernel<false><<<blocks_for(n_envs, 128), 128, 0, st>>>(state, n_envs, feat_out, obs_out, general_out, speeds);
+    return check_launch();
+}
+
+int ss_env_export(const void *state, int64_t n_envs, int64_t first, int64_t count,
+                  int32_t *ints, double *rots, void *stream) {
+    if (!state || !ints || !rots || first < 0 || count <= 0 || first + count > n_envs) return SS_ERR_INVALID_ARG;
+    export_kernel<<<blocks_for(count, 128), 128, 0, (cudaStream_t)stream>>>(state, n_envs, first, count, ints, rots);
+    return check_launch();
+}
+
+int ss_env_import(void *state, int64_t n_envs, int64_t first, int64_t count,
+                  const int32_t *ints, const double *rots, void *stream) {
+    if (!state || !ints || !rots || first < 0 || count <= 0 || first + count > n_envs) return SS_ERR_INVALID_ARG;
+    import_kernel<<<blocks_for(count, 128), 128, 0, (cudaStream_t)stream>>>(state, n_envs, first, count, ints, rots);
+    return check_launch();
+}
+
+int ss_env_apply(void *state, int64_t n_envs, int64_t env, int player, int op, double value,
+                 const void *speeds, uint32_t *status, void *stream) {
+    if (!state || env < 0 || env >= n_envs || player < 0 || player > 1 || op < 0 || op > SS_OP_GAME_TICK)
+        return SS_ERR_INVALID_ARG;
+    apply_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, n_envs, env, player, op, value, speeds, status);
+    return check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,420 @@
+// ss_env_core.cuh -- one SkillshotGame instance held in registers.
+//
+// Every function here is __host__ __device__ so that the identical logic can be
+// (a) inlined into the sm_100a kernels of ss_env.cu and (b) compiled for the
+// host by tests/hostsim (a test-only build used to check the game logic in the
+// GPU-less authoring container; the product never loads it).
+//
+// Numerics contract (SURVEY.md "hard parts" 1-4): actions are float32 values
+// promoted to float64; all physics is float64 with NO fused multiply-add (the
+// reference is CPython: every * and - rounds separately), rounding to integer
+// positions is round-half-to-even (Python round()).  The translation unit is
+// compiled with -fmad=false and the products that feed a rounding use the
+// explicit _rn intrinsics as well.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define SS_HD __host__ __device__ __forceinline__
+#else
+#define SS_HD inline
+#endif
+
+namespace ss {
+
+constexpr int kBoard = 250;        // SkillshotGame.py:11
+constexpr int kPlayerSize = 5;     // Player.py:9-13, 23
+constexpr int kProjSize = 3;       // Projectile.py:5-7, 20
+constexpr int kNumFeat = 18;
+constexpr int kNumObs = 12;
+constexpr double kPi = 3.141592653589793;          // math.pi / np.pi
+constexpr double kHalfPi = 1.5707963267948966;     // math.pi / 2 (exact halving)
+constexpr double kMaxDist = 353.5533905932738;     // (2 * 250**2) ** 0.5, SkillshotLearner.py:43
+
+constexpr uint32_t kStatusNaN = 1u;
+
+// ---- exact (unfused) float64 arithmetic --------------------------------
+SS_HD double mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+SS_HD double add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+SS_HD double sub(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+SS_HD double divd(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+// Python round() -> int: round-half-to-even.  Caller has excluded NaN/inf.
+SS_HD int rint_i(double v) {
+#ifdef __CUDA_ARCH__
+    return __double2int_rn(v);
+#else
+    return (int)rint(v);
+#endif
+}
+SS_HD void sincos_d(double r, double *s, double *c) {
+#ifdef __CUDA_ARCH__
+    sincos(r, s, c);
+#else
+    *s = sin(r); *c = cos(r);
+#endif
+}
+SS_HD bool finite_d(double v) { return v - v == 0.0; }
+
+// Python float % 2 (Objects/floatobject.c float_rem): fmod, result takes the
+// divisor's sign.
+SS_HD double py_mod2(double v) {
+    double m = fmod(v, 2.0);
+    if (m != 0.0) { if (m < 0) m += 2.0; } else { m = 0.0; }
+    return m;
+}
+
+// ---- per-env constants (class attributes in the reference) --------------
+struct Speeds {
+    double speed_move;   // Player.speed_move = 3        Player.py:14
+    double speed_look;   // Player.speed_look = 0.25     Player.py:15
+    double proj_speed;   // Projectile.speed_move = 5    Projectile.py:10
+    int cooldown_max;    // Projectile.cooldown_max = 15 Projectile.py:9
+};
+SS_HD Speeds default_speeds() { return Speeds{3.0, 0.25, 5.0, 15}; }
+
+// ---- one game in registers ----------------------------------------------
+struct Env {
+    double prot[2], qrot[2];
+    int px[2], py[2], qx[2], qy[2];
+    int cd[2], age[2], valid[2];
+    int ticks, live, winner;
+};
+
+// the two 16-byte integer planes of the HBM layout (include/skillshot_b200.h)
+struct Int4 { int x, y, z, w; };
+
+SS_HD void unpack(Env &e, double r0, double r1, double q0, double q1, Int4 a, Int4 b) {
+    e.prot[0] = r0; e.prot[1] = r1; e.qrot[0] = q0; e.qrot[1] = q1;
+    uint32_t pp = (uint32_t)a.x, qq = (uint32_t)a.y;
+    e.px[0] = pp & 255; e.py[0] = (pp >> 8) & 255; e.px[1] = (pp >> 16) & 255; e.py[1] = pp >> 24;
+    e.qx[0] = qq & 255; e.qy[0] = (qq >> 8) & 255; e.qx[1] = (qq >> 16) & 255; e.qy[1] = qq >> 24;
+    e.cd[0] = a.z; e.cd[1] = a.w;
+    e.age[0] = b.x; e.age[1] = b.y; e.ticks = b.z;
+    uint32_t f = (uint32_t)b.w;
+    e.valid[0] = f & 1; e.valid[1] = (f >> 1) & 1; e.live = (f >> 2) & 1; e.winner = (f >> 4) & 3;
+}
+SS_HD void pack(const Env &e, Int4 &a, Int4 &b) {
+    a.x = (int)((uint32_t)e.px[0] | ((uint32_t)e.py[0] << 8) | ((uint32_t)e.px[1] << 16) | ((uint32_t)e.py[1] << 24));
+    a.y = (int)((uint32_t)e.qx[0] | ((uint32_t)e.qy[0] << 8) | ((uint32_t)e.qx[1] << 16) | ((uint32_t)e.qy[1] << 24));
+    a.z = e.cd[0]; a.w = e.cd[1];
+    b.x = e.age[0]; b.y = e.age[1]; b.z = e.ticks;
+    b.w = (int)((uint32_t)e.valid[0] | ((uint32_t)e.valid[1] << 1) | ((uint32_t)e.live << 2) | ((uint32_t)e.winner << 4));
+}
+
+// SkillshotGame.__init__ (SkillshotGame.py:10-25) with given player positions.
+SS_HD void reset_env(Env &e, int p1x, int p1y, int p2x, int p2y) {
+    e.px[0] = p1x; e.py[0] = p1y; e.px[1] = p2x; e.py[1] = p2y;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        e.prot[p] = 0.0;                 // Player.py:21
+        e.qx[p] = 0; e.qy[p] = 0;        // Player.py:25  Projectile((0, 0), ...)
+        e.qrot[p] = 0.0;                 // Projectile.py:14
+        e.cd[p] = 0; e.age[p] = 0;       // Projectile.py:16-17
+        e.valid[p] = 0;                  // Projectile.py:18
+    }
+    e.ticks = 0; e.live = 1; e.winner = 0;   // SkillshotGame.py:23-25
+}
+
+// Player.check_pos_valid (Player.py:70-76)
+SS_HD bool player_pos_valid(int x, int y) {
+    return x + kPlayerSize <= kBoard && x >= 0 && y + kPlayerSize <= kBoard && y >= 0;
+}
+// Projectile.check_pos_valid (Projectile.py:30-36)
+SS_HD bool proj_pos_valid(int x, int y) {
+    return x + kProjSize <= kBoard && x >= 0 && y + kProjSize <= kBoard && y >= 0;
+}
+
+SS_HD double clip_unit(double v) {       // Player.py:36-37, 60-61 (NaN falls through)
+    v = (v >= 1.0) ? 1.0 : v;
+    v = (v <= -1.0) ? -1.0 : v;
+    return v;
+}
+
+// Player.move_direction_float (Player.py:57-68).  (s, c) = sin/cos of the
+// player's rotation BEFORE this tick's turn.
+template <int P>
+SS_HD void move_direction_float(Env &e, double speed, double s, double c, const Speeds &k, uint32_t &status) {
+    speed = clip_unit(speed);
+    double vx = sub((double)e.px[P], mul(mul(s, k.speed_move), speed));   // Player.py:63
+    double vy = sub((double)e.py[P], mul(mul(c, k.speed_move), speed));   // Player.py:64
+    if (!(finite_d(vx) && finite_d(vy))) { status |= kStatusNaN; return; }   // int(round(nan)) raises
+    int nx = rint_i(vx), ny = rint_i(vy);
+    if (player_pos_valid(nx, ny)) { e.px[P] = nx; e.py[P] = ny; }        // Player.py:66-68
+}
+
+// Player.move_look_float (Player.py:33-39)
+template <int P>
+SS_HD void move_look_float(Env &e, double angle, const Speeds &k) {
+    e.prot[P] = add(e.prot[P], mul(clip_unit(angle), k.speed_look));
+}
+
+// Player.move_shoot_projectile (Player.py:78-89)
+template <int P>
+SS_HD bool move_shoot(Env &e, const Speeds &k) {
+    if (e.cd[P] <= 0) {
+        e.qx[P] = e.px[P]; e.qy[P] = e.py[P];
+        e.qrot[P] = e.prot[P];
+        e.valid[P] = 1;
+        e.cd[P] = k.cooldown_max;
+        e.age[P] = 0;
+        return true;
+    }
+    return false;
+}
+
+// Projectile.tick (Projectile.py:38-53).  (s, c) = sin/cos of the projectile
+// rotation.
+template <int P>
+SS_HD void proj_tick(Env &e, double s, double c, const Speeds &k, uint32_t &status) {
+    double vx = sub((double)e.qx[P], mul(s, k.proj_speed));   // Projectile.py:40
+    double vy = sub((double)e.qy[P], mul(c, k.proj_speed));   // Projectile.py:41
+    if (!(finite_d(vx) && finite_d(vy))) { status |= kStatusNaN; vx = -1.0; vy = -1.0; }
+    int nx = rint_i(vx), ny = rint_i(vy);
+    if (e.valid[P] && proj_pos_valid(nx, ny)) { e.qx[P] = nx; e.qy[P] = ny; }   // :43-45
+    else e.valid[P] = 0;                                                        // :47
+    e.cd[P] -= 1;                                                               // :52
+    e.age[P] += 1;                                                              // :53
+}
+
+// One (player P, enemy projectile 1-P) pair of SkillshotGame.check_collision
+// (SkillshotGame.py:58-94).
+template <int P>
+SS_HD bool hit_test(const Env &e) {
+    constexpr int Q = 1 - P;
+    if (!e.valid[Q]) return false;
+    int pl = e.px[P], pr = e.px[P] + kPlayerSize, pt = e.py[P], pb = e.py[P] + kPlayerSize;
+    int jl = e.qx[Q], jr = e.qx[Q] + kProjSize, jt = e.qy[Q], jb = e.qy[Q] - kProjSize;   // :72 minus
+    bool in_x = (pl <= jr && jr <= pr) || (pl <= jl && jl <= pr);
+    bool in_y = (pt <= jt && jt <= pb) || (pt <= jb && jb <= pb);
+    return in_x && in_y;
+}
+
+// SkillshotGame.check_collision: pair (P1, P2's projectile) first; the first hit
+// breaks, so a double hit records id 1 only.  winner_id = the player that was hit.
+SS_HD void check_collision(Env &e) {
+    if (hit_test<0>(e)) { e.winner = 1; e.live = 0; }
+    else if (hit_test<1>(e)) { e.winner = 2; e.live = 0; }
+}
+
+// get_gradient_dir + get_dist_line_point + get_dist_point_point +
+// check_future_collision for player P, as written in the reference
+// (Player.py:91-100, SkillshotGame.py:96-134).
+struct View {
+    double player_grad, player_path_dist, player_dist;
+    double proj_grad, proj_path_dist, proj_dist;
+    int player_x_dir, proj_x_dir, future_collision;
+};
+
+SS_HD double dist_line_point(double g, int lx, int ly, int cx, int cy) {   // SkillshotGame.py:124-130
+    double c = sub((double)ly, mul(g, (double)lx));
+    double num = fabs(add(sub(mul(g, (double)cx), (double)cy), c));
+    return divd(num, sqrt(add(mul(g, g), 1.0)));
+}
+SS_HD double dist_point_point(int ax, int ay, int bx, int by) {             // SkillshotGame.py:132-134
+    int dx = ax - bx, dy = ay - by;
+    return sqrt((double)(dx * dx + dy * dy));
+}
+
+template <int P, bool FULL>
+SS_HD View view_of(const Env &e) {
+    constexpr int O = 1 - P;
+    View v;
+    v.player_grad = tan(add(-e.prot[P], kHalfPi));                            // Player.py:94
+    v.proj_grad = tan(add(-e.qrot[P], kHalfPi));                              // Projectile.py:58
+    if (FULL) {
+        v.player_x_dir = (-sin(e.prot[P]) >= 0.0) ? 1 : -1;                   // Player.py:96
+        v.proj_x_dir = (-sin(e.qrot[P]) >= 0.0) ? 1 : -1;
+    } else {
+        v.player_x_dir = 1; v.proj_x_dir = 1;
+    }
+    v.player_path_dist = dist_line_point(v.player_grad, e.px[P], e.py[P], e.px[O], e.py[O]);
+    v.player_dist = dist_point_point(e.px[P], e.py[P], e.px[O], e.py[O]);
+    v.proj_path_dist = dist_line_point(v.proj_grad, e.qx[P], e.qy[P], e.px[O], e.py[O]);
+    v.proj_dist = dist_point_point(e.qx[P], e.qy[P], e.px[O], e.py[O]);
+    // check_future_collision (SkillshotGame.py:96-113).  The direction guard at
+    // :109 passes for the projectile's own left bound whatever x_dir is, and the
+    // second bound re-tests the same two opponent bounds, so the result is the
+    // OR over the opponent's two x bounds.
+    int fc = 0;
+    if (e.valid[P]) {
+        double yint = sub((double)e.qy[P], mul(v.proj_grad, (double)e.qx[P]));   // Projectile.py:62
+        double lo = (double)e.py[O], hi = (double)(e.py[O] + kPlayerSize);
+        double v0 = add(mul(v.proj_grad, (double)e.px[O]), yint);
+        double v1 = add(mul(v.proj_grad, (double)(e.px[O] + kPlayerSize)), yint);
+        fc = ((lo <= v0 && v0 <= hi) || (lo <= v1 && v1 <= hi)) ? 1 : 0;
+    }
+    v.future_collision = fc;
+    return v;
+}
+
+// get_state per-player feature vector in the dict's key order (SkillshotGame.py:145-162)
+template <int P>
+SS_HD void features_of(const Env &e, double *f) {
+    View v = view_of<P, true>(e);
+    f[0] = v.player_grad; f[1] = (double)v.player_x_dir; f[2] = v.player_path_dist; f[3] = v.player_dist;
+    f[4] = (double)e.px[P]; f[5] = (double)e.py[P]; f[6] = e.prot[P]; f[7] = (double)e.cd[P];
+    f[8] = v.proj_grad; f[9] = (double)v.proj_x_dir; f[10] = v.proj_path_dist;
+    f[11] = (double)e.qx[P]; f[12] = (double)e.qy[P]; f[13] = e.qrot[P]; f[14] = (double)e.age[P];
+    f[15] = (double)e.valid[P]; f[16] = v.proj_dist; f[17] = (double)v.future_collision;
+}
+
+// prepare_states (SkillshotLearner.py:525-539), divisions as written.
+SS_HD double rot_term(double rot) {   // (rot % 2 * np.pi) / 2 * np.pi, literal precedence
+    return mul(divd(mul(py_mod2(rot), kPi), 2.0), kPi);
+}
+template <int P>
+SS_HD void obs_of(const Env &e, const View &v, const Speeds &k, double *o) {
+    o[0] = divd(v.player_path_dist, kMaxDist);
+    o[1] = divd(v.player_dist, kMaxDist);
+    o[2] = divd((double)e.px[P], (double)kBoard);
+    o[3] = divd((double)e.py[P], (double)kBoard);
+    o[4] = rot_term(e.prot[P]);
+    o[5] = divd((double)e.cd[P], (double)k.cooldown_max);
+    o[6] = divd(v.proj_dist, kMaxDist);
+    o[7] = divd((double)e.qx[P], (double)kBoard);
+    o[8] = divd((double)e.qy[P], (double)kBoard);
+    o[9] = rot_term(e.qrot[P]);
+    o[10] = divd(v.proj_path_dist, kMaxDist);
+    o[11] = (double)v.future_collision;
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), counter-based RNG -------------
+struct U4 { uint32_t x, y, z, w; };
+SS_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+SS_HD U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = mulhi32(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = mulhi32(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = U4{hi1 ^ ctr.y ^ k0, lo1, hi0 ^ ctr.w ^ k1, lo0};
+        k0 += W0; k1 += W1;
+    }
+    return ctr;
+}
+// np.random.randint(25, 225) equivalent draw (SkillshotGame.py:15); the MT19937
+// stream itself is not part of the contract (SURVEY hard part 10).
+SS_HD int rand_coord(uint32_t u) { return 25 + (int)mulhi32(u, 200u); }
+
+SS_HD void reset_random(Env &e, uint64_t seed, uint64_t env, uint64_t counter) {
+    U4 r = philox4x32_10(U4{(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)counter, (uint32_t)(counter >> 32)},
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+    reset_env(e, rand_coord(r.x), rand_coord(r.y), rand_coord(r.z), rand_coord(r.w));
+}
+
+// ---- one model_train tick (SkillshotLearner.py:304-315) -----------------
+// Actions of both players + game_tick.  a = (p1 move, p1 look, p2 move, p2 look).
+SS_HD void act_and_tick(Env &e, float a0, float a1, float a2, float a3, const Speeds &k, uint32_t &status) {
+    double s, c;
+    // do_actions(1): SkillshotLearner.py:206-213 -- not gated on game_live
+    sincos_d(e.prot[0], &s, &c);
+    move_direction_float<0>(e, (double)a0, s, c, k, status);
+    move_look_float<0>(e, (double)a1, k);
+    move_shoot<0>(e, k);
+    // do_actions(2)
+    sincos_d(e.prot[1], &s, &c);
+    move_direction_float<1>(e, (double)a2, s, c, k, status);
+    move_look_float<1>(e, (double)a3, k);
+    move_shoot<1>(e, k);
+    // game_tick, SkillshotGame.py:115-122
+    if (e.live) {
+        e.ticks += 1;
+        sincos_d(e.qrot[0], &s, &c);
+        proj_tick<0>(e, s, c, k, status);
+        sincos_d(e.qrot[1], &s, &c);
+        proj_tick<1>(e, s, c, k, status);
+        check_collision(e);
+    }
+}
+
+// reward of a post-tick state for the two reward shapers that need the view
+SS_HD void view_rewards(int reward_mode, const View &v0, const View &v1, float *r) {
+    if (reward_mode == 1) {            // calculate_rewards_looking, SkillshotLearner.py:584
+        r[0] = (float)divd(-v0.player_path_dist, (double)kBoard);
+        r[1] = (float)divd(-v1.player_path_dist, (double)kBoard);
+    } else {                           // calculate_rewards_simple, SkillshotLearner.py:600
+        r[0] = (float)sub(v0.proj_dist, v1.proj_dist);
+        r[1] = (float)sub(v1.proj_dist, v0.proj_dist);
+    }
+}
+
+struct TickParams {
+    int64_t tick_limit;      // <= 0: none (model_param_game_tick_limit, SkillshotLearner.py:62, 302)
+    uint64_t seed, counter;  // Philox key / counter base for random resets
+    int reward_mode, auto_reset, reset_mode;
+};
+
+// One tick of one env as the batched step defines it: both players act, the game
+// ticks, reward / done / winner are taken from the post-tick state, a done env is
+// optionally reset, and the observation (if wanted) is that of the state the
+// actor will see next.  obs = 24 floats (player 1's 12, then player 2's).
+template <bool OBS>
+SS_HD void tick_env(Env &e, float a0, float a1, float a2, float a3, const Speeds &k,
+                    const TickParams &P, uint64_t env_id, int t, bool want_obs,
+                    uint32_t &status, float *r, int &done, int &winner, float *obs) {
+    const int was_live = e.live;
+    act_and_tick(e, a0, a1, a2, a3, k, status);
+    done = ((!e.live) || (P.tick_limit > 0 && e.ticks >= P.tick_limit)) ? 1 : 0;
+    winner = e.winner;
+    const bool will_reset = P.auto_reset && done;
+    const bool reward_view = (P.reward_mode == 1 || P.reward_mode == 3);
+    r[0] = 0.f; r[1] = 0.f;
+    if (P.reward_mode == 2 && was_live && !e.live && e.winner != 0) {   // readme.md:10
+        r[e.winner - 1] = -1.f;       // the player that was hit
+        r[2 - e.winner] = 1.f;        // the shooter
+    }
+    View v0, v1;
+    if (reward_view && will_reset) {  // rare: the reward belongs to the pre-reset state
+        v0 = view_of<0, false>(e); v1 = view_of<1, false>(e);
+        view_rewards(P.reward_mode, v0, v1, r);
+    }
+    if (will_reset) {
+        if (P.reset_mode == 1) reset_random(e, P.seed, env_id, P.counter + (uint64_t)t);
+        else reset_env(e, 50, 50, 200, 200);
+    }
+    const bool need_view = (OBS && want_obs) || (reward_view && !will_reset);
+    if (need_view) { v0 = view_of<0, false>(e); v1 = view_of<1, false>(e); }
+    if (reward_view && !will_reset) view_rewards(P.reward_mode, v0, v1, r);
+    if (OBS && want_obs) {
+        double o[kNumObs];
+        obs_of<0>(e, v0, k, o);
+#pragma unroll
+        for (int j = 0; j < kNumObs; ++j) obs[j] = (float)o[j];
+        obs_of<1>(e, v1, k, o);
+#pragma unroll
+        for (int j = 0; j < kNumObs; ++j) obs[kNumObs + j] = (float)o[j];
+    }
+}
+
+}  // namespace ss

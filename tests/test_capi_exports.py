@@ -1,0 +1,42 @@
+"""The C-ABI library loads and exports every symbol include/skillshot_b200.h declares
+(no compute calls: this runs without a GPU)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "skillshot_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ss_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from skillshot_learning_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert "ss_env_step" in names and len(names) >= 8
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in _lib.SIGNATURES, "binding missing for " + n
+    assert lib.ss_version() >= 100
+    lib.ss_state_bytes.restype = ctypes.c_int64
+    assert lib.ss_state_bytes(ctypes.c_int64(10)) == 640
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu():
+    from skillshot_learning_b200 import _lib
+    assert _lib.lib.ss_env_reset(None, 4, None, 0, None, 0, 0, None) == -1
+    assert _lib.lib.ss_env_step(None, 4, None, None, None, None, None, 1, 1, 0, 0, 0, 0, 0, None, None, 0, None) == -1
+
+
+def test_product_package_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "skillshot_learning_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle-free", ""), os.path.join(dirpath, f)
+                assert "hostsim" not in src or f == "ss_env_core.cuh", os.path.join(dirpath, f)
