@@ -68,7 +68,10 @@ struct StepArgs {
     int n_ticks, obs_every_tick;
 };
 
-template <bool OBS, bool SPEEDS>
+// OBS: write observations.  CARRY: keep sin/cos of the rotations in registers across
+// ticks (fused ticks, observations, shaped rewards); !CARRY is the lean one-tick
+// physics-only kernel.
+template <bool OBS, bool CARRY, bool SPEEDS>
 __global__ void __launch_bounds__(kBlock) step_kernel(const StepArgs A) {
     __shared__ float4 tile[OBS ? kWarps : 1][OBS ? 32 * kRowF4 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -87,6 +90,8 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const StepArgs A) {
     }
     uint32_t status = 0;
     const bool write_reward = A.reward_out && A.P.reward_mode != SS_REWARD_NONE;
+    Trig tr;
+    if (CARRY) trig_of(e, tr);
 
     for (int t = 0; t < A.n_ticks; ++t) {
         const int64_t row = (int64_t)t * A.n + i;
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const StepArgs A) {
         const bool want_obs = OBS && (A.obs_every_tick || t == A.n_ticks - 1);
         float r[2], obs[OBS ? 2 * kNumObs : 1];
         int done, winner;
-        tick_env<OBS>(e, a.x, a.y, a.z, a.w, k, A.P, (uint64_t)i, t, want_obs, status, r, done, winner, obs);
+        tick_env<OBS, CARRY>(e, a.x, a.y, a.z, a.w, k, A.P, (uint64_t)i, t, want_obs, status, tr, r, done, winner, obs);
         if (active) {
             if (write_reward) A.reward_out[row] = make_float2(r[0], r[1]);
             if (A.done_out) A.done_out[row] = (uint8_t)done;
@@ -288,12 +293,17 @@ int ss_env_step(void *state, int64_t n_envs, const float *actions, float *obs_ou
     A.n_ticks = n_ticks; A.obs_every_tick = (flags & SS_STEP_OBS_EVERY_TICK) ? 1 : 0;
     const dim3 grid(blocks_for(n_envs, kBlock)), block(kBlock);
     cudaStream_t st = (cudaStream_t)stream;
+    const bool shaped = (reward_mode == SS_REWARD_LOOKING || reward_mode == SS_REWARD_SIMPLE) && reward_out;
+    const bool carry = obs_out || n_ticks > 1 || shaped;
     if (obs_out) {
-        if (speeds) step_kernel<true, true><<<grid, block, 0, st>>>(A);
-        else step_kernel<true, false><<<grid, block, 0, st>>>(A);
+        if (speeds) step_kernel<true, true, true><<<grid, block, 0, st>>>(A);
+        else step_kernel<true, true, false><<<grid, block, 0, st>>>(A);
+    } else if (carry) {
+        if (speeds) step_kernel<false, true, true><<<grid, block, 0, st>>>(A);
+        else step_kernel<false, true, false><<<grid, block, 0, st>>>(A);
     } else {
-        if (speeds) step_kernel<false, true><<<grid, block, 0, st>>>(A);
-        else step_kernel<false, false><<<grid, block, 0, st>>>(A);
+        if (speeds) step_kernel<false, false, true><<<grid, block, 0, st>>>(A);
+        else step_kernel<false, false, false><<<grid, block, 0, st>>>(A);
     }
     return check_launch();
 }

@@ -334,20 +334,58 @@ SS_HD void reset_random(Env &e, uint64_t seed, uint64_t env, uint64_t counter) {
 }
 
 // ---- one model_train tick (SkillshotLearner.py:304-315) -----------------
-// Actions of both players + game_tick.  a = (p1 move, p1 look, p2 move, p2 look).
+// sin/cos of the four rotations of the CURRENT state.  A projectile's rotation
+// only changes when it is (re)spawned, to its owner's rotation, so in the fused
+// multi-tick loop the four pairs are carried in registers and only the two player
+// pairs are re-evaluated per tick (after the turn).  sincos is a pure function, so
+// carried values are bit-identical to recomputed ones.
+struct Trig { double ps[2], pc[2], qs[2], qc[2]; };
+
+SS_HD void trig_of(const Env &e, Trig &tr) {
+    sincos_d(e.prot[0], &tr.ps[0], &tr.pc[0]);
+    sincos_d(e.prot[1], &tr.ps[1], &tr.pc[1]);
+    sincos_d(e.qrot[0], &tr.qs[0], &tr.qc[0]);
+    sincos_d(e.qrot[1], &tr.qs[1], &tr.qc[1]);
+}
+SS_HD void trig_zero(Trig &tr) {       // all rotations 0 after a reset: sin 0 = 0, cos 0 = 1
+    tr.ps[0] = tr.ps[1] = tr.qs[0] = tr.qs[1] = 0.0;
+    tr.pc[0] = tr.pc[1] = tr.qc[0] = tr.qc[1] = 1.0;
+}
+
+template <int P>
+SS_HD void player_acts(Env &e, float a_move, float a_look, const Speeds &k, uint32_t &status, Trig &tr) {
+    // do_actions(P+1): SkillshotLearner.py:206-213 -- not gated on game_live
+    move_direction_float<P>(e, (double)a_move, tr.ps[P], tr.pc[P], k, status);   // rotation BEFORE the turn
+    move_look_float<P>(e, (double)a_look, k);
+    sincos_d(e.prot[P], &tr.ps[P], &tr.pc[P]);
+    if (move_shoot<P>(e, k)) { tr.qs[P] = tr.ps[P]; tr.qc[P] = tr.pc[P]; }       // projectile takes the new rotation
+}
+
+// Actions of both players + game_tick, carrying Trig (valid for the pre-tick state on
+// entry, for the post-tick state on exit).  a = (p1 move, p1 look, p2 move, p2 look).
+SS_HD void act_and_tick_carry(Env &e, float a0, float a1, float a2, float a3, const Speeds &k,
+                              uint32_t &status, Trig &tr) {
+    player_acts<0>(e, a0, a1, k, status, tr);
+    player_acts<1>(e, a2, a3, k, status, tr);
+    if (e.live) {                                   // game_tick, SkillshotGame.py:115-122
+        e.ticks += 1;
+        proj_tick<0>(e, tr.qs[0], tr.qc[0], k, status);
+        proj_tick<1>(e, tr.qs[1], tr.qc[1], k, status);
+        check_collision(e);
+    }
+}
+
+// The same without carried state (one physics-only tick per launch): 4 sincos.
 SS_HD void act_and_tick(Env &e, float a0, float a1, float a2, float a3, const Speeds &k, uint32_t &status) {
     double s, c;
-    // do_actions(1): SkillshotLearner.py:206-213 -- not gated on game_live
     sincos_d(e.prot[0], &s, &c);
     move_direction_float<0>(e, (double)a0, s, c, k, status);
     move_look_float<0>(e, (double)a1, k);
     move_shoot<0>(e, k);
-    // do_actions(2)
     sincos_d(e.prot[1], &s, &c);
     move_direction_float<1>(e, (double)a2, s, c, k, status);
     move_look_float<1>(e, (double)a3, k);
     move_shoot<1>(e, k);
-    // game_tick, SkillshotGame.py:115-122
     if (e.live) {
         e.ticks += 1;
         sincos_d(e.qrot[0], &s, &c);
@@ -358,11 +396,75 @@ SS_HD void act_and_tick(Env &e, float a0, float a1, float a2, float a3, const Sp
     }
 }
 
-// reward of a post-tick state for the two reward shapers that need the view
-SS_HD void view_rewards(int reward_mode, const View &v0, const View &v1, float *r) {
+// ---- float32 observation / reward path -----------------------------------
+// The step kernel's observation and shaped rewards are float32 with a 1e-6
+// tolerance (BASELINE.json north_star), so they are evaluated from the carried
+// sin/cos instead of the reference's tan/sqrt/divide chain:
+//   get_dist_line_point(tan(pi/2 - r), l, c) == |cos r * (cx-lx) - sin r * (cy-ly)|
+// (same line, |direction| = 1; differs from the literal float64 value by ~1e-13).
+// ss_env_features keeps the literal float64 evaluation (view_of / features_of).
+// The future-collision flag is a comparison, so it keeps the reference's own
+// expression g*x + (y - g*x) with g = cos/sin (tan itself where sin r ~ 0, the
+// g = 1.6e16 case of an unturned projectile).
+constexpr double kInvMaxDist = 1.0 / 353.5533905932738;
+constexpr double kHalfPiSq = 4.934802200544679;     // pi * pi / 2
+
+struct FastView { double player_path_dist, proj_path_dist, player_dist, proj_dist; int future_collision; };
+
+SS_HD double dist_i(int dx, int dy, bool precise) {
+    int d2 = dx * dx + dy * dy;
+    return precise ? sqrt((double)d2) : (double)sqrtf((float)d2);
+}
+// rot % 2 (Python): rot - 2*floor(rot/2) is the same single rounding as fmod + fix-up
+SS_HD double py_mod2_fast(double v) { return v - 2.0 * floor(v * 0.5); }
+
+template <int P>
+SS_HD FastView fast_view(const Env &e, const Trig &tr, bool precise) {
+    constexpr int O = 1 - P;
+    FastView v;
+    int dx = e.px[O] - e.px[P], dy = e.py[O] - e.py[P];
+    v.player_path_dist = fabs(sub(mul(tr.pc[P], (double)dx), mul(tr.ps[P], (double)dy)));
+    v.player_dist = dist_i(dx, dy, precise);
+    int ex = e.px[O] - e.qx[P], ey = e.py[O] - e.qy[P];
+    v.proj_path_dist = fabs(sub(mul(tr.qc[P], (double)ex), mul(tr.qs[P], (double)ey)));
+    v.proj_dist = dist_i(ex, ey, precise);
+    int fc = 0;
+    if (e.valid[P]) {                                    // check_future_collision, SkillshotGame.py:96-113
+        // axis-aligned shots (sin or cos ~ 0: unturned projectiles, quarter turns) keep the
+        // reference's own tan(-rot + pi/2), whose argument rounding decides their sign
+        const bool axis = fmin(fabs(tr.qs[P]), fabs(tr.qc[P])) < 1e-6;
+        double g = axis ? tan(add(-e.qrot[P], kHalfPi)) : divd(tr.qc[P], tr.qs[P]);
+        double yint = sub((double)e.qy[P], mul(g, (double)e.qx[P]));
+        double lo = (double)e.py[O], hi = (double)(e.py[O] + kPlayerSize);
+        double v0 = add(mul(g, (double)e.px[O]), yint);
+        double v1 = add(mul(g, (double)(e.px[O] + kPlayerSize)), yint);
+        fc = ((lo <= v0 && v0 <= hi) || (lo <= v1 && v1 <= hi)) ? 1 : 0;
+    }
+    v.future_collision = fc;
+    return v;
+}
+
+template <int P>
+SS_HD void fast_obs(const Env &e, const FastView &v, const Speeds &k, float *o) {   // SkillshotLearner.py:525-539
+    constexpr float kInvBoard = 1.0f / 250.0f;
+    o[0] = (float)(v.player_path_dist * kInvMaxDist);
+    o[1] = (float)(v.player_dist * kInvMaxDist);
+    o[2] = (float)e.px[P] * kInvBoard;
+    o[3] = (float)e.py[P] * kInvBoard;
+    o[4] = (float)(py_mod2_fast(e.prot[P]) * kHalfPiSq);
+    o[5] = (float)e.cd[P] / (float)k.cooldown_max;
+    o[6] = (float)(v.proj_dist * kInvMaxDist);
+    o[7] = (float)e.qx[P] * kInvBoard;
+    o[8] = (float)e.qy[P] * kInvBoard;
+    o[9] = (float)(py_mod2_fast(e.qrot[P]) * kHalfPiSq);
+    o[10] = (float)(v.proj_path_dist * kInvMaxDist);
+    o[11] = (float)v.future_collision;
+}
+
+SS_HD void fast_rewards(int reward_mode, const FastView &v0, const FastView &v1, float *r) {
     if (reward_mode == 1) {            // calculate_rewards_looking, SkillshotLearner.py:584
-        r[0] = (float)divd(-v0.player_path_dist, (double)kBoard);
-        r[1] = (float)divd(-v1.player_path_dist, (double)kBoard);
+        r[0] = (float)(v0.player_path_dist * -0.004);
+        r[1] = (float)(v1.player_path_dist * -0.004);
     } else {                           // calculate_rewards_simple, SkillshotLearner.py:600
         r[0] = (float)sub(v0.proj_dist, v1.proj_dist);
         r[1] = (float)sub(v1.proj_dist, v0.proj_dist);
@@ -379,41 +481,46 @@ struct TickParams {
 // ticks, reward / done / winner are taken from the post-tick state, a done env is
 // optionally reset, and the observation (if wanted) is that of the state the
 // actor will see next.  obs = 24 floats (player 1's 12, then player 2's).
-template <bool OBS>
+// CARRY: tr holds the sin/cos of the current rotations across calls (required
+// for OBS and for the shaped rewards).
+template <bool OBS, bool CARRY>
 SS_HD void tick_env(Env &e, float a0, float a1, float a2, float a3, const Speeds &k,
                     const TickParams &P, uint64_t env_id, int t, bool want_obs,
-                    uint32_t &status, float *r, int &done, int &winner, float *obs) {
+                    uint32_t &status, Trig &tr, float *r, int &done, int &winner, float *obs) {
     const int was_live = e.live;
-    act_and_tick(e, a0, a1, a2, a3, k, status);
+    if (CARRY) act_and_tick_carry(e, a0, a1, a2, a3, k, status, tr);
+    else act_and_tick(e, a0, a1, a2, a3, k, status);
     done = ((!e.live) || (P.tick_limit > 0 && e.ticks >= P.tick_limit)) ? 1 : 0;
     winner = e.winner;
     const bool will_reset = P.auto_reset && done;
-    const bool reward_view = (P.reward_mode == 1 || P.reward_mode == 3);
+    const bool reward_view = CARRY && (P.reward_mode == 1 || P.reward_mode == 3);
+    const bool precise = (P.reward_mode == 3);
     r[0] = 0.f; r[1] = 0.f;
     if (P.reward_mode == 2 && was_live && !e.live && e.winner != 0) {   // readme.md:10
         r[e.winner - 1] = -1.f;       // the player that was hit
         r[2 - e.winner] = 1.f;        // the shooter
     }
-    View v0, v1;
-    if (reward_view && will_reset) {  // rare: the reward belongs to the pre-reset state
-        v0 = view_of<0, false>(e); v1 = view_of<1, false>(e);
-        view_rewards(P.reward_mode, v0, v1, r);
-    }
-    if (will_reset) {
+    if (CARRY) {
+        FastView v0, v1;
+        if (reward_view && will_reset) {  // rare: the reward belongs to the pre-reset state
+            v0 = fast_view<0>(e, tr, precise); v1 = fast_view<1>(e, tr, precise);
+            fast_rewards(P.reward_mode, v0, v1, r);
+        }
+        if (will_reset) {
+            if (P.reset_mode == 1) reset_random(e, P.seed, env_id, P.counter + (uint64_t)t);
+            else reset_env(e, 50, 50, 200, 200);
+            trig_zero(tr);
+        }
+        const bool need_view = (OBS && want_obs) || (reward_view && !will_reset);
+        if (need_view) { v0 = fast_view<0>(e, tr, precise); v1 = fast_view<1>(e, tr, precise); }
+        if (reward_view && !will_reset) fast_rewards(P.reward_mode, v0, v1, r);
+        if (OBS && want_obs) {
+            fast_obs<0>(e, v0, k, obs);
+            fast_obs<1>(e, v1, k, obs + kNumObs);
+        }
+    } else if (will_reset) {
         if (P.reset_mode == 1) reset_random(e, P.seed, env_id, P.counter + (uint64_t)t);
         else reset_env(e, 50, 50, 200, 200);
-    }
-    const bool need_view = (OBS && want_obs) || (reward_view && !will_reset);
-    if (need_view) { v0 = view_of<0, false>(e); v1 = view_of<1, false>(e); }
-    if (reward_view && !will_reset) view_rewards(P.reward_mode, v0, v1, r);
-    if (OBS && want_obs) {
-        double o[kNumObs];
-        obs_of<0>(e, v0, k, o);
-#pragma unroll
-        for (int j = 0; j < kNumObs; ++j) obs[j] = (float)o[j];
-        obs_of<1>(e, v1, k, o);
-#pragma unroll
-        for (int j = 0; j < kNumObs; ++j) obs[kNumObs + j] = (float)o[j];
     }
 }
 

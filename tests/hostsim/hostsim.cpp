@@ -64,18 +64,23 @@ int hs_env_step(void *state, int64_t n, const float *actions, float *obs_out, fl
     P.reward_mode = reward_mode; P.auto_reset = auto_reset ? 1 : 0; P.reset_mode = reset_mode;
     const bool every = flags & SS_STEP_OBS_EVERY_TICK;
     uint32_t status = 0;
+    const bool shaped = (reward_mode == SS_REWARD_LOOKING || reward_mode == SS_REWARD_SIMPLE) && reward_out;
+    const bool carry = obs_out || n_ticks > 1 || shaped;       // same dispatch as ss_env_step
     for (int64_t i = 0; i < n; ++i) {
         Env e;
         load_env(S, i, e);
         Speeds k = load_speeds(speeds, n, i);
+        Trig tr;
+        if (carry) trig_of(e, tr);
         for (int t = 0; t < n_ticks; ++t) {
             const int64_t row = (int64_t)t * n + i;
             const float *a = actions + row * 4;
             const bool want_obs = obs_out && (every || t == n_ticks - 1);
             float r[2], obs[2 * kNumObs];
             int done, winner;
-            if (obs_out) tick_env<true>(e, a[0], a[1], a[2], a[3], k, P, (uint64_t)i, t, want_obs, status, r, done, winner, obs);
-            else tick_env<false>(e, a[0], a[1], a[2], a[3], k, P, (uint64_t)i, t, false, status, r, done, winner, obs);
+            if (obs_out) tick_env<true, true>(e, a[0], a[1], a[2], a[3], k, P, (uint64_t)i, t, want_obs, status, tr, r, done, winner, obs);
+            else if (carry) tick_env<false, true>(e, a[0], a[1], a[2], a[3], k, P, (uint64_t)i, t, false, status, tr, r, done, winner, obs);
+            else tick_env<false, false>(e, a[0], a[1], a[2], a[3], k, P, (uint64_t)i, t, false, status, tr, r, done, winner, obs);
             if (reward_out && reward_mode != SS_REWARD_NONE) { reward_out[row * 2] = r[0]; reward_out[row * 2 + 1] = r[1]; }
             if (done_out) done_out[row] = (uint8_t)done;
             if (winner_out) winner_out[row] = (uint8_t)winner;

@@ -36,6 +36,39 @@ def start_from_golden(make, g, **kw):
     return envs
 
 
+def ambiguous_future_collision(st, proj_grad):
+    """bool [n,2]: views whose check_future_collision (SkillshotGame.py:96-113) is decided by
+    rounding noise in the reference itself: the line value g*x + (y - g*x) lands on a box
+    bound (typically projectile x == opponent bound x and projectile y == a y bound, an
+    integer coincidence), so the comparison's outcome depends on the last bits of the host
+    libm's tan().  No independent implementation can reproduce those bits; the flag is
+    compared exactly everywhere else.  proj_grad = reference projectile_grad, float64 [n,2]."""
+    out = np.zeros(st["qx"].shape, bool)
+    for p in range(2):
+        o = 1 - p
+        g = proj_grad[:, p]
+        qx, qy = st["qx"][:, p].astype(float), st["qy"][:, p].astype(float)
+        ox, oy = st["px"][:, o].astype(float), st["py"][:, o].astype(float)
+        tol = 1e-9 * (1.0 + np.abs(g) * 250.0)
+        d = np.full(len(g), np.inf)
+        for xb in (ox, ox + 5):
+            v = qy + g * (xb - qx)
+            d = np.minimum(d, np.minimum(np.abs(v - oy), np.abs(v - (oy + 5))))
+        out[:, p] = (st["valid"][:, p] == 1) & (d <= tol)
+    return out
+
+
+def assert_obs_close(obs, ref_obs, st, proj_grad, msg):
+    """float32 observations: 1e-6 relative (+1e-6 absolute); the future-collision flag
+    (column 11) exact except on the ambiguous set."""
+    obs, ref_obs = np.array(obs, copy=True), np.asarray(ref_obs, np.float32)
+    amb = ambiguous_future_collision(st, proj_grad)
+    obs[..., 11] = np.where(amb, ref_obs[..., 11], obs[..., 11])
+    np.testing.assert_array_equal(obs[..., 11], ref_obs[..., 11], err_msg=msg + " future-collision flag")
+    np.testing.assert_allclose(obs, ref_obs, rtol=OBS_RTOL, atol=OBS_ATOL, err_msg=msg)
+    return int(amb.sum())
+
+
 def assert_state_equal(st, ref, msg):
     for k in INT_FIELDS + ("ticks", "live", "winner"):
         np.testing.assert_array_equal(st[k], ref[k], err_msg=f"{msg} {k}")
@@ -61,17 +94,18 @@ def check_golden_lockstep(make, name):
     for t in range(T):
         out = envs.step(g["actions"][:, t])
         ref = {k: g[k][:, t + 1] for k in INT_FIELDS + ("ticks", "live", "winner", "prot", "qrot")}
-        assert_state_equal(envs.export_state(), ref, f"{name} t={t + 1}")
+        st = envs.export_state()
+        assert_state_equal(st, ref, f"{name} t={t + 1}")
         np.testing.assert_array_equal(to_np(out["winner"]), g["winner"][:, t + 1])
         np.testing.assert_array_equal(to_np(out["done"]), 1 - g["live"][:, t + 1])
-        np.testing.assert_allclose(to_np(out["obs"]), g["obs"][:, t + 1].astype(np.float32),
-                                   rtol=OBS_RTOL, atol=OBS_ATOL, err_msg=f"{name} obs t={t + 1}")
-        # the future-collision flag is a discrete outcome: exact
-        np.testing.assert_array_equal(to_np(out["obs"])[..., 11], g["obs"][:, t + 1, :, 11].astype(np.float32))
+        assert_obs_close(to_np(out["obs"]), g["obs"][:, t + 1], st, g["feat"][:, t + 1, :, 8], f"{name} obs t={t + 1}")
         np.testing.assert_allclose(to_np(out["reward"]), g["rew_looking"][:, t + 1].astype(np.float32),
                                    rtol=OBS_RTOL, atol=OBS_ATOL, err_msg=f"{name} reward t={t + 1}")
         if t % 8 == 0 or t == T - 1:
             feat, obs64, gen = (to_np(x) for x in envs.features())
+            amb = ambiguous_future_collision(st, g["feat"][:, t + 1, :, 8])
+            feat[..., 17] = np.where(amb, g["feat"][:, t + 1, :, 17], feat[..., 17])
+            obs64[..., 11] = np.where(amb, g["obs"][:, t + 1, :, 11], obs64[..., 11])
             assert_features_close(feat, g["feat"][:, t + 1], f"{name} t={t + 1}")
             np.testing.assert_allclose(obs64, g["obs"][:, t + 1], rtol=1e-12, atol=1e-12)
             np.testing.assert_array_equal(gen[:, 0], g["live"][:, t + 1])
@@ -89,8 +123,10 @@ def check_golden_fused(make, name, K=8):
         out = envs.step(a, obs_every_tick=True)
         ref = {k: g[k][:, t0 + K] for k in INT_FIELDS + ("ticks", "live", "winner", "prot", "qrot")}
         assert_state_equal(envs.export_state(), ref, f"{name} fused t={t0 + K}")
-        want_obs = np.swapaxes(g["obs"][:, t0 + 1:t0 + K + 1], 0, 1).astype(np.float32)
-        np.testing.assert_allclose(to_np(out["obs"]), want_obs, rtol=OBS_RTOL, atol=OBS_ATOL)
+        obs = to_np(out["obs"])
+        for c in range(K):
+            stc = {k: g[k][:, t0 + c + 1] for k in ("qx", "qy", "px", "py", "valid")}
+            assert_obs_close(obs[c], g["obs"][:, t0 + c + 1], stc, g["feat"][:, t0 + c + 1, :, 8], f"{name} fused obs t={t0 + c + 1}")
         want_rew = np.swapaxes(g["rew_simple"][:, t0 + 1:t0 + K + 1], 0, 1).astype(np.float32)
         np.testing.assert_allclose(to_np(out["reward"]), want_rew, rtol=OBS_RTOL, atol=1e-4)
         np.testing.assert_array_equal(to_np(out["winner"]), np.swapaxes(g["winner"][:, t0 + 1:t0 + K + 1], 0, 1))
@@ -114,7 +150,7 @@ def check_oracle_lockstep(make, n, T, seed, close=False, reward_mode="looking", 
     orc = OracleEnvs(n, pos)
     envs = make(n, reward_mode=reward_mode)
     envs.reset(positions=pos)
-    hits = 0
+    hits = ambiguous = 0
     for t0 in range(0, T, chunk):
         a = random_actions(rng, (chunk, n, 2, 2))
         if close:
@@ -132,9 +168,9 @@ def check_oracle_lockstep(make, n, T, seed, close=False, reward_mode="looking", 
             elif reward_mode != "none":
                 np.testing.assert_allclose(rew, ro["reward"], rtol=OBS_RTOL, atol=2e-5 if reward_mode == "simple" else OBS_ATOL)
         if (t0 // chunk) % compare_every == 0:
-            assert_state_equal(envs.export_state(), orc.snapshot(), f"t={t0 + chunk}")
-            np.testing.assert_allclose(to_np(out["obs"]), ro["obs"], rtol=OBS_RTOL, atol=OBS_ATOL)
-            np.testing.assert_array_equal(to_np(out["obs"])[..., 11], ro["obs"][..., 11])
+            snap = orc.snapshot()
+            assert_state_equal(envs.export_state(), snap, f"t={t0 + chunk}")
+            ambiguous += assert_obs_close(to_np(out["obs"]), ro["obs"], snap, orc.features()[0][..., 8], f"obs t={t0 + chunk}")
         hits = int((orc.envs["live"] == 0).sum())
     assert_state_equal(envs.export_state(), orc.snapshot(), "final")
     return hits
@@ -151,8 +187,9 @@ def check_auto_reset(make, n=64, T=40, seed=5):
         ro = orc.step(a, tick_limit=7, auto_reset=True)
         np.testing.assert_array_equal(to_np(out["done"]), ro["done"])
         np.testing.assert_allclose(to_np(out["reward"]), ro["reward"], rtol=OBS_RTOL, atol=OBS_ATOL)
-        np.testing.assert_allclose(to_np(out["obs"]), ro["obs"], rtol=OBS_RTOL, atol=OBS_ATOL)
-        assert_state_equal(envs.export_state(), orc.snapshot(), f"auto-reset t={t}")
+        snap = orc.snapshot()
+        assert_obs_close(to_np(out["obs"]), ro["obs"], snap, orc.features()[0][..., 8], f"auto-reset obs t={t}")
+        assert_state_equal(envs.export_state(), snap, f"auto-reset t={t}")
     assert int(ro["done"].sum()) == 0 and T % 7 != 0 or True
 
 
@@ -187,5 +224,6 @@ def check_speeds(make, n=32, T=48, seed=9):
         a = random_actions(rng, (n, 2, 2))
         out = envs.step(a)
         ro = orc.step(a)
-        assert_state_equal(envs.export_state(), orc.snapshot(), f"speeds t={t}")
-        np.testing.assert_allclose(to_np(out["obs"]), ro["obs"], rtol=OBS_RTOL, atol=OBS_ATOL)
+        snap = orc.snapshot()
+        assert_state_equal(envs.export_state(), snap, f"speeds t={t}")
+        assert_obs_close(to_np(out["obs"]), ro["obs"], snap, orc.features()[0][..., 8], f"speeds obs t={t}")
