@@ -8,7 +8,7 @@ GPU, U(-1.2,1.2) float32 random actions, random starts, terminal +1/-1/0 reward,
 2,000-tick limit with auto-reset.  One bench "step" = TICKS ticks of all envs
 (TICKS * 65,536 env-steps per GPU), played by ss_env_step in launches of
 TICKS_PER_LAUNCH fused ticks.  The action stream of a step ([TICKS, E, 2, 2]
-float32 = 268 MB) is larger than the 126 MB L2, so every timed iteration streams
+float32 = 2.1 GB) is larger than the 126 MB L2, so every timed iteration streams
 it from HBM ("inputs larger than L2"); the 4 MB game state is L2-resident by
 design.
 
@@ -39,7 +39,7 @@ if ROOT not in sys.path:
 import numpy as np
 
 ENVS_PER_GPU = 65536
-TICKS = 256                 # ticks per bench step
+TICKS = 2048                # ticks per bench step (one full 2,000-tick episode plus the auto-reset)
 TICKS_PER_LAUNCH = 32       # fused ticks per ss_env_step launch
 TICK_LIMIT = 2000           # SkillshotLearner.py:62
 ALGO_BYTES_PER_ENV_STEP = 202   # SURVEY.md 8(d), physics-only
@@ -72,7 +72,7 @@ def ncu_traffic():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons during the timed region (NVML)."""
 
-    def __init__(self, index: int, period: float = 0.02):
+    def __init__(self, index: int, period: float = 0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -234,7 +234,7 @@ def run_gpu_arm(args):
     envs.check_status()
 
     # ---- end to end through the host-buffer API (e2e) ----
-    e2e_steps, e2e_s = max(3, min(args.steps, 20)), float("nan")
+    e2e_steps, e2e_s = max(3, min(args.steps, 10)), float("nan")
     if not args.no_e2e:
         host_actions = torch.empty((T, E, 2, 2), dtype=torch.float32, pin_memory=True)
         host_actions.copy_(actions)
@@ -288,7 +288,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ticks", type=int, default=TICKS)

@@ -10,6 +10,7 @@
 // The step is HBM-bound by design: no tensor-core work here.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/skillshot_b200.h"
 #include "ss_env_core.cuh"
@@ -51,8 +52,17 @@ __device__ __forceinline__ Speeds load_speeds(const void *speeds, int64_t n, int
     double2 a = ((const double2 *)b)[i];
     const double *p1 = (const double *)(b + 16 * n) + 2 * i;
     long long cm = ((const long long *)(b + 16 * n))[2 * i + 1];
-    return Speeds{a.x, a.y, p1[0], (int)cm};
+    return Speeds{a.x, a.y, p1[0], (int)cm, 1.0f / (float)cm};
 }
+
+// fast_obs sink: the thread's row of the warp's shared-memory staging tile
+struct SmemSink {
+    float4 *row;
+    __device__ __forceinline__ void put(int j, float a, float b, float c, float d) { row[j] = make_float4(a, b, c, d); }
+};
+struct NoSink {
+    __device__ __forceinline__ void put(int, float, float, float, float) {}
+};
 
 struct StepArgs {
     void *state;
@@ -71,8 +81,8 @@ struct StepArgs {
 // OBS: write observations.  CARRY: keep sin/cos of the rotations in registers across
 // ticks (fused ticks, observations, shaped rewards); !CARRY is the lean one-tick
 // physics-only kernel.
-template <bool OBS, bool CARRY, bool SPEEDS>
-__global__ void __launch_bounds__(kBlock) step_kernel(const StepArgs A) {
+template <bool OBS, bool CARRY, bool SPEEDS, int MINB = 1>
+__global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
     __shared__ float4 tile[OBS ? kWarps : 1][OBS ? 32 * kRowF4 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -93,25 +103,25 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const StepArgs A) {
     Trig tr;
     if (CARRY) trig_of(e, tr);
 
+    float4 a_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) a_next = __ldg(A.actions + i);
     for (int t = 0; t < A.n_ticks; ++t) {
         const int64_t row = (int64_t)t * A.n + i;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) a = __ldg(A.actions + row);
+        const float4 a = a_next;
+        if (active && t + 1 < A.n_ticks) a_next = __ldg(A.actions + row + A.n);   // prefetch: hide the load behind this tick
         const bool want_obs = OBS && (A.obs_every_tick || t == A.n_ticks - 1);
-        float r[2], obs[OBS ? 2 * kNumObs : 1];
+        float r[2];
         int done, winner;
-        tick_env<OBS, CARRY>(e, a.x, a.y, a.z, a.w, k, A.P, (uint64_t)i, t, want_obs, status, tr, r, done, winner, obs);
+        SmemSink sink{&tile[OBS ? warp : 0][OBS ? lane * kRowF4 : 0]};
+        tick_env<OBS, CARRY>(e, a.x, a.y, a.z, a.w, k, A.P, (uint64_t)i, t, want_obs, status, tr, r, done, winner, sink);
         if (active) {
             if (write_reward) A.reward_out[row] = make_float2(r[0], r[1]);
             if (A.done_out) A.done_out[row] = (uint8_t)done;
             if (A.winner_out) A.winner_out[row] = (uint8_t)winner;
         }
         if (OBS && want_obs) {
-            // stage the warp's 32 x 24 floats, then write them as 6 coalesced 512-byte requests
-            float4 *mine = &tile[warp][lane * kRowF4];
-#pragma unroll
-            for (int j = 0; j < 6; ++j)
-                mine[j] = make_float4(obs[4 * j], obs[4 * j + 1], obs[4 * j + 2], obs[4 * j + 3]);
+            // the warp's 32 x 24 floats are staged in shared memory (SmemSink); write them as
+            // 6 coalesced 512-byte requests
             __syncwarp();
             const int64_t tick_off = A.obs_every_tick ? (int64_t)t * A.n * 6 : 0;
             float4 *dst = A.obs_out + tick_off + warp_base * 6;
@@ -295,9 +305,18 @@ int ss_env_step(void *state, int64_t n_envs, const float *actions, float *obs_ou
     cudaStream_t st = (cudaStream_t)stream;
     const bool shaped = (reward_mode == SS_REWARD_LOOKING || reward_mode == SS_REWARD_SIMPLE) && reward_out;
     const bool carry = obs_out || n_ticks > 1 || shaped;
+    // The staging tile is 7 KB + 1 KB driver reserve per CTA; ask for a carve-out that fits 8+ CTAs.
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(step_kernel<true, true, false, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        cudaFuncSetAttribute(step_kernel<true, true, true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        configured = true;
+    }
     if (obs_out) {
-        if (speeds) step_kernel<true, true, true><<<grid, block, 0, st>>>(A);
-        else step_kernel<true, true, false><<<grid, block, 0, st>>>(A);
+        // 8 CTAs (16 warps) per SM: capping the observation kernel at 128 registers measured
+        // 83 us vs 100 us uncapped at 1M envs (profiles/README.md)
+        if (speeds) step_kernel<true, true, true, 8><<<grid, block, 0, st>>>(A);
+        else step_kernel<true, true, false, 8><<<grid, block, 0, st>>>(A);
     } else if (carry) {
         if (speeds) step_kernel<false, true, true><<<grid, block, 0, st>>>(A);
         else step_kernel<false, true, false><<<grid, block, 0, st>>>(A);

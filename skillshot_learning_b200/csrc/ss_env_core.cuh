@@ -13,6 +13,7 @@
 // explicit _rn intrinsics as well.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 #include <math.h>
 
 #if defined(__CUDACC__)
@@ -71,12 +72,66 @@ SS_HD int rint_i(double v) {
     return (int)rint(v);
 #endif
 }
-SS_HD void sincos_d(double r, double *s, double *c) {
+// ---- sin/cos ------------------------------------------------------------
+// Library fallback (huge or non-finite arguments only).
+SS_HD void sincos_lib(double r, double *s, double *c) {
 #ifdef __CUDA_ARCH__
     sincos(r, s, c);
 #else
     *s = sin(r); *c = cos(r);
 #endif
+}
+SS_HD int lo_word(double v) {
+#ifdef __CUDA_ARCH__
+    return __double2loint(v);
+#else
+    uint64_t b; memcpy(&b, &v, sizeof b); return (int)(uint32_t)b;
+#endif
+}
+SS_HD double flip_sign_if(double v, int cond) {    // v or -v without a branch
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(v) ^ (cond ? (int)0x80000000 : 0), __double2loint(v));
+#else
+    return cond ? -v : v;
+#endif
+}
+// sin and cos of one float64 rotation: Cody-Waite reduction by pi/2 in three FMA
+// steps (each FMA rounds once, relative to its own result, so the reduced argument
+// keeps full precision), then the fdlibm minimax kernels on [-pi/4, pi/4].
+// Measured max error vs 80-bit libm: 1.52 ulp, mean 0.3 ulp (tests/test_sincos.py; the
+// CUDA library's documented bound is 2 ulp; the kernels alone stay under 0.75 ulp).  Pure IEEE
+// arithmetic with explicit FMAs, so host and device builds return identical bits.
+// About a third of the instructions of the CUDA library sincos (no slow-path call,
+// no local-memory out-parameters), which is what the step kernel's issue rate needs.
+SS_HD void sincos_d(double x, double *sp, double *cp) {
+    if (!(fabs(x) < 1.0e5)) { sincos_lib(x, sp, cp); return; }
+    const double kMagic = 6755399441055744.0;                  // 1.5 * 2^52: round-to-nearest-int trick
+    double q = fma(x, 0.6366197723675814, kMagic);             // x * 2/pi
+    const int k = lo_word(q);
+    q -= kMagic;
+    double t = fma(q, -1.5707963267948966, x);
+    t = fma(q, -6.123233995736766e-17, t);
+    t = fma(q, 1.4973849048591698e-33, t);
+    const double t2 = t * t;
+    double ps = fma(1.58969099521155010221e-10, t2, -2.50507602534068634195e-08);
+    ps = fma(ps, t2, 2.75573137070700676789e-06);
+    ps = fma(ps, t2, -1.98412698298579493134e-04);
+    ps = fma(ps, t2, 8.33333333332248946124e-03);
+    ps = fma(ps, t2, -1.66666666666666324348e-01);
+    const double sn = fma(t * t2, ps, t);
+    double pc = fma(-1.13596475577881948265e-11, t2, 2.08757232129817482790e-09);
+    pc = fma(pc, t2, -2.75573143513906633035e-07);
+    pc = fma(pc, t2, 2.48015872894767294178e-05);
+    pc = fma(pc, t2, -1.38888888888741095749e-03);
+    pc = fma(pc, t2, 4.16666666666666019037e-02);
+    // 1 - t2/2 + t2^2*pc with the rounding error of (1 - t2/2) fed back (fdlibm/musl __cos form)
+    const double hz = 0.5 * t2, w = 1.0 - hz;
+    const double cs = w + (((1.0 - w) - hz) + (t2 * t2) * pc);
+    // quadrant k mod 4: (s,c) = (sn,cs), (cs,-sn), (-sn,-cs), (-cs,sn)
+    const int swap = k & 1;
+    const double a = swap ? cs : sn, b = swap ? sn : cs;
+    *sp = flip_sign_if(a, (k & 2) != 0);
+    *cp = flip_sign_if(b, ((k + 1) & 2) != 0);
 }
 SS_HD bool finite_d(double v) { return v - v == 0.0; }
 
@@ -94,8 +149,9 @@ struct Speeds {
     double speed_look;   // Player.speed_look = 0.25     Player.py:15
     double proj_speed;   // Projectile.speed_move = 5    Projectile.py:10
     int cooldown_max;    // Projectile.cooldown_max = 15 Projectile.py:9
+    float inv_cooldown;  // 1 / cooldown_max, for the float32 observation
 };
-SS_HD Speeds default_speeds() { return Speeds{3.0, 0.25, 5.0, 15}; }
+SS_HD Speeds default_speeds() { return Speeds{3.0, 0.25, 5.0, 15, 1.0f / 15.0f}; }
 
 // ---- one game in registers ----------------------------------------------
 struct Env {
@@ -430,35 +486,46 @@ SS_HD FastView fast_view(const Env &e, const Trig &tr, bool precise) {
     v.proj_dist = dist_i(ex, ey, precise);
     int fc = 0;
     if (e.valid[P]) {                                    // check_future_collision, SkillshotGame.py:96-113
-        // axis-aligned shots (sin or cos ~ 0: unturned projectiles, quarter turns) keep the
-        // reference's own tan(-rot + pi/2), whose argument rounding decides their sign
-        const bool axis = fmin(fabs(tr.qs[P]), fabs(tr.qc[P])) < 1e-6;
-        double g = axis ? tan(add(-e.qrot[P], kHalfPi)) : divd(tr.qc[P], tr.qs[P]);
-        double yint = sub((double)e.qy[P], mul(g, (double)e.qx[P]));
-        double lo = (double)e.py[O], hi = (double)(e.py[O] + kPlayerSize);
-        double v0 = add(mul(g, (double)e.px[O]), yint);
-        double v1 = add(mul(g, (double)(e.px[O] + kPlayerSize)), yint);
-        fc = ((lo <= v0 && v0 <= hi) || (lo <= v1 && v1 <= hi)) ? 1 : 0;
+        const double s = tr.qs[P], c = tr.qc[P];
+        const int d0 = e.px[O] - e.qx[P], d1 = d0 + kPlayerSize;     // opponent x bounds relative to the projectile
+        const int l = e.py[O] - e.qy[P], h = l + kPlayerSize;        // opponent y bounds relative to the projectile
+        if (fmin(fabs(s), fabs(c)) < 1e-6) {
+            // axis-aligned shots (sin or cos ~ 0: unturned projectiles, quarter turns) keep the
+            // reference's own expression with g = tan(-rot + pi/2), whose argument rounding decides them
+            double g = tan(add(-e.qrot[P], kHalfPi));
+            double yint = sub((double)e.qy[P], mul(g, (double)e.qx[P]));
+            double lo = (double)e.py[O], hi = (double)(e.py[O] + kPlayerSize);
+            double v0 = add(mul(g, (double)e.px[O]), yint);
+            double v1 = add(mul(g, (double)(e.px[O] + kPlayerSize)), yint);
+            fc = ((lo <= v0 && v0 <= hi) || (lo <= v1 && v1 <= hi)) ? 1 : 0;
+        } else {
+            // lo <= y + (c/s)(x_b - x) <= hi  <=>  l*s <= c*d <= h*s (s > 0; reversed for s < 0):
+            // the same line test without the divide.  It can differ from the reference only
+            // where the reference's own value is rounding noise (the line through a box corner).
+            const double ls = (double)l * s, hs = (double)h * s;
+            const double lo = fmin(ls, hs), hi = fmax(ls, hs);
+            const double c0 = c * (double)d0, c1 = c * (double)d1;
+            fc = ((lo <= c0 && c0 <= hi) || (lo <= c1 && c1 <= hi)) ? 1 : 0;
+        }
     }
     v.future_collision = fc;
     return v;
 }
 
-template <int P>
-SS_HD void fast_obs(const Env &e, const FastView &v, const Speeds &k, float *o) {   // SkillshotLearner.py:525-539
+// The 12 observation floats of player P, handed to `sink` four at a time (slots
+// 3P .. 3P+2 of the env's six float4) so that no more than four are live at once.
+template <int P, class Sink>
+SS_HD void fast_obs(const Env &e, const FastView &v, const Speeds &k, Sink &sink) {   // SkillshotLearner.py:525-539
     constexpr float kInvBoard = 1.0f / 250.0f;
-    o[0] = (float)(v.player_path_dist * kInvMaxDist);
-    o[1] = (float)(v.player_dist * kInvMaxDist);
-    o[2] = (float)e.px[P] * kInvBoard;
-    o[3] = (float)e.py[P] * kInvBoard;
-    o[4] = (float)(py_mod2_fast(e.prot[P]) * kHalfPiSq);
-    o[5] = (float)e.cd[P] / (float)k.cooldown_max;
-    o[6] = (float)(v.proj_dist * kInvMaxDist);
-    o[7] = (float)e.qx[P] * kInvBoard;
-    o[8] = (float)e.qy[P] * kInvBoard;
-    o[9] = (float)(py_mod2_fast(e.qrot[P]) * kHalfPiSq);
-    o[10] = (float)(v.proj_path_dist * kInvMaxDist);
-    o[11] = (float)v.future_collision;
+    sink.put(3 * P + 0,
+             (float)(v.player_path_dist * kInvMaxDist), (float)(v.player_dist * kInvMaxDist),
+             (float)e.px[P] * kInvBoard, (float)e.py[P] * kInvBoard);
+    sink.put(3 * P + 1,
+             (float)(py_mod2_fast(e.prot[P]) * kHalfPiSq), (float)e.cd[P] * k.inv_cooldown,
+             (float)(v.proj_dist * kInvMaxDist), (float)e.qx[P] * kInvBoard);
+    sink.put(3 * P + 2,
+             (float)e.qy[P] * kInvBoard, (float)(py_mod2_fast(e.qrot[P]) * kHalfPiSq),
+             (float)(v.proj_path_dist * kInvMaxDist), (float)v.future_collision);
 }
 
 SS_HD void fast_rewards(int reward_mode, const FastView &v0, const FastView &v1, float *r) {
@@ -483,10 +550,10 @@ struct TickParams {
 // actor will see next.  obs = 24 floats (player 1's 12, then player 2's).
 // CARRY: tr holds the sin/cos of the current rotations across calls (required
 // for OBS and for the shaped rewards).
-template <bool OBS, bool CARRY>
+template <bool OBS, bool CARRY, class Sink>
 SS_HD void tick_env(Env &e, float a0, float a1, float a2, float a3, const Speeds &k,
                     const TickParams &P, uint64_t env_id, int t, bool want_obs,
-                    uint32_t &status, Trig &tr, float *r, int &done, int &winner, float *obs) {
+                    uint32_t &status, Trig &tr, float *r, int &done, int &winner, Sink &sink) {
     const int was_live = e.live;
     if (CARRY) act_and_tick_carry(e, a0, a1, a2, a3, k, status, tr);
     else act_and_tick(e, a0, a1, a2, a3, k, status);
@@ -515,8 +582,8 @@ SS_HD void tick_env(Env &e, float a0, float a1, float a2, float a3, const Speeds
         if (need_view) { v0 = fast_view<0>(e, tr, precise); v1 = fast_view<1>(e, tr, precise); }
         if (reward_view && !will_reset) fast_rewards(P.reward_mode, v0, v1, r);
         if (OBS && want_obs) {
-            fast_obs<0>(e, v0, k, obs);
-            fast_obs<1>(e, v1, k, obs + kNumObs);
+            fast_obs<0>(e, v0, k, sink);
+            fast_obs<1>(e, v1, k, sink);
         }
     } else if (will_reset) {
         if (P.reset_mode == 1) reset_random(e, P.seed, env_id, P.counter + (uint64_t)t);

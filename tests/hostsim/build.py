@@ -12,6 +12,6 @@ def build():
     newest = max(os.path.getmtime(src), os.path.getmtime(core))
     if not os.path.exists(SO) or os.path.getmtime(SO) < newest:
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+        subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-mfma",
                         "-Wno-unknown-pragmas", "-o", SO, src, "-lm"], check=True)
     return SO

@@ -34,11 +34,20 @@ Speeds load_speeds(const void *speeds, int64_t n, int64_t i) {
     const double *a = (const double *)b + 2 * i;
     const double *p1 = (const double *)(b + 16 * n) + 2 * i;
     long long cm = ((const long long *)(b + 16 * n))[2 * i + 1];
-    return Speeds{a[0], a[1], p1[0], (int)cm};
+    return Speeds{a[0], a[1], p1[0], (int)cm, 1.0f / (float)cm};
 }
+struct HostSink {
+    float *obs;
+    void put(int j, float a, float b, float c, float d) { float *o = obs + 4 * j; o[0] = a; o[1] = b; o[2] = c; o[3] = d; }
+};
 }  // namespace
 
 extern "C" {
+
+// the kernel core's sincos, for tests/test_sincos.py
+void hs_sincos(const double *x, int64_t n, double *s, double *c) {
+    for (int64_t i = 0; i < n; ++i) sincos_d(x[i], s + i, c + i);
+}
 
 int hs_env_reset(void *state, int64_t n, const uint8_t *mask, int reset_mode, const int32_t *positions,
                  uint64_t seed, uint64_t counter) {
@@ -78,9 +87,10 @@ int hs_env_step(void *state, int64_t n, const float *actions, float *obs_out, fl
             const bool want_obs = obs_out && (every || t == n_ticks - 1);
             float r[2], obs[2 * kNumObs];
             int done, winner;
-            if (obs_out) tick_env<true, true>(e, a[0], a[1], a[2], a[3], k, P, (uint64_t)i, t, want_obs, status, tr, r, done, winner, obs);
-            else if (carry) tick_env<false, true>(e, a[0], a[1], a[2], a[3], k, P, (uint64_t)i, t, false, status, tr, r, done, winner, obs);
-            else tick_env<false, false>(e, a[0], a[1], a[2], a[3], k, P, (uint64_t)i, t, false, status, tr, r, done, winner, obs);
+            HostSink sink{obs};
+            if (obs_out) tick_env<true, true>(e, a[0], a[1], a[2], a[3], k, P, (uint64_t)i, t, want_obs, status, tr, r, done, winner, sink);
+            else if (carry) tick_env<false, true>(e, a[0], a[1], a[2], a[3], k, P, (uint64_t)i, t, false, status, tr, r, done, winner, sink);
+            else tick_env<false, false>(e, a[0], a[1], a[2], a[3], k, P, (uint64_t)i, t, false, status, tr, r, done, winner, sink);
             if (reward_out && reward_mode != SS_REWARD_NONE) { reward_out[row * 2] = r[0]; reward_out[row * 2 + 1] = r[1]; }
             if (done_out) done_out[row] = (uint8_t)done;
             if (winner_out) winner_out[row] = (uint8_t)winner;
