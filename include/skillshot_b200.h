@@ -134,6 +134,108 @@ int ss_env_import(void *state, int64_t n_envs, int64_t first, int64_t count,
 int ss_env_apply(void *state, int64_t n_envs, int64_t env, int player, int op, double value,
                  const void *speeds, uint32_t *status, void *stream);
 
+/* ==== learner path =========================================================
+ * The actor and critic of SkillshotLearner.model_define_actor / _critic
+ * (SkillshotLearner.py:70-121).  A network's parameters are ONE flat float32
+ * vector in Keras get_weights() order, Dense kernels stored [in][out]:
+ *   actor   W1[12][256] b1[256] W2[256][128] b2[128] W3[128][2] b3[2]     36,482
+ *   critic  W1[12][256] b1[256] W2[258][128] b2[128] W3[128][1] b3[1]     36,609
+ * (critic W2 rows 0..255 take the dropped-out hidden layer, rows 256..257 the
+ * action: concatenate([layer_model, actor_input]), SkillshotLearner.py:106).
+ * Gradients, Adam moments and target networks use the same layout, so one
+ * all-reduce over a flat buffer is the only exchange step of a multi-GPU update.
+ * All matrices of samples are row-major float32: obs [n][12], act [n][2].
+ * Parameter vectors must be 16-byte aligned. */
+#define SS_DIM_STATE 12
+#define SS_DIM_ACTION 2
+#define SS_HIDDEN1 256
+#define SS_HIDDEN2 128
+#define SS_ACTOR_PARAMS 36482
+#define SS_CRITIC_PARAMS 36609
+#define SS_LEARNER_MAX_PARTS 512   /* most CTAs a gradient kernel will use */
+
+/* Bytes of scratch the gradient entry points need (per-CTA gradient slices). */
+int64_t ss_learner_workspace_bytes(void);
+
+/* model_act / model_act_action_noise / model_act_param_noise
+ * (SkillshotLearner.py:215-281) for n observations, without the env side effects
+ * (do_actions is ss_env_step / ss_env_apply):  act_out[n][2] = actor(obs).
+ *   param_noise_sd > 0: the actor is evaluated with w + w * N(0, sd) on all six
+ *     arrays (SkillshotLearner.py:260-265); one draw is shared by `noise_group`
+ *     consecutive rows (1 = the reference's fresh draw per call), drawn from
+ *     Philox4x32-10(seed; parameter index, group index, counter);
+ *   action_noise_sd > 0: act_out += N(0, sd)  (SkillshotLearner.py:238).
+ * float32 arithmetic throughout (the exact path). */
+int ss_actor_forward(const float *actor_params, const float *obs, float *act_out, int64_t n,
+                     float param_noise_sd, int64_t noise_group, float action_noise_sd,
+                     uint64_t seed, uint64_t counter, void *stream);
+
+/* out[p] = params[p] + params[p] * (sd * eps_p): the perturbed vector
+ * ss_actor_forward uses for noise group `group` (introspection and tests). */
+int ss_param_noise(const float *params, float *out, int64_t n_params, float sd, uint64_t seed,
+                   uint64_t group, uint64_t counter, void *stream);
+
+/* q_out[n] = critic([obs, act]), Dropout off (a model call / predict). */
+int ss_critic_forward(const float *critic_params, const float *obs, const float *act, float *q_out,
+                      int64_t n, void *stream);
+
+/* y[n] = reward + gamma * (1 - done) * Q'(next_obs, mu'(next_obs)) with the target
+ * networks.  The reference regresses the critic on the immediate reward
+ * (SkillshotLearner.py:434): that is gamma = 0.  done may be NULL. */
+int ss_ddpg_targets(const float *target_actor_params, const float *target_critic_params,
+                    const float *reward, const float *next_obs, const uint8_t *done, float gamma,
+                    float *y_out, int64_t n, void *stream);
+
+/* Gradient of the critic's Keras "mse" loss for one batch (model_critic.fit,
+ * SkillshotLearner.py:118, 434):  grad_out[36609] = d/dphi sum_i (q_i - target_i)^2 / n_global,
+ * sse_out[1] = sum_i (q_i - target_i)^2  (may be NULL).
+ *   dropout_rate  Dropout(0.2) of SkillshotLearner.py:105 as applied during fit; 0 = off.
+ *   dropout_keep  NULL: mask from Philox(seed; unit, (row_offset + row) / 4, counter);
+ *                 else uint8 [n][256], 1 = keep (parity tests inject Keras' choice).
+ *   n_global      divisor of the mean when n is one GPU's shard of a batch (<= 0: n).
+ * The gradient is summed in a fixed order: bit-identical from run to run. */
+int ss_critic_grad(const float *critic_params, const float *obs, const float *act, const float *target,
+                   const uint8_t *dropout_keep, float dropout_rate, uint64_t seed, uint64_t counter,
+                   int64_t n, int64_t n_global, int64_t row_offset, float *grad_out, float *sse_out,
+                   void *workspace, int64_t workspace_bytes, void *stream);
+
+/* model_actor_fit_step (SkillshotLearner.py:386-417) up to the optimiser:
+ * a = actor(obs); q = critic([obs, a]) with Dropout off;
+ * grad_out[36482] = d a / d theta contracted with -dq/da, summed over the batch
+ * (tape.gradient of a non-scalar sums); q_sum_out[1] = sum q (may be NULL). */
+int ss_actor_grad(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
+                  float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes,
+                  void *stream);
+
+/* tf.keras.optimizers.Adam.apply_gradients (SkillshotLearner.py:68, 118, 417), step t >= 1:
+ *   g = grads * grad_scale; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ *   params -= lr * sqrt(1 - b2^t) / (1 - b1^t) * m / (sqrt(v) + eps)     (Keras: eps = 1e-7)
+ * and, when target_params != NULL, the DDPG soft update
+ *   target = tau * params + (1 - tau) * target                          (tau = 1: copy). */
+int ss_adam_tf(float *params, const float *grads, float *m, float *v, float *target_params, int64_t n,
+               int64_t step, float lr, float beta1, float beta2, float eps, float tau, float grad_scale,
+               void *stream);
+
+/* Device-resident replay ring, structure of arrays with `capacity` rows:
+ * obs [cap][12], act [cap][2], reward [cap], next_obs [cap][12], done [cap] u8.
+ * The reference's "buffer" is one episode used once (SkillshotLearner.py:334-361);
+ * a ring of that size consumed in order reproduces it.
+ * push: rows write_pos .. write_pos+n-1 (mod capacity) <- the n transitions; done
+ *       has one entry per `done_div` rows (2 when it is the per-env flag of ss_env_step). */
+int ss_replay_push(float *ring_obs, float *ring_act, float *ring_reward, float *ring_next_obs,
+                   uint8_t *ring_done, int64_t capacity, int64_t write_pos, const float *obs,
+                   const float *act, const float *reward, const float *next_obs, const uint8_t *done,
+                   int done_div, int64_t n, void *stream);
+
+/* sample: batch rows gathered from the first `size` rows; indices int64 [batch]
+ * given (parity: np.random.shuffle order, SkillshotLearner.py:426-431) or NULL =
+ * uniform with replacement from Philox(seed; counter). indices_out may be NULL. */
+int ss_replay_sample(const float *ring_obs, const float *ring_act, const float *ring_reward,
+                     const float *ring_next_obs, const uint8_t *ring_done, int64_t capacity, int64_t size,
+                     const int64_t *indices, uint64_t seed, uint64_t counter, int64_t batch,
+                     float *obs, float *act, float *reward, float *next_obs, uint8_t *done,
+                     int64_t *indices_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,11 @@ STATUS_NAN = 1
  OP_LOOK_LEFT, OP_LOOK_RIGHT, OP_GAME_TICK) = range(8)
 
 _vp, _i64, _i32, _u64, _f64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint64, ctypes.c_double
+_f32 = ctypes.c_float
+
+# learner constants of include/skillshot_b200.h
+DIM_STATE, DIM_ACTION, HIDDEN1, HIDDEN2 = 12, 2, 256, 128
+ACTOR_PARAMS, CRITIC_PARAMS = 36482, 36609
 
 # name -> (restype, argtypes); every symbol the header declares
 SIGNATURES = {
@@ -36,6 +41,17 @@ SIGNATURES = {
     "ss_env_export": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ss_env_import": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ss_env_apply": (_i32, [_vp, _i64, _i64, _i32, _i32, _f64, _vp, _vp, _vp]),
+    "ss_learner_workspace_bytes": (_i64, []),
+    "ss_actor_forward": (_i32, [_vp, _vp, _vp, _i64, _f32, _i64, _f32, _u64, _u64, _vp]),
+    "ss_param_noise": (_i32, [_vp, _vp, _i64, _f32, _u64, _u64, _u64, _vp]),
+    "ss_critic_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "ss_ddpg_targets": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp]),
+    "ss_critic_grad": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _u64, _u64, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "ss_actor_grad": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "ss_adam_tf": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "ss_replay_push": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
+    "ss_replay_sample": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _u64, _u64, _i64,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

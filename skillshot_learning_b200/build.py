@@ -1,6 +1,8 @@
 """Builds libskillshot_b200.so (sm_100a only) in-tree with nvcc.
 
-    python -m skillshot_learning_b200.build
+    python skillshot_learning_b200/build.py [--force] [-v]
+
+(run as a script: importing the package needs the library this produces)
 
 The .so is git-ignored but travels to the GPU box with the repo snapshot.
 """
@@ -23,6 +25,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # FMA: the reference is CPython float arithmetic (SURVEY.md hard part 3).
 UNITS = {
     "ss_env.cu": ["-fmad=false"],
+    "ss_learner.cu": [],
 }
 
 

@@ -1,0 +1,745 @@
+// ss_learner.cu -- float32 kernels of the learner path and their C ABI
+// (include/skillshot_b200.h): actor / critic forward, the critic's MSE gradient,
+// the actor's deterministic-policy-gradient step, tf.keras Adam (+ soft target
+// update), the replay ring, Philox parameter noise.
+//
+// This translation unit is the EXACT path: float32 everywhere, the arithmetic the
+// reference's Keras graph does (SkillshotLearner.py:70-121, 245-281, 386-443).
+// It serves the reference's own configuration (batches of 16, per-call parameter
+// noise) and is the numerical yardstick for the bf16 tensor-core kernels of
+// ss_mlp_tc.cu, which take over the large rollout batches.
+//
+// Scheme: a CTA of 256 threads owns a tile of 32 samples.  Activations live in
+// shared memory TRANSPOSED, [feature][sample] with a row pitch of 36 floats, so a
+// thread that owns one output unit sweeps the reduction dimension reading one
+// coalesced weight (Keras kernels are [in][out], out contiguous) and broadcast
+// float4s of the 32 samples.  Weight gradients are accumulated per CTA in a
+// private slice of an L2-resident workspace and summed in a fixed order by
+// reduce_kernel, so the result does not depend on scheduling (deterministic, and
+// identical whatever the number of CTAs that took part).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/skillshot_b200.h"
+#include "ss_rng.cuh"
+
+namespace {
+
+using namespace ss;
+
+constexpr int TB = 32;        // samples per tile
+constexpr int PITCH = 36;     // floats per shared-memory row: conflict-free float4 row stores
+constexpr int NT = 256;       // threads per CTA
+
+constexpr int DS = SS_DIM_STATE, DA = SS_DIM_ACTION, H1 = SS_HIDDEN1, H2 = SS_HIDDEN2;
+// flat parameter vectors in Keras get_weights() order
+constexpr int A_W1 = 0, A_B1 = A_W1 + DS * H1, A_W2 = A_B1 + H1, A_B2 = A_W2 + H1 * H2, A_W3 = A_B2 + H2,
+              A_B3 = A_W3 + H2 * DA, A_N = A_B3 + DA;
+constexpr int C_W1 = 0, C_B1 = C_W1 + DS * H1, C_W2 = C_B1 + H1, C_B2 = C_W2 + (H1 + DA) * H2,
+              C_W3 = C_B2 + H2, C_B3 = C_W3 + H2, C_N = C_B3 + 1;
+static_assert(A_N == SS_ACTOR_PARAMS && C_N == SS_CRITIC_PARAMS, "parameter counts");
+
+enum { ACT_NONE = 0, ACT_RELU = 1 };
+
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+
+// outT[j][t] = act(b[j] + sum_i W[i*N + j] * inT[i][t])        Dense, x @ W[in,out] + b
+template <int N, int ACT>
+__device__ __forceinline__ void dense_fwd(const float *W, const float *b, const float *inT, int K, float *outT) {
+    constexpr int TPC = NT / N;       // threads per output unit (1 or 2)
+    constexpr int TS = TB / TPC;      // samples per thread
+    const int j = threadIdx.x % N, t0 = (threadIdx.x / N) * TS;
+    float acc[TS];
+    const float bias = b[j];
+#pragma unroll
+    for (int t = 0; t < TS; ++t) acc[t] = bias;
+#pragma unroll 4
+    for (int i = 0; i < K; ++i) {
+        const float w = W[i * N + j];
+        const float *row = inT + i * PITCH + t0;
+#pragma unroll
+        for (int q = 0; q < TS / 4; ++q) {
+            const float4 x = ld4(row + 4 * q);
+            acc[4 * q + 0] = fmaf(x.x, w, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(x.y, w, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(x.z, w, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(x.w, w, acc[4 * q + 3]);
+        }
+    }
+    float *o = outT + j * PITCH + t0;
+#pragma unroll
+    for (int q = 0; q < TS / 4; ++q) {
+        float4 v = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        if (ACT == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        st4(o + 4 * q, v);
+    }
+}
+
+// Back-propagation to a hidden layer of H1 units through a [.., H2] kernel whose
+// first H1 rows are W:  d[i][t] = sum_k W[i*H2 + k] * doutT[k][t], then the ReLU
+// (and inverted-dropout) mask of the layer's own output held in ioT:
+// ioT[i][t] = ioT[i][t] > 0 ? d * scale : 0.   Thread i owns row i.
+__device__ __forceinline__ void dense_bwd_input(const float *W, const float *doutT, float *ioT, float scale) {
+    const int i = threadIdx.x;
+    float acc[TB];
+#pragma unroll
+    for (int t = 0; t < TB; ++t) acc[t] = 0.f;
+    const float *wrow = W + i * H2;
+#pragma unroll 1
+    for (int k4 = 0; k4 < H2 / 4; ++k4) {
+        const float4 w = ld4(wrow + 4 * k4);
+        const float wk[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const float *row = doutT + (4 * k4 + kk) * PITCH;
+#pragma unroll
+            for (int q = 0; q < TB / 4; ++q) {
+                const float4 x = ld4(row + 4 * q);
+                acc[4 * q + 0] = fmaf(x.x, wk[kk], acc[4 * q + 0]);
+                acc[4 * q + 1] = fmaf(x.y, wk[kk], acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(x.z, wk[kk], acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(x.w, wk[kk], acc[4 * q + 3]);
+            }
+        }
+    }
+    float *o = ioT + i * PITCH;
+#pragma unroll
+    for (int q = 0; q < TB / 4; ++q) {
+        const float4 h = ld4(o + 4 * q);
+        st4(o + 4 * q, make_float4(h.x > 0.f ? acc[4 * q] * scale : 0.f, h.y > 0.f ? acc[4 * q + 1] * scale : 0.f,
+                                   h.z > 0.f ? acc[4 * q + 2] * scale : 0.f, h.w > 0.f ? acc[4 * q + 3] * scale : 0.f));
+    }
+}
+
+// CTA-private gradient slice in the workspace: first tile overwrites, later tiles add.
+__device__ __forceinline__ void accum(float *p, float v, bool first) {
+    __stcg(p, first ? v : __ldcg(p) + v);
+}
+
+// gW[i*N + k] += sum_t inT[i][t] * doutT[k][t]  (i < K);   gb[k] += sum_t doutT[k][t]
+template <int N>
+__device__ __forceinline__ void dense_bwd_weight(const float *inT, int K, const float *doutT, float *gW, float *gb,
+                                                 bool first) {
+    constexpr int TPC = NT / N;
+    const int k = threadIdx.x % N, part = threadIdx.x / N;
+    float dz[TB];
+#pragma unroll
+    for (int q = 0; q < TB / 4; ++q) {
+        const float4 x = ld4(doutT + k * PITCH + 4 * q);
+        dz[4 * q] = x.x; dz[4 * q + 1] = x.y; dz[4 * q + 2] = x.z; dz[4 * q + 3] = x.w;
+    }
+    if (part == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < TB; ++t) s += dz[t];
+        accum(gb + k, s, first);
+    }
+#pragma unroll 2
+    for (int i = part; i < K; i += TPC) {
+        const float *row = inT + i * PITCH;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int q = 0; q < TB / 4; ++q) {
+            const float4 x = ld4(row + 4 * q);
+            a0 = fmaf(x.x, dz[4 * q + 0], a0);
+            a1 = fmaf(x.y, dz[4 * q + 1], a1);
+            a2 = fmaf(x.z, dz[4 * q + 2], a2);
+            a3 = fmaf(x.w, dz[4 * q + 3], a3);
+        }
+        accum(gW + i * N + k, (a0 + a1) + (a2 + a3), first);
+    }
+}
+
+// rows of a [n][W] float32 matrix -> transposed tile dstT[c][t], zero beyond n
+template <int W>
+__device__ __forceinline__ void load_tile_T(const float *src, int64_t base, int64_t n, float *dstT) {
+    for (int e = threadIdx.x; e < TB * W; e += NT) {
+        const int t = e / W, c = e - t * W;
+        dstT[c * PITCH + t] = (base + t < n) ? src[(base + t) * W + c] : 0.f;
+    }
+}
+
+// actor output layer: aT[m][t] = tanh(b3[m] + sum_k W3[k*2 + m] * h2T[k][t])
+__device__ __forceinline__ void actor_out(const float *W3, const float *b3, const float *h2T, float *aT) {
+    if (threadIdx.x < TB * DA) {
+        const int t = threadIdx.x & (TB - 1), m = threadIdx.x / TB;
+        float z = b3[m];
+#pragma unroll 8
+        for (int k = 0; k < H2; ++k) z = fmaf(W3[k * DA + m], h2T[k * PITCH + t], z);
+        aT[m * PITCH + t] = tanhf(z);
+    }
+}
+// critic output layer: q[t] = b3 + sum_k W3[k] * h2T[k][t]
+__device__ __forceinline__ void critic_out(const float *W3, const float *b3, const float *h2T, float *q) {
+    if (threadIdx.x < TB) {
+        const int t = threadIdx.x;
+        float z = b3[0];
+#pragma unroll 8
+        for (int k = 0; k < H2; ++k) z = fmaf(W3[k], h2T[k * PITCH + t], z);
+        q[t] = z;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// actor forward (+ parameter noise, + action noise)
+// ---------------------------------------------------------------------------
+struct ActorFwdArgs {
+    const float *theta, *obs;
+    float *act;
+    int64_t n, group;           // samples; samples per parameter-noise draw
+    float param_sd, action_sd;
+    uint64_t seed, counter;
+};
+
+// model_act / model_act_action_noise / model_act_param_noise (SkillshotLearner.py:215-281)
+// without the env side effects.  NOISY: the CTA keeps a private perturbed copy of
+// the 36,482 actor parameters in shared memory, w + w * (sd * eps), eps ~ N(0,1) from
+// Philox keyed by (parameter index, noise group, counter): group size 1 is the
+// reference's fresh draw per call, larger groups share one draw between
+// consecutive samples.
+template <bool NOISY>
+__global__ void __launch_bounds__(NT) actor_fwd_kernel(const ActorFwdArgs A) {
+    extern __shared__ __align__(16) float smem[];
+    float *sT = smem, *h1T = sT + DS * PITCH, *h2T = h1T + H1 * PITCH, *aT = h2T + H2 * PITCH;
+    float *wS = aT + DA * PITCH;
+    const float *P = NOISY ? wS : A.theta;
+
+    // work units never straddle a noise group
+    const int64_t group = NOISY ? A.group : A.n;
+    const int64_t upg = (group + TB - 1) / TB;
+    const int64_t n_groups = (A.n + group - 1) / group;
+    const int64_t units = n_groups * upg;
+    const int64_t u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+    int64_t have_group = -1;
+    for (int64_t u = u0; u < u1; ++u) {
+        const int64_t g = u / upg, base = g * group + (u - g * upg) * TB;
+        const int64_t end = min(A.n, (g + 1) * group);
+        if (base >= end) continue;
+        __syncthreads();                                  // previous unit done with smem
+        if (NOISY && g != have_group) {
+            for (int q = threadIdx.x; q < (A_N + 3) / 4; q += NT) {
+                float z[4];
+                normal4(A.seed, kTagParamNoise, (uint32_t)q, (uint32_t)g, A.counter, z);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int p = 4 * q + e;
+                    if (p < A_N) { const float w = A.theta[p]; wS[p] = w + w * (A.param_sd * z[e]); }
+                }
+            }
+            have_group = g;
+        }
+        load_tile_T<DS>(A.obs, base, end, sT);
+        __syncthreads();
+        dense_fwd<H1, ACT_RELU>(P + A_W1, P + A_B1, sT, DS, h1T);
+        __syncthreads();
+        dense_fwd<H2, ACT_RELU>(P + A_W2, P + A_B2, h1T, H1, h2T);
+        __syncthreads();
+        actor_out(P + A_W3, P + A_B3, h2T, aT);
+        __syncthreads();
+        if (threadIdx.x < TB && base + threadIdx.x < end) {
+            const int64_t row = base + threadIdx.x;
+            float a0 = aT[threadIdx.x], a1 = aT[PITCH + threadIdx.x];
+            if (A.action_sd > 0.f) {                      // predictions += N(0, sd), SkillshotLearner.py:238
+                float z[4];
+                normal4(A.seed, kTagActionNoise, (uint32_t)row, (uint32_t)(row >> 32), A.counter, z);
+                a0 += A.action_sd * z[0];
+                a1 += A.action_sd * z[1];
+            }
+            reinterpret_cast<float2 *>(A.act)[row] = make_float2(a0, a1);
+        }
+    }
+}
+
+// The perturbed parameter vector itself (tests, and the host facade's introspection).
+__global__ void param_noise_kernel(const float *theta, float *out, int64_t n_params, float sd, uint64_t seed,
+                                   uint64_t group, uint64_t counter) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (4 * q >= n_params) return;
+    float z[4];
+    normal4(seed, kTagParamNoise, (uint32_t)q, (uint32_t)group, counter, z);
+    for (int e = 0; e < 4; ++e) {
+        const int64_t p = 4 * q + e;
+        if (p < n_params) { const float w = theta[p]; out[p] = w + w * (sd * z[e]); }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// critic forward, optionally on the actor's own action, optionally as TD target
+// ---------------------------------------------------------------------------
+struct CriticFwdArgs {
+    const float *theta;      // actor parameters, or NULL: use `act`
+    const float *phi, *obs, *act;
+    const float *reward;     // NULL: out = q;  else out = reward + gamma * (1 - done) * q
+    const uint8_t *done;
+    float gamma;
+    float *out;
+    int64_t n;
+};
+
+template <bool WITH_ACTOR>
+__global__ void __launch_bounds__(NT) critic_fwd_kernel(const CriticFwdArgs A) {
+    extern __shared__ __align__(16) float smem[];
+    float *sT = smem, *x2T = sT + DS * PITCH, *c2T = x2T + (H1 + DA) * PITCH, *qv = c2T + H2 * PITCH;
+    float *h1T = qv + TB, *h2T = h1T + H1 * PITCH;       // WITH_ACTOR only
+    const int64_t tiles = (A.n + TB - 1) / TB;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t base = tile * TB;
+        __syncthreads();
+        load_tile_T<DS>(A.obs, base, A.n, sT);
+        if (!WITH_ACTOR) load_tile_T<DA>(A.act, base, A.n, x2T + H1 * PITCH);
+        __syncthreads();
+        if (WITH_ACTOR) {
+            dense_fwd<H1, ACT_RELU>(A.theta + A_W1, A.theta + A_B1, sT, DS, h1T);
+            __syncthreads();
+            dense_fwd<H2, ACT_RELU>(A.theta + A_W2, A.theta + A_B2, h1T, H1, h2T);
+            __syncthreads();
+            actor_out(A.theta + A_W3, A.theta + A_B3, h2T, x2T + H1 * PITCH);
+        }
+        dense_fwd<H1, ACT_RELU>(A.phi + C_W1, A.phi + C_B1, sT, DS, x2T);
+        __syncthreads();
+        dense_fwd<H2, ACT_RELU>(A.phi + C_W2, A.phi + C_B2, x2T, H1 + DA, c2T);
+        __syncthreads();
+        critic_out(A.phi + C_W3, A.phi + C_B3, c2T, qv);
+        __syncthreads();
+        if (threadIdx.x < TB && base + threadIdx.x < A.n) {
+            const int64_t row = base + threadIdx.x;
+            float q = qv[threadIdx.x];
+            if (A.reward) q = A.reward[row] + A.gamma * (A.done && A.done[row] ? 0.f : 1.f) * q;
+            A.out[row] = q;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// critic MSE gradient (one Keras fit batch, SkillshotLearner.py:434)
+// ---------------------------------------------------------------------------
+struct CriticGradArgs {
+    const float *phi, *obs, *act, *target;
+    const uint8_t *keep;     // injected dropout mask [n][256] (1 = keep), or NULL: Philox
+    float rate;              // dropout rate (0 = off)
+    uint64_t seed, counter;
+    int64_t n, n_global, row_offset;   // row_offset: global index of row 0 (Philox dropout of a shard)
+    float *work;             // [gridDim.x][C_N + 1]
+};
+
+__global__ void __launch_bounds__(NT) critic_grad_kernel(const CriticGradArgs A) {
+    extern __shared__ __align__(16) float smem[];
+    float *sT = smem, *x2T = sT + DS * PITCH, *h2T = x2T + (H1 + DA) * PITCH, *qv = h2T + H2 * PITCH, *dq = qv + TB;
+    float *g = A.work + (int64_t)blockIdx.x * (C_N + 1);
+    const float inv_keep = A.rate > 0.f ? 1.0f / (1.0f - A.rate) : 1.0f;
+    const uint32_t thresh = (uint32_t)fmin(4294967295.0, (double)A.rate * 4294967296.0);
+    const int64_t tiles = (A.n + TB - 1) / TB;
+    float sse = 0.f;
+    bool first = true;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
+        const int64_t base = tile * TB;
+        __syncthreads();
+        load_tile_T<DS>(A.obs, base, A.n, sT);
+        load_tile_T<DA>(A.act, base, A.n, x2T + H1 * PITCH);
+        __syncthreads();
+        dense_fwd<H1, ACT_RELU>(A.phi + C_W1, A.phi + C_B1, sT, DS, x2T);
+        if (A.rate > 0.f) {                                 // Dropout(0.2), training=True: h * keep / (1 - rate)
+            const int j = threadIdx.x;                      // this thread wrote row j
+            float *row = x2T + j * PITCH;
+            if (A.keep) {
+                for (int t = 0; t < TB; ++t)
+                    row[t] = (base + t < A.n && A.keep[(base + t) * H1 + j]) ? row[t] * inv_keep : 0.f;
+            } else {
+                for (int q = 0; q < TB / 4; ++q) {
+                    const uint64_t quad = (uint64_t)(A.row_offset + base) / 4 + q;     // 4 consecutive samples per draw
+                    const U4 u = draw4(A.seed, kTagDropout, (uint32_t)j, (uint32_t)quad, A.counter);
+                    row[4 * q + 0] = u.x >= thresh ? row[4 * q + 0] * inv_keep : 0.f;
+                    row[4 * q + 1] = u.y >= thresh ? row[4 * q + 1] * inv_keep : 0.f;
+                    row[4 * q + 2] = u.z >= thresh ? row[4 * q + 2] * inv_keep : 0.f;
+                    row[4 * q + 3] = u.w >= thresh ? row[4 * q + 3] * inv_keep : 0.f;
+                }
+            }
+        }
+        __syncthreads();
+        dense_fwd<H2, ACT_RELU>(A.phi + C_W2, A.phi + C_B2, x2T, H1 + DA, h2T);
+        __syncthreads();
+        critic_out(A.phi + C_W3, A.phi + C_B3, h2T, qv);
+        __syncthreads();
+        if (threadIdx.x < TB) {                             // loss "mse": mean over the (global) batch
+            const int t = threadIdx.x;
+            float d = 0.f;
+            if (base + t < A.n) {
+                const float e = qv[t] - A.target[base + t];
+                sse += e * e;
+                d = 2.0f * e / (float)A.n_global;
+            }
+            dq[t] = d;
+        }
+        __syncthreads();
+        if (threadIdx.x < H2) {                             // output layer gradients; then dz2 in place
+            const int k = threadIdx.x;
+            float *row = h2T + k * PITCH;
+            const float w3 = A.phi[C_W3 + k];
+            float s = 0.f;
+#pragma unroll
+            for (int t = 0; t < TB; ++t) {
+                const float h = row[t], d = dq[t];
+                s = fmaf(h, d, s);
+                row[t] = h > 0.f ? d * w3 : 0.f;
+            }
+            accum(g + C_W3 + k, s, first);
+        } else if (threadIdx.x == H2) {
+            float s = 0.f;
+            for (int t = 0; t < TB; ++t) s += dq[t];
+            accum(g + C_B3, s, first);
+        }
+        __syncthreads();
+        dense_bwd_weight<H2>(x2T, H1 + DA, h2T, g + C_W2, g + C_B2, first);
+        __syncthreads();
+        dense_bwd_input(A.phi + C_W2, h2T, x2T, inv_keep);
+        __syncthreads();
+        dense_bwd_weight<H1>(sT, DS, x2T, g + C_W1, g + C_B1, first);
+    }
+    // sum of squared errors of this CTA's tiles (threads 0..31 hold the partial sums)
+    if (threadIdx.x < 32) {
+        for (int o = 16; o > 0; o >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, o);
+        if (threadIdx.x == 0) g[C_N] = sse;
+    }
+    if (first) {   // this CTA had no tile: its slice must still read as zero
+        for (int p = threadIdx.x; p < C_N; p += NT) g[p] = 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// actor deterministic-policy-gradient (model_actor_fit_step, SkillshotLearner.py:386-417)
+// ---------------------------------------------------------------------------
+struct ActorGradArgs {
+    const float *theta, *phi, *obs;
+    int64_t n;
+    float *work;             // [gridDim.x][A_N + 1]
+};
+
+__global__ void __launch_bounds__(NT) actor_grad_kernel(const ActorGradArgs A) {
+    extern __shared__ __align__(16) float smem[];
+    float *sT = smem, *h1T = sT + DS * PITCH, *h2T = h1T + H1 * PITCH, *aT = h2T + H2 * PITCH;
+    float *x2T = aT + DA * PITCH, *c2T = x2T + (H1 + DA) * PITCH, *dz3T = c2T + H2 * PITCH, *qv = dz3T + DA * PITCH;
+    float *g = A.work + (int64_t)blockIdx.x * (A_N + 1);
+    const int64_t tiles = (A.n + TB - 1) / TB;
+    float qsum = 0.f;
+    bool first = true;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
+        const int64_t base = tile * TB;
+        __syncthreads();
+        load_tile_T<DS>(A.obs, base, A.n, sT);
+        __syncthreads();
+        // a = actor(s)
+        dense_fwd<H1, ACT_RELU>(A.theta + A_W1, A.theta + A_B1, sT, DS, h1T);
+        // critic's first layer depends on s only (model called directly: Dropout off)
+        dense_fwd<H1, ACT_RELU>(A.phi + C_W1, A.phi + C_B1, sT, DS, x2T);
+        __syncthreads();
+        dense_fwd<H2, ACT_RELU>(A.theta + A_W2, A.theta + A_B2, h1T, H1, h2T);
+        __syncthreads();
+        actor_out(A.theta + A_W3, A.theta + A_B3, h2T, aT);
+        __syncthreads();
+        if (threadIdx.x < TB * DA) {
+            const int t = threadIdx.x & (TB - 1), m = threadIdx.x / TB;
+            x2T[(H1 + m) * PITCH + t] = aT[m * PITCH + t];
+        }
+        __syncthreads();
+        // q = critic([s, a])
+        dense_fwd<H2, ACT_RELU>(A.phi + C_W2, A.phi + C_B2, x2T, H1 + DA, c2T);
+        __syncthreads();
+        critic_out(A.phi + C_W3, A.phi + C_B3, c2T, qv);
+        __syncthreads();
+        if (threadIdx.x < TB && base + threadIdx.x < A.n) qsum += qv[threadIdx.x];
+        // dq/da: only the two action rows of the critic's second kernel matter
+        if (threadIdx.x < TB * DA) {
+            const int t = threadIdx.x & (TB - 1), m = threadIdx.x / TB;
+            const float *w = A.phi + C_W2 + (H1 + m) * H2;
+            float da = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < H2; ++k) da = fmaf(c2T[k * PITCH + t] > 0.f ? A.phi[C_W3 + k] : 0.f, w[k], da);
+            const float a = aT[m * PITCH + t];
+            // output_gradients = -dq/da (SkillshotLearner.py:410), through tanh
+            dz3T[m * PITCH + t] = (base + t < A.n) ? -da * (1.0f - a * a) : 0.f;
+        }
+        __syncthreads();
+        if (threadIdx.x < H2) {                             // actor output layer gradients; dz2 -> c2T
+            const int k = threadIdx.x;
+            const float w0 = A.theta[A_W3 + k * DA], w1 = A.theta[A_W3 + k * DA + 1];
+            const float *hrow = h2T + k * PITCH;
+            float *orow = c2T + k * PITCH;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < TB; ++t) {
+                const float h = hrow[t], d0 = dz3T[t], d1 = dz3T[PITCH + t];
+                s0 = fmaf(h, d0, s0);
+                s1 = fmaf(h, d1, s1);
+                orow[t] = h > 0.f ? fmaf(d0, w0, d1 * w1) : 0.f;
+            }
+            accum(g + A_W3 + k * DA, s0, first);
+            accum(g + A_W3 + k * DA + 1, s1, first);
+        } else if (threadIdx.x < H2 + DA) {
+            const int m = threadIdx.x - H2;
+            float s = 0.f;
+            for (int t = 0; t < TB; ++t) s += dz3T[m * PITCH + t];
+            accum(g + A_B3 + m, s, first);
+        }
+        __syncthreads();
+        dense_bwd_weight<H2>(h1T, H1, c2T, g + A_W2, g + A_B2, first);
+        __syncthreads();
+        dense_bwd_input(A.theta + A_W2, c2T, h1T, 1.0f);
+        __syncthreads();
+        dense_bwd_weight<H1>(sT, DS, h1T, g + A_W1, g + A_B1, first);
+    }
+    if (threadIdx.x < 32) {
+        for (int o = 16; o > 0; o >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
+        if (threadIdx.x == 0) g[A_N] = qsum;
+    }
+    if (first) {
+        for (int p = threadIdx.x; p < A_N; p += NT) g[p] = 0.f;
+    }
+}
+
+// grad[p] = sum over CTA slices, fixed order; aux[0] = sum of the slices' extra slot
+__global__ void reduce_kernel(const float *work, int parts, int n_params, float *grad, float *aux) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > n_params) return;
+    float s = 0.f;
+    for (int c = 0; c < parts; ++c) s += work[(int64_t)c * (n_params + 1) + p];
+    if (p < n_params) grad[p] = s;
+    else if (aux) aux[0] = s;
+}
+
+// tf.keras.optimizers.Adam.apply_gradients (SkillshotLearner.py:68, 118, 417) and the
+// DDPG soft target update (tau = 1 copies; target == NULL skips it).
+__global__ void adam_kernel(float *params, const float *grads, float *m, float *v, float *target, int64_t n,
+                            float lr_t, float beta1, float beta2, float eps, float tau, float grad_scale) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float gr = grads[p] * grad_scale;
+    const float mm = beta1 * m[p] + (1.0f - beta1) * gr;
+    const float vv = beta2 * v[p] + (1.0f - beta2) * gr * gr;
+    m[p] = mm;
+    v[p] = vv;
+    const float w = params[p] - lr_t * mm / (sqrtf(vv) + eps);
+    params[p] = w;
+    if (target) target[p] = tau * w + (1.0f - tau) * target[p];
+}
+
+// ---------------------------------------------------------------------------
+// replay ring: SoA of (s[12], a[2], r, s'[12], done) rows
+// ---------------------------------------------------------------------------
+struct Ring {
+    float *s, *a, *r, *s2;
+    uint8_t *done;
+    int64_t capacity;
+};
+
+__global__ void replay_push_kernel(Ring R, int64_t pos, const float *s, const float *a, const float *r,
+                                   const float *s2, const uint8_t *done, int done_div, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 3 * n) return;
+    const int64_t row = e / 3, part = e - row * 3;
+    const int64_t dst = (pos + row) % R.capacity;
+    reinterpret_cast<float4 *>(R.s)[dst * 3 + part] = reinterpret_cast<const float4 *>(s)[e];
+    reinterpret_cast<float4 *>(R.s2)[dst * 3 + part] = reinterpret_cast<const float4 *>(s2)[e];
+    if (part == 0) {
+        reinterpret_cast<float2 *>(R.a)[dst] = reinterpret_cast<const float2 *>(a)[row];
+        R.r[dst] = r[row];
+        R.done[dst] = done ? done[row / done_div] : 0;
+    }
+}
+
+__global__ void replay_sample_kernel(Ring R, int64_t size, const int64_t *indices, uint64_t seed, uint64_t counter,
+                                     int64_t batch, float *s, float *a, float *r, float *s2, uint8_t *done,
+                                     int64_t *indices_out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 3 * batch) return;
+    const int64_t b = e / 3, part = e - b * 3;
+    int64_t src;
+    if (indices) {
+        src = indices[b];
+    } else {                     // uniform with replacement over the filled part of the ring
+        const U4 u = draw4(seed, kTagReplay, (uint32_t)(b / 4), (uint32_t)((b / 4) >> 32), counter);
+        const uint32_t x = (b & 3) == 0 ? u.x : (b & 3) == 1 ? u.y : (b & 3) == 2 ? u.z : u.w;
+        src = (int64_t)(((uint64_t)x * (uint64_t)size) >> 32);      // size < 2^32 rows
+    }
+    reinterpret_cast<float4 *>(s)[e] = reinterpret_cast<const float4 *>(R.s)[src * 3 + part];
+    reinterpret_cast<float4 *>(s2)[e] = reinterpret_cast<const float4 *>(R.s2)[src * 3 + part];
+    if (part == 0) {
+        reinterpret_cast<float2 *>(a)[b] = reinterpret_cast<const float2 *>(R.a)[src];
+        r[b] = R.r[src];
+        done[b] = R.done[src];
+        if (indices_out) indices_out[b] = src;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------
+constexpr size_t kSmemActorFwd = (size_t)(DS + H1 + H2 + DA) * PITCH * 4;
+constexpr size_t kSmemActorFwdNoisy = kSmemActorFwd + (size_t)((A_N + 3) / 4 * 4) * 4;
+constexpr size_t kSmemCriticFwd = (size_t)(DS + H1 + DA + H2) * PITCH * 4 + TB * 4;
+constexpr size_t kSmemCriticFwdActor = kSmemCriticFwd + (size_t)(H1 + H2) * PITCH * 4;
+constexpr size_t kSmemCriticGrad = (size_t)(DS + H1 + DA + H2) * PITCH * 4 + 2 * TB * 4;
+constexpr size_t kSmemActorGrad = (size_t)(DS + H1 + H2 + DA + H1 + DA + H2 + DA) * PITCH * 4 + TB * 4;
+
+inline int check_launch() { return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA; }
+
+template <class K>
+int max_ctas(K kernel, size_t smem) {
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NT, smem) != cudaSuccess) return -1;
+    return sms * (per_sm > 0 ? per_sm : 1);
+}
+
+// persistent grid: one CTA per tile up to the number of resident CTAs
+template <class K>
+int grid_for(K kernel, size_t smem, int64_t tiles, int cap) {
+    int m = max_ctas(kernel, smem);
+    if (m <= 0) return -1;
+    if (cap > 0 && m > cap) m = cap;
+    return (int)(tiles < m ? (tiles > 0 ? tiles : 1) : m);
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t ss_learner_workspace_bytes(void) {
+    return (int64_t)SS_LEARNER_MAX_PARTS * (SS_CRITIC_PARAMS + 1) * sizeof(float);
+}
+
+int ss_actor_forward(const float *actor_params, const float *obs, float *act_out, int64_t n,
+                     float param_noise_sd, int64_t noise_group, float action_noise_sd,
+                     uint64_t seed, uint64_t counter, void *stream) {
+    if (!actor_params || !obs || !act_out || n <= 0 || param_noise_sd < 0.f || action_noise_sd < 0.f)
+        return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)actor_params & 15) || ((uintptr_t)act_out & 7)) return SS_ERR_INVALID_ARG;
+    const bool noisy = param_noise_sd > 0.f;
+    if (noisy && noise_group <= 0) return SS_ERR_INVALID_ARG;
+    ActorFwdArgs A{actor_params, obs, act_out, n, noisy ? noise_group : n, param_noise_sd, action_noise_sd, seed, counter};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (noisy) {
+        const int64_t upg = (noise_group + TB - 1) / TB, groups = (n + noise_group - 1) / noise_group;
+        const int grid = grid_for(actor_fwd_kernel<true>, kSmemActorFwdNoisy, groups * upg, 0);
+        if (grid < 0) return SS_ERR_CUDA;
+        actor_fwd_kernel<true><<<grid, NT, kSmemActorFwdNoisy, st>>>(A);
+    } else {
+        const int grid = grid_for(actor_fwd_kernel<false>, kSmemActorFwd, (n + TB - 1) / TB, 0);
+        if (grid < 0) return SS_ERR_CUDA;
+        actor_fwd_kernel<false><<<grid, NT, kSmemActorFwd, st>>>(A);
+    }
+    return check_launch();
+}
+
+int ss_param_noise(const float *params, float *out, int64_t n_params, float sd, uint64_t seed,
+                   uint64_t group, uint64_t counter, void *stream) {
+    if (!params || !out || n_params <= 0) return SS_ERR_INVALID_ARG;
+    const int64_t quads = (n_params + 3) / 4;
+    param_noise_kernel<<<(unsigned)((quads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(params, out, n_params, sd,
+                                                                                          seed, group, counter);
+    return check_launch();
+}
+
+int ss_critic_forward(const float *critic_params, const float *obs, const float *act, float *q_out, int64_t n,
+                      void *stream) {
+    if (!critic_params || !obs || !act || !q_out || n <= 0) return SS_ERR_INVALID_ARG;
+    CriticFwdArgs A{nullptr, critic_params, obs, act, nullptr, nullptr, 0.f, q_out, n};
+    const int grid = grid_for(critic_fwd_kernel<false>, kSmemCriticFwd, (n + TB - 1) / TB, 0);
+    if (grid < 0) return SS_ERR_CUDA;
+    critic_fwd_kernel<false><<<grid, NT, kSmemCriticFwd, (cudaStream_t)stream>>>(A);
+    return check_launch();
+}
+
+int ss_ddpg_targets(const float *target_actor_params, const float *target_critic_params, const float *reward,
+                    const float *next_obs, const uint8_t *done, float gamma, float *y_out, int64_t n, void *stream) {
+    if (!target_actor_params || !target_critic_params || !reward || !next_obs || !y_out || n <= 0)
+        return SS_ERR_INVALID_ARG;
+    CriticFwdArgs A{target_actor_params, target_critic_params, next_obs, nullptr, reward, done, gamma, y_out, n};
+    const int grid = grid_for(critic_fwd_kernel<true>, kSmemCriticFwdActor, (n + TB - 1) / TB, 0);
+    if (grid < 0) return SS_ERR_CUDA;
+    critic_fwd_kernel<true><<<grid, NT, kSmemCriticFwdActor, (cudaStream_t)stream>>>(A);
+    return check_launch();
+}
+
+int ss_critic_grad(const float *critic_params, const float *obs, const float *act, const float *target,
+                   const uint8_t *dropout_keep, float dropout_rate, uint64_t seed, uint64_t counter,
+                   int64_t n, int64_t n_global, int64_t row_offset, float *grad_out, float *sse_out,
+                   void *workspace, int64_t workspace_bytes, void *stream) {
+    if (!critic_params || !obs || !act || !target || !grad_out || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
+    if (dropout_rate < 0.f || dropout_rate >= 1.f) return SS_ERR_INVALID_ARG;
+    if ((uintptr_t)critic_params & 15) return SS_ERR_INVALID_ARG;
+    const int cap = (int)(workspace_bytes / ((int64_t)(C_N + 1) * 4));
+    if (cap < 1) return SS_ERR_INVALID_ARG;
+    const int grid = grid_for(critic_grad_kernel, kSmemCriticGrad, (n + TB - 1) / TB,
+                              cap < SS_LEARNER_MAX_PARTS ? cap : SS_LEARNER_MAX_PARTS);
+    if (grid < 0) return SS_ERR_CUDA;
+    CriticGradArgs A{critic_params, obs, act, target, dropout_keep, dropout_rate, seed, counter,
+                     n, n_global > 0 ? n_global : n, row_offset, (float *)workspace};
+    cudaStream_t st = (cudaStream_t)stream;
+    critic_grad_kernel<<<grid, NT, kSmemCriticGrad, st>>>(A);
+    reduce_kernel<<<(C_N + 1 + 255) / 256, 256, 0, st>>>((const float *)workspace, grid, C_N, grad_out, sse_out);
+    return check_launch();
+}
+
+int ss_actor_grad(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
+                  float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, void *stream) {
+    if (!actor_params || !critic_params || !obs || !grad_out || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)actor_params | (uintptr_t)critic_params) & 15) return SS_ERR_INVALID_ARG;
+    const int cap = (int)(workspace_bytes / ((int64_t)(A_N + 1) * 4));
+    if (cap < 1) return SS_ERR_INVALID_ARG;
+    const int grid = grid_for(actor_grad_kernel, kSmemActorGrad, (n + TB - 1) / TB,
+                              cap < SS_LEARNER_MAX_PARTS ? cap : SS_LEARNER_MAX_PARTS);
+    if (grid < 0) return SS_ERR_CUDA;
+    ActorGradArgs A{actor_params, critic_params, obs, n, (float *)workspace};
+    cudaStream_t st = (cudaStream_t)stream;
+    actor_grad_kernel<<<grid, NT, kSmemActorGrad, st>>>(A);
+    reduce_kernel<<<(A_N + 1 + 255) / 256, 256, 0, st>>>((const float *)workspace, grid, A_N, grad_out, q_sum_out);
+    return check_launch();
+}
+
+int ss_adam_tf(float *params, const float *grads, float *m, float *v, float *target_params, int64_t n,
+               int64_t step, float lr, float beta1, float beta2, float eps, float tau, float grad_scale,
+               void *stream) {
+    if (!params || !grads || !m || !v || n <= 0 || step < 1) return SS_ERR_INVALID_ARG;
+    // lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), evaluated in double on the host like Keras does in Python
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, target_params, n,
+                                                                               (float)lr_t, beta1, beta2, eps, tau,
+                                                                               grad_scale);
+    return check_launch();
+}
+
+int ss_replay_push(float *ring_obs, float *ring_act, float *ring_reward, float *ring_next_obs, uint8_t *ring_done,
+                   int64_t capacity, int64_t write_pos, const float *obs, const float *act, const float *reward,
+                   const float *next_obs, const uint8_t *done, int done_div, int64_t n, void *stream) {
+    if (!ring_obs || !ring_act || !ring_reward || !ring_next_obs || !ring_done || !obs || !act || !reward || !next_obs)
+        return SS_ERR_INVALID_ARG;
+    if (capacity <= 0 || n <= 0 || n > capacity || write_pos < 0 || write_pos >= capacity || done_div < 1)
+        return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)ring_obs | (uintptr_t)ring_next_obs | (uintptr_t)obs | (uintptr_t)next_obs) & 15)
+        return SS_ERR_INVALID_ARG;
+    Ring R{ring_obs, ring_act, ring_reward, ring_next_obs, ring_done, capacity};
+    replay_push_kernel<<<(unsigned)((3 * n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(R, write_pos, obs, act, reward,
+                                                                                         next_obs, done, done_div, n);
+    return check_launch();
+}
+
+int ss_replay_sample(const float *ring_obs, const float *ring_act, const float *ring_reward,
+                     const float *ring_next_obs, const uint8_t *ring_done, int64_t capacity, int64_t size,
+                     const int64_t *indices, uint64_t seed, uint64_t counter, int64_t batch,
+                     float *obs, float *act, float *reward, float *next_obs, uint8_t *done, int64_t *indices_out,
+                     void *stream) {
+    if (!ring_obs || !ring_act || !ring_reward || !ring_next_obs || !ring_done || !obs || !act || !reward ||
+        !next_obs || !done)
+        return SS_ERR_INVALID_ARG;
+    if (capacity <= 0 || size <= 0 || size > capacity || batch <= 0) return SS_ERR_INVALID_ARG;
+    Ring R{(float *)ring_obs, (float *)ring_act, (float *)ring_reward, (float *)ring_next_obs, (uint8_t *)ring_done,
+           capacity};
+    replay_sample_kernel<<<(unsigned)((3 * batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        R, size, indices, seed, counter, batch, obs, act, reward, next_obs, done, indices_out);
+    return check_launch();
+}
+
+}  // extern "C"

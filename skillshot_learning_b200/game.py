@@ -131,7 +131,8 @@ class SkillshotEnvs:
                                   flags, _stream(self.device)), "ss_env_step")
         self.counter += K
 
-    def step(self, actions: torch.Tensor, want_obs: bool = True, obs_every_tick: bool = False):
+    def step(self, actions: torch.Tensor, want_obs: bool = True, obs_every_tick: bool = False,
+             obs_out: Optional[torch.Tensor] = None):
         """actions float32 [n,2,2] (one tick) or [K,n,2,2] (K ticks fused in one launch).
 
         Returns dict(obs [n,2,12] | [K,n,2,12] | None, reward [K,n,2], done [K,n], winner [K,n]);
@@ -152,6 +153,10 @@ class SkillshotEnvs:
             if obs_every_tick and K > 1:
                 obs = torch.empty((K, self.n_envs, 2, _lib.NUM_OBS), dtype=torch.float32, device=self.device)
                 flags |= _lib.STEP_OBS_EVERY_TICK
+            elif obs_out is not None:      # caller-owned float32 [n,2,12] (the rollout's double buffer)
+                if obs_out.dtype != torch.float32 or not obs_out.is_contiguous() or obs_out.numel() != self.n_envs * 24:
+                    raise ValueError("obs_out must be a contiguous float32 [n,2,12] tensor")
+                obs = obs_out
             else:
                 obs = self._obs
         self._launch(a, obs, buf["reward"], buf["done"], buf["winner"], K, flags)

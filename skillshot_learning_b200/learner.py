@@ -1,0 +1,602 @@
+"""The learner path on the GPU: actor / critic networks, parameter-noise
+exploration, replay ring, critic fit and actor policy-gradient step.
+
+Three layers, all ending in launches of the CUDA library (C ABI:
+include/skillshot_b200.h); there is no CPU path.
+
+* :class:`ActorCritic` -- the two networks of SkillshotLearner.model_define_actor /
+  model_define_critic (SkillshotLearner.py:70-121) as flat float32 parameter
+  vectors with their tf.keras Adam state and (DDPG) target copies, and the batched
+  device operations on them.
+* :class:`ReplayRing` -- device-resident transitions.
+* :class:`SkillshotLearner` -- the reference's class surface (same method names,
+  argument meaning and attribute-style hyper-parameters) over one SkillshotGame.
+* :class:`SelfPlayTrainer` -- the same loop for many envs at once: rollout of N
+  games with the shared actor, replay, sharded update with one gradient all-reduce.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+from .game import FEATURE_KEYS, SkillshotEnvs, SkillshotGame
+
+A_N, C_N = _lib.ACTOR_PARAMS, _lib.CRITIC_PARAMS
+ACTOR_SHAPES = [(12, 256), (256,), (256, 128), (128,), (128, 2), (2,)]       # Keras get_weights() order
+CRITIC_SHAPES = [(12, 256), (256,), (258, 128), (128,), (128, 1), (1,)]
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _f32(x, device, shape=None):
+    if not torch.is_tensor(x):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    x = x.to(device=device, dtype=torch.float32).contiguous()
+    return x if shape is None else x.reshape(shape)
+
+
+def split_params(flat, shapes):
+    """Views of a flat parameter vector in Keras get_weights() order."""
+    out, o = [], 0
+    for s in shapes:
+        n = int(np.prod(s))
+        out.append(flat[o:o + n].reshape(s))
+        o += n
+    return out
+
+
+class ActorCritic:
+    """Actor and critic parameters, optimiser state and target copies on one GPU.
+
+    Hyper-parameters default to the reference's: tf.keras Adam lr 1e-3, betas
+    0.9 / 0.999, eps 1e-7 for both networks (SkillshotLearner.py:68, 118),
+    Dropout(0.2) in the critic (SkillshotLearner.py:105).  gamma = 0 and tau = 1
+    are the reference's update (critic regresses on the immediate reward, no
+    target network); other values give DDPG proper.
+    """
+
+    def __init__(self, device="cuda", seed: int = 0, lr_actor: float = 1e-3, lr_critic: float = 1e-3,
+                 gamma: float = 0.0, tau: float = 1.0, dropout: float = 0.2, process_group=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("skillshot_learning_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.seed = int(seed)
+        self.lr_actor, self.lr_critic = float(lr_actor), float(lr_critic)
+        self.beta1, self.beta2, self.eps = 0.9, 0.999, 1e-7
+        self.gamma, self.tau, self.dropout = float(gamma), float(tau), float(dropout)
+        self.group = process_group
+        dev = self.device
+        # one allocation: [actor | pad | critic] so both vectors are 16-byte aligned
+        self._a_off, self._c_off = 0, (A_N + 3) // 4 * 4
+        total = self._c_off + C_N
+        self.params = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.target = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.stats = torch.zeros(2, dtype=torch.float32, device=dev)        # [sum sq err, sum q] of the last steps
+        self.workspace = torch.empty(int(lib.ss_learner_workspace_bytes()), dtype=torch.uint8, device=dev)
+        self.step_actor = 0
+        self.step_critic = 0
+        self.counter = 0            # Philox counter: advances with every noisy call
+        self.init_weights(seed)
+
+    # -- parameter views -----------------------------------------------------
+    @property
+    def actor(self):
+        return self.params[self._a_off:self._a_off + A_N]
+
+    @property
+    def critic(self):
+        return self.params[self._c_off:self._c_off + C_N]
+
+    @property
+    def target_actor(self):
+        return self.target[self._a_off:self._a_off + A_N]
+
+    @property
+    def target_critic(self):
+        return self.target[self._c_off:self._c_off + C_N]
+
+    def _slice(self, buf, which):
+        return buf[self._a_off:self._a_off + A_N] if which == "actor" else buf[self._c_off:self._c_off + C_N]
+
+    def init_weights(self, seed: int):
+        """Keras initialisers of the reference's layers: actor kernels RandomNormal(0, 0.05)
+        (SkillshotLearner.py:74), critic hidden kernels glorot-uniform (the Dense default),
+        critic output kernel "RandomNormal" = N(0, 0.05) (SkillshotLearner.py:113), biases 0."""
+        g = torch.Generator(device="cpu")
+        g.manual_seed(int(seed))
+        a = [torch.randn(s, generator=g) * 0.05 if len(s) == 2 else torch.zeros(s) for s in ACTOR_SHAPES]
+        c = []
+        for i, s in enumerate(CRITIC_SHAPES):
+            if len(s) == 1:
+                c.append(torch.zeros(s))
+            elif i == 4:
+                c.append(torch.randn(s, generator=g) * 0.05)
+            else:
+                lim = float(np.sqrt(6.0 / (s[0] + s[1])))
+                c.append((torch.rand(s, generator=g) * 2.0 - 1.0) * lim)
+        self.set_weights(torch.cat([t.reshape(-1) for t in a]), torch.cat([t.reshape(-1) for t in c]))
+
+    def set_weights(self, actor=None, critic=None, reset_optimizer: bool = True):
+        """Install flat parameter vectors (Keras get_weights() order); targets are set equal."""
+        if actor is not None:
+            self.actor.copy_(_f32(actor, self.device, (A_N,)))
+        if critic is not None:
+            self.critic.copy_(_f32(critic, self.device, (C_N,)))
+        self.target.copy_(self.params)
+        if reset_optimizer:
+            self.adam_m.zero_()
+            self.adam_v.zero_()
+            self.step_actor = self.step_critic = 0
+
+    def get_weights(self, which="actor"):
+        """List of numpy arrays like keras Model.get_weights()."""
+        flat = self._slice(self.params, which).detach().cpu().numpy()
+        return [w.copy() for w in split_params(flat, ACTOR_SHAPES if which == "actor" else CRITIC_SHAPES)]
+
+    # -- forward ---------------------------------------------------------------
+    def actor_forward(self, obs, param_noise_sd: float = 0.0, noise_group: int = 1, action_noise_sd: float = 0.0,
+                      out: Optional[torch.Tensor] = None, target: bool = False, counter: Optional[int] = None,
+                      precision: str = "f32"):
+        """actions [n,2] = actor(obs [n,12]) (model_act*, SkillshotLearner.py:215-281)."""
+        obs = _f32(obs, self.device).reshape(-1, 12)
+        n = obs.shape[0]
+        if out is None:
+            out = torch.empty((n, 2), dtype=torch.float32, device=self.device)
+        theta = self.target_actor if target else self.actor
+        if counter is None:
+            counter = self.counter
+            if param_noise_sd > 0 or action_noise_sd > 0:
+                self.counter += 1
+        if precision not in ("f32", "bf16"):
+            raise ValueError("precision must be 'f32' (exact path) or 'bf16' (tensor cores)")
+        fn = lib.ss_actor_forward if precision == "f32" else lib.ss_actor_forward_tc
+        with torch.cuda.device(self.device):
+            check(fn(theta.data_ptr(), obs.data_ptr(), out.data_ptr(), n, float(param_noise_sd), int(noise_group),
+                     float(action_noise_sd), self.seed, int(counter), _stream(self.device)), "ss_actor_forward")
+        return out
+
+    def noisy_actor_params(self, sd: float, group: int = 0, counter: Optional[int] = None):
+        """The perturbed parameter vector actor_forward uses for one noise group."""
+        out = torch.empty(A_N, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.ss_param_noise(self.actor.data_ptr(), out.data_ptr(), A_N, float(sd), self.seed, int(group),
+                                     int(self.counter if counter is None else counter), _stream(self.device)),
+                  "ss_param_noise")
+        return out
+
+    def critic_forward(self, obs, act, target: bool = False):
+        obs, act = _f32(obs, self.device).reshape(-1, 12), _f32(act, self.device).reshape(-1, 2)
+        q = torch.empty(obs.shape[0], dtype=torch.float32, device=self.device)
+        phi = self.target_critic if target else self.critic
+        with torch.cuda.device(self.device):
+            check(lib.ss_critic_forward(phi.data_ptr(), obs.data_ptr(), act.data_ptr(), q.data_ptr(), obs.shape[0],
+                                        _stream(self.device)), "ss_critic_forward")
+        return q
+
+    def td_targets(self, reward, next_obs, done=None):
+        """y = r + gamma (1 - done) Q'(s', mu'(s')); gamma = 0 returns the reward itself
+        (the reference's critic target, SkillshotLearner.py:434)."""
+        reward = _f32(reward, self.device).reshape(-1)
+        if self.gamma == 0.0:
+            return reward
+        next_obs = _f32(next_obs, self.device).reshape(-1, 12)
+        y = torch.empty_like(reward)
+        if done is not None:
+            done = done.to(device=self.device, dtype=torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            check(lib.ss_ddpg_targets(self.target_actor.data_ptr(), self.target_critic.data_ptr(), reward.data_ptr(),
+                                      next_obs.data_ptr(), _ptr(done), self.gamma, y.data_ptr(), reward.shape[0],
+                                      _stream(self.device)), "ss_ddpg_targets")
+        return y
+
+    # -- update ----------------------------------------------------------------
+    def _world(self):
+        if self.group is None:
+            return 1
+        import torch.distributed as dist
+        return dist.get_world_size(self.group) if self.group is not True else dist.get_world_size()
+
+    def _allreduce(self, t):
+        """The one exchange step of a sharded update: sum the flat gradient over ranks."""
+        if self.group is None:
+            return
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=None if self.group is True else self.group)
+
+    def critic_grad(self, obs, act, y, keep=None, n_global: int = 0, row_offset: int = 0):
+        """grads[critic] <- d/dphi mean (q - y)^2 of this (shard of a) batch; returns the gradient view."""
+        obs, act = _f32(obs, self.device).reshape(-1, 12), _f32(act, self.device).reshape(-1, 2)
+        y = _f32(y, self.device).reshape(-1)
+        n = obs.shape[0]
+        if keep is not None:
+            keep = torch.as_tensor(keep).to(device=self.device, dtype=torch.uint8).contiguous()
+        g = self._slice(self.grads, "critic")
+        with torch.cuda.device(self.device):
+            check(lib.ss_critic_grad(self.critic.data_ptr(), obs.data_ptr(), act.data_ptr(), y.data_ptr(), _ptr(keep),
+                                     self.dropout, self.seed, self.counter, n, int(n_global), int(row_offset),
+                                     g.data_ptr(), self.stats[0:1].data_ptr(), self.workspace.data_ptr(),
+                                     self.workspace.numel(), _stream(self.device)), "ss_critic_grad")
+        self.counter += 1
+        return g
+
+    def actor_grad(self, obs):
+        """grads[actor] <- -sum_batch dQ/da da/dtheta (model_actor_fit_step, SkillshotLearner.py:395-410)."""
+        obs = _f32(obs, self.device).reshape(-1, 12)
+        g = self._slice(self.grads, "actor")
+        with torch.cuda.device(self.device):
+            check(lib.ss_actor_grad(self.actor.data_ptr(), self.critic.data_ptr(), obs.data_ptr(), obs.shape[0],
+                                    g.data_ptr(), self.stats[1:2].data_ptr(), self.workspace.data_ptr(),
+                                    self.workspace.numel(), _stream(self.device)), "ss_actor_grad")
+        return g
+
+    def apply_adam(self, which: str, grad_scale: float = 1.0):
+        """tf.keras Adam.apply_gradients on one network (+ soft target update with self.tau)."""
+        n = A_N if which == "actor" else C_N
+        if which == "actor":
+            self.step_actor += 1
+            step, lr = self.step_actor, self.lr_actor
+        else:
+            self.step_critic += 1
+            step, lr = self.step_critic, self.lr_critic
+        with torch.cuda.device(self.device):
+            check(lib.ss_adam_tf(self._slice(self.params, which).data_ptr(), self._slice(self.grads, which).data_ptr(),
+                                 self._slice(self.adam_m, which).data_ptr(), self._slice(self.adam_v, which).data_ptr(),
+                                 self._slice(self.target, which).data_ptr(), n, step, lr, self.beta1, self.beta2,
+                                 self.eps, self.tau, float(grad_scale), _stream(self.device)), "ss_adam_tf")
+
+    def critic_step(self, obs, act, y, keep=None):
+        """One batch of model_critic.fit (SkillshotLearner.py:434): gradient of the batch-mean
+        squared error, all-reduced when sharded, then Adam.  Returns the (device) sum of squared errors."""
+        n = int(np.prod(y.shape))
+        world = self._world()
+        rank_off = 0
+        if world > 1:
+            import torch.distributed as dist
+            rank_off = dist.get_rank(None if self.group is True else self.group) * n
+        g = self.critic_grad(obs, act, y, keep, n_global=n * world, row_offset=rank_off)
+        self._allreduce(g)
+        self.apply_adam("critic")
+        return self.stats[0]
+
+    def actor_step(self, obs):
+        """model_actor_fit_step (SkillshotLearner.py:386-417).  Returns the (device) sum of q."""
+        g = self.actor_grad(obs)
+        self._allreduce(g)
+        self.apply_adam("actor")
+        return self.stats[1]
+
+    # -- checkpoint ------------------------------------------------------------
+    def state_dict(self):
+        return dict(params=self.params.cpu(), target=self.target.cpu(), adam_m=self.adam_m.cpu(),
+                    adam_v=self.adam_v.cpu(), step_actor=self.step_actor, step_critic=self.step_critic,
+                    counter=self.counter, seed=self.seed)
+
+    def load_state_dict(self, sd):
+        for k in ("params", "target", "adam_m", "adam_v"):
+            getattr(self, k).copy_(sd[k].to(self.device))
+        self.step_actor, self.step_critic = int(sd["step_actor"]), int(sd["step_critic"])
+        self.counter, self.seed = int(sd["counter"]), int(sd["seed"])
+
+
+class ReplayRing:
+    """Device-resident replay ring (structure of arrays).  The reference keeps one episode in
+    Python lists and uses it once (SkillshotLearner.py:292-361); a ring sized to the episode and
+    read back in order is that buffer."""
+
+    def __init__(self, capacity: int, device="cuda", seed: int = 0):
+        self.capacity, self.device, self.seed = int(capacity), torch.device(device), int(seed)
+        c, dev = self.capacity, self.device
+        self.obs = torch.zeros((c, 12), dtype=torch.float32, device=dev)
+        self.act = torch.zeros((c, 2), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(c, dtype=torch.float32, device=dev)
+        self.next_obs = torch.zeros((c, 12), dtype=torch.float32, device=dev)
+        self.done = torch.zeros(c, dtype=torch.uint8, device=dev)
+        self.pos = 0
+        self.size = 0
+        self.counter = 0
+
+    def push(self, obs, act, reward, next_obs, done=None, done_div: int = 1):
+        obs, next_obs = _f32(obs, self.device).reshape(-1, 12), _f32(next_obs, self.device).reshape(-1, 12)
+        act, reward = _f32(act, self.device).reshape(-1, 2), _f32(reward, self.device).reshape(-1)
+        n = obs.shape[0]
+        if n > self.capacity:
+            raise ValueError("push of %d rows into a ring of %d" % (n, self.capacity))
+        if done is not None:
+            done = done.to(device=self.device, dtype=torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            check(lib.ss_replay_push(self.obs.data_ptr(), self.act.data_ptr(), self.reward.data_ptr(),
+                                     self.next_obs.data_ptr(), self.done.data_ptr(), self.capacity, self.pos,
+                                     obs.data_ptr(), act.data_ptr(), reward.data_ptr(), next_obs.data_ptr(),
+                                     _ptr(done), int(done_div), n, _stream(self.device)), "ss_replay_push")
+        self.pos = (self.pos + n) % self.capacity
+        self.size = min(self.capacity, self.size + n)
+
+    def sample(self, batch: int, indices=None, out: Optional[dict] = None):
+        """dict(obs, act, reward, next_obs, done, indices) of `batch` rows: the rows `indices` or a
+        uniform draw with replacement from the filled part of the ring."""
+        if self.size == 0:
+            raise ValueError("sampling from an empty ring")
+        dev = self.device
+        if out is None or out["reward"].shape[0] != batch:
+            out = dict(obs=torch.empty((batch, 12), dtype=torch.float32, device=dev),
+                       act=torch.empty((batch, 2), dtype=torch.float32, device=dev),
+                       reward=torch.empty(batch, dtype=torch.float32, device=dev),
+                       next_obs=torch.empty((batch, 12), dtype=torch.float32, device=dev),
+                       done=torch.empty(batch, dtype=torch.uint8, device=dev),
+                       indices=torch.empty(batch, dtype=torch.int64, device=dev))
+        if indices is not None:
+            indices = torch.as_tensor(indices).to(device=dev, dtype=torch.int64).contiguous()
+            if indices.numel() != batch:
+                raise ValueError("indices must have `batch` entries")
+        with torch.cuda.device(dev):
+            check(lib.ss_replay_sample(self.obs.data_ptr(), self.act.data_ptr(), self.reward.data_ptr(),
+                                       self.next_obs.data_ptr(), self.done.data_ptr(), self.capacity, self.size,
+                                       _ptr(indices), self.seed, self.counter, batch, out["obs"].data_ptr(),
+                                       out["act"].data_ptr(), out["reward"].data_ptr(), out["next_obs"].data_ptr(),
+                                       out["done"].data_ptr(), out["indices"].data_ptr(), _stream(dev)),
+                  "ss_replay_sample")
+        self.counter += 1
+        return out
+
+
+class SkillshotLearner:
+    """The reference SkillshotLearner surface (SkillshotLearner.py:12-693) over the CUDA
+    library: one SkillshotGame, two players sharing one actor, critic fitted on the
+    immediate reward, actor stepped along dQ/da, multiplicative parameter noise.
+
+    Hyper-parameters are plain attributes as in the reference
+    (`learner.model_param_game_tick_limit = 200`, SkillshotLearner.py:688).
+    """
+    game_state_features = list(FEATURE_KEYS)          # SkillshotLearner.py:17-36
+
+    def __init__(self, device="cuda", seed: Optional[int] = None):
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        # environment (SkillshotLearner.py:41-44)
+        self.game_environment = SkillshotGame(device=device)
+        self.player_ids = (1, 2)
+        self.max_dist_normaliser = (2 * (250 ** 2)) ** 0.5
+        self.use_random_start = True
+        # dir locations (SkillshotLearner.py:47-51)
+        self.save_location = "training_models"
+        self.actor_dir_name = "actor"
+        self.critic_dir_name = "critic"
+        self.training_progress_dir_name = "training_progress"
+        self.training_boards_dir_name = "training_boards"
+        # model (SkillshotLearner.py:54-58)
+        self.dim_state_space = 12
+        self.dim_action_space = 2
+        self.dim_reward_space = 1
+        self.networks = ActorCritic(device=device, seed=seed)
+        # model hyper-params (SkillshotLearner.py:61-64)
+        self.model_param_batch_size = 16
+        self.model_param_game_tick_limit = 2000
+        self.action_noise_sd = 0.15
+        self.param_noise_sd = 0.5
+        self._rng = np.random.RandomState(seed)      # the shuffles the reference takes from np.random
+        self.last_fit = {}
+
+    # -- acting (SkillshotLearner.py:206-281) ------------------------------------
+    def do_actions(self, player_id, predictions):
+        player = self.game_environment.get_player_by_id(player_id)
+        player.move_direction_float(float(predictions[0]))
+        player.move_look_float(float(predictions[1]))
+        player.move_shoot_projectile()           # attempted every time, SkillshotLearner.py:212-213
+
+    def _predict(self, game_state, player_id, **noise):
+        features = np.asarray(self.prepare_states([game_state], player_id)[0], dtype=np.float32)
+        return self.networks.actor_forward(features[None, :], **noise).cpu().numpy()
+
+    def model_act(self, game_state, player_id):
+        predictions = self._predict(game_state, player_id)
+        self.do_actions(player_id, predictions[0])
+        return predictions
+
+    def model_act_action_noise(self, game_state, player_id):
+        predictions = self._predict(game_state, player_id, action_noise_sd=self.action_noise_sd)
+        self.do_actions(player_id, predictions[0])
+        return predictions
+
+    def model_act_param_noise(self, game_state, player_id):
+        predictions = self._predict(game_state, player_id, param_noise_sd=self.param_noise_sd, noise_group=1)
+        self.do_actions(player_id, predictions[0])
+        return predictions
+
+    # -- dataset preparation (SkillshotLearner.py:512-573) ------------------------
+    def prepare_states(self, game_states, player_id):
+        board = self.game_environment.board_size
+        cooldown_max = self.game_environment.get_player_by_id(player_id).projectile.cooldown_max
+        norm = self.max_dist_normaliser
+        rows = []
+        for state in game_states:
+            p = state.get(player_id)
+            rows.append([
+                p.get("player_path_dist_opponent") / norm,
+                p.get("player_dist_opponent") / norm,
+                p.get("player_pos_x") / board[0],
+                p.get("player_pos_y") / board[1],
+                (p.get("player_rotation") % 2 * np.pi) / 2 * np.pi,        # precedence as written, :529
+                p.get("projectile_cooldown") / cooldown_max,
+                p.get("projectile_dist_opponent") / norm,
+                p.get("projectile_pos_x") / board[0],
+                p.get("projectile_pos_y") / board[1],
+                (p.get("projectile_rotation") % 2 * np.pi) / 2 * np.pi,
+                p.get("projectile_path_dist_opponent") / norm,
+                int(p.get("projectile_future_collision_opponent")),
+            ])
+        return rows
+
+    @staticmethod
+    def prepare_actions(actions, player_id):
+        return [a[0] for a in actions.get(player_id)]
+
+    @staticmethod
+    def prepare_rewards(rewards, player_id):
+        return list(rewards.get(player_id))
+
+    # -- rewards (SkillshotLearner.py:575-603) -------------------------------------
+    def calculate_rewards_looking(self, game_states):
+        size = self.game_environment.board_size[0]
+        return [{pid: -s[pid]["player_path_dist_opponent"] / size for pid in self.player_ids} for s in game_states]
+
+    def calculate_rewards_simple(self, game_states):
+        out = []
+        for s in game_states:
+            out.append({pid: s[pid]["projectile_dist_opponent"] - s[opp]["projectile_dist_opponent"]
+                        for pid, opp in zip(self.player_ids, self.player_ids[::-1])})
+        return out
+
+    # -- fitting (SkillshotLearner.py:386-443) --------------------------------------
+    def model_actor_fit_step(self, state_tensor):
+        """One deterministic-policy-gradient step of the actor on a batch of states."""
+        self.networks.actor_step(np.asarray(state_tensor, dtype=np.float32))
+
+    def models_fit(self, states, actions, rewards):
+        assert len(states) == len(actions) == len(rewards)
+        states = np.asarray(states, np.float32)
+        actions = np.asarray(actions, np.float32).reshape(len(states), -1)
+        rewards = np.asarray(rewards, np.float32)
+        assert states.shape[0] == actions.shape[0] == rewards.shape[0]
+        indices = np.arange(states.shape[0])
+        self._rng.shuffle(indices)                                   # SkillshotLearner.py:426-431
+        dev = self.networks.device
+        s, a, r = (torch.from_numpy(x[indices]).to(dev) for x in (states, actions, rewards))
+        bs = self.model_param_batch_size
+        # critic.fit: one epoch, Keras reshuffles, batches of 16 with the short last batch kept
+        order = torch.from_numpy(self._rng.permutation(len(indices))).to(dev)
+        sse = torch.zeros((), device=dev)
+        for b in range(0, len(indices), bs):
+            idx = order[b:b + bs]
+            sse += self.networks.critic_step(s[idx], a[idx], r[idx])
+        # then the actor, consecutive batches of the shuffled states (SkillshotLearner.py:440-443)
+        qsum = torch.zeros((), device=dev)
+        for b in range(0, len(indices), bs):
+            qsum += self.networks.actor_step(s[b:b + bs])
+        self.last_fit = dict(critic_loss=float(sse) / len(indices), mean_q=float(qsum) / len(indices))
+
+    # -- training loop (SkillshotLearner.py:283-384) -----------------------------------
+    def model_train(self, epochs, save_progress=False, save_boards=False):
+        total = dict(epoch_ticks=[], epoch_winner=[], epoch_board_sequences=[])
+        game = self.game_environment
+        for epoch in range(epochs):
+            game.game_reset(random_positions=self.use_random_start)
+            states, boards = [game.get_state()], []
+            actions = {pid: [] for pid in self.player_ids}
+            while game.game_live and game.ticks < self.model_param_game_tick_limit:
+                game_state = states[-1]
+                for pid in self.player_ids:      # both act from the same pre-tick state
+                    actions[pid].append(self.model_act_param_noise(game_state, pid))
+                game.game_tick()
+                states.append(game.get_state())
+                if save_boards:
+                    boards.append(game.get_board())
+            print("Begin Fitting for Epoch:", epoch)
+            rewards_per_state = self.calculate_rewards_looking(states[1:])   # reward of action t = state t+1
+            rewards = {pid: [r[pid] for r in rewards_per_state] for pid in self.player_ids}
+            ts, ta, tr = [], [], []
+            for pid in self.player_ids:                                      # P1 rows then P2 rows
+                ts += self.prepare_states(states[:-1], pid)
+                ta += self.prepare_actions(actions, pid)
+                tr += self.prepare_rewards(rewards, pid)
+            ts, ta, tr = np.array(ts), np.array(ta), np.array(tr)
+            assert ts.shape == ((len(states) - 1) * 2, self.dim_state_space)
+            assert ta.shape == (ts.shape[0], self.dim_action_space) and tr.shape == (ts.shape[0],)
+            self.models_fit(ts, ta, tr)
+            total["epoch_ticks"].append(game.ticks)
+            total["epoch_winner"].append(game.winner_id)
+            if save_boards:
+                total["epoch_board_sequences"].append(boards)
+            print("Epoch {} Completed, ticks taken: {}, game winner: {}".format(epoch, game.ticks, game.winner_id))
+        print("All Epochs Completed")
+        if save_progress:
+            self.save_actor_critic_models(epochs)
+        self.training_progress = total
+        return total
+
+    # -- persistence (SkillshotLearner.py:123-162, naming kept, bugs not) ------------------
+    def save_actor_critic_models(self, epochs):
+        """training_models/{actor,critic}/{start}_{end}_model.npz (the reference writes .h5 through
+        Keras; same directory layout and epoch-range naming, arrays in get_weights() order)."""
+        for which, dir_name in (("actor", self.actor_dir_name), ("critic", self.critic_dir_name)):
+            d = os.path.join(self.save_location, dir_name)
+            os.makedirs(d, exist_ok=True)
+            ends = [int(f.split("_")[1]) for f in os.listdir(d) if f.endswith("_model.npz")]
+            start = max(ends) if ends else 0
+            np.savez(os.path.join(d, "%d_%d_model.npz" % (start, start + epochs)), *self.networks.get_weights(which))
+        torch.save(self.networks.state_dict(), os.path.join(self.save_location, "learner_state.pt"))
+
+    def load_actor_critic_models(self, load_index=-1):
+        flat = {}
+        for which, dir_name in (("actor", self.actor_dir_name), ("critic", self.critic_dir_name)):
+            d = os.path.join(self.save_location, dir_name)
+            files = sorted((f for f in os.listdir(d) if f.endswith("_model.npz")), key=lambda x: int(x.split("_")[1]))
+            z = np.load(os.path.join(d, files[load_index]))
+            flat[which] = np.concatenate([z[k].ravel() for k in z.files])
+        self.networks.set_weights(flat["actor"], flat["critic"])
+        full = os.path.join(self.save_location, "learner_state.pt")
+        if os.path.exists(full):
+            self.networks.load_state_dict(torch.load(full))
+
+
+class SelfPlayTrainer:
+    """Batched self-play: E games stepped together, both players driven by the shared actor
+    with parameter-noise exploration, transitions kept in a device replay ring, critic and
+    actor updated on sampled minibatches.  One rank per GPU; with a process group the only
+    exchange is the all-reduce of the flat gradients (envs and replay shard naturally).
+    """
+
+    def __init__(self, n_envs: int, device="cuda", seed: int = 0, replay_capacity: Optional[int] = None,
+                 batch_size: int = 4096, gamma: float = 0.0, tau: float = 1.0, param_noise_sd: float = 0.5,
+                 noise_group: int = 128, reward_mode: str = "looking", tick_limit: int = 2000,
+                 random_positions: bool = True, process_group=None, precision: str = "f32"):
+        self.device = torch.device(device)
+        self.envs = SkillshotEnvs(n_envs, device=device, random_positions=random_positions, seed=seed,
+                                  reward_mode=reward_mode, tick_limit=tick_limit, auto_reset=True)
+        self.networks = ActorCritic(device=device, seed=seed if process_group is None else 0, gamma=gamma, tau=tau,
+                                    process_group=process_group)
+        self.networks.seed = seed          # exploration / dropout streams differ per rank, weights do not
+        self.replay = ReplayRing(replay_capacity or 2 * n_envs * 8, device=device, seed=seed)
+        self.batch_size, self.param_noise_sd, self.noise_group = int(batch_size), float(param_noise_sd), int(noise_group)
+        self.precision = precision
+        n = n_envs
+        self.obs = self.envs.observe().contiguous()                       # [n,2,12] seen by the actor next
+        self.prev_obs = torch.empty_like(self.obs)
+        self.actions = torch.empty((n, 2, 2), dtype=torch.float32, device=self.device)
+        self._batch = None
+        self.ticks = 0
+
+    def rollout_tick(self, store: bool = True):
+        """One tick of every env: actor forward on both players' observations (fresh parameter
+        noise per noise group), env step, transition push."""
+        self.prev_obs, self.obs = self.obs, self.prev_obs
+        self.networks.actor_forward(self.prev_obs, param_noise_sd=self.param_noise_sd, noise_group=self.noise_group,
+                                    out=self.actions.view(-1, 2), precision=self.precision)
+        out = self.envs.step(self.actions, obs_out=self.obs)
+        if store:
+            self.replay.push(self.prev_obs, self.actions, out["reward"], self.obs, out["done"], done_div=2)
+        self.ticks += 1
+        return out
+
+    def update(self):
+        """One critic step and one actor step on a sampled minibatch."""
+        self._batch = b = self.replay.sample(self.batch_size, out=self._batch)
+        net = self.networks
+        y = net.td_targets(b["reward"], b["next_obs"], b["done"])
+        sse = net.critic_step(b["obs"], b["act"], y)
+        q = net.actor_step(b["obs"])
+        return sse, q

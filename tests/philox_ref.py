@@ -1,0 +1,70 @@
+"""Host restatement (numpy) of the library's counter-based draws
+(skillshot_learning_b200/csrc/ss_rng.cuh, ss_env_core.cuh): Philox4x32-10, the
+(seed, tag, a, b, counter) keying, the open-interval uniform and Box-Muller.
+Test infrastructure: the GPU tests compare kernels that draw on the device with it."""
+import numpy as np
+
+M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+W0, W1 = 0x9E3779B9, 0xBB67AE85
+TAG_PARAM_NOISE, TAG_DROPOUT, TAG_ACTION_NOISE, TAG_REPLAY = 1, 2, 3, 4
+MASK = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised over numpy arrays of uint32 counters; scalar key."""
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & MASK for c in np.broadcast_arrays(c0, c1, c2, c3))
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ np.uint64(k0)) & MASK, lo1, (hi0 ^ c3 ^ np.uint64(k1)) & MASK, lo0
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def draw4(seed, tag, a, b, counter):
+    seed, counter = int(seed), int(counter)
+    return philox4x32_10(a, b, counter & 0xFFFFFFFF, tag ^ (counter >> 32), seed & 0xFFFFFFFF, seed >> 32)
+
+
+def unit_open(x):
+    return ((x >> np.uint32(8)).astype(np.float64) + 0.5) / 16777216.0
+
+
+def normal4(seed, tag, a, b, counter):
+    """[..., 4] standard normals (float64 evaluation of the device's float32 Box-Muller)."""
+    x, y, z, w = draw4(seed, tag, a, b, counter)
+    out = []
+    for u, v in ((x, y), (z, w)):
+        r = np.sqrt(-2.0 * np.log(unit_open(u)))
+        th = 2.0 * np.pi * unit_open(v)
+        out += [r * np.cos(th), r * np.sin(th)]
+    return np.stack(out, axis=-1)
+
+
+def param_noise_eps(n_params, seed, group, counter):
+    """eps_p for p < n_params as ss_param_noise / ss_actor_forward draw them."""
+    quads = (n_params + 3) // 4
+    z = normal4(seed, TAG_PARAM_NOISE, np.arange(quads, dtype=np.uint64), np.uint64(group), counter)
+    return z.reshape(-1)[:n_params]
+
+
+def dropout_keep(n, seed, counter, rate, row_offset=0):
+    """keep mask uint8 [n, 256] of ss_critic_grad's Philox dropout."""
+    thresh = min(4294967295.0, rate * 4294967296.0)
+    thresh = np.uint32(int(thresh))
+    rows = np.arange(n) + row_offset
+    quads = (rows // 4).astype(np.uint64)
+    j = np.arange(256, dtype=np.uint64)
+    u = draw4(seed, TAG_DROPOUT, j[None, :], quads[:, None], counter)      # each [n,256]
+    lane = (rows % 4)[:, None]
+    sel = np.where(lane == 0, u[0], np.where(lane == 1, u[1], np.where(lane == 2, u[2], u[3])))
+    return (sel >= thresh).astype(np.uint8)
+
+
+def replay_indices(batch, size, seed, counter):
+    b = np.arange(batch)
+    u = draw4(seed, TAG_REPLAY, (b // 4).astype(np.uint64), np.uint64(0), counter)
+    lane = b % 4
+    x = np.where(lane == 0, u[0], np.where(lane == 1, u[1], np.where(lane == 2, u[2], u[3]))).astype(np.uint64)
+    return ((x * np.uint64(size)) >> np.uint64(32)).astype(np.int64)

@@ -1,0 +1,276 @@
+"""GPU parity of the learner kernels (through the C ABI) with the CPU oracle
+(oracle/learner_oracle.py; parity unpinned -- see its header) on identical seeded
+inputs, every random choice injected or re-derived with tests/philox_ref.py.
+
+Tolerances (float32 kernels against a float32/float64 restatement, different
+summation order): forward values 2e-5 relative, gradients 2e-4 relative to the
+gradient's scale, parameters after k Adam steps 1e-5 absolute (Adam normalises
+the step to ~lr = 1e-3, so this is 1 % of one step)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import learner_oracle as lo
+from tests import philox_ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def net():
+    from skillshot_learning_b200 import ActorCritic
+    ac = ActorCritic(device="cuda:0", seed=11)
+    rng = np.random.default_rng(5)
+    theta, phi = lo.init_actor(rng), lo.init_critic(rng)
+    # non-zero biases so that every term of the backward pass is exercised
+    theta[3072:3328] = rng.normal(0, 0.05, 256); theta[36096:36224] = rng.normal(0, 0.05, 128)
+    theta[36480:] = rng.normal(0, 0.05, 2)
+    phi[3072:3328] = rng.normal(0, 0.05, 256); phi[36352:36480] = rng.normal(0, 0.05, 128); phi[36608] = 0.1
+    ac.set_weights(theta, phi)
+    return ac, theta, phi
+
+
+def _batch(n, seed=0):
+    rng = np.random.default_rng(seed)
+    s = rng.uniform(0, 1, (n, 12)).astype(np.float32)
+    s[:, 4] *= 9.8; s[:, 9] *= 9.8; s[:, 11] = rng.integers(0, 2, n)      # ranges of prepare_states
+    a = np.tanh(rng.normal(size=(n, 2))).astype(np.float32)
+    r = (-rng.uniform(0, 1, n)).astype(np.float32)
+    return s, a, r
+
+
+def _scale_close(got, want, rel):
+    scale = np.abs(want).max() + 1e-12
+    np.testing.assert_allclose(got / scale, want / scale, rtol=0, atol=rel)
+
+
+@pytest.mark.parametrize("n", [1, 16, 33, 1000, 40000])
+def test_actor_and_critic_forward(net, n):
+    ac, theta, phi = net
+    s, a, _ = _batch(n, n)
+    got = ac.actor_forward(s).cpu().numpy()
+    np.testing.assert_allclose(got, lo.actor_forward(theta, s), rtol=2e-5, atol=2e-6)
+    q = ac.critic_forward(s, a).cpu().numpy()
+    np.testing.assert_allclose(q, lo.critic_forward(phi, s, a), rtol=2e-5, atol=2e-6)
+
+
+def test_param_noise_vector_matches_the_host_philox(net):
+    ac, theta, _ = net
+    for group, counter in ((0, 0), (3, 7), (123456, 2 ** 33 + 5)):
+        got = ac.noisy_actor_params(0.5, group=group, counter=counter).cpu().numpy()
+        eps = philox_ref.param_noise_eps(lo.ACTOR_PARAMS, ac.seed, group, counter)
+        np.testing.assert_allclose(got, lo.noisy_actor_params(theta, eps, 0.5), rtol=1e-5, atol=1e-7)
+    eps = philox_ref.param_noise_eps(lo.ACTOR_PARAMS, ac.seed, 0, 0)
+    assert abs(eps.mean()) < 0.02 and abs(eps.std() - 1) < 0.02          # N(0,1), SkillshotLearner.py:263
+
+
+@pytest.mark.parametrize("group", [1, 5, 32, 100])
+def test_param_noise_forward_uses_one_draw_per_group(net, group):
+    ac, theta, _ = net
+    n = 230
+    s, _, _ = _batch(n, 77)
+    got = ac.actor_forward(s, param_noise_sd=0.5, noise_group=group, counter=9).cpu().numpy()
+    want = np.empty_like(got)
+    for g in range((n + group - 1) // group):
+        eps = philox_ref.param_noise_eps(lo.ACTOR_PARAMS, ac.seed, g, 9)
+        sl = slice(g * group, min(n, (g + 1) * group))
+        want[sl] = lo.actor_forward(lo.noisy_actor_params(theta, eps, 0.5), s[sl])
+    np.testing.assert_allclose(got, want, rtol=5e-5, atol=5e-6)
+    again = ac.actor_forward(s, param_noise_sd=0.5, noise_group=group, counter=9).cpu().numpy()
+    assert np.array_equal(got, again)                                      # counter-based: reproducible
+    other = ac.actor_forward(s, param_noise_sd=0.5, noise_group=group, counter=10).cpu().numpy()
+    assert not np.allclose(got, other)
+
+
+def test_action_noise_distribution(net):
+    ac, theta, _ = net
+    s, _, _ = _batch(20000, 3)
+    clean = ac.actor_forward(s).cpu().numpy()
+    noisy = ac.actor_forward(s, action_noise_sd=0.15, counter=4).cpu().numpy()
+    d = noisy - clean
+    assert abs(d.mean()) < 0.005 and abs(d.std() - 0.15) < 0.005           # N(0, 0.15), SkillshotLearner.py:238
+    assert abs(np.corrcoef(d[:, 0], d[:, 1])[0, 1]) < 0.03
+
+
+@pytest.mark.parametrize("gamma", [0.0, 0.95])
+def test_td_targets(net, gamma):
+    ac, theta, phi = net
+    s2, _, r = _batch(777, 8)
+    done = (np.random.default_rng(1).uniform(size=777) < 0.2)
+    ac.gamma = gamma
+    try:
+        y = ac.td_targets(r, s2, torch.from_numpy(done.astype(np.uint8))).cpu().numpy()
+    finally:
+        ac.gamma = 0.0
+    np.testing.assert_allclose(y, lo.ddpg_targets(theta, phi, r, s2, done, gamma), rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("n", [16, 5, 37, 1000, 20000])
+def test_critic_gradient_with_injected_dropout(net, n):
+    ac, theta, phi = net
+    s, a, r = _batch(n, 100 + n)
+    keep = (np.random.default_rng(n).uniform(size=(n, 256)) >= 0.2).astype(np.uint8)
+    g = ac.critic_grad(s, a, r, keep=keep).cpu().numpy()
+    sse = float(ac.stats[0])
+    want, want_sse = lo.critic_grad(phi.astype(np.float64), s, a, r, keep.astype(np.float64), 0.2, dtype=torch.float64)
+    _scale_close(g, want, 2e-4)
+    assert abs(sse - want_sse) <= 1e-4 * max(1.0, want_sse)
+    g2 = ac.critic_grad(s, a, r, keep=keep).cpu().numpy()
+    assert np.array_equal(g, g2)                                           # fixed-order reduction
+
+
+def test_critic_gradient_with_philox_dropout(net):
+    ac, theta, phi = net
+    n = 300
+    s, a, r = _batch(n, 41)
+    ac.counter = 1234
+    g = ac.critic_grad(s, a, r, row_offset=64).cpu().numpy()
+    keep = philox_ref.dropout_keep(n, ac.seed, 1234, 0.2, row_offset=64)
+    assert abs(keep.mean() - 0.8) < 0.01                                   # Dropout(0.2), SkillshotLearner.py:105
+    want, _ = lo.critic_grad(phi.astype(np.float64), s, a, r, keep.astype(np.float64), 0.2, dtype=torch.float64)
+    _scale_close(g, want, 2e-4)
+
+
+def test_sharded_critic_gradient_sums_to_the_full_batch(net):
+    ac, theta, phi = net
+    n = 512
+    s, a, r = _batch(n, 55)
+    keep = (np.random.default_rng(2).uniform(size=(n, 256)) >= 0.2).astype(np.uint8)
+    full = ac.critic_grad(s, a, r, keep=keep).cpu().numpy()
+    h = n // 2
+    parts = [ac.critic_grad(s[i:i + h], a[i:i + h], r[i:i + h], keep=keep[i:i + h], n_global=n).cpu().numpy().copy()
+             for i in (0, h)]
+    _scale_close(parts[0] + parts[1], full, 2e-6)
+
+
+@pytest.mark.parametrize("n", [16, 7, 45, 3000])
+def test_actor_policy_gradient(net, n):
+    ac, theta, phi = net
+    s, _, _ = _batch(n, 200 + n)
+    g = ac.actor_grad(s).cpu().numpy()
+    qsum = float(ac.stats[1])
+    want, want_q = lo.actor_grad(theta.astype(np.float64), phi.astype(np.float64), s, dtype=torch.float64)
+    _scale_close(g, want, 2e-4)
+    assert abs(qsum - want_q) <= 1e-4 * max(1.0, abs(want_q))
+
+
+def test_adam_and_soft_update(net):
+    from skillshot_learning_b200 import ActorCritic
+    ac0, theta, phi = net
+    ac = ActorCritic(device="cuda:0", seed=1, tau=0.25)
+    ac.set_weights(theta, phi)
+    opt = lo.AdamTF(lo.CRITIC_PARAMS)
+    p, tgt = phi.copy(), phi.copy()
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        g = rng.normal(0, 0.01, lo.CRITIC_PARAMS).astype(np.float32)
+        ac.grads[ac._c_off:].copy_(torch.from_numpy(g))
+        ac.apply_adam("critic")
+        p = opt.step(p, g)
+        tgt = lo.soft_update(tgt, p, 0.25)
+    np.testing.assert_allclose(ac.critic.cpu().numpy(), p, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(ac.target_critic.cpu().numpy(), tgt, rtol=0, atol=2e-6)
+    assert np.array_equal(ac.actor.cpu().numpy(), theta)                   # the other network is untouched
+
+
+def test_models_fit_tracks_the_reference_learner(net):
+    """One episode through models_fit's schedule (SkillshotLearner.py:419-443): critic fitted in
+    shuffled batches of 16 (short last batch kept, Dropout on), then the actor stepped on
+    consecutive batches; losses and parameters against the oracle with the same orders/masks."""
+    from skillshot_learning_b200 import ActorCritic
+    _, theta, phi = net
+    n, bs = 203, 16
+    s, a, r = _batch(n, 999)
+    rng = np.random.default_rng(17)
+    order = rng.permutation(n)
+    keep = (rng.uniform(size=(n, 256)) >= 0.2).astype(np.uint8)
+    orc = lo.LearnerOracle(theta, phi, bs)
+    want_losses = orc.critic_fit(s, a, r, order, keep.astype(np.float32))
+    want_q = orc.actor_fit(s)
+
+    ac = ActorCritic(device="cuda:0", seed=3)
+    ac.set_weights(theta, phi)
+    ts, ta, tr, tk = (torch.from_numpy(x).cuda() for x in (s, a, r, keep))
+    losses, qs = [], []
+    for b in range(0, n, bs):
+        idx = torch.from_numpy(order[b:b + bs]).cuda()
+        sse = ac.critic_step(ts[idx], ta[idx], tr[idx], keep=tk[idx])
+        losses.append(float(sse) / len(idx))
+    for b in range(0, n, bs):
+        qs.append(float(ac.actor_step(ts[b:b + bs])))
+    np.testing.assert_allclose(losses, want_losses, rtol=2e-3, atol=1e-6)      # stated tolerance on the losses
+    np.testing.assert_allclose(qs, want_q, rtol=2e-3, atol=1e-4)
+    np.testing.assert_allclose(ac.critic.cpu().numpy(), orc.phi, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(ac.actor.cpu().numpy(), orc.theta, rtol=0, atol=1e-5)
+    assert ac.step_critic == 13 and ac.step_actor == 13
+
+
+def test_replay_ring_push_wrap_and_sample():
+    from skillshot_learning_b200 import ReplayRing
+    ring = ReplayRing(100, device="cuda:0", seed=5)
+    rng = np.random.default_rng(0)
+    mirror = dict(obs=np.zeros((100, 12), np.float32), act=np.zeros((100, 2), np.float32), reward=np.zeros(100, np.float32),
+                  next_obs=np.zeros((100, 12), np.float32), done=np.zeros(100, np.uint8))
+    pos = 0
+    for n in (30, 30, 30, 30, 60):                       # wraps twice
+        s, a, r = _batch(n, pos + n)
+        s2 = rng.uniform(size=(n, 12)).astype(np.float32)
+        done_env = rng.integers(0, 2, n // 2).astype(np.uint8)
+        ring.push(s, a, r, s2, torch.from_numpy(done_env), done_div=2)
+        idx = (pos + np.arange(n)) % 100
+        mirror["obs"][idx], mirror["act"][idx], mirror["reward"][idx], mirror["next_obs"][idx] = s, a, r, s2
+        mirror["done"][idx] = np.repeat(done_env, 2)
+        pos = (pos + n) % 100
+    assert ring.pos == pos and ring.size == 100
+    for k in mirror:
+        assert np.array_equal(getattr(ring, k).cpu().numpy(), mirror[k]), k
+    want_idx = rng.integers(0, 100, 64)
+    b = ring.sample(64, indices=want_idx)
+    for k in mirror:
+        assert np.array_equal(b[k].cpu().numpy(), mirror[k][want_idx]), k
+    ring.counter = 3
+    b = ring.sample(1000)
+    idx = b["indices"].cpu().numpy()
+    assert np.array_equal(idx, philox_ref.replay_indices(1000, 100, 5, 3))
+    assert idx.min() >= 0 and idx.max() < 100 and len(np.unique(idx)) > 90
+    assert np.array_equal(b["obs"].cpu().numpy(), mirror["obs"][idx])
+
+
+def test_reference_surface_trains_one_episode(capsys):
+    """SkillshotLearner.main-style use (SkillshotLearner.py:685-693) with a short tick limit."""
+    from skillshot_learning_b200 import SkillshotLearner
+    skl = SkillshotLearner(device="cuda:0", seed=2)
+    skl.model_param_game_tick_limit = 12
+    skl.use_random_start = False
+    before = skl.networks.actor.clone()
+    prog = skl.model_train(epochs=1, save_progress=False, save_boards=True)
+    assert prog["epoch_ticks"] == [12] and prog["epoch_winner"] == [0]
+    assert len(prog["epoch_board_sequences"][0]) == 12 and prog["epoch_board_sequences"][0][0].shape == (250, 250)
+    assert skl.networks.step_critic == 2 and skl.networks.step_actor == 2      # 24 rows in batches of 16
+    assert not torch.equal(before, skl.networks.actor)
+    assert np.isfinite(skl.last_fit["critic_loss"])
+    state = skl.game_environment.get_state()
+    obs = skl.prepare_states([state], 1)[0]
+    assert len(obs) == 12
+    a = skl.model_act(state, 1)
+    assert a.shape == (1, 2) and np.all(np.abs(a) <= 1)
+
+
+def test_selfplay_trainer_rollout_and_update():
+    from skillshot_learning_b200 import SelfPlayTrainer
+    tr = SelfPlayTrainer(512, device="cuda:0", seed=4, batch_size=256, noise_group=32, tick_limit=50)
+    for _ in range(6):
+        out = tr.rollout_tick()
+    assert tr.replay.size == 6 * 1024
+    # stored transitions chain: next_obs of tick t is obs of tick t+1 for envs that did not reset
+    o = tr.replay.obs.cpu().numpy()[:6 * 1024].reshape(6, 1024, 12)
+    o2 = tr.replay.next_obs.cpu().numpy()[:6 * 1024].reshape(6, 1024, 12)
+    assert np.array_equal(o2[:-1], o[1:])
+    r = tr.replay.reward.cpu().numpy()[:1024]
+    live = tr.replay.done.cpu().numpy()[:1024] == 0      # a done env was reset: its s' is the fresh game's
+    assert live.sum() > 900
+    np.testing.assert_allclose(r[live], -o2[0][live, 0] * (353.5533905932738 / 250.0), rtol=2e-5, atol=1e-6)  # looking reward of s'
+    before = tr.networks.params.clone()
+    sse, q = tr.update()
+    assert np.isfinite(float(sse)) and np.isfinite(float(q))
+    assert not torch.equal(before, tr.networks.params)
