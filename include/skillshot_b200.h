@@ -170,6 +170,16 @@ int ss_actor_forward(const float *actor_params, const float *obs, float *act_out
                      float param_noise_sd, int64_t noise_group, float action_noise_sd,
                      uint64_t seed, uint64_t counter, void *stream);
 
+/* The same through the tensor cores: bf16 operands (observations split into a
+ * bf16 high and low part so no input precision is lost), fp32 accumulation in
+ * tensor memory, tcgen05.mma; the 128 -> 2 output layer and tanh in fp32.
+ * `noise_group` must be a multiple of 128 when param_noise_sd > 0.  For the large
+ * rollout batches (BASELINE.json configs 3-4); results agree with
+ * ss_actor_forward to bf16 weight rounding (about 1e-2 absolute on the action). */
+int ss_actor_forward_tc(const float *actor_params, const float *obs, float *act_out, int64_t n,
+                        float param_noise_sd, int64_t noise_group, float action_noise_sd,
+                        uint64_t seed, uint64_t counter, void *stream);
+
 /* out[p] = params[p] + params[p] * (sd * eps_p): the perturbed vector
  * ss_actor_forward uses for noise group `group` (introspection and tests). */
 int ss_param_noise(const float *params, float *out, int64_t n_params, float sd, uint64_t seed,

@@ -26,6 +26,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = {
     "ss_env.cu": ["-fmad=false"],
     "ss_learner.cu": [],
+    "ss_mlp_tc.cu": [],
 }
 
 

@@ -274,3 +274,63 @@ def test_selfplay_trainer_rollout_and_update():
     sse, q = tr.update()
     assert np.isfinite(float(sse)) and np.isfinite(float(q))
     assert not torch.equal(before, tr.networks.params)
+
+
+# ---------------------------------------------------------------------------
+# tensor-core actor forward (ss_actor_forward_tc)
+# ---------------------------------------------------------------------------
+def _bf16(x):
+    """float32 -> bfloat16 (round to nearest even) -> float32, as cvt.rn.bf16.f32 does."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).reshape(np.shape(x))
+
+
+def actor_forward_bf16_model(theta, s):
+    """What the tensor-core kernel computes, restated in numpy: bf16 weights, observation as a
+    bf16 high + low pair, fp32 accumulation (float64 here), hidden layer 1 rounded to bf16,
+    layer 3 and tanh in fp32 (skillshot_learning_b200/csrc/ss_mlp_tc.cu header)."""
+    w1, b1, w2, b2, w3, b3 = lo.split(np.asarray(theta, np.float32), lo.ACTOR_SHAPES)
+    s = np.asarray(s, np.float32)
+    hi = _bf16(s)
+    low = _bf16(s - hi)
+    z1 = (hi.astype(np.float64) + low.astype(np.float64)) @ _bf16(w1).astype(np.float64) + b1
+    h1 = _bf16(np.maximum(z1, 0).astype(np.float32)).astype(np.float64)
+    h2 = np.maximum(h1 @ _bf16(w2).astype(np.float64) + b2, 0)
+    return np.tanh(h2 @ w3.astype(np.float64) + b3).astype(np.float32)
+
+
+@pytest.mark.parametrize("n", [1, 128, 129, 300, 5000, 148 * 128 * 3 + 77])
+def test_tensor_core_actor_forward(net, n):
+    ac, theta, _ = net
+    s, _, _ = _batch(n, 31 + n)
+    got = ac.actor_forward(s, precision="bf16").cpu().numpy()
+    model = actor_forward_bf16_model(theta, s)
+    # against the restated bf16 arithmetic: only fp32 accumulation order and rare 1-ulp flips of
+    # the bf16 rounding of a hidden unit differ
+    np.testing.assert_allclose(got, model, rtol=0, atol=5e-4)
+    # against the exact float32 path: bf16 weight rounding, stated tolerance 2e-2 on actions in [-1, 1]
+    np.testing.assert_allclose(got, lo.actor_forward(theta, s), rtol=0, atol=2e-2)
+
+
+def test_tensor_core_actor_forward_with_noise_groups(net):
+    ac, theta, _ = net
+    n, group = 1000, 256
+    s, _, _ = _batch(n, 78)
+    got = ac.actor_forward(s, param_noise_sd=0.5, noise_group=group, action_noise_sd=0.15, counter=21,
+                           precision="bf16").cpu().numpy()
+    exact = ac.actor_forward(s, param_noise_sd=0.5, noise_group=group, action_noise_sd=0.15, counter=21).cpu().numpy()
+    # same Philox draws as the float32 path: the two differ by bf16 rounding only (noisy weights are
+    # up to ~3x larger than the clean ones, hence the wider band)
+    np.testing.assert_allclose(got, exact, rtol=0, atol=6e-2)
+    assert np.abs(got - exact).mean() < 6e-3
+    want = np.empty((n, 2), np.float32)
+    for g in range((n + group - 1) // group):
+        eps = philox_ref.param_noise_eps(lo.ACTOR_PARAMS, ac.seed, g, 21)
+        sl = slice(g * group, min(n, (g + 1) * group))
+        want[sl] = actor_forward_bf16_model(lo.noisy_actor_params(theta, eps, 0.5), s[sl])
+    rows = np.arange(n, dtype=np.uint64)
+    zn = philox_ref.normal4(ac.seed, philox_ref.TAG_ACTION_NOISE, rows, np.uint64(0), 21)[:, :2]
+    np.testing.assert_allclose(got, want + 0.15 * zn, rtol=0, atol=2e-3)
+    with pytest.raises(Exception):
+        ac.actor_forward(s, param_noise_sd=0.5, noise_group=100, precision="bf16")    # groups are whole tiles
