@@ -20,6 +20,13 @@ design.
   cpu_baseline  the C oracle port (oracle/skillshot_oracle.c, OpenMP over envs)
             on the host cores, on a bounded sample of the same workload
 
+  learner   the other half of BASELINE.json's metric, on the same GPUs in the same run:
+            rollout (configs[2]: 262,144 envs per GPU, tensor-core actor forward with
+            parameter noise + env step with observations + replay push) in env-steps/s and
+            samples/s, the DDPG update (sample, TD targets, critic step, actor step, one
+            gradient all-reduce each) in update samples/s, and the tensor roofline of the
+            actor-forward kernel (72,192 algorithmic FLOP per row against bf16_tflops)
+
 --impl reference times that CPU port alone (the Python reference cannot travel
 to the GPU box) and prints the same line with "impl": "reference".
 """
@@ -152,6 +159,66 @@ def cpu_baseline(target_seconds: float = 4.0):
                       "Python reference (oracle/skillshot_oracle.c)" % (ENVS_PER_GPU, ticks, dt, cores)}
 
 
+ROLLOUT_ENVS = 262144          # BASELINE.json configs[2]
+TRAIN_BATCH = 65536            # update rows per GPU per step
+ACTOR_FLOP_PER_ROW = 72192     # 2 * (12*256 + 256*128 + 128*2)
+
+
+def learner_legs(dev, rank, world, seed, peaks, ticks=64, updates=20):
+    """Rollout, DDPG update and the actor-forward tensor roofline on this rank's GPU.
+    Returns per-rank times in ms: (rollout per tick, update per step, actor forward per launch)."""
+    import torch
+    import torch.distributed as dist
+    from skillshot_learning_b200 import SelfPlayTrainer
+
+    E = ROLLOUT_ENVS
+    group = (2 * E // 148) // 128 * 128          # one parameter-noise draw per SM-sized slice of the batch
+    tr = SelfPlayTrainer(E, device=dev, seed=seed, replay_capacity=2 * E * 4, batch_size=TRAIN_BATCH,
+                         gamma=0.99, tau=0.005, param_noise_sd=0.5, noise_group=group, reward_mode="looking",
+                         tick_limit=TICK_LIMIT, process_group=True if world > 1 else None, precision="bf16")
+
+    def timed(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / iters
+
+    t_roll = timed(tr.rollout_tick, ticks)
+    t_upd = timed(tr.update, updates)
+    obs, act = tr.obs.view(-1, 12), tr.actions.view(-1, 2)
+    t_fwd = timed(lambda: tr.networks.actor_forward(obs, out=act, precision="bf16"), 50)
+    tr.envs.check_status()
+    return t_roll, t_upd, t_fwd
+
+
+def learner_report(t_roll, t_upd, t_fwd, world, peaks, peak_kind):
+    rows = 2 * ROLLOUT_ENVS
+    tf = ACTOR_FLOP_PER_ROW * rows / (t_fwd * 1e-3) / 1e12
+    return {
+        "rollout": {"workload": "262,144 envs per GPU: bf16 tensor-core actor forward on 524,288 observations with "
+                                "parameter noise (sd 0.5) + env step with observations and looking reward + replay push",
+                    "env_steps_per_sec": world * ROLLOUT_ENVS / (t_roll * 1e-3),
+                    "samples_per_sec": world * rows / (t_roll * 1e-3), "ms_per_tick": t_roll},
+        "train": {"workload": "DDPG update, %d rows per GPU: replay sample, TD targets (gamma 0.99), critic step "
+                              "(dropout 0.2), actor step, Adam + soft update (tau 0.005), two flat-gradient all-reduces"
+                              % TRAIN_BATCH,
+                  "samples_per_sec": world * TRAIN_BATCH / (t_upd * 1e-3), "ms_per_update": t_upd, "dtype": "f32"},
+        "actor_forward_roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                                   "frac": tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peak_kind,
+                                   "kernel": "actor_fwd_tc_kernel", "rows_per_launch": rows,
+                                   "algorithmic_flop_per_row": ACTOR_FLOP_PER_ROW, "launch_us": t_fwd * 1e3,
+                                   "dtype": "bf16 operands, f32 accumulate"},
+    }
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -248,10 +315,17 @@ def run_gpu_arm(args):
         barrier()
         e2e_s = time.perf_counter() - t0
 
+    # ---- learner legs: rollout, DDPG update, tensor roofline of the actor forward ----
+    lt = (float("nan"),) * 3
+    if not args.no_learner:
+        del actions
+        torch.cuda.empty_cache()
+        lt = learner_legs(dev, rank, world, 4321 + rank, measured_peaks()[0])
+
     if world > 1:
-        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, e2e_s, *lt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
+        ms, e2e_s, lt = float(t[0]), float(t[1]), tuple(float(x) for x in t[2:])
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -277,6 +351,8 @@ def run_gpu_arm(args):
             "gpu_launches": args.steps * launches_per_step,
             "clocks": clocks,
         }
+        if not args.no_learner:
+            line["learner"] = learner_report(*lt, world, peaks, peak_kind)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
@@ -295,6 +371,7 @@ def main():
     ap.add_argument("--ticks-per-launch", type=int, default=TICKS_PER_LAUNCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--no-learner", action="store_true", help="skip the rollout / update / actor-forward legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -24,7 +24,9 @@
 // to 2^-17 relative) that occupy K = 0..11 and 16..27 of layer 1 against the same
 // weight rows, because positions are multiples of 1/250 and a single bf16 (8 bits)
 // would merge neighbouring pixels.  The hidden activations are rounded to bf16
-// when they become the A operand of layer 2.
+// when they become the A operand of layer 2.  Both biases ride through the tensor
+// core as extra K rows against a constant 1 in the A operand (bias as a bf16 high +
+// low pair: fp32-accurate to 2^-17), so the epilogues are ReLU + pack only.
 //
 // Parameter noise (SkillshotLearner.py:260-265): the CTA perturbs the weights
 // while staging them, w + w * (sd * eps), eps from the same Philox stream as the
@@ -43,7 +45,8 @@ using namespace ss;
 
 constexpr int TM = 128;                  // rows per tile = UMMA M = tensor-memory lanes
 constexpr int DS = SS_DIM_STATE, DA = SS_DIM_ACTION, H1 = SS_HIDDEN1, H2 = SS_HIDDEN2;
-constexpr int K1 = 32;                   // layer-1 K: [obs hi 12 | 0 x4 | obs lo 12 | 0 x4]
+constexpr int K1 = 32;                   // layer-1 K: [obs hi 12 | 1 1 0 0 | obs lo 12 | 0 x4]; rows 12, 13 of B1 = b1 hi, lo
+constexpr int K2 = H1 + 16;              // layer-2 K: [h1 256 | 1 1 0 x14];                rows 256, 257 of B2 = b2 hi, lo
 constexpr int NSLOT = 2;
 constexpr int EPI_WARPS = 4 * NSLOT;     // warp w serves slot w / 4 and TMEM lanes 32 (w % 4) ..
 constexpr int MMA_WARP = EPI_WARPS;
@@ -61,14 +64,14 @@ constexpr uint32_t CHUNK_A = TM * 16;    // 2048: K-chunk stride of an activatio
 constexpr uint32_t CHUNK_B1 = H1 * 16;   // 4096
 constexpr uint32_t CHUNK_B2 = H2 * 16;   // 2048
 constexpr uint32_t SBO = 128;
+constexpr uint32_t A_BYTES = (K2 / 8) * CHUNK_A;            // 69,632 per slot
+constexpr uint32_t ONES = 0x3F803F80u;                      // bf16 {1, 1}
 
 // shared-memory map (bytes)
 constexpr uint32_t SM_B1 = 0;                               // [K1/8][256][8] bf16
-constexpr uint32_t SM_B2 = SM_B1 + K1 * H1 * 2;             // [256/8][128][8] bf16
-constexpr uint32_t SM_A = SM_B2 + H1 * H2 * 2;              // NSLOT x [256/8][128][8] bf16 (layer-1 A aliases its head)
-constexpr uint32_t SM_BIAS1 = SM_A + NSLOT * TM * H1 * 2;
-constexpr uint32_t SM_BIAS2 = SM_BIAS1 + H1 * 4;
-constexpr uint32_t SM_W3 = SM_BIAS2 + H2 * 4;               // [128][2] f32
+constexpr uint32_t SM_B2 = SM_B1 + (K1 / 8) * CHUNK_B1;     // [K2/8][128][8] bf16
+constexpr uint32_t SM_A = SM_B2 + (K2 / 8) * CHUNK_B2;      // NSLOT x [K2/8][128][8] bf16 (layer-1 A aliases its head)
+constexpr uint32_t SM_W3 = SM_A + NSLOT * A_BYTES;          // [128][2] f32
 constexpr uint32_t SM_B3 = SM_W3 + H2 * DA * 4;
 constexpr uint32_t SM_BAR = SM_B3 + 16;                     // NSLOT x {in, d1, h1, d2} mbarriers
 constexpr uint32_t SM_TMEM = SM_BAR + NSLOT * 4 * 8;
@@ -91,6 +94,18 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// non-blocking probe (the MMA warp polls two slots; try_wait would park it on one of them)
+__device__ __forceinline__ bool mbar_probe(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
@@ -144,8 +159,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);     // .x = lo (low half-word)
-    return *reinterpret_cast<const uint32_t *>(&v);
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));        // first source -> upper half
+    return d;
+}
+// ReLU fused into the conversion: max(x, 0) rounded to bf16, two at a time
+__device__ __forceinline__ uint32_t pack_relu_bf16(uint32_t lo, uint32_t hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+    return d;
+}
+// 32 accumulator columns -> ReLU -> bf16 -> four 16-byte K chunks of this thread's A-operand row
+__device__ __forceinline__ void relu_pack_store(const uint32_t (&v)[32], uint8_t *dst) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4 *>(dst + c * CHUNK_A) =
+            make_uint4(pack_relu_bf16(v[c * 8 + 0], v[c * 8 + 1]), pack_relu_bf16(v[c * 8 + 2], v[c * 8 + 3]),
+                       pack_relu_bf16(v[c * 8 + 4], v[c * 8 + 5]), pack_relu_bf16(v[c * 8 + 6], v[c * 8 + 7]));
+}
+// 32 accumulator columns (hidden units col0 ..) -> ReLU -> the two 128 -> 2 dot products, split accumulators
+__device__ __forceinline__ void relu_dot(const uint32_t (&v)[32], const float *w3, float (&z0)[4], float (&z1)[4]) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const float4 w = *reinterpret_cast<const float4 *>(w3 + c * 4);        // W3[col][0..1], W3[col+1][0..1]
+        const float ha = fmaxf(__uint_as_float(v[c * 2 + 0]), 0.f), hb = fmaxf(__uint_as_float(v[c * 2 + 1]), 0.f);
+        z0[(c & 1) * 2 + 0] = fmaf(ha, w.x, z0[(c & 1) * 2 + 0]);
+        z1[(c & 1) * 2 + 0] = fmaf(ha, w.y, z1[(c & 1) * 2 + 0]);
+        z0[(c & 1) * 2 + 1] = fmaf(hb, w.z, z0[(c & 1) * 2 + 1]);
+        z1[(c & 1) * 2 + 1] = fmaf(hb, w.w, z1[(c & 1) * 2 + 1]);
+    }
+}
+__device__ __forceinline__ uint32_t hi_lo_bf16(float w) {                     // {hi, lo} with hi + lo = w to 2^-17
+    const float hi = __bfloat162float(__float2bfloat16_rn(w));
+    return pack_bf16(hi, w - hi);
 }
 
 struct TcArgs {
@@ -156,26 +202,111 @@ struct TcArgs {
     uint64_t seed, counter;
 };
 
-// one parameter -> its place in shared memory (bf16 operand tiles, fp32 biases / layer 3)
-__device__ __forceinline__ void place_param(uint8_t *smem, int p, float w) {
-    if (p < A_B1) {                        // W1[k][n]: against the high and the low half of the observation
-        const int k = p >> 8, n = p & 255;
-        const __nv_bfloat16 b = __float2bfloat16_rn(w);
-        const uint32_t off = SM_B1 + (uint32_t)((k >> 3) * H1 + n) * 16 + (k & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16 *>(smem + off) = b;
-        *reinterpret_cast<__nv_bfloat16 *>(smem + off + 2 * CHUNK_B1) = b;
-    } else if (p < A_W2) {
-        reinterpret_cast<float *>(smem + SM_BIAS1)[p - A_B1] = w;
-    } else if (p < A_B2) {                 // W2[k][n]
-        const int e = p - A_W2, k = e >> 7, n = e & 127;
-        *reinterpret_cast<__nv_bfloat16 *>(smem + SM_B2 + (uint32_t)((k >> 3) * H2 + n) * 16 + (k & 7) * 2) =
-            __float2bfloat16_rn(w);
-    } else if (p < A_W3) {
-        reinterpret_cast<float *>(smem + SM_BIAS2)[p - A_B2] = w;
-    } else if (p < A_B3) {
-        reinterpret_cast<float *>(smem + SM_W3)[p - A_W3] = w;
+// ---- weight staging ------------------------------------------------------------
+// fast N(0,1) quad for the staging loop (same Philox draw as normal4; intrinsic log / sincos:
+// differs from the float32 path's draw by ~1e-6, far below the bf16 rounding that follows)
+__device__ __forceinline__ void normal4_fast(uint64_t seed, uint32_t q, uint32_t g, uint64_t counter, float *z) {
+    const U4 u = draw4(seed, kTagParamNoise, q, g, counter);
+    const float r0 = sqrtf(-2.0f * __logf(unit_open(u.x))), r1 = sqrtf(-2.0f * __logf(unit_open(u.z)));
+    float s0, c0, s1, c1;
+    __sincosf(6.283185307179586f * unit_open(u.y), &s0, &c0);
+    __sincosf(6.283185307179586f * unit_open(u.w), &s1, &c1);
+    z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+}
+
+struct Stager {
+    const float *theta;
+    uint8_t *smem;
+    bool noisy;
+    float sd;
+    uint64_t seed, counter;
+    uint32_t group;
+    // four consecutive parameters starting at p (p % 4 == 0), perturbed if asked
+    __device__ __forceinline__ void perturb(int p, float4 &v) const {
+        if (!noisy) return;
+        float z[4];
+        normal4_fast(seed, (uint32_t)(p >> 2), group, counter, z);
+        v.x += v.x * (sd * z[0]); v.y += v.y * (sd * z[1]); v.z += v.z * (sd * z[2]); v.w += v.w * (sd * z[3]);
+    }
+    __device__ __forceinline__ float4 load(int p) const { return __ldg(reinterpret_cast<const float4 *>(theta + p)); }
+};
+
+// Weights are [k][n] with n contiguous in HBM and [k/8][n][k%8] bf16 in shared memory.  A task takes
+// one K chunk (8 rows) of four consecutive columns: 8 independent 16-byte loads (coalesced over the
+// lanes), 8 Philox quads if the weights are perturbed, then one 16-byte store per column.
+__device__ __forceinline__ void stage_weights(const Stager &S) {
+    constexpr int T_W2 = (H1 / 8) * (H2 / 4), T_W1 = 2 * (H1 / 4), T_B2 = H2 / 4, T_W3 = H2 * DA / 4;
+    for (int t = threadIdx.x; t < T_W2 + T_W1 + T_B2 + T_W3 + 1; t += NTHREADS) {
+        if (t < T_W2) {
+            const int kc = t / (H2 / 4), n = (t % (H2 / 4)) * 4;
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = S.load(A_W2 + (kc * 8 + i) * H2 + n);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) S.perturb(A_W2 + (kc * 8 + i) * H2 + n, v[i]);
+            uint8_t *dst = S.smem + SM_B2 + (uint32_t)(kc * H2 + n) * 16;
+            *reinterpret_cast<uint4 *>(dst + 0) = make_uint4(pack_bf16(v[0].x, v[1].x), pack_bf16(v[2].x, v[3].x), pack_bf16(v[4].x, v[5].x), pack_bf16(v[6].x, v[7].x));
+            *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(pack_bf16(v[0].y, v[1].y), pack_bf16(v[2].y, v[3].y), pack_bf16(v[4].y, v[5].y), pack_bf16(v[6].y, v[7].y));
+            *reinterpret_cast<uint4 *>(dst + 32) = make_uint4(pack_bf16(v[0].z, v[1].z), pack_bf16(v[2].z, v[3].z), pack_bf16(v[4].z, v[5].z), pack_bf16(v[6].z, v[7].z));
+            *reinterpret_cast<uint4 *>(dst + 48) = make_uint4(pack_bf16(v[0].w, v[1].w), pack_bf16(v[2].w, v[3].w), pack_bf16(v[4].w, v[5].w), pack_bf16(v[6].w, v[7].w));
+        } else if (t < T_W2 + T_W1) {
+            // W1 rows 0..7 (chunk 0) or rows 8..11 + the bias pair b1 hi, lo at K = 12, 13 (chunk 1);
+            // the same rows serve the low half of the observation two chunks further on
+            const int tt = t - T_W2, kc = tt / (H1 / 4), n = (tt % (H1 / 4)) * 4;
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = kc * 8 + i;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < DS) { v[i] = S.load(A_W1 + k * H1 + n); S.perturb(A_W1 + k * H1 + n, v[i]); }
+            }
+            uint32_t e45[4] = {0u, 0u, 0u, 0u};
+            if (kc == 1) {
+                float4 b = S.load(A_B1 + n);
+                S.perturb(A_B1 + n, b);
+                e45[0] = hi_lo_bf16(b.x); e45[1] = hi_lo_bf16(b.y); e45[2] = hi_lo_bf16(b.z); e45[3] = hi_lo_bf16(b.w);
+            }
+            uint8_t *dst = S.smem + SM_B1 + (uint32_t)(kc * H1 + n) * 16;
+            const float c[4][8] = {{v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x},
+                                   {v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y},
+                                   {v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z},
+                                   {v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w}};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t w01 = pack_bf16(c[j][0], c[j][1]), w23 = pack_bf16(c[j][2], c[j][3]);
+                const uint32_t w45 = pack_bf16(c[j][4], c[j][5]), w67 = pack_bf16(c[j][6], c[j][7]);
+                *reinterpret_cast<uint4 *>(dst + j * 16) = make_uint4(w01, w23, kc == 1 ? e45[j] : w45, w67);
+                *reinterpret_cast<uint4 *>(dst + j * 16 + 2 * CHUNK_B1) = make_uint4(w01, w23, kc == 1 ? 0u : w45, w67);
+            }
+        } else if (t < T_W2 + T_W1 + T_B2) {        // b2 hi, lo -> rows 256, 257 of B2
+            const int n = (t - T_W2 - T_W1) * 4;
+            float4 b = S.load(A_B2 + n);
+            S.perturb(A_B2 + n, b);
+            uint8_t *dst = S.smem + SM_B2 + (uint32_t)((H1 / 8) * H2 + n) * 16;
+            *reinterpret_cast<uint4 *>(dst + 0) = make_uint4(hi_lo_bf16(b.x), 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(hi_lo_bf16(b.y), 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(dst + 32) = make_uint4(hi_lo_bf16(b.z), 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(dst + 48) = make_uint4(hi_lo_bf16(b.w), 0u, 0u, 0u);
+        } else if (t < T_W2 + T_W1 + T_B2 + T_W3) {  // W3 [128][2] fp32
+            const int e = (t - T_W2 - T_W1 - T_B2) * 4;
+            float4 w = S.load(A_W3 + e);
+            S.perturb(A_W3 + e, w);
+            *reinterpret_cast<float4 *>(S.smem + SM_W3 + e * 4) = w;
+        } else {                                     // b3: the last, partial quad
+            float4 w = make_float4(S.theta[A_B3], S.theta[A_B3 + 1], 0.f, 0.f);
+            S.perturb(A_B3, w);
+            *reinterpret_cast<float2 *>(S.smem + SM_B3) = make_float2(w.x, w.y);
+        }
+    }
+}
+
+// observation row -> registers (zeros beyond the end of the noise group / batch)
+__device__ __forceinline__ void load_obs(const float *obs, int64_t row, int64_t end, float4 (&x)[3]) {
+    if (row < end) {
+        const float4 *src = reinterpret_cast<const float4 *>(obs + row * DS);
+        x[0] = __ldg(src); x[1] = __ldg(src + 1); x[2] = __ldg(src + 2);
     } else {
-        reinterpret_cast<float *>(smem + SM_B3)[p - A_B3] = w;
+        x[0] = x[1] = x[2] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -199,9 +330,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) actor_fwd_tc_kernel(const TcArgs 
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // rows k = 12..15 and 28..31 of B1 stay zero for the whole kernel
-    for (uint32_t o = threadIdx.x * 16; o < (uint32_t)K1 * H1 * 2; o += NTHREADS * 16)
-        *reinterpret_cast<uint4 *>(smem + SM_B1 + o) = make_uint4(0, 0, 0, 0);
+    // constant parts of the operand tiles: the padding rows of B1 / B2 stay zero, the bias rows of
+    // the activation tiles (K = 256, 257) stay one, for the whole kernel
+    for (uint32_t o = threadIdx.x * 16; o < SM_A; o += NTHREADS * 16)
+        *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
+    if (warp < EPI_WARPS) {
+        uint8_t *abuf = smem + SM_A + (uint32_t)(warp >> 2) * A_BYTES + (uint32_t)((warp & 3) * 32 + lane) * 16;
+        *reinterpret_cast<uint4 *>(abuf + (H1 / 8) * CHUNK_A) = make_uint4(ONES, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(abuf + (H1 / 8 + 1) * CHUNK_A) = make_uint4(0, 0, 0, 0);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -220,21 +357,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) actor_fwd_tc_kernel(const TcArgs 
         const int64_t g = u / upg;
         const int64_t seg_end = min(u1, (g + 1) * upg);
         const int64_t ntiles = seg_end - u;
+        const int64_t end = min(A.n, (g + 1) * group);
 
-        // ---- stage (and perturb) the weights of noise group g -----------------------------
-        for (int q = threadIdx.x; q < (A_N + 3) / 4; q += NTHREADS) {
-            float w[4], z[4] = {0.f, 0.f, 0.f, 0.f};
-            if (4 * q + 3 < A_N) {
-                const float4 v = *reinterpret_cast<const float4 *>(A.theta + 4 * q);
-                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-            } else {
-                for (int e = 0; e < 4; ++e) w[e] = (4 * q + e < A_N) ? A.theta[4 * q + e] : 0.f;
-            }
-            if (noisy) normal4(A.seed, kTagParamNoise, (uint32_t)q, (uint32_t)g, A.counter, z);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (4 * q + e < A_N) place_param(smem, 4 * q + e, noisy ? w[e] + w[e] * (A.param_sd * z[e]) : w[e]);
-        }
+        // the epilogue warps start fetching their first observation rows under the weight staging
+        float4 xin[3];
+        if (warp < EPI_WARPS)
+            load_obs(A.obs, g * group + (u + (warp >> 2) - g * upg) * TM + (warp & 3) * 32 + lane,
+                     (warp >> 2) < ntiles ? end : 0, xin);
+
+        // ---- stage (and perturb) the weights of noise group g ----
+        stage_weights(Stager{A.theta, smem, noisy, A.param_sd, A.seed, A.counter, (uint32_t)g});
         fence_proxy_async();               // generic-proxy writes -> visible to the tensor core's async proxy
         __syncthreads();
 
@@ -242,98 +374,77 @@ __global__ void __launch_bounds__(NTHREADS, 1) actor_fwd_tc_kernel(const TcArgs 
             // ================= epilogue / producer warps of one slot =================
             const int slot = warp >> 2, qd = warp & 3;
             const int r = qd * 32 + lane;                                // row of the tile = tensor-memory lane
-            uint8_t *abuf = smem + SM_A + (uint32_t)slot * (TM * H1 * 2);
+            uint8_t *arow = smem + SM_A + (uint32_t)slot * A_BYTES + (uint32_t)r * 16;
             const uint32_t tlane = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)slot * 256;
-            const float *bias1 = reinterpret_cast<const float *>(smem + SM_BIAS1);
-            const float *bias2 = reinterpret_cast<const float *>(smem + SM_BIAS2);
             const float *w3 = reinterpret_cast<const float *>(smem + SM_W3);
             const float *b3 = reinterpret_cast<const float *>(smem + SM_B3);
-            const int64_t end = min(A.n, (g + 1) * group);
             uint32_t ph = phase[slot];
             for (int64_t k = slot; k < ntiles; k += NSLOT) {
-                const int64_t base = g * group + (u + k - g * upg) * TM;
-                const int64_t row = base + r;
-                // ---- 1. observation -> A0 = [hi | lo] bf16, K = 32 ----
-                float x[12];
-                if (row < end) {
-                    const float4 *src = reinterpret_cast<const float4 *>(A.obs + row * DS);
-                    const float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2);
-                    x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y;
-                    x[6] = v1.z; x[7] = v1.w; x[8] = v2.x; x[9] = v2.y; x[10] = v2.z; x[11] = v2.w;
-                } else {
+                const int64_t row = g * group + (u + k - g * upg) * TM + r;
+                // ---- 1. observation -> A0 = [hi | 1 1 | lo] bf16, K = 32 ----
+                {
+                    const float x[12] = {xin[0].x, xin[0].y, xin[0].z, xin[0].w, xin[1].x, xin[1].y,
+                                         xin[1].z, xin[1].w, xin[2].x, xin[2].y, xin[2].z, xin[2].w};
+                    float hi[12], lo[12];
 #pragma unroll
-                    for (int e = 0; e < 12; ++e) x[e] = 0.f;
+                    for (int e = 0; e < 12; ++e) {
+                        hi[e] = __bfloat162float(__float2bfloat16_rn(x[e]));
+                        lo[e] = x[e] - hi[e];
+                    }
+                    *reinterpret_cast<uint4 *>(arow + 0 * CHUNK_A) = make_uint4(
+                        pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
+                    *reinterpret_cast<uint4 *>(arow + 1 * CHUNK_A) =
+                        make_uint4(pack_bf16(hi[8], hi[9]), pack_bf16(hi[10], hi[11]), ONES, 0u);
+                    *reinterpret_cast<uint4 *>(arow + 2 * CHUNK_A) = make_uint4(
+                        pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+                    *reinterpret_cast<uint4 *>(arow + 3 * CHUNK_A) =
+                        make_uint4(pack_bf16(lo[8], lo[9]), pack_bf16(lo[10], lo[11]), 0u, 0u);
                 }
-                float lo[12];
-#pragma unroll
-                for (int e = 0; e < 12; ++e) {
-                    const float hi = __bfloat162float(__float2bfloat16_rn(x[e]));
-                    lo[e] = x[e] - hi;
-                    x[e] = hi;
-                }
-                *reinterpret_cast<uint4 *>(abuf + 0 * CHUNK_A + r * 16) =
-                    make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
-                *reinterpret_cast<uint4 *>(abuf + 1 * CHUNK_A + r * 16) =
-                    make_uint4(pack_bf16(x[8], x[9]), pack_bf16(x[10], x[11]), 0u, 0u);
-                *reinterpret_cast<uint4 *>(abuf + 2 * CHUNK_A + r * 16) =
-                    make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
-                *reinterpret_cast<uint4 *>(abuf + 3 * CHUNK_A + r * 16) =
-                    make_uint4(pack_bf16(lo[8], lo[9]), pack_bf16(lo[10], lo[11]), 0u, 0u);
                 fence_proxy_async();
                 tc_fence_before();         // orders this thread's earlier tcgen05.ld (previous tile) before the next MMA
                 mbar_arrive(bar(slot, BAR_IN));
+                // next tile's observation row: in flight during this tile's two GEMMs
+                load_obs(A.obs, row + NSLOT * TM, (k + NSLOT < ntiles) ? end : 0, xin);
 
-                // ---- 2. D1 -> bias, ReLU, bf16 -> A1 ----
+                // ---- 2. D1 (bias included) -> ReLU, bf16 -> A1; tensor-memory loads double-buffered ----
                 mbar_wait(bar(slot, BAR_D1), ph);
                 tc_fence_after();
-#pragma unroll 1
-                for (int j = 0; j < H1 / 32; ++j) {
-                    uint32_t v[32];
-                    tmem_ld32(tlane + j * 32, v);
-                    tmem_wait_ld();
+                {
+                    uint32_t va[32], vb[32];
+                    tmem_ld32(tlane, va);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int col = j * 32 + c * 8;
-                        const float4 b0 = *reinterpret_cast<const float4 *>(bias1 + col);
-                        const float4 b1 = *reinterpret_cast<const float4 *>(bias1 + col + 4);
-                        const float h0 = fmaxf(__uint_as_float(v[c * 8 + 0]) + b0.x, 0.f);
-                        const float h1 = fmaxf(__uint_as_float(v[c * 8 + 1]) + b0.y, 0.f);
-                        const float h2 = fmaxf(__uint_as_float(v[c * 8 + 2]) + b0.z, 0.f);
-                        const float h3 = fmaxf(__uint_as_float(v[c * 8 + 3]) + b0.w, 0.f);
-                        const float h4 = fmaxf(__uint_as_float(v[c * 8 + 4]) + b1.x, 0.f);
-                        const float h5 = fmaxf(__uint_as_float(v[c * 8 + 5]) + b1.y, 0.f);
-                        const float h6 = fmaxf(__uint_as_float(v[c * 8 + 6]) + b1.z, 0.f);
-                        const float h7 = fmaxf(__uint_as_float(v[c * 8 + 7]) + b1.w, 0.f);
-                        *reinterpret_cast<uint4 *>(abuf + (uint32_t)(col >> 3) * CHUNK_A + r * 16) =
-                            make_uint4(pack_bf16(h0, h1), pack_bf16(h2, h3), pack_bf16(h4, h5), pack_bf16(h6, h7));
+                    for (int j = 0; j < H1 / 32; j += 2) {
+                        tmem_wait_ld();
+                        tmem_ld32(tlane + (j + 1) * 32, vb);
+                        relu_pack_store(va, arow + (uint32_t)(j * 4) * CHUNK_A);
+                        tmem_wait_ld();
+                        if (j + 2 < H1 / 32) tmem_ld32(tlane + (j + 2) * 32, va);
+                        relu_pack_store(vb, arow + (uint32_t)((j + 1) * 4) * CHUNK_A);
                     }
                 }
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(bar(slot, BAR_H1));
 
-                // ---- 3. D2 -> bias, ReLU, layer 3 (128 -> 2), tanh -> actions ----
+                // ---- 3. D2 (bias included) -> ReLU, layer 3 (128 -> 2), tanh -> actions ----
                 mbar_wait(bar(slot, BAR_D2), ph);
                 tc_fence_after();
-                float z0 = b3[0], z1 = b3[1];
-#pragma unroll 1
-                for (int j = 0; j < H2 / 32; ++j) {
-                    uint32_t v[32];
-                    tmem_ld32(tlane + j * 32, v);
-                    tmem_wait_ld();
+                float z0[4] = {b3[0], 0.f, 0.f, 0.f}, z1[4] = {b3[1], 0.f, 0.f, 0.f};
+                {
+                    uint32_t va[32], vb[32];
+                    tmem_ld32(tlane, va);
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const int col = j * 32 + c * 2;
-                        const float2 b = *reinterpret_cast<const float2 *>(bias2 + col);
-                        const float4 w = *reinterpret_cast<const float4 *>(w3 + col * 2);
-                        const float ha = fmaxf(__uint_as_float(v[c * 2 + 0]) + b.x, 0.f);
-                        const float hb = fmaxf(__uint_as_float(v[c * 2 + 1]) + b.y, 0.f);
-                        z0 = fmaf(ha, w.x, z0); z1 = fmaf(ha, w.y, z1);
-                        z0 = fmaf(hb, w.z, z0); z1 = fmaf(hb, w.w, z1);
+                    for (int j = 0; j < H2 / 32; j += 2) {
+                        tmem_wait_ld();
+                        tmem_ld32(tlane + (j + 1) * 32, vb);
+                        relu_dot(va, w3 + j * 64, z0, z1);
+                        tmem_wait_ld();
+                        if (j + 2 < H2 / 32) tmem_ld32(tlane + (j + 2) * 32, va);
+                        relu_dot(vb, w3 + (j + 1) * 64, z0, z1);
                     }
                 }
                 if (row < end) {
-                    float a0 = tanhf(z0), a1 = tanhf(z1);
+                    float a0 = tanhf((z0[0] + z0[1]) + (z0[2] + z0[3])), a1 = tanhf((z1[0] + z1[1]) + (z1[2] + z1[3]));
                     if (A.action_sd > 0.f) {                             // SkillshotLearner.py:238
                         float zn[4];
                         normal4(A.seed, kTagActionNoise, (uint32_t)row, (uint32_t)(row >> 32), A.counter, zn);
@@ -359,10 +470,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) actor_fwd_tc_kernel(const TcArgs 
 #pragma unroll
                 for (int s = 0; s < NSLOT; ++s) {
                     if (left[s] <= 0) continue;
-                    const uint32_t a_addr = sbase + SM_A + (uint32_t)s * (TM * H1 * 2);
+                    const uint32_t a_addr = sbase + SM_A + (uint32_t)s * A_BYTES;
                     const uint32_t d_addr = tmem + (uint32_t)s * 256;
                     if (stage[s] == 0) {
-                        if (!mbar_test(bar(s, BAR_IN), phase[s])) continue;
+                        if (!mbar_probe(bar(s, BAR_IN), phase[s])) continue;
                         tc_fence_after();
                         if (lane == 0) {
                             const uint64_t ad = umma_desc(a_addr, CHUNK_A, SBO), bd = umma_desc(sbase + SM_B1, CHUNK_B1, SBO);
@@ -375,12 +486,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) actor_fwd_tc_kernel(const TcArgs 
                         __syncwarp();
                         stage[s] = 1;
                     } else {
-                        if (!mbar_test(bar(s, BAR_H1), phase[s])) continue;
+                        if (!mbar_probe(bar(s, BAR_H1), phase[s])) continue;
                         tc_fence_after();
                         if (lane == 0) {
                             const uint64_t ad = umma_desc(a_addr, CHUNK_A, SBO), bd = umma_desc(sbase + SM_B2, CHUNK_B2, SBO);
 #pragma unroll
-                            for (int ks = 0; ks < H1 / 16; ++ks)
+                            for (int ks = 0; ks < K2 / 16; ++ks)
                                 umma_bf16(d_addr, ad + (uint64_t)((2 * CHUNK_A * ks) >> 4),
                                           bd + (uint64_t)((2 * CHUNK_B2 * ks) >> 4), kIdesc2, ks > 0);
                             umma_commit(bar(s, BAR_D2));

@@ -56,6 +56,28 @@ def split_params(flat, shapes):
     return out
 
 
+def shard_info(n_local: int, group=None):
+    """(world, n_global, row_offset) of a batch sharded evenly over the ranks of `group`
+    (None: not distributed; True: the default group).  Rank r owns global rows
+    [r * n_local, (r + 1) * n_local): the critic's mean divides by n_global and Philox dropout is
+    keyed by the global row, so a sharded update equals the single-GPU update of the whole batch."""
+    if group is None:
+        return 1, n_local, 0
+    import torch.distributed as dist
+    g = None if group is True else group
+    world, rank = dist.get_world_size(g), dist.get_rank(g)
+    return world, n_local * world, rank * n_local
+
+
+def allreduce_sum(t: torch.Tensor, group=None):
+    """The one exchange step of a sharded update: sum the flat gradient over ranks (NCCL on GPUs)."""
+    if group is None:
+        return t
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=None if group is True else group)
+    return t
+
+
 class ActorCritic:
     """Actor and critic parameters, optimiser state and target copies on one GPU.
 
@@ -206,18 +228,8 @@ class ActorCritic:
         return y
 
     # -- update ----------------------------------------------------------------
-    def _world(self):
-        if self.group is None:
-            return 1
-        import torch.distributed as dist
-        return dist.get_world_size(self.group) if self.group is not True else dist.get_world_size()
-
     def _allreduce(self, t):
-        """The one exchange step of a sharded update: sum the flat gradient over ranks."""
-        if self.group is None:
-            return
-        import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=None if self.group is True else self.group)
+        allreduce_sum(t, self.group)
 
     def critic_grad(self, obs, act, y, keep=None, n_global: int = 0, row_offset: int = 0):
         """grads[critic] <- d/dphi mean (q - y)^2 of this (shard of a) batch; returns the gradient view."""
@@ -263,13 +275,8 @@ class ActorCritic:
     def critic_step(self, obs, act, y, keep=None):
         """One batch of model_critic.fit (SkillshotLearner.py:434): gradient of the batch-mean
         squared error, all-reduced when sharded, then Adam.  Returns the (device) sum of squared errors."""
-        n = int(np.prod(y.shape))
-        world = self._world()
-        rank_off = 0
-        if world > 1:
-            import torch.distributed as dist
-            rank_off = dist.get_rank(None if self.group is True else self.group) * n
-        g = self.critic_grad(obs, act, y, keep, n_global=n * world, row_offset=rank_off)
+        _, n_global, row_offset = shard_info(int(np.prod(y.shape)), self.group)
+        g = self.critic_grad(obs, act, y, keep, n_global=n_global, row_offset=row_offset)
         self._allreduce(g)
         self.apply_adam("critic")
         return self.stats[0]
