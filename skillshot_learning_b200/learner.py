@@ -468,6 +468,34 @@ class SkillshotLearner:
                         for pid, opp in zip(self.player_ids, self.player_ids[::-1])})
         return out
 
+    def calculate_rewards(self, game_states, on_target_multiplier_reduction=0.25, loss_reward_multiplier=2,
+                          base_reward_multiplier=0.75):
+        """The distance-shaped reward of SkillshotLearner.py:605-661, behaviour kept as written:
+        reward = (opponent projectile's distance to me - multiplier * my projectile's distance to the
+        opponent) / max_dist, multiplier 0.75, 0.5 while my projectile is on target, 2.75 for the player
+        that was not `game_winner`; the `game_winner` player's entry at its projectile's firing tick is
+        overwritten with 1.  The reference reads "projectile_cooldown" / "projectile_age" from the
+        OUTER state dict where they do not exist, so its best-distance bonus is always 0 (:643-648)."""
+        p1, p2 = self.player_ids
+        rewards = []
+        for index, state in enumerate(game_states):
+            dist = {p1: state[p1]["projectile_dist_opponent"], p2: state[p2]["projectile_dist_opponent"]}
+            loser_id = 0
+            winner_id = state.get("game_winner")
+            if winner_id != 0:
+                rewards[index - state[winner_id]["projectile_age"]][winner_id] = 1    # Python indexing, as written
+                loser_id = p2 if winner_id == p1 else p1
+            entry = {}
+            for pid, opp in ((p1, p2), (p2, p1)):
+                multi = base_reward_multiplier
+                if state[pid]["projectile_future_collision_opponent"]:
+                    multi = base_reward_multiplier - on_target_multiplier_reduction
+                if pid == loser_id:
+                    multi = base_reward_multiplier + loss_reward_multiplier
+                entry[pid] = ((dist[opp] - dist[pid] * multi) + 0 * 2) / self.max_dist_normaliser
+            rewards.append(entry)
+        return rewards
+
     # -- fitting (SkillshotLearner.py:386-443) --------------------------------------
     def model_actor_fit_step(self, state_tensor):
         """One deterministic-policy-gradient step of the actor on a batch of states."""
