@@ -162,6 +162,7 @@ def cpu_baseline(target_seconds: float = 4.0):
 ROLLOUT_ENVS = 262144          # BASELINE.json configs[2]
 TRAIN_BATCH = 65536            # update rows per GPU per step
 ACTOR_FLOP_PER_ROW = 72192     # 2 * (12*256 + 256*128 + 128*2)
+UPDATE_FLOP_PER_ROW = 638976   # full DDPG update with target actor + critic forward on s'
 
 
 def learner_legs(dev, rank, world, seed, peaks, ticks=64, updates=20):
@@ -192,14 +193,17 @@ def learner_legs(dev, rank, world, seed, peaks, ticks=64, updates=20):
         return e0.elapsed_time(e1) / iters
 
     t_roll = timed(tr.rollout_tick, ticks)
-    t_upd = timed(tr.update, updates)
+    t_upd = timed(tr.update, updates)                 # gradient GEMMs on tcgen05 (bf16 operands, f32 accumulate)
+    tr.networks.update_precision = "f32"
+    t_upd32 = timed(tr.update, max(3, updates // 4))  # the exact float32 kernels, same schedule
+    tr.networks.update_precision = "bf16"
     obs, act = tr.obs.view(-1, 12), tr.actions.view(-1, 2)
     t_fwd = timed(lambda: tr.networks.actor_forward(obs, out=act, precision="bf16"), 50)
     tr.envs.check_status()
-    return t_roll, t_upd, t_fwd
+    return t_roll, t_upd, t_fwd, t_upd32
 
 
-def learner_report(t_roll, t_upd, t_fwd, world, peaks, peak_kind):
+def learner_report(t_roll, t_upd, t_fwd, t_upd32, world, peaks, peak_kind):
     rows = 2 * ROLLOUT_ENVS
     tf = ACTOR_FLOP_PER_ROW * rows / (t_fwd * 1e-3) / 1e12
     return {
@@ -210,7 +214,10 @@ def learner_report(t_roll, t_upd, t_fwd, world, peaks, peak_kind):
         "train": {"workload": "DDPG update, %d rows per GPU: replay sample, TD targets (gamma 0.99), critic step "
                               "(dropout 0.2), actor step, Adam + soft update (tau 0.005), two flat-gradient all-reduces"
                               % TRAIN_BATCH,
-                  "samples_per_sec": world * TRAIN_BATCH / (t_upd * 1e-3), "ms_per_update": t_upd, "dtype": "f32"},
+                  "samples_per_sec": world * TRAIN_BATCH / (t_upd * 1e-3), "ms_per_update": t_upd,
+                  "dtype": "bf16 operands, f32 accumulate (tcgen05); Adam and parameters f32",
+                  "algorithmic_tflops": world * TRAIN_BATCH * UPDATE_FLOP_PER_ROW / (t_upd * 1e-3) / 1e12,
+                  "f32_path_samples_per_sec": world * TRAIN_BATCH / (t_upd32 * 1e-3)},
         "actor_forward_roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                                    "frac": tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peak_kind,
                                    "kernel": "actor_fwd_tc_kernel", "rows_per_launch": rows,
@@ -316,7 +323,7 @@ def run_gpu_arm(args):
         e2e_s = time.perf_counter() - t0
 
     # ---- learner legs: rollout, DDPG update, tensor roofline of the actor forward ----
-    lt = (float("nan"),) * 3
+    lt = (float("nan"),) * 4
     if not args.no_learner:
         del actions
         torch.cuda.empty_cache()

@@ -180,6 +180,29 @@ int ss_actor_forward_tc(const float *actor_params, const float *obs, float *act_
                         float param_noise_sd, int64_t noise_group, float action_noise_sd,
                         uint64_t seed, uint64_t counter, void *stream);
 
+/* q = critic([obs, act]) on the tensor cores (Dropout off), any of:
+ *   q_out[n]; neg_dq_da_out[n][2] = -dQ/da (the output_gradients of SkillshotLearner.py:410);
+ *   y_out[n] = reward + gamma * (1 - done) * q  (the TD target when the parameters are the target critic's). */
+int ss_critic_forward_tc(const float *critic_params, const float *obs, const float *act, int64_t n,
+                         float *q_out, float *neg_dq_da_out, const float *reward, const uint8_t *done,
+                         float gamma, float *y_out, void *stream);
+
+/* Tensor-core versions of ss_critic_grad / ss_actor_grad / ss_ddpg_targets for large batches: the
+ * layer GEMMs of the forward AND backward pass run as tcgen05.mma on bf16 operands with fp32
+ * accumulation, the weight-gradient sums stay in tensor memory across the batch.  Same arguments
+ * and outputs; gradients agree with the float32 entry points to about 1e-3 of their scale.
+ * `workspace` must hold ss_learner_workspace_bytes() + 32 * n bytes. */
+int ss_critic_grad_tc(const float *critic_params, const float *obs, const float *act, const float *target,
+                      const uint8_t *dropout_keep, float dropout_rate, uint64_t seed, uint64_t counter,
+                      int64_t n, int64_t n_global, int64_t row_offset, float *grad_out, float *sse_out,
+                      void *workspace, int64_t workspace_bytes, void *stream);
+int ss_actor_grad_tc(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
+                     float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes,
+                     void *stream);
+int ss_ddpg_targets_tc(const float *target_actor_params, const float *target_critic_params,
+                       const float *reward, const float *next_obs, const uint8_t *done, float gamma,
+                       float *y_out, int64_t n, void *workspace, int64_t workspace_bytes, void *stream);
+
 /* out[p] = params[p] + params[p] * (sd * eps_p): the perturbed vector
  * ss_actor_forward uses for noise group `group` (introspection and tests). */
 int ss_param_noise(const float *params, float *out, int64_t n_params, float sd, uint64_t seed,
@@ -200,7 +223,7 @@ int ss_ddpg_targets(const float *target_actor_params, const float *target_critic
  * SkillshotLearner.py:118, 434):  grad_out[36609] = d/dphi sum_i (q_i - target_i)^2 / n_global,
  * sse_out[1] = sum_i (q_i - target_i)^2  (may be NULL).
  *   dropout_rate  Dropout(0.2) of SkillshotLearner.py:105 as applied during fit; 0 = off.
- *   dropout_keep  NULL: mask from Philox(seed; unit, (row_offset + row) / 4, counter);
+ *   dropout_keep  NULL: mask from Philox(seed; row_offset + row, unit / 8, counter), 16 bits per unit;
  *                 else uint8 [n][256], 1 = keep (parity tests inject Keras' choice).
  *   n_global      divisor of the mean when n is one GPU's shard of a batch (<= 0: n).
  * The gradient is summed in a fixed order: bit-identical from run to run. */

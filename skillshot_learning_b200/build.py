@@ -27,6 +27,7 @@ UNITS = {
     "ss_env.cu": ["-fmad=false"],
     "ss_learner.cu": [],
     "ss_mlp_tc.cu": [],
+    "ss_mlp_grad_tc.cu": [],
 }
 
 

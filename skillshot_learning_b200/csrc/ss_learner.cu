@@ -328,7 +328,6 @@ __global__ void __launch_bounds__(NT) critic_grad_kernel(const CriticGradArgs A)
     float *sT = smem, *x2T = sT + DS * PITCH, *h2T = x2T + (H1 + DA) * PITCH, *qv = h2T + H2 * PITCH, *dq = qv + TB;
     float *g = A.work + (int64_t)blockIdx.x * (C_N + 1);
     const float inv_keep = A.rate > 0.f ? 1.0f / (1.0f - A.rate) : 1.0f;
-    const uint32_t thresh = (uint32_t)fmin(4294967295.0, (double)A.rate * 4294967296.0);
     const int64_t tiles = (A.n + TB - 1) / TB;
     float sse = 0.f;
     bool first = true;
@@ -346,13 +345,17 @@ __global__ void __launch_bounds__(NT) critic_grad_kernel(const CriticGradArgs A)
                 for (int t = 0; t < TB; ++t)
                     row[t] = (base + t < A.n && A.keep[(base + t) * H1 + j]) ? row[t] * inv_keep : 0.f;
             } else {
-                for (int q = 0; q < TB / 4; ++q) {
-                    const uint64_t quad = (uint64_t)(A.row_offset + base) / 4 + q;     // 4 consecutive samples per draw
-                    const U4 u = draw4(A.seed, kTagDropout, (uint32_t)j, (uint32_t)quad, A.counter);
-                    row[4 * q + 0] = u.x >= thresh ? row[4 * q + 0] * inv_keep : 0.f;
-                    row[4 * q + 1] = u.y >= thresh ? row[4 * q + 1] * inv_keep : 0.f;
-                    row[4 * q + 2] = u.z >= thresh ? row[4 * q + 2] * inv_keep : 0.f;
-                    row[4 * q + 3] = u.w >= thresh ? row[4 * q + 3] * inv_keep : 0.f;
+                // one Philox draw per (global row, 8 units): 16 bits per unit, this thread's unit is lane j % 8
+                // (the keying of the tensor-core kernel, where a thread owns a row: ss_mlp_grad_tc.cu)
+                const uint32_t thresh16 = (uint32_t)(A.rate * 65536.0f);
+                for (int t = 0; t < TB; ++t) {
+                    const uint64_t grow = (uint64_t)(A.row_offset + base + t);
+                    const U4 u = draw4(A.seed, kTagDropout, (uint32_t)grow, (uint32_t)(j >> 3) | ((uint32_t)(grow >> 32) << 8),
+                                       A.counter);
+                    const int e = j & 7;
+                    const uint32_t w = (e >> 1) == 0 ? u.x : (e >> 1) == 1 ? u.y : (e >> 1) == 2 ? u.z : u.w;
+                    const uint32_t v = (e & 1) ? (w >> 16) : (w & 0xFFFFu);
+                    row[t] = v >= thresh16 ? row[t] * inv_keep : 0.f;
                 }
             }
         }

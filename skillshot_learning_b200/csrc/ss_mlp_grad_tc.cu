@@ -1,0 +1,524 @@
+// ss_mlp_grad_tc.cu -- forward + backward pass of the actor / critic MLP on the tensor cores
+// (tcgen05.mma, sm_100a): the gradient half of model_critic.fit (SkillshotLearner.py:434) and of
+// model_actor_fit_step (SkillshotLearner.py:386-417) for large batches.
+//
+// Per 128-row tile the dense work is seven GEMM groups, all bf16 x bf16 -> fp32 in tensor memory:
+//
+//   L1a/L1b  z1[:, half]   = X0 . W1'                 128 x 128 x 32     (bias row included)
+//   L2       z2            = X2 . W2'                 128 x 128 x 272    (bias / action rows included)
+//   G3       dW3^T        += H2^T . DZ3               128 x 16  x 128 rows
+//   G2       dW2'^T       += DZ2^T . X2               128 x 272 x 128 rows
+//   BXa/BXb  dx2[:, half]  = DZ2 . W2^T               128 x 128 x 128
+//   G1       dW1'^T[half] += DZ1[:, half]^T . X0      128 x 32  x 128 rows
+//
+// The weight-gradient GEMMs reduce over the ROWS of the tile.  Their operands are the very
+// activation tiles the forward pass wrote, read MN-major instead of K-major (ss_tc_common.cuh),
+// and their accumulators (272 + 64 + 16 tensor-memory columns) stay resident for every tile the
+// CTA processes: nothing but the final sums ever leaves the SM.  Because the bias rows are part of
+// W1' / W2' (constant-one columns in X0 / X2), db1 and db2 fall out of G1 / G2 for free, as do the
+// gradients of the critic's two action rows.  The element-wise steps between the GEMMs (ReLU,
+// inverted dropout, the 128 -> 1|2 output layer, loss / upstream gradient, ReLU masks) run on four
+// epilogue warps, one thread per row, between tcgen05.ld and the shared-memory tile stores.
+// One tile is in flight per CTA (the accumulators take 352 of the 512 columns), 148 CTAs.
+//
+// Gradients are therefore computed from bf16 operands (products exact, fp32 accumulation):
+// relative error ~1e-3 against the float32 path of ss_learner.cu, which remains the exact one.
+// Per-CTA partial gradients go to the same workspace layout and fixed-order reduction as there.
+#include "ss_tc_common.cuh"
+
+namespace {
+
+using namespace sstc;
+
+constexpr int EPI_WARPS = 4, MMA_WARP = 4, NTHREADS = 160;
+
+// shared-memory map (bytes)
+constexpr uint32_t SM_B1 = 0;
+constexpr uint32_t SM_B2 = SM_B1 + B1_BYTES;
+constexpr uint32_t SM_X2 = SM_B2 + B2_BYTES;                // [K2/8][128][8]: h1 | tail, later dz1
+constexpr uint32_t SM_DZ2 = SM_X2 + X2_BYTES;               // [16][128][8]: dz2; its head holds X0 (4 chunks) before / after
+constexpr uint32_t SM_H2 = SM_DZ2 + 16 * CHUNK_A;           // [16][128][8]: h2
+constexpr uint32_t SM_DZ3 = SM_H2 + 16 * CHUNK_A;           // [2][128][8]: {d0 hi, d1 hi, d0 lo, d1 lo, 0..}, chunk 1 = 0
+constexpr uint32_t SM_W3 = SM_DZ3 + 2 * CHUNK_A;            // [128] float4
+constexpr uint32_t SM_B3 = SM_W3 + H2 * 16;
+constexpr uint32_t SM_BAR = SM_B3 + 16;                     // {epilogue -> MMA (128 arrivals), MMA -> epilogue (commit)}
+constexpr uint32_t SM_TMEM = SM_BAR + 16;
+constexpr uint32_t SM_RED = SM_TMEM + 16;                   // 4 warps x 4 floats
+constexpr uint32_t SM_TOTAL = SM_RED + 64;
+static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+
+// tensor-memory columns
+constexpr uint32_t T_W2T = 0;        // dW2'^T  [128 units][272]
+constexpr uint32_t T_W1T = 272;      // dW1'^T  2 x [128 units][32]
+constexpr uint32_t T_W3T = 336;      // dW3^T   [128 units][16]
+constexpr uint32_t T_WORK = 384;     // z1 halves, z2, dx2 halves  [128 rows][128]
+
+struct GradArgs {
+    const float *params, *obs;
+    const float *act, *target;       // critic: actions [n][2], regression target [n]
+    const float *up;                 // actor: upstream gradient on the action [n][2] (= -dQ/da)
+    const uint8_t *keep;             // critic: injected dropout mask [n][256] or NULL (Philox)
+    float rate;
+    uint64_t seed, counter;
+    int64_t n, n_global, row_offset;
+    float *work;                     // [gridDim.x][params + 1]
+};
+
+// inverted-dropout keep bits of 8 consecutive hidden-1 units of one row: one Philox draw, 16 bits per unit
+__device__ __forceinline__ uint32_t keep8(const GradArgs &A, int64_t grow, int chunk, uint32_t thresh16) {
+    const U4 u = draw4(A.seed, kTagDropout, (uint32_t)grow, (uint32_t)chunk | ((uint32_t)(grow >> 32) << 8), A.counter);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t bits = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t v = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xFFFFu);
+        bits |= (v >= thresh16 ? 1u : 0u) << e;
+    }
+    return bits;
+}
+
+template <int NET>
+__global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs A) {
+    constexpr int PN = NET == NET_ACTOR ? A_N : C_N;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_mma = sbase + SM_BAR, bar_epi = sbase + SM_BAR + 8;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_mma, 128);
+        mbar_init(bar_epi, 1);
+        mbar_fence_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(sbase + SM_TMEM, 512);
+    // zero everything that is only partly rewritten: weight images (padding rows), DZ3 (chunk 1), X2 tail chunks
+    for (uint32_t o = threadIdx.x * 16; o < SM_X2; o += NTHREADS * 16) *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
+    for (uint32_t o = threadIdx.x * 16; o < 2 * CHUNK_A; o += NTHREADS * 16) {
+        *reinterpret_cast<uint4 *>(smem + SM_DZ3 + o) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(smem + SM_X2 + (H1 / 8) * CHUNK_A + o) = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    if (warp < EPI_WARPS && NET == NET_ACTOR)
+        *reinterpret_cast<uint4 *>(smem + SM_X2 + (H1 / 8) * CHUNK_A + threadIdx.x * 16) = tail_chunk_actor();
+    stage_weights<NET, NTHREADS>(Stager{A.params, smem + SM_B1, smem + SM_B2, reinterpret_cast<float4 *>(smem + SM_W3),
+                                        reinterpret_cast<float *>(smem + SM_B3), false, 0.f, 0, 0, 0});
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<const volatile uint32_t *>(smem + SM_TMEM);
+
+    const int64_t tiles = (A.n + TM - 1) / TM;
+    float *g = A.work + (int64_t)blockIdx.x * (PN + 1);
+
+    if (warp < EPI_WARPS) {
+        // ======================= epilogue warps: thread r owns row r of the tile =======================
+        const int r = threadIdx.x;
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        uint8_t *x2row = smem + SM_X2 + r * 16, *dz2row = smem + SM_DZ2 + r * 16, *h2row = smem + SM_H2 + r * 16;
+        const float4 *w3x = reinterpret_cast<const float4 *>(smem + SM_W3);      // critic layout
+        const float2 *w3a = reinterpret_cast<const float2 *>(smem + SM_W3);      // actor layout: W3[128][2] as stored
+        const float *b3 = reinterpret_cast<const float *>(smem + SM_B3);
+        const float inv_keep = (NET == NET_CRITIC && A.rate > 0.f) ? 1.0f / (1.0f - A.rate) : 1.0f;
+        const uint32_t thresh16 = (uint32_t)(A.rate * 65536.0f);
+        uint32_t ph = 0;
+        float stat = 0.f, dsum0 = 0.f, dsum1 = 0.f;      // sum of squared errors; db3 partials
+        auto to_mma = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(bar_mma); };
+        auto from_mma = [&]() { mbar_wait(bar_epi, ph); ph ^= 1; tc_fence_after(); };
+
+        // hidden layer 1, one 128-unit half: WORK -> ReLU (+ dropout) -> bf16 -> X2 chunks 16 * half ..
+        auto hidden1 = [&](int half, int64_t row, bool valid) {
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {                 // 16 columns = 2 chunks per step
+                uint32_t v[16];
+                tmem_ld16(tl + T_WORK + j * 16, v);
+                uint32_t kb = 0xFFFFu;
+                if (NET == NET_CRITIC && A.rate > 0.f) {
+                    const int c0 = half * 16 + j * 2;
+                    if (A.keep) {
+                        kb = 0;
+                        if (valid) {
+                            const uint4 m = __ldg(reinterpret_cast<const uint4 *>(A.keep + row * H1 + c0 * 8));
+                            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) kb |= (((mw[e >> 2] >> ((e & 3) * 8)) & 0xFFu) ? 1u : 0u) << e;
+                        }
+                    } else {
+                        kb = keep8(A, A.row_offset + row, c0, thresh16) | (keep8(A, A.row_offset + row, c0 + 1, thresh16) << 8);
+                    }
+                }
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float h[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        h[e] = ((kb >> (c * 8 + e)) & 1u) ? __uint_as_float(v[c * 8 + e]) * inv_keep : 0.f;
+                    *reinterpret_cast<uint4 *>(x2row + (uint32_t)(half * 16 + j * 2 + c) * CHUNK_A) = make_uint4(
+                        pack_relu_bf16(h[0], h[1]), pack_relu_bf16(h[2], h[3]), pack_relu_bf16(h[4], h[5]), pack_relu_bf16(h[6], h[7]));
+                }
+            }
+        };
+        // back through hidden layer 1, one half: WORK = dx2 -> mask of the stored activation -> bf16 -> same chunks
+        auto back1 = [&](int half) {
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+                uint32_t v[16];
+                tmem_ld16(tl + T_WORK + j * 16, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint4 *p = reinterpret_cast<uint4 *>(x2row + (uint32_t)(half * 16 + j * 2 + c) * CHUNK_A);
+                    const uint4 x = *p;
+                    const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
+                    float d[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float act = (e & 1) ? bf16_hi(xw[e >> 1]) : bf16_lo(xw[e >> 1]);
+                        d[e] = act > 0.f ? __uint_as_float(v[c * 8 + e]) * inv_keep : 0.f;
+                    }
+                    *p = make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
+                }
+            }
+        };
+
+        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int64_t row = tile * TM + r;
+            const bool valid = row < A.n;
+            // ---- stage: X0 -> head of the DZ2 buffer; critic: action -> tail chunk of X2 ----
+            float4 xin[3];
+            load_obs(A.obs, row, A.n, xin);
+            store_obs_row(xin, dz2row);
+            if (NET == NET_CRITIC) {
+                float2 a = make_float2(0.f, 0.f);
+                if (valid) a = __ldg(reinterpret_cast<const float2 *>(A.act) + row);
+                *reinterpret_cast<uint4 *>(x2row + (H1 / 8) * CHUNK_A) = tail_chunk_critic(a.x, a.y);
+            }
+            to_mma();                                     // -> L1a
+            from_mma();
+            hidden1(0, row, valid);
+            to_mma();                                     // -> L1b
+            from_mma();
+            hidden1(1, row, valid);
+            to_mma();                                     // -> L2
+            from_mma();
+            // ---- output layer, loss / upstream gradient (fp32) ----
+            float z0 = 0.f, z1 = 0.f;
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+                uint32_t v[16];
+                tmem_ld16(tl + T_WORK + j * 16, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float h = fmaxf(__uint_as_float(v[c]), 0.f);
+                    if (NET == NET_ACTOR) {
+                        const float2 w = w3a[j * 16 + c];
+                        z0 = fmaf(h, w.x, z0);
+                        z1 = fmaf(h, w.y, z1);
+                    } else {
+                        z0 = fmaf(h, w3x[j * 16 + c].x, z0);
+                    }
+                }
+            }
+            float d0 = 0.f, d1 = 0.f;
+            if (NET == NET_CRITIC) {
+                if (valid) {                              // loss "mse": mean over the global batch
+                    const float e = (z0 + b3[0]) - A.target[row];
+                    stat += e * e;
+                    d0 = 2.0f * e / (float)A.n_global;
+                }
+            } else if (valid) {                           // through tanh, upstream = -dQ/da (SkillshotLearner.py:408-410)
+                const float a0 = tanhf(z0 + b3[0]), a1 = tanhf(z1 + b3[1]);
+                const float2 up = __ldg(reinterpret_cast<const float2 *>(A.up) + row);
+                d0 = up.x * (1.0f - a0 * a0);
+                d1 = up.y * (1.0f - a1 * a1);
+            }
+            dsum0 += d0;
+            dsum1 += d1;
+            {
+                const float h0 = bf16_round(d0), h1 = bf16_round(d1);
+                *reinterpret_cast<uint4 *>(smem + SM_DZ3 + r * 16) = make_uint4(pack_bf16(h0, h1), pack_bf16(d0 - h0, d1 - h1), 0u, 0u);
+            }
+            // ---- h2 and dz2 tiles (second sweep over z2) ----
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+                uint32_t v[16];
+                tmem_ld16(tl + T_WORK + j * 16, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float gz[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float up;
+                        if (NET == NET_ACTOR) {
+                            const float2 w = w3a[j * 16 + c * 8 + e];
+                            up = fmaf(d1, w.y, d0 * w.x);
+                        } else {
+                            up = d0 * w3x[j * 16 + c * 8 + e].x;
+                        }
+                        gz[e] = __uint_as_float(v[c * 8 + e]) > 0.f ? up : 0.f;
+                    }
+                    *reinterpret_cast<uint4 *>(h2row + (uint32_t)(j * 2 + c) * CHUNK_A) = make_uint4(
+                        pack_relu_bf16(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1])),
+                        pack_relu_bf16(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3])),
+                        pack_relu_bf16(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5])),
+                        pack_relu_bf16(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7])));
+                    *reinterpret_cast<uint4 *>(dz2row + (uint32_t)(j * 2 + c) * CHUNK_A) =
+                        make_uint4(pack_bf16(gz[0], gz[1]), pack_bf16(gz[2], gz[3]), pack_bf16(gz[4], gz[5]), pack_bf16(gz[6], gz[7]));
+                }
+            }
+            to_mma();                                     // -> G3, G2, BXa
+            from_mma();
+            back1(0);
+            to_mma();                                     // -> BXb
+            from_mma();
+            back1(1);
+            store_obs_row(xin, dz2row);                   // X0 again (the DZ2 buffer is free: BXb has retired)
+            to_mma();                                     // -> G1
+            from_mma();                                   // tiles free for the next round
+        }
+
+        // ======================= write this CTA's partial gradient =======================
+        // thread r = hidden-2 unit r for dW2'^T and dW3^T, = hidden-1 unit 128 h + r for dW1'^T
+        {
+#pragma unroll 1
+            for (int j = 0; j < H1 / 16; ++j) {
+                uint32_t v[16];
+                tmem_ld16(tl + T_W2T + j * 16, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) __stcg(g + P_W2 + (j * 16 + c) * H2 + r, __uint_as_float(v[c]));
+            }
+            uint32_t t[16];
+            tmem_ld16(tl + T_W2T + H1, t);
+            tmem_wait_ld();
+            if (NET == NET_ACTOR) {
+                __stcg(g + A_B2 + r, __uint_as_float(t[0]));
+            } else {                                      // action rows (hi + lo parts of the action), then b2
+                __stcg(g + P_W2 + H1 * H2 + r, __uint_as_float(t[0]) + __uint_as_float(t[2]));
+                __stcg(g + P_W2 + (H1 + 1) * H2 + r, __uint_as_float(t[1]) + __uint_as_float(t[3]));
+                __stcg(g + C_B2 + r, __uint_as_float(t[4]));
+            }
+            tmem_ld16(tl + T_W3T, t);
+            tmem_wait_ld();
+            if (NET == NET_ACTOR) {
+                __stcg(g + A_W3 + r * DA + 0, __uint_as_float(t[0]) + __uint_as_float(t[2]));
+                __stcg(g + A_W3 + r * DA + 1, __uint_as_float(t[1]) + __uint_as_float(t[3]));
+            } else {
+                __stcg(g + C_W3 + r, __uint_as_float(t[0]) + __uint_as_float(t[2]));
+            }
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                uint32_t a[16], b[16];
+                tmem_ld16(tl + T_W1T + h * 32, a);
+                tmem_ld16(tl + T_W1T + h * 32 + 16, b);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < DS; ++i)
+                    __stcg(g + P_W1 + i * H1 + h * 128 + r, __uint_as_float(a[i]) + __uint_as_float(b[i]));
+                __stcg(g + P_B1 + h * 128 + r, __uint_as_float(a[12]));
+            }
+            // db3 and the loss statistic: sums over the rows
+            float s0 = dsum0, s1 = dsum1, s2 = stat;
+            for (int o = 16; o > 0; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            float *red = reinterpret_cast<float *>(smem + SM_RED);
+            if (lane == 0) { red[warp * 4 + 0] = s0; red[warp * 4 + 1] = s1; red[warp * 4 + 2] = s2; }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (r == 0) {
+                const float t0 = (red[0] + red[4]) + (red[8] + red[12]), t1 = (red[1] + red[5]) + (red[9] + red[13]);
+                const float t2 = (red[2] + red[6]) + (red[10] + red[14]);
+                if (NET == NET_ACTOR) { g[A_B3] = t0; g[A_B3 + 1] = t1; g[PN] = 0.f; }
+                else { g[C_B3] = t0; g[PN] = t2; }
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ======================= the MMA-issuing warp =======================
+        uint32_t ph = 0;
+        const uint32_t work = tmem + T_WORK;
+        const uint32_t b1 = sbase + SM_B1, b2 = sbase + SM_B2, x2 = sbase + SM_X2, dz2 = sbase + SM_DZ2;
+        const uint32_t h2 = sbase + SM_H2, dz3 = sbase + SM_DZ3;
+        constexpr uint32_t kFwd = umma_idesc(TM, 128);                // K-major x K-major
+        constexpr uint32_t kBx = umma_idesc(TM, 128, 0, 1);           // dz2 (K-major) x W2 image (MN-major)
+        constexpr uint32_t kG256 = umma_idesc(TM, 256, 1, 1), kG16 = umma_idesc(TM, 16, 1, 1), kG32 = umma_idesc(TM, 32, 1, 1);
+        auto wait_epi = [&]() { mbar_wait(bar_mma, ph); ph ^= 1; tc_fence_after(); };
+        uint32_t acc = 0;                                             // 0 on the CTA's first tile: accumulators start fresh
+        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, acc = 1) {
+            for (int half = 0; half < 2; ++half) {                    // L1a, L1b
+                wait_epi();
+                if (lane == 0) {
+                    const uint64_t ad = desc_kmajor(dz2, CHUNK_A), bd = desc_kmajor(b1 + half * 128 * 16, CHUNK_B1);
+#pragma unroll
+                    for (int ks = 0; ks < K1 / 16; ++ks)
+                        umma_bf16(work, desc_advance(ad, 2 * CHUNK_A * ks), desc_advance(bd, 2 * CHUNK_B1 * ks), kFwd, ks > 0);
+                    umma_commit(bar_epi);
+                }
+                __syncwarp();
+            }
+            wait_epi();                                               // L2
+            if (lane == 0) {
+                const uint64_t ad = desc_kmajor(x2, CHUNK_A), bd = desc_kmajor(b2, CHUNK_B2);
+#pragma unroll
+                for (int ks = 0; ks < K2 / 16; ++ks)
+                    umma_bf16(work, desc_advance(ad, 2 * CHUNK_A * ks), desc_advance(bd, 2 * CHUNK_B2 * ks), kFwd, ks > 0);
+                umma_commit(bar_epi);
+            }
+            __syncwarp();
+            wait_epi();                                               // G3, G2, BXa
+            if (lane == 0) {
+                const uint64_t h2t = desc_mnmajor(h2, CHUNK_A), dz3t = desc_mnmajor(dz3, CHUNK_A);
+                const uint64_t dz2t = desc_mnmajor(dz2, CHUNK_A), x2t = desc_mnmajor(x2, CHUNK_A);
+                const uint64_t x2tail = desc_mnmajor(x2 + (H1 / 8) * CHUNK_A, CHUNK_A);
+#pragma unroll
+                for (int ks = 0; ks < TM / 16; ++ks) {                // reduction over the 128 rows, 16 per step
+                    const uint32_t off = 2 * CORE * ks, a = acc | (ks > 0);
+                    umma_bf16(tmem + T_W3T, desc_advance(h2t, off), desc_advance(dz3t, off), kG16, a);
+                    umma_bf16(tmem + T_W2T, desc_advance(dz2t, off), desc_advance(x2t, off), kG256, a);
+                    umma_bf16(tmem + T_W2T + H1, desc_advance(dz2t, off), desc_advance(x2tail, off), kG16, a);
+                }
+                const uint64_t ad = desc_kmajor(dz2, CHUNK_A), bd = desc_mnmajor(b2, CHUNK_B2);
+#pragma unroll
+                for (int ks = 0; ks < H2 / 16; ++ks)
+                    umma_bf16(work, desc_advance(ad, 2 * CHUNK_A * ks), desc_advance(bd, 2 * CORE * ks), kBx, ks > 0);
+                umma_commit(bar_epi);
+            }
+            __syncwarp();
+            wait_epi();                                               // BXb
+            if (lane == 0) {
+                const uint64_t ad = desc_kmajor(dz2, CHUNK_A), bd = desc_mnmajor(b2 + 16 * CHUNK_B2, CHUNK_B2);
+#pragma unroll
+                for (int ks = 0; ks < H2 / 16; ++ks)
+                    umma_bf16(work, desc_advance(ad, 2 * CHUNK_A * ks), desc_advance(bd, 2 * CORE * ks), kBx, ks > 0);
+                umma_commit(bar_epi);
+            }
+            __syncwarp();
+            wait_epi();                                               // G1
+            if (lane == 0) {
+                const uint64_t x0t = desc_mnmajor(dz2, CHUNK_A);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint64_t dz1t = desc_mnmajor(x2 + half * 16 * CHUNK_A, CHUNK_A);
+#pragma unroll
+                    for (int ks = 0; ks < TM / 16; ++ks)
+                        umma_bf16(tmem + T_W1T + half * 32, desc_advance(dz1t, 2 * CORE * ks), desc_advance(x0t, 2 * CORE * ks),
+                                  kG32, acc | (ks > 0));
+                }
+                umma_commit(bar_epi);
+            }
+            __syncwarp();
+        }
+    }
+
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// grad[p] = sum over CTA slices, fixed order; aux[0] = sum of the slices' extra slot
+__global__ void reduce_parts_kernel(const float *work, int parts, int n_params, float *grad, float *aux) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > n_params) return;
+    float s = 0.f;
+    for (int c = 0; c < parts; ++c) s += work[(int64_t)c * (n_params + 1) + p];
+    if (p < n_params) grad[p] = s;
+    else if (aux) aux[0] = s;
+}
+
+// out[0] = sum of x[0..n) in a fixed order (one CTA)
+__global__ void sum_f32_kernel(const float *x, int64_t n, float *out) {
+    __shared__ float red[1024];
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) s += x[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+}
+
+template <int NET>
+int launch_grad(const GradArgs &A0, float *grad_out, float *aux_out, int64_t workspace_bytes, void *stream) {
+    constexpr int PN = NET == NET_ACTOR ? A_N : C_N;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return SS_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SS_ERR_CUDA;
+    if (cudaFuncSetAttribute(mlp_grad_tc_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL) != cudaSuccess)
+        return SS_ERR_CUDA;
+    const int64_t tiles = (A0.n + TM - 1) / TM;
+    int64_t cap = workspace_bytes / ((int64_t)(PN + 1) * 4);
+    if (cap > sms) cap = sms;
+    if (cap < 1) return SS_ERR_INVALID_ARG;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    cudaStream_t st = (cudaStream_t)stream;
+    mlp_grad_tc_kernel<NET><<<grid, NTHREADS, SM_TOTAL, st>>>(A0);
+    reduce_parts_kernel<<<(PN + 1 + 255) / 256, 256, 0, st>>>(A0.work, grid, PN, grad_out, aux_out);
+    return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ss_critic_grad_tc(const float *critic_params, const float *obs, const float *act, const float *target,
+                      const uint8_t *dropout_keep, float dropout_rate, uint64_t seed, uint64_t counter,
+                      int64_t n, int64_t n_global, int64_t row_offset, float *grad_out, float *sse_out,
+                      void *workspace, int64_t workspace_bytes, void *stream) {
+    if (!critic_params || !obs || !act || !target || !grad_out || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
+    if (dropout_rate < 0.f || dropout_rate >= 1.f) return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)critic_params | (uintptr_t)obs | (uintptr_t)dropout_keep) & 15 || ((uintptr_t)act & 7))
+        return SS_ERR_INVALID_ARG;
+    GradArgs A{};
+    A.params = critic_params; A.obs = obs; A.act = act; A.target = target; A.keep = dropout_keep; A.rate = dropout_rate;
+    A.seed = seed; A.counter = counter; A.n = n; A.n_global = n_global > 0 ? n_global : n; A.row_offset = row_offset;
+    A.work = (float *)workspace;
+    return launch_grad<NET_CRITIC>(A, grad_out, sse_out, workspace_bytes, stream);
+}
+
+int ss_actor_grad_tc(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
+                     float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, void *stream) {
+    if (!actor_params || !critic_params || !obs || !grad_out || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)actor_params | (uintptr_t)critic_params | (uintptr_t)obs | (uintptr_t)workspace) & 15)
+        return SS_ERR_INVALID_ARG;
+    // scratch behind the gradient slices: the actor's actions, -dQ/da and Q per row
+    const int64_t scratch = ((n * 2 + 3) / 4 * 4) * 2 + (n + 3) / 4 * 4;
+    const int64_t slice_bytes = workspace_bytes - scratch * 4;
+    if (slice_bytes < (int64_t)(A_N + 1) * 4) return SS_ERR_INVALID_ARG;
+    float *act = (float *)((char *)workspace + slice_bytes / 16 * 16);
+    float *up = act + (n * 2 + 3) / 4 * 4;
+    float *q = up + (n * 2 + 3) / 4 * 4;
+    // a = actor(s);  q, -dq/da = critic([s, a]) with Dropout off;  then the actor's backward pass
+    int rc = ss_actor_forward_tc(actor_params, obs, act, n, 0.f, 0, 0.f, 0, 0, stream);
+    if (rc != SS_OK) return rc;
+    rc = ss_critic_forward_tc(critic_params, obs, act, n, q_sum_out ? q : nullptr, up, nullptr, nullptr, 0.f, nullptr, stream);
+    if (rc != SS_OK) return rc;
+    GradArgs A{};
+    A.params = actor_params; A.obs = obs; A.up = up; A.n = n; A.n_global = n; A.work = (float *)workspace;
+    rc = launch_grad<NET_ACTOR>(A, grad_out, nullptr, slice_bytes / 16 * 16, stream);
+    if (rc != SS_OK) return rc;
+    if (q_sum_out) sum_f32_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(q, n, q_sum_out);
+    return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
+}
+
+int ss_ddpg_targets_tc(const float *target_actor_params, const float *target_critic_params, const float *reward,
+                       const float *next_obs, const uint8_t *done, float gamma, float *y_out, int64_t n,
+                       void *workspace, int64_t workspace_bytes, void *stream) {
+    if (!target_actor_params || !target_critic_params || !reward || !next_obs || !y_out || !workspace || n <= 0)
+        return SS_ERR_INVALID_ARG;
+    if (workspace_bytes < n * 8 || ((uintptr_t)workspace & 15)) return SS_ERR_INVALID_ARG;
+    float *act = (float *)workspace;
+    int rc = ss_actor_forward_tc(target_actor_params, next_obs, act, n, 0.f, 0, 0.f, 0, 0, stream);
+    if (rc != SS_OK) return rc;
+    return ss_critic_forward_tc(target_critic_params, next_obs, act, n, nullptr, nullptr, reward, done, gamma, y_out, stream);
+}
+
+}  // extern "C"

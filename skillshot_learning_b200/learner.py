@@ -89,7 +89,8 @@ class ActorCritic:
     """
 
     def __init__(self, device="cuda", seed: int = 0, lr_actor: float = 1e-3, lr_critic: float = 1e-3,
-                 gamma: float = 0.0, tau: float = 1.0, dropout: float = 0.2, process_group=None):
+                 gamma: float = 0.0, tau: float = 1.0, dropout: float = 0.2, process_group=None,
+                 update_precision: str = "f32"):
         if not torch.cuda.is_available():
             raise RuntimeError("skillshot_learning_b200 needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device)
@@ -100,6 +101,9 @@ class ActorCritic:
         self.beta1, self.beta2, self.eps = 0.9, 0.999, 1e-7
         self.gamma, self.tau, self.dropout = float(gamma), float(tau), float(dropout)
         self.group = process_group
+        if update_precision not in ("f32", "bf16"):
+            raise ValueError("update_precision must be 'f32' (exact path) or 'bf16' (tensor cores)")
+        self.update_precision = update_precision     # gradient / TD-target kernels: float32 CUDA cores or tcgen05
         dev = self.device
         # one allocation: [actor | pad | critic] so both vectors are 16-byte aligned
         self._a_off, self._c_off = 0, (A_N + 3) // 4 * 4
@@ -110,7 +114,8 @@ class ActorCritic:
         self.adam_v = torch.zeros(total, dtype=torch.float32, device=dev)
         self.target = torch.zeros(total, dtype=torch.float32, device=dev)
         self.stats = torch.zeros(2, dtype=torch.float32, device=dev)        # [sum sq err, sum q] of the last steps
-        self.workspace = torch.empty(int(lib.ss_learner_workspace_bytes()), dtype=torch.uint8, device=dev)
+        self._ws_base = int(lib.ss_learner_workspace_bytes())
+        self.workspace = torch.empty(self._ws_base, dtype=torch.uint8, device=dev)
         self.step_actor = 0
         self.step_critic = 0
         self.counter = 0            # Philox counter: advances with every noisy call
@@ -202,12 +207,19 @@ class ActorCritic:
                   "ss_param_noise")
         return out
 
-    def critic_forward(self, obs, act, target: bool = False):
+    def critic_forward(self, obs, act, target: bool = False, precision: str = "f32", want_dq_da: bool = False):
+        """q [n] = critic([obs, act]) with Dropout off; with want_dq_da (bf16 path) also -dQ/da [n,2]."""
         obs, act = _f32(obs, self.device).reshape(-1, 12), _f32(act, self.device).reshape(-1, 2)
-        q = torch.empty(obs.shape[0], dtype=torch.float32, device=self.device)
+        n = obs.shape[0]
+        q = torch.empty(n, dtype=torch.float32, device=self.device)
         phi = self.target_critic if target else self.critic
         with torch.cuda.device(self.device):
-            check(lib.ss_critic_forward(phi.data_ptr(), obs.data_ptr(), act.data_ptr(), q.data_ptr(), obs.shape[0],
+            if precision == "bf16":
+                up = torch.empty((n, 2), dtype=torch.float32, device=self.device) if want_dq_da else None
+                check(lib.ss_critic_forward_tc(phi.data_ptr(), obs.data_ptr(), act.data_ptr(), n, q.data_ptr(), _ptr(up),
+                                               None, None, 0.0, None, _stream(self.device)), "ss_critic_forward_tc")
+                return (q, up) if want_dq_da else q
+            check(lib.ss_critic_forward(phi.data_ptr(), obs.data_ptr(), act.data_ptr(), q.data_ptr(), n,
                                         _stream(self.device)), "ss_critic_forward")
         return q
 
@@ -221,11 +233,27 @@ class ActorCritic:
         y = torch.empty_like(reward)
         if done is not None:
             done = done.to(device=self.device, dtype=torch.uint8).contiguous()
+        n = reward.shape[0]
         with torch.cuda.device(self.device):
-            check(lib.ss_ddpg_targets(self.target_actor.data_ptr(), self.target_critic.data_ptr(), reward.data_ptr(),
-                                      next_obs.data_ptr(), _ptr(done), self.gamma, y.data_ptr(), reward.shape[0],
-                                      _stream(self.device)), "ss_ddpg_targets")
+            if self.update_precision == "bf16":
+                ws = self._workspace_for(n)
+                check(lib.ss_ddpg_targets_tc(self.target_actor.data_ptr(), self.target_critic.data_ptr(),
+                                             reward.data_ptr(), next_obs.data_ptr(), _ptr(done), self.gamma,
+                                             y.data_ptr(), n, ws.data_ptr(), ws.numel(), _stream(self.device)),
+                      "ss_ddpg_targets_tc")
+            else:
+                check(lib.ss_ddpg_targets(self.target_actor.data_ptr(), self.target_critic.data_ptr(), reward.data_ptr(),
+                                          next_obs.data_ptr(), _ptr(done), self.gamma, y.data_ptr(), n,
+                                          _stream(self.device)), "ss_ddpg_targets")
         return y
+
+    def _workspace_for(self, n: int) -> torch.Tensor:
+        """Scratch for the gradient kernels: per-CTA gradient slices (+ 32 bytes per row for the
+        tensor-core entry points: actions, -dQ/da and Q of the actor step)."""
+        need = self._ws_base + (32 * n if self.update_precision == "bf16" else 0)
+        if self.workspace.numel() < need:
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self.workspace
 
     # -- update ----------------------------------------------------------------
     def _allreduce(self, t):
@@ -239,11 +267,13 @@ class ActorCritic:
         if keep is not None:
             keep = torch.as_tensor(keep).to(device=self.device, dtype=torch.uint8).contiguous()
         g = self._slice(self.grads, "critic")
+        fn = lib.ss_critic_grad_tc if self.update_precision == "bf16" else lib.ss_critic_grad
+        ws = self._workspace_for(n)
         with torch.cuda.device(self.device):
-            check(lib.ss_critic_grad(self.critic.data_ptr(), obs.data_ptr(), act.data_ptr(), y.data_ptr(), _ptr(keep),
-                                     self.dropout, self.seed, self.counter, n, int(n_global), int(row_offset),
-                                     g.data_ptr(), self.stats[0:1].data_ptr(), self.workspace.data_ptr(),
-                                     self.workspace.numel(), _stream(self.device)), "ss_critic_grad")
+            check(fn(self.critic.data_ptr(), obs.data_ptr(), act.data_ptr(), y.data_ptr(), _ptr(keep),
+                     self.dropout, self.seed, self.counter, n, int(n_global), int(row_offset),
+                     g.data_ptr(), self.stats[0:1].data_ptr(), ws.data_ptr(), ws.numel(), _stream(self.device)),
+                  "ss_critic_grad")
         self.counter += 1
         return g
 
@@ -251,10 +281,12 @@ class ActorCritic:
         """grads[actor] <- -sum_batch dQ/da da/dtheta (model_actor_fit_step, SkillshotLearner.py:395-410)."""
         obs = _f32(obs, self.device).reshape(-1, 12)
         g = self._slice(self.grads, "actor")
+        fn = lib.ss_actor_grad_tc if self.update_precision == "bf16" else lib.ss_actor_grad
+        ws = self._workspace_for(obs.shape[0])
         with torch.cuda.device(self.device):
-            check(lib.ss_actor_grad(self.actor.data_ptr(), self.critic.data_ptr(), obs.data_ptr(), obs.shape[0],
-                                    g.data_ptr(), self.stats[1:2].data_ptr(), self.workspace.data_ptr(),
-                                    self.workspace.numel(), _stream(self.device)), "ss_actor_grad")
+            check(fn(self.actor.data_ptr(), self.critic.data_ptr(), obs.data_ptr(), obs.shape[0],
+                     g.data_ptr(), self.stats[1:2].data_ptr(), ws.data_ptr(), ws.numel(), _stream(self.device)),
+                  "ss_actor_grad")
         return g
 
     def apply_adam(self, which: str, grad_scale: float = 1.0):
@@ -603,7 +635,7 @@ class SelfPlayTrainer:
         self.envs = SkillshotEnvs(n_envs, device=device, random_positions=random_positions, seed=seed,
                                   reward_mode=reward_mode, tick_limit=tick_limit, auto_reset=True)
         self.networks = ActorCritic(device=device, seed=seed if process_group is None else 0, gamma=gamma, tau=tau,
-                                    process_group=process_group)
+                                    process_group=process_group, update_precision=precision)
         self.networks.seed = seed          # exploration / dropout streams differ per rank, weights do not
         self.replay = ReplayRing(replay_capacity or 2 * n_envs * 8, device=device, seed=seed)
         self.batch_size, self.param_noise_sd, self.noise_group = int(batch_size), float(param_noise_sd), int(noise_group)

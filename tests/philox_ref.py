@@ -50,16 +50,18 @@ def param_noise_eps(n_params, seed, group, counter):
 
 
 def dropout_keep(n, seed, counter, rate, row_offset=0):
-    """keep mask uint8 [n, 256] of ss_critic_grad's Philox dropout."""
-    thresh = min(4294967295.0, rate * 4294967296.0)
-    thresh = np.uint32(int(thresh))
-    rows = np.arange(n) + row_offset
-    quads = (rows // 4).astype(np.uint64)
-    j = np.arange(256, dtype=np.uint64)
-    u = draw4(seed, TAG_DROPOUT, j[None, :], quads[:, None], counter)      # each [n,256]
-    lane = (rows % 4)[:, None]
-    sel = np.where(lane == 0, u[0], np.where(lane == 1, u[1], np.where(lane == 2, u[2], u[3])))
-    return (sel >= thresh).astype(np.uint8)
+    """keep mask uint8 [n, 256] of the Philox dropout of ss_critic_grad / ss_critic_grad_tc: one draw per
+    (global row, 8 units), 16 bits per unit, kept when the 16-bit value >= floor(rate * 65536)."""
+    thresh = np.uint32(int(np.float32(rate) * np.float32(65536.0)))
+    rows = (np.arange(n) + row_offset).astype(np.uint64)
+    chunks = np.arange(32, dtype=np.uint64)
+    u = draw4(seed, TAG_DROPOUT, rows[:, None], chunks[None, :], counter)          # 4 x [n, 32]
+    keep = np.zeros((n, 256), np.uint8)
+    for e in range(8):
+        w = u[e >> 1]
+        v = (w >> np.uint32(16)) if (e & 1) else (w & np.uint32(0xFFFF))
+        keep[:, e::8] = (v >= thresh).astype(np.uint8)
+    return keep
 
 
 def replay_indices(batch, size, seed, counter):

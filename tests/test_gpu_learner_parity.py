@@ -334,3 +334,112 @@ def test_tensor_core_actor_forward_with_noise_groups(net):
     np.testing.assert_allclose(got, want + 0.15 * zn, rtol=0, atol=2e-3)
     with pytest.raises(Exception):
         ac.actor_forward(s, param_noise_sd=0.5, noise_group=100, precision="bf16")    # groups are whole tiles
+
+
+# ---------------------------------------------------------------------------
+# tensor-core critic forward / gradients (ss_critic_forward_tc, ss_critic_grad_tc, ss_actor_grad_tc)
+# ---------------------------------------------------------------------------
+# Stated tolerances: the operands of every GEMM are bf16 (weights, activations, upstream gradients;
+# inputs as hi + lo pairs), accumulation is fp32.  Forward values agree with the float32 path to
+# 2e-2 absolute (critic outputs are O(1)), gradients to 2e-2 of the gradient's largest entry
+# (typically ~3e-3), after Adam the parameters move by ~lr so they agree to 1e-3 * steps * lr scale.
+def _tc_net(net):
+    from skillshot_learning_b200 import ActorCritic
+    _, theta, phi = net
+    ac = ActorCritic(device="cuda:0", seed=11, update_precision="bf16")
+    ac.set_weights(theta, phi)
+    return ac
+
+
+@pytest.mark.parametrize("n", [1, 128, 333, 20000])
+def test_tensor_core_critic_forward_and_dq_da(net, n):
+    ac, theta, phi = net
+    s, a, _ = _batch(n, 900 + n)
+    q, up = ac.critic_forward(s, a, precision="bf16", want_dq_da=True)
+    q, up = q.cpu().numpy(), up.cpu().numpy()
+    np.testing.assert_allclose(q, lo.critic_forward(phi, s, a), rtol=0, atol=2e-2)
+    at = torch.tensor(a, dtype=torch.float64, requires_grad=True)
+    qq = lo.critic_forward_t(torch.tensor(phi, dtype=torch.float64), torch.tensor(s, dtype=torch.float64), at)
+    qq.sum().backward()
+    # dQ/da sums W3[k] W2[256+m][k] over the ACTIVE hidden units: a unit whose pre-activation sits within
+    # bf16 rounding of zero can flip, which moves one row's value by one such term (~5e-3); hence a loose
+    # bound on the worst row and a tight one on the average
+    want, scale = -at.grad.numpy(), np.abs(at.grad.numpy()).max()
+    assert np.abs(up - want).max() <= 0.15 * scale + 5e-3
+    assert np.abs(up - want).mean() <= 1e-2 * scale + 5e-4
+
+
+@pytest.mark.parametrize("n", [128, 77, 1000, 20000])
+def test_tensor_core_critic_gradient(net, n):
+    ac = _tc_net(net)
+    _, theta, phi = net
+    s, a, r = _batch(n, 300 + n)
+    keep = (np.random.default_rng(n).uniform(size=(n, 256)) >= 0.2).astype(np.uint8)
+    g = ac.critic_grad(s, a, r, keep=keep).cpu().numpy()
+    sse = float(ac.stats[0])
+    want, want_sse = lo.critic_grad(phi.astype(np.float64), s, a, r, keep.astype(np.float64), 0.2, dtype=torch.float64)
+    _scale_close(g, want, 2e-2)
+    assert np.abs(g - want).mean() < 2e-3 * np.abs(want).max()
+    assert abs(sse - want_sse) <= 2e-2 * max(1.0, want_sse)
+    again = ac.critic_grad(s, a, r, keep=keep).cpu().numpy()
+    assert np.array_equal(g, again)
+
+
+def test_tensor_core_critic_gradient_philox_dropout_matches_float32_path(net):
+    ac = _tc_net(net)
+    ac32, theta, phi = net
+    n = 1000
+    s, a, r = _batch(n, 42)
+    ac.counter = ac32.counter = 77
+    ac.seed = ac32.seed
+    g = ac.critic_grad(s, a, r, row_offset=5).cpu().numpy()
+    ac32.counter = 77
+    want = ac32.critic_grad(s, a, r, row_offset=5).cpu().numpy()      # same Philox mask in both kernels
+    _scale_close(g, want, 2e-2)
+
+
+@pytest.mark.parametrize("n", [128, 45, 3000, 20000])
+def test_tensor_core_actor_policy_gradient(net, n):
+    ac = _tc_net(net)
+    _, theta, phi = net
+    s, _, _ = _batch(n, 500 + n)
+    g = ac.actor_grad(s).cpu().numpy()
+    qsum = float(ac.stats[1])
+    want, want_q = lo.actor_grad(theta.astype(np.float64), phi.astype(np.float64), s, dtype=torch.float64)
+    _scale_close(g, want, 2e-2)
+    assert np.abs(g - want).mean() < 2e-3 * np.abs(want).max()
+    assert abs(qsum - want_q) <= 2e-2 * max(1.0, abs(want_q))
+
+
+def test_tensor_core_td_targets(net):
+    ac = _tc_net(net)
+    _, theta, phi = net
+    s2, _, r = _batch(3000, 8)
+    done = (np.random.default_rng(1).uniform(size=3000) < 0.2)
+    ac.gamma = 0.95
+    y = ac.td_targets(r, s2, torch.from_numpy(done.astype(np.uint8))).cpu().numpy()
+    np.testing.assert_allclose(y, lo.ddpg_targets(theta, phi, r, s2, done, 0.95), rtol=0, atol=2e-2)
+    assert np.array_equal(y[done], r[done])
+
+
+def test_tensor_core_update_tracks_the_float32_update(net):
+    """Twenty DDPG updates of 4,096 rows with the tensor-core kernels against the same updates with the
+    float32 kernels (same batches, injected masks): the losses track, the parameters stay close."""
+    from skillshot_learning_b200 import ActorCritic
+    _, theta, phi = net
+    nets = [ActorCritic(device="cuda:0", seed=1, gamma=0.9, tau=0.05, update_precision=p) for p in ("f32", "bf16")]
+    for ac in nets:
+        ac.set_weights(theta, phi)
+    rng = np.random.default_rng(3)
+    losses = [[], []]
+    for it in range(20):
+        s, a, r = _batch(4096, 7000 + it)
+        s2, _, _ = _batch(4096, 8000 + it)
+        keep = torch.from_numpy((rng.uniform(size=(4096, 256)) >= 0.2).astype(np.uint8)).cuda()
+        for k, ac in enumerate(nets):
+            y = ac.td_targets(r, s2)
+            losses[k].append(float(ac.critic_step(s, a, y, keep=keep)) / 4096)
+            ac.actor_step(s)
+    np.testing.assert_allclose(losses[1], losses[0], rtol=3e-2, atol=1e-4)
+    d = (nets[0].params - nets[1].params).abs()
+    assert float(d.max()) < 20 * 1e-3 * 0.5 and float(d.mean()) < 1e-3          # a fraction of the distance moved
