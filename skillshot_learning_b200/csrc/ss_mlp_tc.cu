@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_fwd_tc_kernel(const FwdArgs A
                 const uint32_t a_addr = sbase + SM_A + (uint32_t)s * X2_BYTES;
                 const uint32_t d_addr = tmem + (uint32_t)s * 256;
                 if (stage == 0) {
-                    if (!mbar_probe(bar(s, BAR_IN), phase)) return;
+                    if (!mbar_test(bar(s, BAR_IN), phase)) return;
                     tc_fence_after();
                     if (lane == 0) {
                         const uint64_t ad = desc_kmajor(a_addr, CHUNK_A), bd = desc_kmajor(sbase + SM_B1, CHUNK_B1);
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_fwd_tc_kernel(const FwdArgs A
                     __syncwarp();
                     stage = 1;
                 } else {
-                    if (!mbar_probe(bar(s, BAR_H1), phase)) return;
+                    if (!mbar_test(bar(s, BAR_H1), phase)) return;
                     tc_fence_after();
                     if (lane == 0) {
                         const uint64_t ad = desc_kmajor(a_addr, CHUNK_A), bd = desc_kmajor(sbase + SM_B2, CHUNK_B2);
