@@ -500,14 +500,24 @@ __global__ void __launch_bounds__(NT) actor_grad_kernel(const ActorGradArgs A) {
     }
 }
 
-// grad[p] = sum over CTA slices, fixed order; aux[0] = sum of the slices' extra slot
+// grad[p] = sum over CTA slices in a fixed order (bit-identical from run to run): four interleaved
+// groups of slices are summed by four threads per parameter and combined 0+1+2+3 through shared memory;
+// aux[0] = the same sum of the slices' extra slot
 __global__ void reduce_kernel(const float *work, int parts, int n_params, float *grad, float *aux) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p > n_params) return;
+    __shared__ float red[4][64];
+    const int p = blockIdx.x * 64 + threadIdx.x, q = threadIdx.y;
     float s = 0.f;
-    for (int c = 0; c < parts; ++c) s += work[(int64_t)c * (n_params + 1) + p];
-    if (p < n_params) grad[p] = s;
-    else if (aux) aux[0] = s;
+    if (p <= n_params) {
+#pragma unroll 4
+        for (int c = q; c < parts; c += 4) s += __ldcg(work + (int64_t)c * (n_params + 1) + p);
+    }
+    red[q][threadIdx.x] = s;
+    __syncthreads();
+    if (q == 0 && p <= n_params) {
+        const float t = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
+        if (p < n_params) grad[p] = t;
+        else if (aux) aux[0] = t;
+    }
 }
 
 // tf.keras.optimizers.Adam.apply_gradients (SkillshotLearner.py:68, 118, 417) and the
@@ -682,7 +692,7 @@ int ss_critic_grad(const float *critic_params, const float *obs, const float *ac
                      n, n_global > 0 ? n_global : n, row_offset, (float *)workspace};
     cudaStream_t st = (cudaStream_t)stream;
     critic_grad_kernel<<<grid, NT, kSmemCriticGrad, st>>>(A);
-    reduce_kernel<<<(C_N + 1 + 255) / 256, 256, 0, st>>>((const float *)workspace, grid, C_N, grad_out, sse_out);
+    reduce_kernel<<<(C_N + 1 + 63) / 64, dim3(64, 4), 0, st>>>((const float *)workspace, grid, C_N, grad_out, sse_out);
     return check_launch();
 }
 
@@ -698,7 +708,7 @@ int ss_actor_grad(const float *actor_params, const float *critic_params, const f
     ActorGradArgs A{actor_params, critic_params, obs, n, (float *)workspace};
     cudaStream_t st = (cudaStream_t)stream;
     actor_grad_kernel<<<grid, NT, kSmemActorGrad, st>>>(A);
-    reduce_kernel<<<(A_N + 1 + 255) / 256, 256, 0, st>>>((const float *)workspace, grid, A_N, grad_out, q_sum_out);
+    reduce_kernel<<<(A_N + 1 + 63) / 64, dim3(64, 4), 0, st>>>((const float *)workspace, grid, A_N, grad_out, q_sum_out);
     return check_launch();
 }
 

@@ -422,14 +422,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
     }
 }
 
-// grad[p] = sum over CTA slices, fixed order; aux[0] = sum of the slices' extra slot
+// grad[p] = sum over CTA slices in a fixed order (bit-identical from run to run): four interleaved
+// groups of slices are summed by four threads per parameter and combined 0+1+2+3 through shared memory;
+// aux[0] = the same sum of the slices' extra slot
 __global__ void reduce_parts_kernel(const float *work, int parts, int n_params, float *grad, float *aux) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p > n_params) return;
+    __shared__ float red[4][64];
+    const int p = blockIdx.x * 64 + threadIdx.x, q = threadIdx.y;
     float s = 0.f;
-    for (int c = 0; c < parts; ++c) s += work[(int64_t)c * (n_params + 1) + p];
-    if (p < n_params) grad[p] = s;
-    else if (aux) aux[0] = s;
+    if (p <= n_params) {
+#pragma unroll 4
+        for (int c = q; c < parts; c += 4) s += __ldcg(work + (int64_t)c * (n_params + 1) + p);
+    }
+    red[q][threadIdx.x] = s;
+    __syncthreads();
+    if (q == 0 && p <= n_params) {
+        const float t = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
+        if (p < n_params) grad[p] = t;
+        else if (aux) aux[0] = t;
+    }
 }
 
 // out[0] = sum of x[0..n) in a fixed order (one CTA)
@@ -461,7 +471,7 @@ int launch_grad(const GradArgs &A0, float *grad_out, float *aux_out, int64_t wor
     const int grid = (int)(tiles < cap ? tiles : cap);
     cudaStream_t st = (cudaStream_t)stream;
     mlp_grad_tc_kernel<NET><<<grid, NTHREADS, SM_TOTAL, st>>>(A0);
-    reduce_parts_kernel<<<(PN + 1 + 255) / 256, 256, 0, st>>>(A0.work, grid, PN, grad_out, aux_out);
+    reduce_parts_kernel<<<(PN + 1 + 63) / 64, dim3(64, 4), 0, st>>>(A0.work, grid, PN, grad_out, aux_out);
     return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
 }
 

@@ -1,61 +1,42 @@
-// ss_mlp_tc.cu -- the actor forward pass on the 5th-generation tensor cores
+// ss_mlp_tc.cu -- actor and critic forward passes on the 5th-generation tensor cores
 // (tcgen05.mma, accumulators in tensor memory), sm_100a only.
 //
 // model_act* of the reference (SkillshotLearner.py:215-281) evaluates
 // 12 -> 256 relu -> 128 relu -> 2 tanh for ONE observation per Keras predict().
 // The batched rollout evaluates it for 2 x envs observations per tick
-// (BASELINE.json configs 3-4: 524,288 .. 2,097,152 rows), which is two GEMMs:
+// (BASELINE.json configs 3-4: 524,288 .. 2,097,152 rows), which is two GEMMs per
+// 128-row tile:
 //
-//   layer 1   D1[128 x 256] = A0[128 x 32]  . B1[32 x 256]     (K = 12 padded; see below)
-//   layer 2   D2[128 x 128] = A1[128 x 256] . B2[256 x 128]    (91 % of the MACs)
-//   layer 3   128 -> 2 and tanh on the CUDA cores in the epilogue (fp32)
+//   layer 1   D1[128 x 256] = X0[128 x 16]  . W1'[16 x 256]     fp16 operands, K = 12 + bias rows
+//   layer 2   D2[128 x 128] = A1[128 x 272] . W2'[272 x 128]    bf16 operands, K = 256 + bias (+ action) rows
+//   layer 3   128 -> 2 (actor, tanh) or 128 -> 1 (critic) on the CUDA cores in the epilogue, fp32
 //
-// One persistent CTA per SM keeps the bf16 weights resident in shared memory in
-// the UMMA canonical K-major (no-swizzle) layout and streams 128-row tiles
-// through two SLOTS.  Each slot has its own 64 KB activation buffer, its own 256
-// tensor-memory columns and its own four epilogue warps; one extra warp issues
-// every tcgen05.mma.  While the tensor core works on one slot's GEMM the other
-// slot's warps run their epilogue (bias, ReLU, bf16 pack -> next A operand; or
-// layer 3 + tanh -> global), so the tensor pipe and the CUDA cores overlap.
-// Synchronisation is mbarrier-only (tcgen05.commit arrives when the MMAs retire).
+// The critic (SkillshotLearner.py:98-121, Dropout off) is the same pipeline: its action enters
+// layer 2 through the tail chunk of A1, and its epilogue also produces -dQ/da (the upstream
+// gradient of model_actor_fit_step) and the TD target r + gamma (1 - done) Q.
 //
-// Precision: weights bf16 (fp32 master copy stays in HBM), accumulation fp32.
-// The observation is split into a bf16 high part and a bf16 low part (x = hi + lo
-// to 2^-17 relative) that occupy K = 0..11 and 16..27 of layer 1 against the same
-// weight rows, because positions are multiples of 1/250 and a single bf16 (8 bits)
-// would merge neighbouring pixels.  The hidden activations are rounded to bf16
-// when they become the A operand of layer 2.  Both biases ride through the tensor
-// core as extra K rows against a constant 1 in the A operand (bias as a bf16 high +
-// low pair: fp32-accurate to 2^-17), so the epilogues are ReLU + pack only.
+// One persistent CTA per SM keeps the weights resident in shared memory in the UMMA canonical
+// K-major no-swizzle layout (ss_tc_common.cuh) and streams tiles through the role pipeline
+// described above the kernel.  Synchronisation is mbarrier-only (tcgen05.commit arrives when
+// the MMAs retire).
 //
-// Parameter noise (SkillshotLearner.py:260-265): the CTA perturbs the weights
-// while staging them, w + w * (sd * eps), eps from the same Philox stream as the
-// float32 path (ss_rng.cuh), one draw per noise group; groups are multiples of
-// the 128-row tile so a tile never mixes two draws.
+// Precision: fp32 master weights stay in HBM; accumulation is fp32.  Layer 1 runs in fp16: the
+// observation's positions are multiples of 1/250 and fp16's 11-bit significand resolves them
+// 8x finer than a pixel (a single bf16 would merge neighbouring pixels), the weights keep 11
+// bits too, and K = 16 is a single MMA step.  Layer 2 runs in bf16 (the hidden activations are
+// rounded to bf16 when they become its A operand).  All biases ride through the tensor core as
+// extra K rows against a constant 1 in the A operand (bias as a high + low pair, accurate to
+// 2^-17 or better), so epilogue 1 is tcgen05.ld -> cvt.rn.relu.bf16x2 -> st.shared only.
+//
+// Parameter noise (SkillshotLearner.py:260-265): the CTA perturbs the weights while staging
+// them, w + w * (sd * eps), eps from the same Philox stream as the float32 path (ss_rng.cuh),
+// one draw per noise group; groups are multiples of the 128-row tile so a tile never mixes two
+// draws.
 #include "ss_tc_common.cuh"
 
 namespace {
 
 using namespace sstc;
-
-constexpr int NSLOT = 2;
-constexpr int EPI_WARPS = 4 * NSLOT;     // warp w serves slot w / 4 and TMEM lanes 32 (w % 4) ..
-constexpr int MMA_WARP = EPI_WARPS;
-constexpr int NTHREADS = 32 * (EPI_WARPS + 1);
-
-// shared-memory map (bytes)
-constexpr uint32_t SM_B1 = 0;                               // [K1/8][256][8] bf16
-constexpr uint32_t SM_B2 = SM_B1 + B1_BYTES;                // [K2/8][128][8] bf16
-constexpr uint32_t SM_A = SM_B2 + B2_BYTES;                 // NSLOT x [K2/8][128][8] bf16 (layer-1 A aliases its head)
-constexpr uint32_t SM_W3 = SM_A + NSLOT * X2_BYTES;         // [128] float4 (layer 3, see Stager::w3x)
-constexpr uint32_t SM_B3 = SM_W3 + H2 * 16;
-constexpr uint32_t SM_BAR = SM_B3 + 16;                     // NSLOT x {in, d1, h1, d2} mbarriers
-constexpr uint32_t SM_TMEM = SM_BAR + NSLOT * 4 * 8;
-constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
-static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
-static_assert(NSLOT == 2, "the MMA warp services exactly two slots");
-
-enum { BAR_IN = 0, BAR_D1 = 1, BAR_H1 = 2, BAR_D2 = 3 };
 
 struct FwdArgs {
     const float *params, *obs;
@@ -72,6 +53,7 @@ struct FwdArgs {
     const float *reward;
     const uint8_t *done;
     float gamma;
+    long long *trace;        // development: event timestamps of CTA 0 (NULL in production)
 };
 
 // 32 accumulator columns (hidden-2 units) -> ReLU -> layer 3, four split accumulators per output.
@@ -102,125 +84,168 @@ __device__ __forceinline__ void layer3(const uint32_t (&v)[32], const float4 *w3
     }
 }
 
+// ---- the kernel ------------------------------------------------------------------------
+// Three roles run as a software pipeline over the CTA's 128-row tiles:
+//
+//   P warps (4)   stage X0(t+2);  wait MMA1(t);  D1 -> ReLU -> bf16 -> A1[t % 2]       (layer-1 epilogue)
+//   Q warps (4)   wait MMA2(t);  D2[t % 2] -> ReLU -> layer 3 -> output
+//   MMA warp      MMA1(t+1): D1 = X0[(t+1) % 2] . W1'    then    MMA2(t): D2[t % 2] = A1[t % 2] . W2'
+//
+// A1, X0 and D2 are double-buffered, D1 is single (256 + 2 x 128 tensor-memory columns, 220 KB of shared
+// memory).  Per tile the MMA warp waits twice and commits twice.  History (profiles/README.md): a first
+// version gave each of two whole-tile "slots" its own four warps for the entire chain stage -> MMA1 ->
+// epilogue 1 -> MMA2 -> epilogue 2 (tensor pipe 43-47 % busy: the chain is ~4x a tile's MMA time and there
+// is no shared memory for a third 68 KB tile); a 64-column block pipeline between the layers ran 2x SLOWER
+// (issue-bound: 25 MMAs, 10 waits, 10 commits per tile on the one issuing thread).  An event trace of this
+// version (tools/tc_trace.py) shows the MMA warp as the pacing role.
+namespace pipe {
+
+constexpr int P_WARPS = 4, Q_WARPS = 4, MMA_W = 8, NTH = 32 * 9;
+
+constexpr uint32_t SMP_B1 = 0;                              // [K1F/8][256][8] fp16
+constexpr uint32_t SMP_B2 = SMP_B1 + (K1F / 8) * CHUNK_B1;  // [K2/8][128][8] bf16
+constexpr uint32_t SMP_A1 = SMP_B2 + B2_BYTES;              // 2 x [K2/8][128][8] bf16: hidden layer 1 (+ tail) of tile t in A1[t & 1]
+constexpr uint32_t SMP_X0 = SMP_A1 + 2 * X2_BYTES;          // 2 x [K1F/8][128][8] fp16: observations of tile t in X0[t & 1]
+constexpr uint32_t X0_BYTES = (K1F / 8) * CHUNK_A;
+constexpr uint32_t SMP_W3 = SMP_X0 + 2 * X0_BYTES;
+constexpr uint32_t SMP_B3 = SMP_W3 + H2 * 16;
+constexpr uint32_t SMP_BAR = SMP_B3 + 16;
+// barriers: X (producers -> MMA warp, one arrival round per hand-off), Z (MMA1 retired), Y[2] (MMA2 retired),
+// D2E[2] (output warps have read D2[s])
+constexpr int B_X = 0, B_Z = 1, B_Y = 2, B_D2E = 4, B_COUNT = 6;
+constexpr uint32_t SMP_TMEM = SMP_BAR + B_COUNT * 8;
+constexpr uint32_t SMP_TOTAL = SMP_TMEM + 16;
+static_assert(SMP_TOTAL <= 227 * 1024, "shared memory budget");
+
 template <int NET>
-__global__ void __launch_bounds__(NTHREADS, 1) mlp_fwd_tc_kernel(const FwdArgs A) {
+__global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    auto bar = [&](int slot, int which) -> uint32_t { return sbase + SM_BAR + (uint32_t)(slot * 4 + which) * 8; };
+    auto bar = [&](int idx) -> uint32_t { return sbase + SMP_BAR + (uint32_t)idx * 8; };
+    // development trace (A.trace != NULL): role 0 = producer warp 0, 1 = output warp 4, 2 = MMA warp
+    int tr_n = 0;
+    auto trace = [&](int role, int code) {
+        if (A.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == P_WARPS || warp == MMA_W) && tr_n < 256) {
+            A.trace[(role * 256 + tr_n) * 2] = clock64();
+            A.trace[(role * 256 + tr_n) * 2 + 1] = code;
+            ++tr_n;
+        }
+    };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSLOT; ++s) {
-            mbar_init(bar(s, BAR_IN), 128);
-            mbar_init(bar(s, BAR_D1), 1);
-            mbar_init(bar(s, BAR_H1), 128);
-            mbar_init(bar(s, BAR_D2), 1);
-        }
+        mbar_init(bar(B_X), 128);
+        mbar_init(bar(B_Z), 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(bar(B_Y + i), 1); mbar_init(bar(B_D2E + i), 128); }
         mbar_fence_init();
     }
-    if (warp == MMA_WARP) tmem_alloc(sbase + SM_TMEM, 512);     // one warp owns the allocation (all 512 columns)
-    // constant parts of the operand tiles: the padding rows of B1 / B2 stay zero, the bias columns of
-    // the activation tiles (K = 256.. ) stay one, for the whole kernel
-    for (uint32_t o = threadIdx.x * 16; o < SM_A; o += NTHREADS * 16)
-        *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
-    if (warp < EPI_WARPS) {
-        uint8_t *arow = smem + SM_A + (uint32_t)(warp >> 2) * X2_BYTES + (uint32_t)((warp & 3) * 32 + lane) * 16;
-        *reinterpret_cast<uint4 *>(arow + (H1 / 8) * CHUNK_A) = tail_chunk_actor();
-        *reinterpret_cast<uint4 *>(arow + (H1 / 8 + 1) * CHUNK_A) = make_uint4(0, 0, 0, 0);
+    if (warp == MMA_W) tmem_alloc(sbase + SMP_TMEM, 512);
+    for (uint32_t o = threadIdx.x * 16; o < SMP_A1; o += NTH * 16) *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
+    if (warp < P_WARPS) {                                    // tail chunks of both activation tiles: actor {1 1 0 ..} | 0
+        for (int t = 0; t < 2; ++t) {
+            uint8_t *arow = smem + SMP_A1 + t * X2_BYTES + threadIdx.x * 16;
+            *reinterpret_cast<uint4 *>(arow + (H1 / 8) * CHUNK_A) = tail_chunk_actor();
+            *reinterpret_cast<uint4 *>(arow + (H1 / 8 + 1) * CHUNK_A) = make_uint4(0, 0, 0, 0);
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<const volatile uint32_t *>(smem + SM_TMEM);
+    const uint32_t tmem = *reinterpret_cast<const volatile uint32_t *>(smem + SMP_TMEM);
 
     const bool noisy = NET == NET_ACTOR && A.param_sd > 0.f;
     const int64_t group = noisy ? A.group : A.n;
-    const int64_t upg = (group + TM - 1) / TM;                 // tiles per noise group
+    const int64_t upg = (group + TM - 1) / TM;
     const int64_t n_groups = (A.n + group - 1) / group;
     const int64_t units = n_groups * upg;
     const int64_t u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
 
-    // parity of a slot's barriers (each completes once per tile): the epilogue warps track their own
-    // slot, the MMA warp both
-    uint32_t ph = 0, mma_phase0 = 0, mma_phase1 = 0;
+    uint32_t tcount = 0;                                     // tiles done by this CTA: buffers = tcount & 1, parities from tcount
+    uint32_t xph = 0;                                        // MMA warp: parity of the next X hand-off
 
     for (int64_t u = u0; u < u1;) {
         const int64_t g = u / upg;
         const int64_t seg_end = min(u1, (g + 1) * upg);
         const int64_t ntiles = seg_end - u;
         const int64_t end = min(A.n, (g + 1) * group);
+        const int64_t row0 = g * group + (u - g * upg) * TM;      // first row of the segment's first tile
+        const int r = (warp & 3) * 32 + lane;                     // row of the tile = tensor-memory lane
 
-        // the epilogue warps start fetching their first observation rows under the weight staging
         float4 xin[3];
-        if (warp < EPI_WARPS)
-            load_obs(A.obs, g * group + (u + (warp >> 2) - g * upg) * TM + (warp & 3) * 32 + lane,
-                     (warp >> 2) < ntiles ? end : 0, xin);
-
-        // ---- stage (and perturb) the weights of noise group g ----
-        stage_weights<NET, NTHREADS>(Stager{A.params, smem + SM_B1, smem + SM_B2, reinterpret_cast<float4 *>(smem + SM_W3),
-                                            reinterpret_cast<float *>(smem + SM_B3), noisy, A.param_sd, A.seed,
-                                            A.counter, (uint32_t)g});
-        fence_proxy_async();               // generic-proxy writes -> visible to the tensor core's async proxy
+        if (warp < P_WARPS) load_obs(A.obs, row0 + r, end, xin);
+        stage_weights<NET, NTH, true>(Stager{A.params, smem + SMP_B1, smem + SMP_B2, reinterpret_cast<float4 *>(smem + SMP_W3),
+                                             reinterpret_cast<float *>(smem + SMP_B3), noisy, A.param_sd, A.seed, A.counter,
+                                             (uint32_t)g});
+        fence_proxy_async();
         __syncthreads();
 
-        if (warp < EPI_WARPS) {
-            // ================= epilogue / producer warps of one slot =================
-            const int slot = warp >> 2, qd = warp & 3;
-            const int r = qd * 32 + lane;                                // row of the tile = tensor-memory lane
-            uint8_t *arow = smem + SM_A + (uint32_t)slot * X2_BYTES + (uint32_t)r * 16;
-            const uint32_t tlane = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)slot * 256;
-            const float4 *w3x = reinterpret_cast<const float4 *>(smem + SM_W3);
-            const float *b3 = reinterpret_cast<const float *>(smem + SM_B3);
-            for (int64_t k = slot; k < ntiles; k += NSLOT) {
-                const int64_t row = g * group + (u + k - g * upg) * TM + r;
-                // ---- 1. observation -> layer-1 A operand (K = 32); critic: the action into the layer-2 tail chunk ----
-                store_obs_row(xin, arow);
-                if (NET == NET_CRITIC) {
-                    float2 a = make_float2(0.f, 0.f);
-                    if (row < end) a = __ldg(reinterpret_cast<const float2 *>(A.act_in) + row);
-                    *reinterpret_cast<uint4 *>(arow + (H1 / 8) * CHUNK_A) = tail_chunk_critic(a.x, a.y);
-                }
-                fence_proxy_async();
-                tc_fence_before();         // orders this thread's earlier tcgen05.ld (previous tile) before the next MMA
-                mbar_arrive(bar(slot, BAR_IN));
-                // next tile's observation row: in flight during this tile's two GEMMs
-                load_obs(A.obs, row + NSLOT * TM, (k + NSLOT < ntiles) ? end : 0, xin);
-
-                // ---- 2. D1 (bias included) -> ReLU, bf16 -> A1; tensor-memory loads double-buffered ----
-                mbar_wait(bar(slot, BAR_D1), ph);
+        if (warp < P_WARPS) {
+            // ============ producer warps: observation staging and the layer-1 epilogue ============
+            const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+            auto stage_x0 = [&](int64_t i) {                      // observations of tile i -> X0[(tcount + i) & 1]
+                store_obs_row_f16(xin, smem + SMP_X0 + ((tcount + (uint32_t)i) & 1) * X0_BYTES + r * 16);
+                load_obs(A.obs, row0 + (i + 1) * TM + r, (i + 1 < ntiles) ? end : 0, xin);   // prefetch the next tile's row
+            };
+            stage_x0(0);
+            fence_proxy_async();
+            mbar_arrive(bar(B_X));                                // -> MMA1(tile 0)
+            if (ntiles > 1) stage_x0(1);
+            for (int64_t i = 0; i < ntiles; ++i) {
+                const uint32_t tc = tcount + (uint32_t)i;
+                uint8_t *arow = smem + SMP_A1 + (tc & 1) * X2_BYTES + r * 16;
+                float2 act = make_float2(0.f, 0.f);
+                if (NET == NET_CRITIC && row0 + i * TM + r < end) act = __ldg(reinterpret_cast<const float2 *>(A.act_in) + row0 + i * TM + r);
+                trace(0, 100 + (int)i);
+                // MMA1(tile) retired: D1 holds layer 1 and X0[tc & 1] is dead.  The tensor pipe retires one thread's MMAs
+                // in issue order and MMA2(tile - 2) was issued before MMA1(tile), so A1[tc & 1] is free as well.
+                mbar_wait(bar(B_Z), tc & 1);
                 tc_fence_after();
+                trace(0, 200 + (int)i);
+                if (NET == NET_CRITIC) *reinterpret_cast<uint4 *>(arow + (H1 / 8) * CHUNK_A) = tail_chunk_critic(act.x, act.y);
                 {
                     uint32_t va[32], vb[32];
-                    tmem_ld32(tlane, va);
+                    tmem_ld32(tl, va);
 #pragma unroll
                     for (int j = 0; j < H1 / 32; j += 2) {
                         tmem_wait_ld();
-                        tmem_ld32(tlane + (j + 1) * 32, vb);
+                        tmem_ld32(tl + (j + 1) * 32, vb);
                         relu_pack_store(va, arow + (uint32_t)(j * 4) * CHUNK_A);
                         tmem_wait_ld();
-                        if (j + 2 < H1 / 32) tmem_ld32(tlane + (j + 2) * 32, va);
+                        if (j + 2 < H1 / 32) tmem_ld32(tl + (j + 2) * 32, va);
                         relu_pack_store(vb, arow + (uint32_t)((j + 1) * 4) * CHUNK_A);
                     }
                 }
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(bar(slot, BAR_H1));
-
-                // ---- 3. D2 (bias included) -> ReLU, layer 3, output ----
-                mbar_wait(bar(slot, BAR_D2), ph);
+                mbar_arrive(bar(B_X));                            // A1[tile] full, D1 free, X0(tile + 1) staged
+                trace(0, 500 + (int)i);
+                if (i + 2 < ntiles) stage_x0(i + 2);              // into X0[tc & 1]
+            }
+        } else if (warp < P_WARPS + Q_WARPS) {
+            // ============ output warps: layer 3 on D2 ============
+            const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256;
+            const float4 *w3x = reinterpret_cast<const float4 *>(smem + SMP_W3);
+            const float *b3 = reinterpret_cast<const float *>(smem + SMP_B3);
+            for (int64_t i = 0; i < ntiles; ++i) {
+                const uint32_t tc = tcount + (uint32_t)i, slot = tc & 1;
+                const int64_t row = row0 + i * TM + r;
+                trace(1, 100 + (int)i);
+                mbar_wait(bar(B_Y + slot), (tc >> 1) & 1);
                 tc_fence_after();
+                trace(1, 200 + (int)i);
                 float acc[3][4] = {{b3[0], 0.f, 0.f, 0.f}, {NET == NET_ACTOR ? b3[1] : 0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
                 {
-                    constexpr int kW3Step = NET == NET_ACTOR ? 16 : 32;        // float4 entries per 32 units
+                    constexpr int kW3Step = NET == NET_ACTOR ? 16 : 32;
                     uint32_t va[32], vb[32];
-                    tmem_ld32(tlane, va);
+                    tmem_ld32(tl + slot * 128, va);
 #pragma unroll
                     for (int j = 0; j < H2 / 32; j += 2) {
                         tmem_wait_ld();
-                        tmem_ld32(tlane + (j + 1) * 32, vb);
+                        tmem_ld32(tl + slot * 128 + (j + 1) * 32, vb);
                         layer3<NET>(va, w3x + j * kW3Step, acc);
                         tmem_wait_ld();
-                        if (j + 2 < H2 / 32) tmem_ld32(tlane + (j + 2) * 32, va);
+                        if (j + 2 < H2 / 32) tmem_ld32(tl + slot * 128 + (j + 2) * 32, va);
+                        else { tc_fence_before(); mbar_arrive(bar(B_D2E + slot)); }     // D2[slot] fully read
                         layer3<NET>(vb, w3x + (j + 1) * kW3Step, acc);
                     }
                 }
@@ -230,7 +255,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_fwd_tc_kernel(const FwdArgs A
                 if (row < end) {
                     if (NET == NET_ACTOR) {
                         float a0 = tanhf(out0), a1 = tanhf(out1);
-                        if (A.action_sd > 0.f) {                         // SkillshotLearner.py:238
+                        if (A.action_sd > 0.f) {
                             float zn[4];
                             normal4(A.seed, kTagActionNoise, (uint32_t)row, (uint32_t)(row >> 32), A.counter, zn);
                             a0 += A.action_sd * zn[0];
@@ -238,85 +263,82 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_fwd_tc_kernel(const FwdArgs A
                         }
                         reinterpret_cast<float2 *>(A.act_out)[row] = make_float2(a0, a1);
                     } else {
-                        const float q = out0;
-                        if (A.q_out) A.q_out[row] = q;
-                        if (A.up_out)                                    // output_gradients = -dq/da, SkillshotLearner.py:410
-                            reinterpret_cast<float2 *>(A.up_out)[row] =
-                                make_float2(-out1, -out2);
-                        if (A.y_out)
-                            A.y_out[row] = A.reward[row] + A.gamma * ((A.done && A.done[row]) ? 0.f : 1.f) * q;
+                        if (A.q_out) A.q_out[row] = out0;
+                        if (A.up_out) reinterpret_cast<float2 *>(A.up_out)[row] = make_float2(-out1, -out2);
+                        if (A.y_out) A.y_out[row] = A.reward[row] + A.gamma * ((A.done && A.done[row]) ? 0.f : 1.f) * out0;
                     }
                 }
-                ph ^= 1;
             }
-            tc_fence_before();
         } else {
-            // ================= the MMA-issuing warp =================
-            // per slot: tiles left in this segment and which barrier the slot waits on next (0: inputs, 1: hidden 1)
-            int64_t left0 = ntiles > 0 ? (ntiles + 1) / 2 : 0, left1 = ntiles > 1 ? ntiles / 2 : 0;
-            int stage0 = 0, stage1 = 0;
-            constexpr uint32_t kIdesc1 = umma_idesc(TM, H1), kIdesc2 = umma_idesc(TM, H2);
-            auto service = [&](const int s, int64_t &left, int &stage, uint32_t &phase) {
-                if (left <= 0) return;
-                const uint32_t a_addr = sbase + SM_A + (uint32_t)s * X2_BYTES;
-                const uint32_t d_addr = tmem + (uint32_t)s * 256;
-                if (stage == 0) {
-                    if (!mbar_test(bar(s, BAR_IN), phase)) return;
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint64_t ad = desc_kmajor(a_addr, CHUNK_A), bd = desc_kmajor(sbase + SM_B1, CHUNK_B1);
-#pragma unroll
-                        for (int ks = 0; ks < K1 / 16; ++ks)
-                            umma_bf16(d_addr, desc_advance(ad, 2 * CHUNK_A * ks), desc_advance(bd, 2 * CHUNK_B1 * ks),
-                                      kIdesc1, ks > 0);
-                        umma_commit(bar(s, BAR_D1));
-                    }
-                    __syncwarp();
-                    stage = 1;
-                } else {
-                    if (!mbar_test(bar(s, BAR_H1), phase)) return;
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint64_t ad = desc_kmajor(a_addr, CHUNK_A), bd = desc_kmajor(sbase + SM_B2, CHUNK_B2);
-#pragma unroll
-                        for (int ks = 0; ks < K2 / 16; ++ks)
-                            umma_bf16(d_addr, desc_advance(ad, 2 * CHUNK_A * ks), desc_advance(bd, 2 * CHUNK_B2 * ks),
-                                      kIdesc2, ks > 0);
-                        umma_commit(bar(s, BAR_D2));
-                    }
-                    __syncwarp();
-                    stage = 0;
-                    left -= 1;
-                    phase ^= 1;
+            // ============ the MMA-issuing warp ============
+            // Measured on B200 (tools/umma_probe.cu): ~54 cycles to issue one tcgen05.mma, ~50 per commit and ~170 for a
+            // wait even on a completed barrier, against 68 cycles of execution for a 128 x 128 x 16 MMA: per tile this
+            // warp can afford two waits and two commits, not more.  (Slotting the next tile's hand-off into the middle
+            // of the layer-2 chain was tried and gained nothing: with the epilogue warps reading tensor memory at the
+            // same time the MMAs themselves retire at ~95 cycles apiece and the issue stream is never far ahead.)
+            constexpr uint32_t kI1 = umma_idesc_f16(TM, H1), kI2 = umma_idesc(TM, H2);
+            const uint64_t a1d = desc_kmajor(sbase + SMP_A1, CHUNK_A), x0d = desc_kmajor(sbase + SMP_X0, CHUNK_A);
+            const uint64_t b1d = desc_kmajor(sbase + SMP_B1, CHUNK_B1), b2d = desc_kmajor(sbase + SMP_B2, CHUNK_B2);
+            const uint32_t tc0 = __shfl_sync(0xffffffffu, tcount, 0);     // warp-uniform for the descriptor arithmetic
+            auto mma1 = [&](uint32_t tc) {                        // D1 = X0(tile tc) . W1'   (fp16, one K step)
+                if (lane == 0) {
+                    umma_bf16(tmem, desc_advance(x0d, (tc & 1) * X0_BYTES), b1d, kI1, 0);
+                    umma_commit(bar(B_Z));
                 }
             };
-            while (left0 > 0 || left1 > 0) {
-                service(0, left0, stage0, mma_phase0);
-                service(1, left1, stage1, mma_phase1);
+            mbar_wait(bar(B_X), xph); xph ^= 1;
+            tc_fence_after();
+            mma1(tc0);
+            for (int64_t i = 0; i < ntiles; ++i) {
+                const uint32_t tc = __shfl_sync(0xffffffffu, tc0 + (uint32_t)i, 0), slot = tc & 1;
+                trace(2, 100 + (int)i);
+                mbar_wait(bar(B_X), xph); xph ^= 1;               // A1[tile] full, D1 free, X0(tile + 1) staged
+                tc_fence_after();
+                trace(2, 200 + (int)i);
+                if (i + 1 < ntiles) mma1(tc + 1);
+                trace(2, 300 + (int)i);
+                mbar_wait(bar(B_D2E + slot), ((tc >> 1) & 1) ^ 1);    // the output warps have drained D2[slot]
+                tc_fence_after();
+                trace(2, 400 + (int)i);
+                if (lane == 0) {
+                    const uint64_t ad = desc_advance(a1d, slot * X2_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < K2 / 16; ++ks)
+                        umma_bf16(tmem + 256 + slot * 128, desc_advance(ad, 2 * CHUNK_A * ks), desc_advance(b2d, 2 * CHUNK_B2 * ks),
+                                  kI2, ks > 0);
+                    umma_commit(bar(B_Y + slot));
+                }
+                trace(2, 500 + (int)i);
             }
         }
+        tcount += (uint32_t)ntiles;
         u = seg_end;
-        __syncthreads();                   // every MMA of the segment has retired (the epilogue waited on D2)
+        tc_fence_before();
+        __syncthreads();                   // pipeline drained: the output warps have read the last D2
+        tc_fence_after();
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == MMA_WARP) {
+    if (warp == MMA_W) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
 }
+
+}  // namespace pipe
 
 template <int NET>
 int launch_fwd(const FwdArgs &A, void *stream) {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return SS_ERR_CUDA;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SS_ERR_CUDA;
-    if (cudaFuncSetAttribute(mlp_fwd_tc_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL) != cudaSuccess)
-        return SS_ERR_CUDA;
     const int64_t units = ((A.n + A.group - 1) / A.group) * ((A.group + TM - 1) / TM);
     const int grid = (int)(units < sms ? units : sms);
-    mlp_fwd_tc_kernel<NET><<<grid, NTHREADS, SM_TOTAL, (cudaStream_t)stream>>>(A);
+    if (cudaFuncSetAttribute(pipe::mlp_fwd_pipe_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)pipe::SMP_TOTAL) != cudaSuccess)
+        return SS_ERR_CUDA;
+    pipe::mlp_fwd_pipe_kernel<NET><<<grid, pipe::NTH, pipe::SMP_TOTAL, (cudaStream_t)stream>>>(A);
     return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
 }
 
@@ -333,6 +355,14 @@ extern "C" int ss_actor_forward_tc(const float *actor_params, const float *obs, 
     FwdArgs A{};
     A.params = actor_params; A.obs = obs; A.n = n; A.group = noisy ? noise_group : n;
     A.act_out = act_out; A.param_sd = param_noise_sd; A.action_sd = action_noise_sd; A.seed = seed; A.counter = counter;
+    return launch_fwd<NET_ACTOR>(A, stream);
+}
+
+// development: the actor forward with an event trace of CTA 0 (3 roles x 256 events x {clock, code}); tools/tc_trace.py
+extern "C" int ss_debug_actor_forward_trace(const float *actor_params, const float *obs, float *act_out, int64_t n,
+                                            long long *trace, void *stream) {
+    FwdArgs A{};
+    A.params = actor_params; A.obs = obs; A.n = n; A.group = n; A.act_out = act_out; A.trace = trace;
     return launch_fwd<NET_ACTOR>(A, stream);
 }
 

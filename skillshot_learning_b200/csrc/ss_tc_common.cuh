@@ -15,6 +15,7 @@
 // (MN-major) alike.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,6 +32,9 @@ constexpr int TM = 128;                  // rows per tile = UMMA M = tensor-memo
 constexpr int DS = SS_DIM_STATE, DA = SS_DIM_ACTION, H1 = SS_HIDDEN1, H2 = SS_HIDDEN2;
 // layer-1 K: [s hi 12 | 1 1 0 0 | s lo 12 | 0 x4]; rows 12, 13 of B1 = b1 hi, lo
 constexpr int K1 = 32;
+// the forward kernels run layer 1 in fp16 instead (11-bit significands on both operands: finer than a pixel on
+// the positions and finer than bf16 on the weights), K = 16: [s 12 | 1 1 0 0]; rows 12, 13 of B1 = b1 hi, lo (fp16)
+constexpr int K1F = 16;
 // layer-2 K: [h1 256 | tail 8 | 0 x8]; tail = actor {1 1 0..}            B2 rows 256.. = {b2 hi, b2 lo}
 //                                      critic {a0h a1h a0l a1l 1 1 0 0}  B2 rows 256.. = {W2[256] W2[257] W2[256] W2[257] b2 hi, b2 lo}
 constexpr int K2 = H1 + 16;
@@ -82,8 +86,14 @@ __device__ __forceinline__ bool mbar_probe(uint32_t bar, uint32_t parity) {     
         : "memory");
     return ok != 0;
 }
+// Waits for the phase with the given parity.  try_wait parks the thread in hardware for a bounded
+// time per call; a barrier that never completes is a protocol bug, so give up after ~10^6 attempts
+// and trap instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_test(bar, parity)) {}
+    uint32_t spins = 0;
+    while (!mbar_test(bar, parity)) {
+        if (++spins > (1u << 22)) __trap();
+    }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -117,6 +127,10 @@ __device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { r
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn = 0, int b_mn = 0) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// the same with A = B = fp16 (format code 0), both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -168,6 +182,15 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
 }
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));         // first source -> upper half
+    return d;
+}
+__device__ __forceinline__ uint32_t hi_lo_f16(float w) {                       // fp16 {hi, lo} with hi + lo = w to 2^-22
+    const float hi = __half2float(__float2half_rn(w));
+    return pack_f16(hi, w - hi);
+}
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ uint32_t hi_lo_bf16(float w) {                     // {hi, lo} with hi + lo = w to 2^-17
     const float hi = bf16_round(w);
@@ -214,6 +237,12 @@ __device__ __forceinline__ void store_obs_row(const float4 (&xin)[3], uint8_t *r
     *reinterpret_cast<uint4 *>(row + 2 * CHUNK_A) =
         make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
     *reinterpret_cast<uint4 *>(row + 3 * CHUNK_A) = make_uint4(pack_bf16(lo[8], lo[9]), pack_bf16(lo[10], lo[11]), 0u, 0u);
+}
+// observation row -> the two fp16 layer-1 chunks [x 0..7][x 8..11, 1, 1, 0, 0] of the forward kernels (K = 16)
+__device__ __forceinline__ void store_obs_row_f16(const float4 (&x)[3], uint8_t *row) {
+    *reinterpret_cast<uint4 *>(row) =
+        make_uint4(pack_f16(x[0].x, x[0].y), pack_f16(x[0].z, x[0].w), pack_f16(x[1].x, x[1].y), pack_f16(x[1].z, x[1].w));
+    *reinterpret_cast<uint4 *>(row + CHUNK_A) = make_uint4(pack_f16(x[2].x, x[2].y), pack_f16(x[2].z, x[2].w), 0x3C003C00u, 0u);
 }
 // the constant / action chunk of the layer-2 tile (chunk 32): actor {1 1 0..}, critic {a0h a1h a0l a1l 1 1 0 0}
 __device__ __forceinline__ uint4 tail_chunk_actor() { return make_uint4(ONES, 0u, 0u, 0u); }
@@ -264,7 +293,7 @@ struct Stager {
 // Weights are [k][n] with n contiguous in HBM and [k/8][n][k%8] bf16 in shared memory.  A task takes
 // one K chunk (8 rows) of four consecutive columns: 8 independent 16-byte loads (coalesced over the
 // lanes), 8 Philox quads if the weights are perturbed, then one 16-byte store per column.
-template <int NET, int NTHREADS>
+template <int NET, int NTHREADS, bool L1F16 = false>
 __device__ __forceinline__ void stage_weights(const Stager &S) {
     constexpr int T_W2 = (H1 / 8) * (H2 / 4), T_W1 = 2 * (H1 / 4), T_TAIL = H2 / 4;
     for (int t = threadIdx.x; t < T_W2 + T_W1 + T_TAIL + 1; t += NTHREADS) {
@@ -295,7 +324,8 @@ __device__ __forceinline__ void stage_weights(const Stager &S) {
             if (kc == 1) {
                 float4 b = S.load(P_B1 + n);
                 S.perturb(P_B1 + n, b);
-                e45[0] = hi_lo_bf16(b.x); e45[1] = hi_lo_bf16(b.y); e45[2] = hi_lo_bf16(b.z); e45[3] = hi_lo_bf16(b.w);
+                if (L1F16) { e45[0] = hi_lo_f16(b.x); e45[1] = hi_lo_f16(b.y); e45[2] = hi_lo_f16(b.z); e45[3] = hi_lo_f16(b.w); }
+                else { e45[0] = hi_lo_bf16(b.x); e45[1] = hi_lo_bf16(b.y); e45[2] = hi_lo_bf16(b.z); e45[3] = hi_lo_bf16(b.w); }
             }
             uint8_t *dst = S.b1 + (uint32_t)(kc * H1 + n) * 16;
             const float c[4][8] = {{v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x},
@@ -304,10 +334,16 @@ __device__ __forceinline__ void stage_weights(const Stager &S) {
                                    {v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w}};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const uint32_t w01 = pack_bf16(c[j][0], c[j][1]), w23 = pack_bf16(c[j][2], c[j][3]);
-                const uint32_t w45 = pack_bf16(c[j][4], c[j][5]), w67 = pack_bf16(c[j][6], c[j][7]);
-                *reinterpret_cast<uint4 *>(dst + j * 16) = make_uint4(w01, w23, kc == 1 ? e45[j] : w45, w67);
-                *reinterpret_cast<uint4 *>(dst + j * 16 + 2 * CHUNK_B1) = make_uint4(w01, w23, kc == 1 ? 0u : w45, w67);
+                if (L1F16) {      // one fp16 image, K = 16
+                    const uint32_t w01 = pack_f16(c[j][0], c[j][1]), w23 = pack_f16(c[j][2], c[j][3]);
+                    const uint32_t w45 = pack_f16(c[j][4], c[j][5]), w67 = pack_f16(c[j][6], c[j][7]);
+                    *reinterpret_cast<uint4 *>(dst + j * 16) = make_uint4(w01, w23, kc == 1 ? e45[j] : w45, w67);
+                } else {          // bf16 image against the high and the low half of the observation, K = 32
+                    const uint32_t w01 = pack_bf16(c[j][0], c[j][1]), w23 = pack_bf16(c[j][2], c[j][3]);
+                    const uint32_t w45 = pack_bf16(c[j][4], c[j][5]), w67 = pack_bf16(c[j][6], c[j][7]);
+                    *reinterpret_cast<uint4 *>(dst + j * 16) = make_uint4(w01, w23, kc == 1 ? e45[j] : w45, w67);
+                    *reinterpret_cast<uint4 *>(dst + j * 16 + 2 * CHUNK_B1) = make_uint4(w01, w23, kc == 1 ? 0u : w45, w67);
+                }
             }
         } else if (t < T_W2 + T_W1 + T_TAIL) {
             // four hidden-2 units n..n+3: b2 (and the critic's two action rows of W2) -> chunk 32 of B2; layer 3

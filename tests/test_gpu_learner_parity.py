@@ -286,15 +286,17 @@ def _bf16(x):
     return u.astype(np.uint32).view(np.float32).reshape(np.shape(x))
 
 
+def _f16(x):
+    return np.asarray(x, np.float32).astype(np.float16).astype(np.float64)
+
+
 def actor_forward_bf16_model(theta, s):
-    """What the tensor-core kernel computes, restated in numpy: bf16 weights, observation as a
-    bf16 high + low pair, fp32 accumulation (float64 here), hidden layer 1 rounded to bf16,
-    layer 3 and tanh in fp32 (skillshot_learning_b200/csrc/ss_mlp_tc.cu header)."""
+    """What the tensor-core kernel computes, restated in numpy: layer 1 with fp16 observations and
+    fp16 weights, layer 2 with bf16 weights and hidden layer 1 rounded to bf16, fp32 accumulation
+    (float64 here), layer 3 and tanh in fp32 (skillshot_learning_b200/csrc/ss_mlp_tc.cu header)."""
     w1, b1, w2, b2, w3, b3 = lo.split(np.asarray(theta, np.float32), lo.ACTOR_SHAPES)
     s = np.asarray(s, np.float32)
-    hi = _bf16(s)
-    low = _bf16(s - hi)
-    z1 = (hi.astype(np.float64) + low.astype(np.float64)) @ _bf16(w1).astype(np.float64) + b1
+    z1 = _f16(s) @ _f16(w1) + b1
     h1 = _bf16(np.maximum(z1, 0).astype(np.float32)).astype(np.float64)
     h2 = np.maximum(h1 @ _bf16(w2).astype(np.float64) + b2, 0)
     return np.tanh(h2 @ w3.astype(np.float64) + b3).astype(np.float32)
