@@ -165,7 +165,7 @@ ACTOR_FLOP_PER_ROW = 72192     # 2 * (12*256 + 256*128 + 128*2)
 UPDATE_FLOP_PER_ROW = 638976   # full DDPG update with target actor + critic forward on s'
 
 
-def learner_legs(dev, rank, world, seed, peaks, ticks=64, updates=20):
+def learner_legs(dev, rank, world, seed, peaks, collective, ticks=64, updates=20):
     """Rollout, DDPG update and the actor-forward tensor roofline on this rank's GPU.
     Returns per-rank times in ms: (rollout per tick, update per step, actor forward per launch)."""
     import torch
@@ -176,7 +176,8 @@ def learner_legs(dev, rank, world, seed, peaks, ticks=64, updates=20):
     group = (2 * E // 148) // 128 * 128          # one parameter-noise draw per SM-sized slice of the batch
     tr = SelfPlayTrainer(E, device=dev, seed=seed, replay_capacity=2 * E * 4, batch_size=TRAIN_BATCH,
                          gamma=0.99, tau=0.005, param_noise_sd=0.5, noise_group=group, reward_mode="looking",
-                         tick_limit=TICK_LIMIT, process_group=True if world > 1 else None, precision="bf16")
+                         tick_limit=TICK_LIMIT, process_group=True if world > 1 else None, precision="bf16",
+                         collective=collective)
 
     def timed(fn, iters, warm=3):
         for _ in range(warm):
@@ -203,7 +204,7 @@ def learner_legs(dev, rank, world, seed, peaks, ticks=64, updates=20):
     return t_roll, t_upd, t_fwd, t_upd32
 
 
-def learner_report(t_roll, t_upd, t_fwd, t_upd32, world, peaks, peak_kind):
+def learner_report(t_roll, t_upd, t_fwd, t_upd32, world, peaks, peak_kind, collective="nccl"):
     rows = 2 * ROLLOUT_ENVS
     tf = ACTOR_FLOP_PER_ROW * rows / (t_fwd * 1e-3) / 1e12
     return {
@@ -212,8 +213,9 @@ def learner_report(t_roll, t_upd, t_fwd, t_upd32, world, peaks, peak_kind):
                     "env_steps_per_sec": world * ROLLOUT_ENVS / (t_roll * 1e-3),
                     "samples_per_sec": world * rows / (t_roll * 1e-3), "ms_per_tick": t_roll},
         "train": {"workload": "DDPG update, %d rows per GPU: replay sample, TD targets (gamma 0.99), critic step "
-                              "(dropout 0.2), actor step, Adam + soft update (tau 0.005), two flat-gradient all-reduces"
-                              % TRAIN_BATCH,
+                              "(dropout 0.2), actor step, Adam + soft update (tau 0.005), two flat-gradient exchanges (%s)"
+                              % (TRAIN_BATCH, "single GPU: none" if world == 1 else
+                                 ("fused NVLink peer-memory reduce-push + Adam" if collective == "peer" else "NCCL all-reduce")),
                   "samples_per_sec": world * TRAIN_BATCH / (t_upd * 1e-3), "ms_per_update": t_upd,
                   "dtype": "bf16 operands, f32 accumulate (tcgen05); Adam and parameters f32",
                   "algorithmic_tflops": world * TRAIN_BATCH * UPDATE_FLOP_PER_ROW / (t_upd * 1e-3) / 1e12,
@@ -327,7 +329,7 @@ def run_gpu_arm(args):
     if not args.no_learner:
         del actions
         torch.cuda.empty_cache()
-        lt = learner_legs(dev, rank, world, 4321 + rank, measured_peaks()[0])
+        lt = learner_legs(dev, rank, world, 4321 + rank, measured_peaks()[0], args.collective)
 
     if world > 1:
         t = torch.tensor([ms, e2e_s, *lt], dtype=torch.float64, device=dev)
@@ -359,7 +361,7 @@ def run_gpu_arm(args):
             "clocks": clocks,
         }
         if not args.no_learner:
-            line["learner"] = learner_report(*lt, world, peaks, peak_kind)
+            line["learner"] = learner_report(*lt, world, peaks, peak_kind, args.collective)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
@@ -379,6 +381,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--no-learner", action="store_true", help="skip the rollout / update / actor-forward legs")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="gradient exchange of the update at N > 1: fused NVLink peer-memory kernels, or an NCCL all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

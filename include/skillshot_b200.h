@@ -60,6 +60,7 @@ extern "C" {
 
 /* status bits OR-ed into *status by the kernels */
 #define SS_STATUS_NAN 1       /* where the reference raises ValueError: int(round(nan)), Player.py:63 */
+#define SS_STATUS_PEER_TIMEOUT 2   /* ss_peer_adam_tf gave up waiting for a peer's gradient */
 
 /* ops of ss_env_apply: the single-object methods of the reference */
 #define SS_OP_MOVE_DIRECTION_FLOAT 0  /* Player.move_direction_float(value), Player.py:57-68 */
@@ -248,6 +249,39 @@ int ss_actor_grad(const float *actor_params, const float *critic_params, const f
 int ss_adam_tf(float *params, const float *grads, float *m, float *v, float *target_params, int64_t n,
                int64_t step, float lr, float beta1, float beta2, float eps, float tau, float grad_scale,
                void *stream);
+
+/* ---- multi-GPU: the gradient all-reduce fused with its neighbours over NVLink peer memory ----
+ * One exchange allocation per rank = flags[2][world] | inbox[2][world][capacity floats], made by
+ * ss_peer_alloc and shared between the processes of one node through CUDA IPC (export on the owner,
+ * import on every other rank; these five helpers are the library's only allocating calls).
+ *
+ * A sharded update step (ranks hold equal shards of the batch):
+ *   1. ss_critic_grad / ss_actor_grad / *_tc with grad_out == NULL: only the per-CTA gradient
+ *      slices are left in `workspace`; the call returns their number (> 0) instead of 0;
+ *   2. ss_peer_reduce_push: sums the slices in a fixed order and stores the result into slot `rank`
+ *      of EVERY rank's inbox (peer stores), then raises this rank's flag for `epoch` everywhere;
+ *      aux_out[0] = sum of the slices' extra slot (the shard's squared error / Q sum), or NULL;
+ *   3. ss_peer_adam_tf: waits for all `world` flags of `epoch`, sums the inbox slots in rank order
+ *      (bit-identical on every rank), then does exactly what ss_adam_tf does; grad_out (may be NULL)
+ *      receives the summed gradient.  A peer that never arrives sets SS_STATUS_PEER_TIMEOUT.
+ * `epoch` starts at 1 and increases by 1 per exchange, identically on all ranks; `done_counter` is a
+ * zero-initialised uint32 on the device.  peer_bases_host[world] are the exchange allocations as
+ * mapped in this process (own allocation at index rank). */
+#define SS_PEER_MAX_WORLD 8
+#define SS_PEER_HANDLE_BYTES 64
+int64_t ss_peer_bytes(int world, int64_t capacity);
+int ss_peer_alloc(int world, int64_t capacity, void **base_out);
+int ss_peer_free(void *base);
+int ss_peer_export(void *base, void *handle_out_host);          /* 64-byte CUDA IPC handle */
+int ss_peer_import(const void *handle_host, void **base_out);
+int ss_peer_close(void *imported_base);
+int ss_peer_reduce_push(const void *workspace, int parts, int n_params, float *aux_out,
+                        void *const *peer_bases_host, int world, int rank, int64_t capacity,
+                        uint32_t epoch, uint32_t *done_counter, void *stream);
+int ss_peer_adam_tf(void *own_base, int world, int64_t capacity, uint32_t epoch, float *params, float *m,
+                    float *v, float *target_params, float *grad_out, int64_t n, int64_t step, float lr,
+                    float beta1, float beta2, float eps, float tau, float grad_scale, uint32_t *status,
+                    void *stream);
 
 /* Device-resident replay ring, structure of arrays with `capacity` rows:
  * obs [cap][12], act [cap][2], reward [cap], next_obs [cap][12], done [cap] u8.

@@ -20,6 +20,7 @@ REWARD_NONE, REWARD_LOOKING, REWARD_TERMINAL, REWARD_SIMPLE = 0, 1, 2, 3
 RESET_FIXED, RESET_RANDOM, RESET_GIVEN = 0, 1, 2
 STEP_OBS_EVERY_TICK = 1
 STATUS_NAN = 1
+STATUS_PEER_TIMEOUT = 2
 (OP_MOVE_DIRECTION_FLOAT, OP_MOVE_LOOK_FLOAT, OP_SHOOT, OP_MOVE_FORWARDS, OP_MOVE_BACKWARDS,
  OP_LOOK_LEFT, OP_LOOK_RIGHT, OP_GAME_TICK) = range(8)
 
@@ -29,6 +30,7 @@ _f32 = ctypes.c_float
 # learner constants of include/skillshot_b200.h
 DIM_STATE, DIM_ACTION, HIDDEN1, HIDDEN2 = 12, 2, 256, 128
 ACTOR_PARAMS, CRITIC_PARAMS = 36482, 36609
+PEER_MAX_WORLD, PEER_HANDLE_BYTES = 8, 64
 
 # name -> (restype, argtypes); every symbol the header declares
 SIGNATURES = {
@@ -48,6 +50,15 @@ SIGNATURES = {
     "ss_critic_grad_tc": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _u64, _u64, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
     "ss_actor_grad_tc": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "ss_ddpg_targets_tc": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _i64, _vp]),
+    "ss_peer_bytes": (_i64, [_i32, _i64]),
+    "ss_peer_alloc": (_i32, [_i32, _i64, _vp]),
+    "ss_peer_free": (_i32, [_vp]),
+    "ss_peer_export": (_i32, [_vp, _vp]),
+    "ss_peer_import": (_i32, [_vp, _vp]),
+    "ss_peer_close": (_i32, [_vp]),
+    "ss_peer_reduce_push": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _i64, ctypes.c_uint32, _vp, _vp]),
+    "ss_peer_adam_tf": (_i32, [_vp, _i32, _i64, ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
+                                _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
     "ss_param_noise": (_i32, [_vp, _vp, _i64, _f32, _u64, _u64, _u64, _vp]),
     "ss_critic_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "ss_ddpg_targets": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp]),

@@ -28,6 +28,7 @@ UNITS = {
     "ss_learner.cu": [],
     "ss_mlp_tc.cu": [],
     "ss_mlp_grad_tc.cu": [],
+    "ss_peer.cu": [],
 }
 
 

@@ -680,7 +680,7 @@ int ss_critic_grad(const float *critic_params, const float *obs, const float *ac
                    const uint8_t *dropout_keep, float dropout_rate, uint64_t seed, uint64_t counter,
                    int64_t n, int64_t n_global, int64_t row_offset, float *grad_out, float *sse_out,
                    void *workspace, int64_t workspace_bytes, void *stream) {
-    if (!critic_params || !obs || !act || !target || !grad_out || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
+    if (!critic_params || !obs || !act || !target || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
     if (dropout_rate < 0.f || dropout_rate >= 1.f) return SS_ERR_INVALID_ARG;
     if ((uintptr_t)critic_params & 15) return SS_ERR_INVALID_ARG;
     const int cap = (int)(workspace_bytes / ((int64_t)(C_N + 1) * 4));
@@ -692,13 +692,14 @@ int ss_critic_grad(const float *critic_params, const float *obs, const float *ac
                      n, n_global > 0 ? n_global : n, row_offset, (float *)workspace};
     cudaStream_t st = (cudaStream_t)stream;
     critic_grad_kernel<<<grid, NT, kSmemCriticGrad, st>>>(A);
+    if (!grad_out) return check_launch() == SS_OK ? grid : SS_ERR_CUDA;      // slices only (ss_peer_reduce_push follows)
     reduce_kernel<<<(C_N + 1 + 63) / 64, dim3(64, 4), 0, st>>>((const float *)workspace, grid, C_N, grad_out, sse_out);
     return check_launch();
 }
 
 int ss_actor_grad(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
                   float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, void *stream) {
-    if (!actor_params || !critic_params || !obs || !grad_out || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
+    if (!actor_params || !critic_params || !obs || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
     if (((uintptr_t)actor_params | (uintptr_t)critic_params) & 15) return SS_ERR_INVALID_ARG;
     const int cap = (int)(workspace_bytes / ((int64_t)(A_N + 1) * 4));
     if (cap < 1) return SS_ERR_INVALID_ARG;
@@ -708,6 +709,7 @@ int ss_actor_grad(const float *actor_params, const float *critic_params, const f
     ActorGradArgs A{actor_params, critic_params, obs, n, (float *)workspace};
     cudaStream_t st = (cudaStream_t)stream;
     actor_grad_kernel<<<grid, NT, kSmemActorGrad, st>>>(A);
+    if (!grad_out) return check_launch() == SS_OK ? grid : SS_ERR_CUDA;
     reduce_kernel<<<(A_N + 1 + 63) / 64, dim3(64, 4), 0, st>>>((const float *)workspace, grid, A_N, grad_out, q_sum_out);
     return check_launch();
 }

@@ -471,6 +471,7 @@ int launch_grad(const GradArgs &A0, float *grad_out, float *aux_out, int64_t wor
     const int grid = (int)(tiles < cap ? tiles : cap);
     cudaStream_t st = (cudaStream_t)stream;
     mlp_grad_tc_kernel<NET><<<grid, NTHREADS, SM_TOTAL, st>>>(A0);
+    if (!grad_out) return cudaGetLastError() == cudaSuccess ? grid : SS_ERR_CUDA;   // slices only (ss_peer_reduce_push follows)
     reduce_parts_kernel<<<(PN + 1 + 63) / 64, dim3(64, 4), 0, st>>>(A0.work, grid, PN, grad_out, aux_out);
     return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
 }
@@ -483,7 +484,7 @@ int ss_critic_grad_tc(const float *critic_params, const float *obs, const float 
                       const uint8_t *dropout_keep, float dropout_rate, uint64_t seed, uint64_t counter,
                       int64_t n, int64_t n_global, int64_t row_offset, float *grad_out, float *sse_out,
                       void *workspace, int64_t workspace_bytes, void *stream) {
-    if (!critic_params || !obs || !act || !target || !grad_out || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
+    if (!critic_params || !obs || !act || !target || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
     if (dropout_rate < 0.f || dropout_rate >= 1.f) return SS_ERR_INVALID_ARG;
     if (((uintptr_t)critic_params | (uintptr_t)obs | (uintptr_t)dropout_keep) & 15 || ((uintptr_t)act & 7))
         return SS_ERR_INVALID_ARG;
@@ -496,7 +497,7 @@ int ss_critic_grad_tc(const float *critic_params, const float *obs, const float 
 
 int ss_actor_grad_tc(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
                      float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, void *stream) {
-    if (!actor_params || !critic_params || !obs || !grad_out || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
+    if (!actor_params || !critic_params || !obs || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
     if (((uintptr_t)actor_params | (uintptr_t)critic_params | (uintptr_t)obs | (uintptr_t)workspace) & 15)
         return SS_ERR_INVALID_ARG;
     // scratch behind the gradient slices: the actor's actions, -dQ/da and Q per row
@@ -514,9 +515,9 @@ int ss_actor_grad_tc(const float *actor_params, const float *critic_params, cons
     GradArgs A{};
     A.params = actor_params; A.obs = obs; A.up = up; A.n = n; A.n_global = n; A.work = (float *)workspace;
     rc = launch_grad<NET_ACTOR>(A, grad_out, nullptr, slice_bytes / 16 * 16, stream);
-    if (rc != SS_OK) return rc;
+    if (rc < 0) return rc;
     if (q_sum_out) sum_f32_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(q, n, q_sum_out);
-    return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? rc : SS_ERR_CUDA;
 }
 
 int ss_ddpg_targets_tc(const float *target_actor_params, const float *target_critic_params, const float *reward,

@@ -16,6 +16,7 @@ include/skillshot_b200.h); there is no CPU path.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Optional
 
@@ -78,6 +79,70 @@ def allreduce_sum(t: torch.Tensor, group=None):
     return t
 
 
+class PeerExchange:
+    """The gradient exchange of a sharded update over NVLink peer memory (csrc/ss_peer.cu): every rank
+    owns an inbox {flags | 2 x world x capacity floats} shared with the other processes of the node
+    through CUDA IPC; a rank's gradient reduction kernel stores its result into every inbox, and each
+    rank's Adam kernel sums its inbox in rank order.  Replaces the NCCL all-reduce call between the
+    gradient kernel and Adam (one node, up to 8 ranks)."""
+
+    def __init__(self, group, device, capacity: int = max(A_N, C_N)):
+        import torch.distributed as dist
+        g = None if group is True else group
+        self.group, self.device, self.capacity = g, torch.device(device), int(capacity)
+        self.world, self.rank = dist.get_world_size(g), dist.get_rank(g)
+        if self.world > _lib.PEER_MAX_WORLD:
+            raise ValueError("peer exchange supports up to %d ranks of one node" % _lib.PEER_MAX_WORLD)
+        self._own = ctypes.c_void_p()
+        self._imported = []
+        with torch.cuda.device(self.device):
+            check(lib.ss_peer_alloc(self.world, self.capacity, ctypes.byref(self._own)), "ss_peer_alloc")
+            handle = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES)()
+            check(lib.ss_peer_export(self._own, handle), "ss_peer_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=g)
+            self.bases = (ctypes.c_void_p * self.world)()
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.bases[r] = self._own.value
+                else:
+                    buf = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES).from_buffer_copy(h)
+                    ptr = ctypes.c_void_p()
+                    check(lib.ss_peer_import(buf, ctypes.byref(ptr)), "ss_peer_import")
+                    self.bases[r] = ptr.value
+                    self._imported.append(ptr)
+        self.done_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.epoch = 0
+        dist.barrier(g)
+
+    def reduce_push(self, workspace: torch.Tensor, parts: int, n_params: int, aux: Optional[torch.Tensor]):
+        """Slices in `workspace` -> this rank's slot of every inbox; starts a new epoch."""
+        self.epoch += 1
+        with torch.cuda.device(self.device):
+            check(lib.ss_peer_reduce_push(workspace.data_ptr(), int(parts), int(n_params), _ptr(aux), self.bases, self.world,
+                                          self.rank, self.capacity, self.epoch, self.done_counter.data_ptr(),
+                                          _stream(self.device)), "ss_peer_reduce_push")
+
+    def check_status(self):
+        if int(self.status.item()) & _lib.STATUS_PEER_TIMEOUT:
+            self.status.zero_()
+            raise RuntimeError("peer exchange: a rank's gradient never arrived")
+
+    def close(self):
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for ptr in self._imported:
+                lib.ss_peer_close(ptr)
+            self._imported = []
+            if self._own:
+                import torch.distributed as dist
+                if dist.is_initialized():
+                    dist.barrier(self.group)          # nobody may still be storing into this inbox
+                lib.ss_peer_free(self._own)
+                self._own = ctypes.c_void_p()
+
+
 class ActorCritic:
     """Actor and critic parameters, optimiser state and target copies on one GPU.
 
@@ -90,7 +155,7 @@ class ActorCritic:
 
     def __init__(self, device="cuda", seed: int = 0, lr_actor: float = 1e-3, lr_critic: float = 1e-3,
                  gamma: float = 0.0, tau: float = 1.0, dropout: float = 0.2, process_group=None,
-                 update_precision: str = "f32"):
+                 update_precision: str = "f32", collective: str = "nccl"):
         if not torch.cuda.is_available():
             raise RuntimeError("skillshot_learning_b200 needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device)
@@ -104,6 +169,10 @@ class ActorCritic:
         if update_precision not in ("f32", "bf16"):
             raise ValueError("update_precision must be 'f32' (exact path) or 'bf16' (tensor cores)")
         self.update_precision = update_precision     # gradient / TD-target kernels: float32 CUDA cores or tcgen05
+        if collective not in ("nccl", "peer"):
+            raise ValueError("collective must be 'nccl' (torch.distributed all-reduce) or 'peer' (fused NVLink exchange)")
+        # the exchange step of a sharded update: an all-reduce call, or the fused peer-memory kernels
+        self.peer = PeerExchange(process_group, self.device) if (process_group is not None and collective == "peer") else None
         dev = self.device
         # one allocation: [actor | pad | critic] so both vectors are 16-byte aligned
         self._a_off, self._c_off = 0, (A_N + 3) // 4 * 4
@@ -259,8 +328,9 @@ class ActorCritic:
     def _allreduce(self, t):
         allreduce_sum(t, self.group)
 
-    def critic_grad(self, obs, act, y, keep=None, n_global: int = 0, row_offset: int = 0):
-        """grads[critic] <- d/dphi mean (q - y)^2 of this (shard of a) batch; returns the gradient view."""
+    def critic_grad(self, obs, act, y, keep=None, n_global: int = 0, row_offset: int = 0, slices_only: bool = False):
+        """grads[critic] <- d/dphi mean (q - y)^2 of this (shard of a) batch; returns the gradient view.
+        slices_only: leave the per-CTA slices in the workspace and return their number (peer exchange)."""
         obs, act = _f32(obs, self.device).reshape(-1, 12), _f32(act, self.device).reshape(-1, 2)
         y = _f32(y, self.device).reshape(-1)
         n = obs.shape[0]
@@ -270,27 +340,34 @@ class ActorCritic:
         fn = lib.ss_critic_grad_tc if self.update_precision == "bf16" else lib.ss_critic_grad
         ws = self._workspace_for(n)
         with torch.cuda.device(self.device):
-            check(fn(self.critic.data_ptr(), obs.data_ptr(), act.data_ptr(), y.data_ptr(), _ptr(keep),
-                     self.dropout, self.seed, self.counter, n, int(n_global), int(row_offset),
-                     g.data_ptr(), self.stats[0:1].data_ptr(), ws.data_ptr(), ws.numel(), _stream(self.device)),
-                  "ss_critic_grad")
+            rc = fn(self.critic.data_ptr(), obs.data_ptr(), act.data_ptr(), y.data_ptr(), _ptr(keep),
+                    self.dropout, self.seed, self.counter, n, int(n_global), int(row_offset),
+                    None if slices_only else g.data_ptr(), self.stats[0:1].data_ptr(), ws.data_ptr(), ws.numel(),
+                    _stream(self.device))
         self.counter += 1
+        if slices_only and rc > 0:
+            return rc
+        check(rc, "ss_critic_grad")
         return g
 
-    def actor_grad(self, obs):
+    def actor_grad(self, obs, slices_only: bool = False):
         """grads[actor] <- -sum_batch dQ/da da/dtheta (model_actor_fit_step, SkillshotLearner.py:395-410)."""
         obs = _f32(obs, self.device).reshape(-1, 12)
         g = self._slice(self.grads, "actor")
         fn = lib.ss_actor_grad_tc if self.update_precision == "bf16" else lib.ss_actor_grad
         ws = self._workspace_for(obs.shape[0])
         with torch.cuda.device(self.device):
-            check(fn(self.actor.data_ptr(), self.critic.data_ptr(), obs.data_ptr(), obs.shape[0],
-                     g.data_ptr(), self.stats[1:2].data_ptr(), ws.data_ptr(), ws.numel(), _stream(self.device)),
-                  "ss_actor_grad")
+            rc = fn(self.actor.data_ptr(), self.critic.data_ptr(), obs.data_ptr(), obs.shape[0],
+                    None if slices_only else g.data_ptr(), self.stats[1:2].data_ptr(), ws.data_ptr(), ws.numel(),
+                    _stream(self.device))
+        if slices_only and rc > 0:
+            return rc
+        check(rc, "ss_actor_grad")
         return g
 
-    def apply_adam(self, which: str, grad_scale: float = 1.0):
-        """tf.keras Adam.apply_gradients on one network (+ soft target update with self.tau)."""
+    def apply_adam(self, which: str, grad_scale: float = 1.0, from_peers: bool = False):
+        """tf.keras Adam.apply_gradients on one network (+ soft target update with self.tau).
+        from_peers: the gradient is the rank-ordered sum of this rank's peer inbox (fused exchange)."""
         n = A_N if which == "actor" else C_N
         if which == "actor":
             self.step_actor += 1
@@ -298,6 +375,16 @@ class ActorCritic:
         else:
             self.step_critic += 1
             step, lr = self.step_critic, self.lr_critic
+        if from_peers:
+            px = self.peer
+            with torch.cuda.device(self.device):
+                check(lib.ss_peer_adam_tf(px.bases[px.rank], px.world, px.capacity, px.epoch,
+                                          self._slice(self.params, which).data_ptr(), self._slice(self.adam_m, which).data_ptr(),
+                                          self._slice(self.adam_v, which).data_ptr(), self._slice(self.target, which).data_ptr(),
+                                          self._slice(self.grads, which).data_ptr(), n, step, lr, self.beta1, self.beta2,
+                                          self.eps, self.tau, float(grad_scale), px.status.data_ptr(), _stream(self.device)),
+                      "ss_peer_adam_tf")
+            return
         with torch.cuda.device(self.device):
             check(lib.ss_adam_tf(self._slice(self.params, which).data_ptr(), self._slice(self.grads, which).data_ptr(),
                                  self._slice(self.adam_m, which).data_ptr(), self._slice(self.adam_v, which).data_ptr(),
@@ -308,6 +395,11 @@ class ActorCritic:
         """One batch of model_critic.fit (SkillshotLearner.py:434): gradient of the batch-mean
         squared error, all-reduced when sharded, then Adam.  Returns the (device) sum of squared errors."""
         _, n_global, row_offset = shard_info(int(np.prod(y.shape)), self.group)
+        if self.peer is not None:      # slices -> every rank's inbox -> Adam on the rank-ordered sum
+            parts = self.critic_grad(obs, act, y, keep, n_global=n_global, row_offset=row_offset, slices_only=True)
+            self.peer.reduce_push(self.workspace, parts, C_N, self.stats[0:1])
+            self.apply_adam("critic", from_peers=True)
+            return self.stats[0]
         g = self.critic_grad(obs, act, y, keep, n_global=n_global, row_offset=row_offset)
         self._allreduce(g)
         self.apply_adam("critic")
@@ -315,6 +407,12 @@ class ActorCritic:
 
     def actor_step(self, obs):
         """model_actor_fit_step (SkillshotLearner.py:386-417).  Returns the (device) sum of q."""
+        if self.peer is not None:
+            parts = self.actor_grad(obs, slices_only=True)
+            # the tensor-core actor step sums Q with its own kernel; the float32 one through the slices' extra slot
+            self.peer.reduce_push(self.workspace, parts, A_N, None if self.update_precision == "bf16" else self.stats[1:2])
+            self.apply_adam("actor", from_peers=True)
+            return self.stats[1]
         g = self.actor_grad(obs)
         self._allreduce(g)
         self.apply_adam("actor")
@@ -630,12 +728,12 @@ class SelfPlayTrainer:
     def __init__(self, n_envs: int, device="cuda", seed: int = 0, replay_capacity: Optional[int] = None,
                  batch_size: int = 4096, gamma: float = 0.0, tau: float = 1.0, param_noise_sd: float = 0.5,
                  noise_group: int = 128, reward_mode: str = "looking", tick_limit: int = 2000,
-                 random_positions: bool = True, process_group=None, precision: str = "f32"):
+                 random_positions: bool = True, process_group=None, precision: str = "f32", collective: str = "nccl"):
         self.device = torch.device(device)
         self.envs = SkillshotEnvs(n_envs, device=device, random_positions=random_positions, seed=seed,
                                   reward_mode=reward_mode, tick_limit=tick_limit, auto_reset=True)
         self.networks = ActorCritic(device=device, seed=seed if process_group is None else 0, gamma=gamma, tau=tau,
-                                    process_group=process_group, update_precision=precision)
+                                    process_group=process_group, update_precision=precision, collective=collective)
         self.networks.seed = seed          # exploration / dropout streams differ per rank, weights do not
         self.replay = ReplayRing(replay_capacity or 2 * n_envs * 8, device=device, seed=seed)
         self.batch_size, self.param_noise_sd, self.noise_group = int(batch_size), float(param_noise_sd), int(noise_group)
