@@ -173,7 +173,7 @@ def learner_legs(dev, rank, world, seed, peaks, collective, ticks=64, updates=20
     from skillshot_learning_b200 import SelfPlayTrainer
 
     E = ROLLOUT_ENVS
-    group = (2 * E // 148) // 128 * 128          # one parameter-noise draw per SM-sized slice of the batch
+    group = -(-(2 * E // 128) // 148) * 128       # one parameter-noise draw per SM-sized slice of the batch (28 tiles)
     tr = SelfPlayTrainer(E, device=dev, seed=seed, replay_capacity=2 * E * 4, batch_size=TRAIN_BATCH,
                          gamma=0.99, tau=0.005, param_noise_sd=0.5, noise_group=group, reward_mode="looking",
                          tick_limit=TICK_LIMIT, process_group=True if world > 1 else None, precision="bf16",
@@ -193,7 +193,8 @@ def learner_legs(dev, rank, world, seed, peaks, collective, ticks=64, updates=20
         torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1) / iters
 
-    t_roll = timed(tr.rollout_tick, ticks)
+    chunk = 16                                     # ticks enqueued per library call (ss_selfplay_rollout)
+    t_roll = timed(lambda: tr.rollout(chunk), max(1, ticks // chunk)) / chunk
     t_upd = timed(tr.update, updates)                 # gradient GEMMs on tcgen05 (bf16 operands, f32 accumulate)
     tr.networks.update_precision = "f32"
     t_upd32 = timed(tr.update, max(3, updates // 4))  # the exact float32 kernels, same schedule
@@ -209,7 +210,8 @@ def learner_report(t_roll, t_upd, t_fwd, t_upd32, world, peaks, peak_kind, colle
     tf = ACTOR_FLOP_PER_ROW * rows / (t_fwd * 1e-3) / 1e12
     return {
         "rollout": {"workload": "262,144 envs per GPU: bf16 tensor-core actor forward on 524,288 observations with "
-                                "parameter noise (sd 0.5) + env step with observations and looking reward + replay push",
+                                "parameter noise (sd 0.5) + env step with observations and looking reward + replay push, "
+                                "16 ticks per ss_selfplay_rollout call",
                     "env_steps_per_sec": world * ROLLOUT_ENVS / (t_roll * 1e-3),
                     "samples_per_sec": world * rows / (t_roll * 1e-3), "ms_per_tick": t_roll},
         "train": {"workload": "DDPG update, %d rows per GPU: replay sample, TD targets (gamma 0.99), critic step "

@@ -250,6 +250,22 @@ int ss_adam_tf(float *params, const float *grads, float *m, float *v, float *tar
                int64_t step, float lr, float beta1, float beta2, float eps, float tau, float grad_scale,
                void *stream);
 
+/* n_ticks iterations of the rollout loop of model_train (SkillshotLearner.py:302-315) for n_envs games,
+ * enqueued back to back from one host call: actor forward on both players' observations (2 n_envs rows;
+ * tensor_cores != 0: ss_actor_forward_tc) -> ss_env_step with auto-reset -> ss_replay_push (skipped when
+ * ring_obs == NULL).  obs_a / obs_b are a double buffer [n_envs][2][12]: obs_a holds the current
+ * observation on entry, and after the call it is in obs_a if n_ticks is even, in obs_b otherwise.
+ * actions [n_envs][2][2], reward [n_envs][2], done / winner [n_envs] hold the last tick's values on return.
+ * Tick t uses Philox counters env_counter + t and noise_counter + t; ring rows advance by 2 n_envs per tick. */
+int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_params, float *obs_a, float *obs_b,
+                        float *actions, float *reward, uint8_t *done, uint8_t *winner,
+                        float *ring_obs, float *ring_act, float *ring_reward, float *ring_next_obs,
+                        uint8_t *ring_done, int64_t capacity, int64_t write_pos, int n_ticks,
+                        float param_noise_sd, int64_t noise_group, float action_noise_sd, int tensor_cores,
+                        int reward_mode, int64_t tick_limit, int reset_mode, uint64_t env_seed,
+                        uint64_t env_counter, uint64_t noise_seed, uint64_t noise_counter, const void *speeds,
+                        uint32_t *status, void *stream);
+
 /* ---- multi-GPU: the gradient all-reduce fused with its neighbours over NVLink peer memory ----
  * One exchange allocation per rank = flags[2][world] | inbox[2][world][capacity floats], made by
  * ss_peer_alloc and shared between the processes of one node through CUDA IPC (export on the owner,

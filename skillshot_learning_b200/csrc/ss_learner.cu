@@ -757,4 +757,38 @@ int ss_replay_sample(const float *ring_obs, const float *ring_act, const float *
     return check_launch();
 }
 
+int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_params, float *obs_a, float *obs_b,
+                        float *actions, float *reward, uint8_t *done, uint8_t *winner,
+                        float *ring_obs, float *ring_act, float *ring_reward, float *ring_next_obs, uint8_t *ring_done,
+                        int64_t capacity, int64_t write_pos, int n_ticks, float param_noise_sd, int64_t noise_group,
+                        float action_noise_sd, int tensor_cores, int reward_mode, int64_t tick_limit, int reset_mode,
+                        uint64_t env_seed, uint64_t env_counter, uint64_t noise_seed, uint64_t noise_counter,
+                        const void *speeds, uint32_t *status, void *stream) {
+    if (!env_state || !actor_params || !obs_a || !obs_b || !actions || !reward || !done || n_envs <= 0 || n_ticks <= 0)
+        return SS_ERR_INVALID_ARG;
+    const bool store = ring_obs != nullptr;
+    if (store && (2 * n_envs > capacity || write_pos < 0 || write_pos >= capacity)) return SS_ERR_INVALID_ARG;
+    for (int t = 0; t < n_ticks; ++t) {
+        float *cur = (t & 1) ? obs_b : obs_a, *next = (t & 1) ? obs_a : obs_b;
+        // both players of every env act from the same pre-tick observation (SkillshotLearner.py:304-310)
+        int rc = tensor_cores
+                     ? ss_actor_forward_tc(actor_params, cur, actions, 2 * n_envs, param_noise_sd, noise_group, action_noise_sd,
+                                           noise_seed, noise_counter + (uint64_t)t, stream)
+                     : ss_actor_forward(actor_params, cur, actions, 2 * n_envs, param_noise_sd, noise_group, action_noise_sd,
+                                        noise_seed, noise_counter + (uint64_t)t, stream);
+        if (rc != SS_OK) return rc;
+        // game_tick, reward of the post-tick state, next observation; finished games restart (SkillshotLearner.py:312-315)
+        rc = ss_env_step(env_state, n_envs, actions, next, reward, done, winner, 1, reward_mode, tick_limit, 1, reset_mode,
+                         env_seed, env_counter + (uint64_t)t, speeds, status, 0, stream);
+        if (rc != SS_OK) return rc;
+        if (store) {
+            rc = ss_replay_push(ring_obs, ring_act, ring_reward, ring_next_obs, ring_done, capacity,
+                                (write_pos + (int64_t)t * 2 * n_envs) % capacity, cur, actions, reward, next, done, 2,
+                                2 * n_envs, stream);
+            if (rc != SS_OK) return rc;
+        }
+    }
+    return SS_OK;
+}
+
 }  // extern "C"

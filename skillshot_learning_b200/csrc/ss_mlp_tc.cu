@@ -333,8 +333,12 @@ int launch_fwd(const FwdArgs &A, void *stream) {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return SS_ERR_CUDA;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SS_ERR_CUDA;
-    const int64_t units = ((A.n + A.group - 1) / A.group) * ((A.group + TM - 1) / TM);
-    const int grid = (int)(units < sms ? units : sms);
+    const int64_t n_groups = (A.n + A.group - 1) / A.group;
+    const int64_t units = n_groups * ((A.group + TM - 1) / TM);
+    int grid = (int)(units < sms ? units : sms);
+    // perturbed weights are staged once per noise group a CTA touches: when the groups fit the SMs, give every CTA
+    // exactly one group (the kernel's even split of units is then group-aligned) instead of letting ranges straddle two
+    if (A.group < A.n && n_groups <= sms) grid = (int)n_groups;
     if (cudaFuncSetAttribute(pipe::mlp_fwd_pipe_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)pipe::SMP_TOTAL) != cudaSuccess)
         return SS_ERR_CUDA;

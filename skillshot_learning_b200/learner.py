@@ -25,7 +25,7 @@ import torch
 
 from . import _lib
 from ._lib import check, lib
-from .game import FEATURE_KEYS, SkillshotEnvs, SkillshotGame
+from .game import FEATURE_KEYS, REWARD_MODES, SkillshotEnvs, SkillshotGame
 
 A_N, C_N = _lib.ACTOR_PARAMS, _lib.CRITIC_PARAMS
 ACTOR_SHAPES = [(12, 256), (256,), (256, 128), (128,), (128, 2), (2,)]       # Keras get_weights() order
@@ -756,6 +756,36 @@ class SelfPlayTrainer:
             self.replay.push(self.prev_obs, self.actions, out["reward"], self.obs, out["done"], done_div=2)
         self.ticks += 1
         return out
+
+    def rollout(self, n_ticks: int, store: bool = True):
+        """n_ticks rollout ticks enqueued by ONE library call (ss_selfplay_rollout): same kernels and Philox
+        counters as n_ticks calls of rollout_tick, without the per-tick host work."""
+        envs, net, rp = self.envs, self.networks, self.replay
+        if not envs.auto_reset:
+            raise ValueError("the batched rollout needs auto_reset envs")
+        if store and 2 * envs.n_envs > rp.capacity:
+            raise ValueError("replay ring smaller than one tick of transitions")
+        out = envs._buffers(1)
+        # the current observation is in self.obs; it becomes buffer A of the call
+        a, b = self.obs, self.prev_obs
+        with torch.cuda.device(self.device):
+            check(lib.ss_selfplay_rollout(
+                envs.state.data_ptr(), envs.n_envs, net.actor.data_ptr(), a.data_ptr(), b.data_ptr(), self.actions.data_ptr(),
+                out["reward"].data_ptr(), out["done"].data_ptr(), out["winner"].data_ptr(),
+                rp.obs.data_ptr() if store else None, rp.act.data_ptr(), rp.reward.data_ptr(), rp.next_obs.data_ptr(),
+                rp.done.data_ptr(), rp.capacity, rp.pos, int(n_ticks), self.param_noise_sd, self.noise_group, 0.0,
+                1 if self.precision == "bf16" else 0, REWARD_MODES[envs.reward_mode], envs.tick_limit,
+                _lib.RESET_RANDOM if envs.random_positions else _lib.RESET_FIXED, envs.seed, envs.counter, net.seed,
+                net.counter, _ptr(envs.speeds), envs.status.data_ptr(), _stream(self.device)), "ss_selfplay_rollout")
+        envs.counter += n_ticks
+        net.counter += n_ticks
+        if store:
+            rp.pos = (rp.pos + 2 * envs.n_envs * n_ticks) % rp.capacity
+            rp.size = min(rp.capacity, rp.size + 2 * envs.n_envs * n_ticks)
+        if n_ticks & 1:
+            self.obs, self.prev_obs = b, a
+        self.ticks += n_ticks
+        return dict(obs=self.obs, reward=out["reward"][0], done=out["done"][0], winner=out["winner"][0])
 
     def update(self):
         """One critic step and one actor step on a sampled minibatch."""

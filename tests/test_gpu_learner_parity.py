@@ -445,3 +445,22 @@ def test_tensor_core_update_tracks_the_float32_update(net):
     np.testing.assert_allclose(losses[1], losses[0], rtol=3e-2, atol=1e-4)
     d = (nets[0].params - nets[1].params).abs()
     assert float(d.max()) < 20 * 1e-3 * 0.5 and float(d.mean()) < 1e-3          # a fraction of the distance moved
+
+
+def test_library_side_rollout_loop_equals_per_tick_calls():
+    """ss_selfplay_rollout (n ticks enqueued by one call) against n rollout_tick calls: same kernels, same Philox
+    counters -> identical env state, observations and replay rows."""
+    from skillshot_learning_b200 import SelfPlayTrainer
+    trs = [SelfPlayTrainer(1024, device="cuda:0", seed=9, batch_size=256, noise_group=128, tick_limit=30, precision=p)
+           for p in ("f32", "f32", "bf16", "bf16")]
+    for k in (0, 2):
+        for _ in range(7):
+            trs[k].rollout_tick()
+        trs[k + 1].rollout(4)
+        trs[k + 1].rollout(3)
+        a, b = trs[k], trs[k + 1]
+        assert a.replay.size == b.replay.size == 7 * 2048 and a.replay.pos == b.replay.pos
+        for name in ("obs", "act", "reward", "next_obs", "done"):
+            assert torch.equal(getattr(a.replay, name), getattr(b.replay, name)), name
+        assert torch.equal(a.obs, b.obs) and torch.equal(a.envs.state, b.envs.state)
+        assert a.envs.counter == b.envs.counter and a.networks.counter == b.networks.counter

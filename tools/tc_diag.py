@@ -44,7 +44,7 @@ for n in (131072, 524288, 2097152):
     obs = torch.rand((n, 12), device="cuda")
     out = torch.empty((n, 2), device="cuda")
     t_tc = timeit(lambda: ac.actor_forward(obs, out=out, precision="bf16"))
-    t_tcn = timeit(lambda: ac.actor_forward(obs, out=out, precision="bf16", param_noise_sd=0.5, noise_group=n // 148 // 128 * 128 or 128))
+    t_tcn = timeit(lambda: ac.actor_forward(obs, out=out, precision="bf16", param_noise_sd=0.5, noise_group=-(-(n // 128) // 148) * 128))
     t_f32 = timeit(lambda: ac.actor_forward(obs, out=out), iters=5)
     print("n=%d  tc %.1f us (%.3g samples/s, %.1f TFLOP/s)  tc+noise %.1f us  f32 %.1f us (%.3g samples/s)" % (
         n, t_tc, n / t_tc * 1e6, n * 72192 / t_tc * 1e6 / 1e12, t_tcn, t_f32, n / t_f32 * 1e6), flush=True)
