@@ -273,9 +273,14 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
             // ============ the MMA-issuing warp ============
             // Measured on B200 (tools/umma_probe.cu): ~54 cycles to issue one tcgen05.mma, ~50 per commit and ~170 for a
             // wait even on a completed barrier, against 68 cycles of execution for a 128 x 128 x 16 MMA: per tile this
-            // warp can afford two waits and two commits, not more.  (Slotting the next tile's hand-off into the middle
-            // of the layer-2 chain was tried and gained nothing: with the epilogue warps reading tensor memory at the
-            // same time the MMAs themselves retire at ~95 cycles apiece and the issue stream is never far ahead.)
+            // warp can afford two waits and two commits, not more.  Tried and measured, none of them a gain:
+            //  * slotting the next tile's hand-off into the middle of the layer-2 chain -- with the epilogue warps
+            //    reading tensor memory at the same time the MMAs retire at ~95 cycles apiece and the issue stream is
+            //    never far ahead of the pipe;
+            //  * two issuing warps alternating tiles -- the tensor pipe is one in-order queue, so MMA1(t+1), which the
+            //    producers wait for, lands behind the other warp's 17-step MMA2 chain;
+            //  * eight producer warps (two per tensor-memory lane quadrant) -- 12 % SLOWER: more concurrent tcgen05.ld
+            //    traffic slows the MMAs' accumulator updates further.
             constexpr uint32_t kI1 = umma_idesc_f16(TM, H1), kI2 = umma_idesc(TM, H2);
             const uint64_t a1d = desc_kmajor(sbase + SMP_A1, CHUNK_A), x0d = desc_kmajor(sbase + SMP_X0, CHUNK_A);
             const uint64_t b1d = desc_kmajor(sbase + SMP_B1, CHUNK_B1), b2d = desc_kmajor(sbase + SMP_B2, CHUNK_B2);
