@@ -32,6 +32,24 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     assert _lib.lib.ss_env_step(None, 4, None, None, None, None, None, 1, 1, 0, 0, 0, 0, 0, None, None, 0, None) == -1
 
 
+def test_learner_entry_points_reject_invalid_arguments_without_a_gpu():
+    from skillshot_learning_b200 import _lib
+    L = _lib.lib
+    assert L.ss_learner_workspace_bytes() >= 148 * (36609 + 1) * 4
+    assert L.ss_actor_forward(None, None, None, 16, 0.0, 1, 0.0, 0, 0, None) == -1
+    assert L.ss_actor_forward_tc(None, None, None, 16, 0.0, 1, 0.0, 0, 0, None) == -1
+    assert L.ss_critic_forward(None, None, None, None, 16, None) == -1
+    assert L.ss_critic_forward_tc(None, None, None, 16, None, None, None, None, 0.0, None, None) == -1
+    assert L.ss_critic_grad(None, None, None, None, None, 0.2, 0, 0, 16, 16, 0, None, None, None, 0, None) == -1
+    assert L.ss_critic_grad_tc(None, None, None, None, None, 0.2, 0, 0, 16, 16, 0, None, None, None, 0, None) == -1
+    assert L.ss_actor_grad(None, None, None, 16, None, None, None, 0, None) == -1
+    assert L.ss_actor_grad_tc(None, None, None, 16, None, None, None, 0, None) == -1
+    assert L.ss_adam_tf(None, None, None, None, None, 10, 1, 1e-3, 0.9, 0.999, 1e-7, 1.0, 1.0, None) == -1
+    assert L.ss_replay_push(None, None, None, None, None, 10, 0, None, None, None, None, None, 1, 4, None) == -1
+    assert L.ss_peer_bytes(9, 100) == -1 and L.ss_peer_bytes(2, 100) == 256 + 2 * 2 * 100 * 4
+    assert L.ss_peer_reduce_push(None, 1, 10, None, None, 2, 0, 100, 1, None, None) == -1
+
+
 def test_product_package_does_not_touch_the_oracle():
     pkg = os.path.join(ROOT, "skillshot_learning_b200")
     for dirpath, _, files in os.walk(pkg):
