@@ -688,8 +688,11 @@ class SkillshotLearner:
                 total["epoch_board_sequences"].append(boards)
             print("Epoch {} Completed, ticks taken: {}, game winner: {}".format(epoch, game.ticks, game.winner_id))
         print("All Epochs Completed")
-        if save_progress:
+        if save_progress:                                    # SkillshotLearner.py:379-384
             self.save_actor_critic_models(epochs)
+            self.save_training_progress(total)
+        if save_boards:
+            self.save_training_boards(total["epoch_board_sequences"])
         self.training_progress = total
         return total
 
@@ -701,9 +704,38 @@ class SkillshotLearner:
             d = os.path.join(self.save_location, dir_name)
             os.makedirs(d, exist_ok=True)
             ends = [int(f.split("_")[1]) for f in os.listdir(d) if f.endswith("_model.npz")]
-            start = max(ends) if ends else 0
+            start = max(ends) + 1 if ends else 0                  # SkillshotLearner.py:153-157
             np.savez(os.path.join(d, "%d_%d_model.npz" % (start, start + epochs)), *self.networks.get_weights(which))
         torch.save(self.networks.state_dict(), os.path.join(self.save_location, "learner_state.pt"))
+
+    def save_training_progress(self, total_progress):
+        """training_models/training_progress/training_progress.csv, appended (SkillshotLearner.py:164-173):
+        one row per epoch with its tick count and winner (the board rasters go to save_training_boards)."""
+        import pandas as pd
+        d = os.path.join(self.save_location, self.training_progress_dir_name)
+        os.makedirs(d, exist_ok=True)
+        frame = pd.DataFrame(dict(epoch_ticks=total_progress["epoch_ticks"], epoch_winner=total_progress["epoch_winner"]))
+        path = os.path.join(d, "training_progress.csv")
+        frame.to_csv(path, mode="a", header=not os.path.exists(path))
+        print("Training Progress Saved")
+
+    def load_training_progress(self):
+        import pandas as pd
+        return pd.read_csv(os.path.join(self.save_location, self.training_progress_dir_name, "training_progress.csv"))
+
+    def save_training_boards(self, epoch_board_list):
+        """training_models/training_boards/training_boards.npy: per epoch the list of 250 x 250 rasters
+        (SkillshotLearner.py:182-193), the input of SkillshotGameDisplay.display_sequence."""
+        d = os.path.join(self.save_location, self.training_boards_dir_name)
+        os.makedirs(d, exist_ok=True)
+        arr = np.empty(len(epoch_board_list), dtype=object)          # epochs differ in length: ragged
+        for k, boards in enumerate(epoch_board_list):
+            arr[k] = np.asarray(boards)
+        np.save(os.path.join(d, "training_boards"), arr, allow_pickle=True)
+        print("Training Boards Saved")
+
+    def load_training_boards(self):
+        return np.load(os.path.join(self.save_location, self.training_boards_dir_name, "training_boards.npy"), allow_pickle=True)
 
     def load_actor_critic_models(self, load_index=-1):
         flat = {}

@@ -6,6 +6,8 @@ Tolerances (float32 kernels against a float32/float64 restatement, different
 summation order): forward values 2e-5 relative, gradients 2e-4 relative to the
 gradient's scale, parameters after k Adam steps 1e-5 absolute (Adam normalises
 the step to ~lr = 1e-3, so this is 1 % of one step)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -464,3 +466,29 @@ def test_library_side_rollout_loop_equals_per_tick_calls():
             assert torch.equal(getattr(a.replay, name), getattr(b.replay, name)), name
         assert torch.equal(a.obs, b.obs) and torch.equal(a.envs.state, b.envs.state)
         assert a.envs.counter == b.envs.counter and a.networks.counter == b.networks.counter
+
+
+def test_reference_surface_persistence_round_trip(tmp_path, capsys):
+    """save / load of models, progress CSV and board rasters in the reference's directory layout
+    (SkillshotLearner.py:123-204), plus the full optimiser / Philox state for resuming."""
+    from skillshot_learning_b200 import SkillshotLearner
+    skl = SkillshotLearner(device="cuda:0", seed=3)
+    skl.save_location = str(tmp_path / "training_models")
+    skl.model_param_game_tick_limit = 6
+    skl.use_random_start = False
+    skl.model_train(epochs=2, save_progress=True, save_boards=True)
+    assert sorted(os.listdir(os.path.join(skl.save_location, "actor"))) == ["0_2_model.npz"]
+    prog = skl.load_training_progress()
+    assert list(prog["epoch_ticks"]) == [6, 6] and list(prog["epoch_winner"]) == [0, 0]
+    boards = skl.load_training_boards()
+    assert len(boards) == 2 and boards[0].shape == (6, 250, 250)
+    skl.model_train(epochs=1, save_progress=True, save_boards=False)
+    assert sorted(os.listdir(os.path.join(skl.save_location, "critic"))) == ["0_2_model.npz", "3_4_model.npz"]
+    assert len(skl.load_training_progress()) == 3
+    other = SkillshotLearner(device="cuda:0", seed=99)
+    other.save_location = skl.save_location
+    other.load_actor_critic_models()
+    assert torch.equal(other.networks.params, skl.networks.params)
+    assert torch.equal(other.networks.adam_m, skl.networks.adam_m) and other.networks.step_critic == skl.networks.step_critic
+    state = skl.game_environment.get_state()
+    assert np.array_equal(other.model_act(state, 1), skl.model_act(state, 1))
