@@ -210,8 +210,8 @@ def learner_report(t_roll, t_upd, t_fwd, t_upd32, world, peaks, peak_kind, colle
     tf = ACTOR_FLOP_PER_ROW * rows / (t_fwd * 1e-3) / 1e12
     return {
         "rollout": {"workload": "262,144 envs per GPU: bf16 tensor-core actor forward on 524,288 observations with "
-                                "parameter noise (sd 0.5) + env step with observations and looking reward + replay push, "
-                                "16 ticks per ss_selfplay_rollout call",
+                                "parameter noise (sd 0.5) + env step with observations and looking reward, transitions produced "
+                                "in place in the replay ring; 16 ticks per ss_selfplay_rollout call",
                     "env_steps_per_sec": world * ROLLOUT_ENVS / (t_roll * 1e-3),
                     "samples_per_sec": world * rows / (t_roll * 1e-3), "ms_per_tick": t_roll},
         "train": {"workload": "DDPG update, %d rows per GPU: replay sample, TD targets (gamma 0.99), critic step "

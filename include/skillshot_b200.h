@@ -112,6 +112,17 @@ int ss_env_step(void *state, int64_t n_envs, const float *actions, float *obs_ou
                 int reset_mode, uint64_t seed, uint64_t counter, const void *speeds,
                 uint32_t *status, int flags, void *stream);
 
+/* ss_env_step with two extra outputs, so that a rollout can write its transitions straight into the
+ * replay ring instead of copying them there afterwards (one tick per call when obs_out2 is given):
+ *   obs_out2       second copy of the observation, float32 [n_envs][2][12] (the ring's NEXT segment:
+ *                  the next tick's "obs" rows are this tick's "next_obs" rows), or NULL
+ *   done_rows_out  the done flag once per player row, uint8 [n_envs][2], or NULL */
+int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *obs_out, float *obs_out2,
+                     float *reward_out, uint8_t *done_out, uint8_t *done_rows_out, uint8_t *winner_out,
+                     int n_ticks, int reward_mode, int64_t tick_limit, int auto_reset,
+                     int reset_mode, uint64_t seed, uint64_t counter, const void *speeds,
+                     uint32_t *status, int flags, void *stream);
+
 /* SkillshotGame.get_state (SkillshotGame.py:136-166) + prepare_states
  * (SkillshotLearner.py:512-543) in float64, formulas evaluated as written.
  *   feat_out    float64 [n_envs][2][18] in the dict's key order, or NULL
@@ -254,9 +265,13 @@ int ss_adam_tf(float *params, const float *grads, float *m, float *v, float *tar
  * enqueued back to back from one host call: actor forward on both players' observations (2 n_envs rows;
  * tensor_cores != 0: ss_actor_forward_tc) -> ss_env_step with auto-reset -> ss_replay_push (skipped when
  * ring_obs == NULL).  obs_a / obs_b are a double buffer [n_envs][2][12]: obs_a holds the current
- * observation on entry, and after the call it is in obs_a if n_ticks is even, in obs_b otherwise.
+ * observation on entry, and after the call it is in obs_a if n_ticks is even, in obs_b otherwise (but see below).
  * actions [n_envs][2][2], reward [n_envs][2], done / winner [n_envs] hold the last tick's values on return.
- * Tick t uses Philox counters env_counter + t and noise_counter + t; ring rows advance by 2 n_envs per tick. */
+ * Tick t uses Philox counters env_counter + t and noise_counter + t; ring rows advance by 2 n_envs per tick.
+ * When capacity and write_pos are multiples of 2 n_envs the transitions are produced IN the ring (the actor
+ * reads its observations from and writes its actions to the ring's rows, ss_env_step_ring writes reward, done
+ * and both copies of the next observation there): no copy kernel runs, and the current observation is left
+ * in obs_a whatever the parity of n_ticks.  Otherwise ss_replay_push copies each tick's rows. */
 int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_params, float *obs_a, float *obs_b,
                         float *actions, float *reward, uint8_t *done, uint8_t *winner,
                         float *ring_obs, float *ring_act, float *ring_reward, float *ring_next_obs,

@@ -39,6 +39,8 @@ SIGNATURES = {
     "ss_env_reset": (_i32, [_vp, _i64, _vp, _i32, _vp, _u64, _u64, _vp]),
     "ss_env_step": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i32, _u64, _u64,
                             _vp, _vp, _i32, _vp]),
+    "ss_env_step_ring": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i32, _u64, _u64,
+                                 _vp, _vp, _i32, _vp]),
     "ss_env_features": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "ss_env_export": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ss_env_import": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),

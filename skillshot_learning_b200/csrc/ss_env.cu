@@ -72,6 +72,8 @@ struct StepArgs {
     float2 *reward_out;
     uint8_t *done_out;
     uint8_t *winner_out;
+    float4 *obs_out2;          // second copy of the observation (the replay ring's next segment), or NULL
+    uint16_t *done_rows_out;   // done flag once per player row ([n][2] bytes, the replay ring's layout), or NULL
     const void *speeds;
     uint32_t *status;
     TickParams P;
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
         if (active) {
             if (write_reward) A.reward_out[row] = make_float2(r[0], r[1]);
             if (A.done_out) A.done_out[row] = (uint8_t)done;
+            if (A.done_rows_out) A.done_rows_out[row] = (uint16_t)(done ? 0x0101 : 0);
             if (A.winner_out) A.winner_out[row] = (uint8_t)winner;
         }
         if (OBS && want_obs) {
@@ -128,7 +131,11 @@ __global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
                 int idx = j * 32 + lane, rw = idx / 6, cl = idx - rw * 6;
-                if (warp_base + rw < A.n) dst[idx] = tile[warp][rw * kRowF4 + cl];
+                if (warp_base + rw < A.n) {
+                    const float4 v = tile[warp][rw * kRowF4 + cl];
+                    dst[idx] = v;
+                    if (A.obs_out2) A.obs_out2[warp_base * 6 + idx] = v;
+                }
             }
             __syncwarp();
         }
@@ -284,12 +291,14 @@ int ss_env_reset(void *state, int64_t n_envs, const uint8_t *mask, int reset_mod
     return check_launch();
 }
 
-int ss_env_step(void *state, int64_t n_envs, const float *actions, float *obs_out,
-                float *reward_out, uint8_t *done_out, uint8_t *winner_out,
-                int n_ticks, int reward_mode, int64_t tick_limit, int auto_reset,
-                int reset_mode, uint64_t seed, uint64_t counter, const void *speeds,
-                uint32_t *status, int flags, void *stream) {
+int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *obs_out, float *obs_out2,
+                     float *reward_out, uint8_t *done_out, uint8_t *done_rows_out, uint8_t *winner_out,
+                     int n_ticks, int reward_mode, int64_t tick_limit, int auto_reset,
+                     int reset_mode, uint64_t seed, uint64_t counter, const void *speeds,
+                     uint32_t *status, int flags, void *stream) {
     if (!state || !actions || n_envs <= 0 || n_ticks <= 0) return SS_ERR_INVALID_ARG;
+    if ((obs_out2 && (!obs_out || n_ticks != 1)) || ((uintptr_t)obs_out2 & 15) || ((uintptr_t)done_rows_out & 1))
+        return SS_ERR_INVALID_ARG;
     if (reward_mode < 0 || reward_mode > 3) return SS_ERR_INVALID_ARG;
     if (auto_reset && reset_mode != SS_RESET_FIXED && reset_mode != SS_RESET_RANDOM) return SS_ERR_INVALID_ARG;
     if (((uintptr_t)state | (uintptr_t)actions | (uintptr_t)obs_out) & 15) return SS_ERR_INVALID_ARG;
@@ -297,6 +306,7 @@ int ss_env_step(void *state, int64_t n_envs, const float *actions, float *obs_ou
     StepArgs A;
     A.state = state; A.n = n_envs; A.actions = (const float4 *)actions; A.obs_out = (float4 *)obs_out;
     A.reward_out = (float2 *)reward_out; A.done_out = done_out; A.winner_out = winner_out;
+    A.obs_out2 = (float4 *)obs_out2; A.done_rows_out = (uint16_t *)done_rows_out;
     A.speeds = speeds; A.status = status;
     A.P.seed = seed; A.P.counter = counter; A.P.tick_limit = tick_limit;
     A.P.reward_mode = reward_mode; A.P.auto_reset = auto_reset ? 1 : 0; A.P.reset_mode = reset_mode;
@@ -325,6 +335,15 @@ int ss_env_step(void *state, int64_t n_envs, const float *actions, float *obs_ou
         else step_kernel<false, false, false><<<grid, block, 0, st>>>(A);
     }
     return check_launch();
+}
+
+int ss_env_step(void *state, int64_t n_envs, const float *actions, float *obs_out,
+                float *reward_out, uint8_t *done_out, uint8_t *winner_out,
+                int n_ticks, int reward_mode, int64_t tick_limit, int auto_reset,
+                int reset_mode, uint64_t seed, uint64_t counter, const void *speeds,
+                uint32_t *status, int flags, void *stream) {
+    return ss_env_step_ring(state, n_envs, actions, obs_out, nullptr, reward_out, done_out, nullptr, winner_out, n_ticks,
+                            reward_mode, tick_limit, auto_reset, reset_mode, seed, counter, speeds, status, flags, stream);
 }
 
 int ss_env_features(const void *state, int64_t n_envs, double *feat_out, double *obs_out,

@@ -768,6 +768,36 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
         return SS_ERR_INVALID_ARG;
     const bool store = ring_obs != nullptr;
     if (store && (2 * n_envs > capacity || write_pos < 0 || write_pos >= capacity)) return SS_ERR_INVALID_ARG;
+    const int64_t rows = 2 * n_envs;
+    if (store && capacity % rows == 0 && write_pos % rows == 0) {
+        // transitions produced in place: tick t owns ring rows [seg_t * rows, (seg_t + 1) * rows)
+        const int64_t segs = capacity / rows;
+        cudaStream_t st = (cudaStream_t)stream;
+        int64_t seg = write_pos / rows;
+        if (cudaMemcpyAsync(ring_obs + seg * rows * 12, obs_a, (size_t)rows * 48, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            return SS_ERR_CUDA;
+        for (int t = 0; t < n_ticks; ++t, seg = (seg + 1) % segs) {
+            float *o = ring_obs + seg * rows * 12, *a = ring_act + seg * rows * 2;
+            // the last tick's observation goes to the caller's buffer, the others to the next segment's rows
+            float *o_next = (t + 1 < n_ticks) ? ring_obs + ((seg + 1) % segs) * rows * 12 : obs_a;
+            int rc = tensor_cores
+                         ? ss_actor_forward_tc(actor_params, o, a, rows, param_noise_sd, noise_group, action_noise_sd, noise_seed,
+                                               noise_counter + (uint64_t)t, stream)
+                         : ss_actor_forward(actor_params, o, a, rows, param_noise_sd, noise_group, action_noise_sd, noise_seed,
+                                            noise_counter + (uint64_t)t, stream);
+            if (rc != SS_OK) return rc;
+            rc = ss_env_step_ring(env_state, n_envs, a, ring_next_obs + seg * rows * 12, o_next, ring_reward + seg * rows, done,
+                                  ring_done + seg * rows, winner, 1, reward_mode, tick_limit, 1, reset_mode, env_seed,
+                                  env_counter + (uint64_t)t, speeds, status, 0, stream);
+            if (rc != SS_OK) return rc;
+        }
+        // the last tick's actions and rewards for the caller's scratch tensors
+        seg = (seg + segs - 1) % segs;
+        if (cudaMemcpyAsync(actions, ring_act + seg * rows * 2, (size_t)rows * 8, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(reward, ring_reward + seg * rows, (size_t)rows * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            return SS_ERR_CUDA;
+        return SS_OK;
+    }
     for (int t = 0; t < n_ticks; ++t) {
         float *cur = (t & 1) ? obs_b : obs_a, *next = (t & 1) ? obs_a : obs_b;
         // both players of every env act from the same pre-tick observation (SkillshotLearner.py:304-310)

@@ -814,7 +814,8 @@ class SelfPlayTrainer:
         if store:
             rp.pos = (rp.pos + 2 * envs.n_envs * n_ticks) % rp.capacity
             rp.size = min(rp.capacity, rp.size + 2 * envs.n_envs * n_ticks)
-        if n_ticks & 1:
+        in_place = store and rp.capacity % (2 * envs.n_envs) == 0 and (rp.pos - 2 * envs.n_envs * n_ticks) % (2 * envs.n_envs) == 0
+        if (n_ticks & 1) and not in_place:        # (in place, the library leaves the current observation in buffer A)
             self.obs, self.prev_obs = b, a
         self.ticks += n_ticks
         return dict(obs=self.obs, reward=out["reward"][0], done=out["done"][0], winner=out["winner"][0])

@@ -449,12 +449,14 @@ def test_tensor_core_update_tracks_the_float32_update(net):
     assert float(d.max()) < 20 * 1e-3 * 0.5 and float(d.mean()) < 1e-3          # a fraction of the distance moved
 
 
-def test_library_side_rollout_loop_equals_per_tick_calls():
+@pytest.mark.parametrize("capacity", [2048 * 8, 2048 * 8 + 100])
+def test_library_side_rollout_loop_equals_per_tick_calls(capacity):
     """ss_selfplay_rollout (n ticks enqueued by one call) against n rollout_tick calls: same kernels, same Philox
-    counters -> identical env state, observations and replay rows."""
+    counters -> identical env state, observations and replay rows.  With a ring that is a whole number of ticks the
+    library produces the transitions in place in the ring (no copy kernel); otherwise it pushes them tick by tick."""
     from skillshot_learning_b200 import SelfPlayTrainer
-    trs = [SelfPlayTrainer(1024, device="cuda:0", seed=9, batch_size=256, noise_group=128, tick_limit=30, precision=p)
-           for p in ("f32", "f32", "bf16", "bf16")]
+    trs = [SelfPlayTrainer(1024, device="cuda:0", seed=9, batch_size=256, noise_group=128, tick_limit=30, precision=p,
+                           replay_capacity=capacity) for p in ("f32", "f32", "bf16", "bf16")]
     for k in (0, 2):
         for _ in range(7):
             trs[k].rollout_tick()
@@ -465,7 +467,14 @@ def test_library_side_rollout_loop_equals_per_tick_calls():
         for name in ("obs", "act", "reward", "next_obs", "done"):
             assert torch.equal(getattr(a.replay, name), getattr(b.replay, name)), name
         assert torch.equal(a.obs, b.obs) and torch.equal(a.envs.state, b.envs.state)
+        assert torch.equal(a.actions, b.actions)
         assert a.envs.counter == b.envs.counter and a.networks.counter == b.networks.counter
+        b.rollout(12)                                      # wraps the ring
+        for _ in range(12):
+            a.rollout_tick()
+        for name in ("obs", "act", "reward", "next_obs", "done"):
+            assert torch.equal(getattr(a.replay, name), getattr(b.replay, name)), name
+        assert torch.equal(a.obs, b.obs) and a.replay.pos == b.replay.pos and a.replay.size == b.replay.size
 
 
 def test_reference_surface_persistence_round_trip(tmp_path, capsys):
