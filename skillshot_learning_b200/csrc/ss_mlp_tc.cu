@@ -280,7 +280,14 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
             //  * two issuing warps alternating tiles -- the tensor pipe is one in-order queue, so MMA1(t+1), which the
             //    producers wait for, lands behind the other warp's 17-step MMA2 chain;
             //  * eight producer warps (two per tensor-memory lane quadrant) -- 12 % SLOWER: more concurrent tcgen05.ld
-            //    traffic slows the MMAs' accumulator updates further.
+            //    traffic slows the MMAs' accumulator updates further;
+            //  * cta_group::2 (a cluster of two CTAs, one thread issuing M = 256 pair MMAs for both, each CTA holding
+            //    half of the weight images, hand-offs through the cluster address window, multicast commits) --
+            //    correct on the first run and 13 % SLOWER: halving the issue overhead does not help because the
+            //    producers' loop (wait MMA1 -> epilogue 1 -> hand-off -> issuer wake-up -> MMA1) is the pacing chain
+            //    and its MMA1 round trip then crosses SMs.  With D1 single-buffered (tensor memory is full: 256 + 2 x
+            //    128 columns) that round trip cannot be overlapped; a packed fp16 layer-1 accumulator (128 columns)
+            //    would make room for a second D1 and is the remaining idea.
             constexpr uint32_t kI1 = umma_idesc_f16(TM, H1), kI2 = umma_idesc(TM, H2);
             const uint64_t a1d = desc_kmajor(sbase + SMP_A1, CHUNK_A), x0d = desc_kmajor(sbase + SMP_X0, CHUNK_A);
             const uint64_t b1d = desc_kmajor(sbase + SMP_B1, CHUNK_B1), b2d = desc_kmajor(sbase + SMP_B2, CHUNK_B2);
