@@ -199,13 +199,16 @@ def learner_legs(dev, rank, world, seed, peaks, collective, ticks=64, updates=20
     tr.networks.update_precision = "f32"
     t_upd32 = timed(tr.update, max(3, updates // 4))  # the exact float32 kernels, same schedule
     tr.networks.update_precision = "bf16"
+    tr.batch_size, tr._batch = 2 * E, None            # one update on as many rows as one rollout tick produces
+    t_upd_big = timed(tr.update, max(3, updates // 2))
+    tr.batch_size, tr._batch = TRAIN_BATCH, None
     obs, act = tr.obs.view(-1, 12), tr.actions.view(-1, 2)
     t_fwd = timed(lambda: tr.networks.actor_forward(obs, out=act, precision="bf16"), 50)
     tr.envs.check_status()
-    return t_roll, t_upd, t_fwd, t_upd32
+    return t_roll, t_upd, t_fwd, t_upd32, t_upd_big
 
 
-def learner_report(t_roll, t_upd, t_fwd, t_upd32, world, peaks, peak_kind, collective="nccl"):
+def learner_report(t_roll, t_upd, t_fwd, t_upd32, t_upd_big, world, peaks, peak_kind, collective="nccl"):
     rows = 2 * ROLLOUT_ENVS
     tf = ACTOR_FLOP_PER_ROW * rows / (t_fwd * 1e-3) / 1e12
     return {
@@ -221,7 +224,9 @@ def learner_report(t_roll, t_upd, t_fwd, t_upd32, world, peaks, peak_kind, colle
                   "samples_per_sec": world * TRAIN_BATCH / (t_upd * 1e-3), "ms_per_update": t_upd,
                   "dtype": "bf16 operands, f32 accumulate (tcgen05); Adam and parameters f32",
                   "algorithmic_tflops": world * TRAIN_BATCH * UPDATE_FLOP_PER_ROW / (t_upd * 1e-3) / 1e12,
-                  "f32_path_samples_per_sec": world * TRAIN_BATCH / (t_upd32 * 1e-3)},
+                  "f32_path_samples_per_sec": world * TRAIN_BATCH / (t_upd32 * 1e-3),
+                  "rows_524288_per_gpu": {"samples_per_sec": world * rows / (t_upd_big * 1e-3), "ms_per_update": t_upd_big,
+                                          "algorithmic_tflops": world * rows * UPDATE_FLOP_PER_ROW / (t_upd_big * 1e-3) / 1e12}},
         "actor_forward_roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                                    "frac": tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peak_kind,
                                    "kernel": "actor_fwd_tc_kernel", "rows_per_launch": rows,
@@ -348,7 +353,7 @@ def run_gpu_arm(args):
         e2e_s = time.perf_counter() - t0
 
     # ---- learner legs: rollout, DDPG update, tensor roofline of the actor forward ----
-    lt = (float("nan"),) * 4
+    lt = (float("nan"),) * 5
     if not args.no_learner:
         del actions
         torch.cuda.empty_cache()
