@@ -30,7 +30,10 @@ namespace {
 
 using namespace sstc;
 
-constexpr int EPI_WARPS = 4, MMA_WARP = 4, NTHREADS = 160;
+// eight epilogue warps: warps w and w + 4 share tensor-memory lane quadrant w & 3 (rows 32 (w & 3) ..) and split the
+// columns of every element-wise sweep between them; MMAs and sweeps alternate in this kernel, so the extra tcgen05.ld
+// traffic does not compete with the tensor pipe (unlike in the forward kernel)
+constexpr int EPI_WARPS = 8, NSLICE = EPI_WARPS / 4, MMA_WARP = EPI_WARPS, NTHREADS = 32 * (EPI_WARPS + 1);
 
 // shared-memory map (bytes)
 constexpr uint32_t SM_B1 = 0;
@@ -44,7 +47,8 @@ constexpr uint32_t SM_B3 = SM_W3 + H2 * 16;
 constexpr uint32_t SM_BAR = SM_B3 + 16;                     // {epilogue -> MMA (128 arrivals), MMA -> epilogue (commit)}
 constexpr uint32_t SM_TMEM = SM_BAR + 16;
 constexpr uint32_t SM_RED = SM_TMEM + 16;                   // 4 warps x 4 floats
-constexpr uint32_t SM_TOTAL = SM_RED + 64;
+constexpr uint32_t SM_ZP = SM_RED + 64;                     // [NSLICE][128] float2: partial output-layer sums per column slice
+constexpr uint32_t SM_TOTAL = SM_ZP + NSLICE * TM * 8;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 
 // tensor-memory columns
@@ -62,6 +66,7 @@ struct GradArgs {
     uint64_t seed, counter;
     int64_t n, n_global, row_offset;
     float *work;                     // [gridDim.x][params + 1]
+    long long *trace;                // development: event timestamps of CTA 0 (NULL in production)
 };
 
 // inverted-dropout keep bits of 8 consecutive hidden-1 units of one row: one Philox draw, 16 bits per unit
@@ -77,6 +82,27 @@ __device__ __forceinline__ uint32_t keep8(const GradArgs &A, int64_t grow, int c
     return bits;
 }
 
+// The 128 work columns in steps of 16, this warp's steps only (j = cs, cs + NSLICE, ..), tensor-memory loads
+// double-buffered: f(v, j) gets columns 16 j .. 16 j + 15 of this thread's lane while the next step's load is in flight.
+template <class F>
+__device__ __forceinline__ void sweep_work(uint32_t taddr, int cs, F &&f) {
+    constexpr int kSteps = 8 / NSLICE;
+    uint32_t va[16], vb[16];
+    tmem_ld16(taddr + cs * 16, va);
+#pragma unroll
+    for (int k = 0; k < kSteps; k += 2) {
+        const int j = cs + k * NSLICE;
+        tmem_wait_ld();
+        if (k + 1 < kSteps) tmem_ld16(taddr + (j + NSLICE) * 16, vb);
+        f(va, j);
+        if (k + 1 < kSteps) {
+            tmem_wait_ld();
+            if (k + 2 < kSteps) tmem_ld16(taddr + (j + 2 * NSLICE) * 16, va);
+            f(vb, j + NSLICE);
+        }
+    }
+}
+
 template <int NET>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs A) {
     constexpr int PN = NET == NET_ACTOR ? A_N : C_N;
@@ -84,9 +110,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_mma = sbase + SM_BAR, bar_epi = sbase + SM_BAR + 8;
+    int tr_n = 0;                    // development trace: role 0 = epilogue warp 0, role 1 = MMA warp
+    auto trace = [&](int role, int code) {
+        if (A.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == MMA_WARP) && tr_n < 256) {
+            A.trace[(role * 256 + tr_n) * 2] = clock64();
+            A.trace[(role * 256 + tr_n) * 2 + 1] = code;
+            ++tr_n;
+        }
+    };
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_mma, 128);
+        mbar_init(bar_mma, 32 * EPI_WARPS);
         mbar_init(bar_epi, 1);
         mbar_fence_init();
     }
@@ -98,7 +132,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
         *reinterpret_cast<uint4 *>(smem + SM_X2 + (H1 / 8) * CHUNK_A + o) = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    if (warp < EPI_WARPS && NET == NET_ACTOR)
+    if (warp < 4 && NET == NET_ACTOR)
         *reinterpret_cast<uint4 *>(smem + SM_X2 + (H1 / 8) * CHUNK_A + threadIdx.x * 16) = tail_chunk_actor();
     stage_weights<NET, NTHREADS>(Stager{A.params, smem + SM_B1, smem + SM_B2, reinterpret_cast<float4 *>(smem + SM_W3),
                                         reinterpret_cast<float *>(smem + SM_B3), false, 0.f, 0, 0, 0});
@@ -113,8 +147,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
 
     if (warp < EPI_WARPS) {
         // ======================= epilogue warps: thread r owns row r of the tile =======================
-        const int r = threadIdx.x;
-        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        const int r = (warp & 3) * 32 + lane;           // row of the tile = tensor-memory lane
+        const int cs = warp >> 2;                       // column slice of this warp
+        const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint8_t *x2row = smem + SM_X2 + r * 16, *dz2row = smem + SM_DZ2 + r * 16, *h2row = smem + SM_H2 + r * 16;
         const float4 *w3x = reinterpret_cast<const float4 *>(smem + SM_W3);      // critic layout
         const float2 *w3a = reinterpret_cast<const float2 *>(smem + SM_W3);      // actor layout: W3[128][2] as stored
@@ -123,21 +158,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
         const uint32_t thresh16 = (uint32_t)(A.rate * 65536.0f);
         uint32_t ph = 0;
         float stat = 0.f, dsum0 = 0.f, dsum1 = 0.f;      // sum of squared errors; db3 partials
-        auto to_mma = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(bar_mma); };
-        auto from_mma = [&]() { mbar_wait(bar_epi, ph); ph ^= 1; tc_fence_after(); };
+        int ev = 0;
+        auto to_mma = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(bar_mma); trace(0, 100 + ev); };
+        auto from_mma = [&]() { mbar_wait(bar_epi, ph); ph ^= 1; tc_fence_after(); trace(0, 200 + ev); ++ev; };
 
         // hidden layer 1, one 128-unit half: WORK -> ReLU (+ dropout) -> bf16 -> X2 chunks 16 * half ..
-        auto hidden1 = [&](int half, int64_t row, bool valid) {
-#pragma unroll 1
-            for (int j = 0; j < 8; ++j) {                 // 16 columns = 2 chunks per step
-                uint32_t v[16];
-                tmem_ld16(tl + T_WORK + j * 16, v);
-                uint32_t kb = 0xFFFFu;
-                if (NET == NET_CRITIC && A.rate > 0.f) {
-                    const int c0 = half * 16 + j * 2;
+        // Inverted-dropout keep bits of this thread's row for the columns its warp handles: 2 halves x 4 steps x 16
+        // units = 128 bits.  They are generated one tile AHEAD, while the warp would otherwise idle in the wait for the
+        // two long MMA phases (32 Philox draws per row and tile cost ~5 k cycles when computed inside hidden1).
+        uint32_t kb_cur[4] = {~0u, ~0u, ~0u, ~0u}, kb_next[4] = {~0u, ~0u, ~0u, ~0u};
+        auto make_keep = [&](int64_t tile, int half) {
+            if (!(NET == NET_CRITIC && A.rate > 0.f) || tile >= tiles) return;
+            const int64_t row = tile * TM + r;
+            kb_next[half * 2] = kb_next[half * 2 + 1] = 0u;
+            {
+#pragma unroll
+                for (int k = 0; k < 8 / NSLICE; ++k) {
+                    const int c0 = half * 16 + (cs + k * NSLICE) * 2;          // first of the step's two 8-unit chunks
+                    uint32_t kb = 0;
                     if (A.keep) {
-                        kb = 0;
-                        if (valid) {
+                        if (row < A.n) {
                             const uint4 m = __ldg(reinterpret_cast<const uint4 *>(A.keep + row * H1 + c0 * 8));
                             const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
@@ -146,8 +186,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                     } else {
                         kb = keep8(A, A.row_offset + row, c0, thresh16) | (keep8(A, A.row_offset + row, c0 + 1, thresh16) << 8);
                     }
+                    kb_next[half * 2 + (k >> 1)] |= kb << ((k & 1) * 16);
                 }
-                tmem_wait_ld();
+            }
+        };
+        // hidden layer 1, one 128-unit half: WORK -> ReLU (+ dropout) -> bf16 -> X2 chunks 16 * half ..
+        auto hidden1 = [&](int half) {
+            sweep_work(tl + T_WORK, cs, [&](const uint32_t (&v)[16], int j) {      // 16 columns = 2 chunks per step
+                const int k = (j - cs) / NSLICE;
+                const uint32_t kb = (kb_cur[half * 2 + (k >> 1)] >> ((k & 1) * 16)) & 0xFFFFu;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     float h[8];
@@ -157,15 +204,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                     *reinterpret_cast<uint4 *>(x2row + (uint32_t)(half * 16 + j * 2 + c) * CHUNK_A) = make_uint4(
                         pack_relu_bf16(h[0], h[1]), pack_relu_bf16(h[2], h[3]), pack_relu_bf16(h[4], h[5]), pack_relu_bf16(h[6], h[7]));
                 }
-            }
+            });
         };
         // back through hidden layer 1, one half: WORK = dx2 -> mask of the stored activation -> bf16 -> same chunks
         auto back1 = [&](int half) {
-#pragma unroll 1
-            for (int j = 0; j < 8; ++j) {
-                uint32_t v[16];
-                tmem_ld16(tl + T_WORK + j * 16, v);
-                tmem_wait_ld();
+            sweep_work(tl + T_WORK, cs, [&](const uint32_t (&v)[16], int j) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint4 *p = reinterpret_cast<uint4 *>(x2row + (uint32_t)(half * 16 + j * 2 + c) * CHUNK_A);
@@ -179,36 +222,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                     }
                     *p = make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
                 }
-            }
+            });
         };
 
+        // this row's inputs of the NEXT tile are fetched while the current tile is processed
+        float4 xnext[3];
+        float2 side_next = make_float2(0.f, 0.f);        // critic: action; actor: upstream gradient
+        float tgt_next = 0.f;
+        auto fetch = [&](int64_t tile) {
+            const int64_t row = tile * TM + r;
+            load_obs(A.obs, row, tile < tiles ? A.n : 0, xnext);
+            side_next = make_float2(0.f, 0.f);
+            tgt_next = 0.f;
+            if (tile < tiles && row < A.n) {
+                side_next = __ldg(reinterpret_cast<const float2 *>(NET == NET_CRITIC ? A.act : A.up) + row);
+                if (NET == NET_CRITIC) tgt_next = __ldg(A.target + row);
+            }
+        };
+        fetch(blockIdx.x);
+        make_keep(blockIdx.x, 0);
+        make_keep(blockIdx.x, 1);
         for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int64_t row = tile * TM + r;
             const bool valid = row < A.n;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) kb_cur[w] = kb_next[w];
             // ---- stage: X0 -> head of the DZ2 buffer; critic: action -> tail chunk of X2 ----
-            float4 xin[3];
-            load_obs(A.obs, row, A.n, xin);
-            store_obs_row(xin, dz2row);
-            if (NET == NET_CRITIC) {
-                float2 a = make_float2(0.f, 0.f);
-                if (valid) a = __ldg(reinterpret_cast<const float2 *>(A.act) + row);
-                *reinterpret_cast<uint4 *>(x2row + (H1 / 8) * CHUNK_A) = tail_chunk_critic(a.x, a.y);
-            }
+            float4 xin[3] = {xnext[0], xnext[1], xnext[2]};
+            const float2 side = side_next;
+            const float tgt = tgt_next;
+            fetch(tile + gridDim.x);
+            store_obs_half(xin, dz2row, cs);
+            if (NET == NET_CRITIC && cs == 0)
+                *reinterpret_cast<uint4 *>(x2row + (H1 / 8) * CHUNK_A) = tail_chunk_critic(side.x, side.y);
             to_mma();                                     // -> L1a
             from_mma();
-            hidden1(0, row, valid);
+            hidden1(0);
             to_mma();                                     // -> L1b
             from_mma();
-            hidden1(1, row, valid);
+            hidden1(1);
             to_mma();                                     // -> L2
+            make_keep(tile + gridDim.x, 0);               // in the shadow of the 17-step layer-2 chain
             from_mma();
             // ---- output layer, loss / upstream gradient (fp32) ----
             float z0 = 0.f, z1 = 0.f;
-#pragma unroll 1
-            for (int j = 0; j < 8; ++j) {
-                uint32_t v[16];
-                tmem_ld16(tl + T_WORK + j * 16, v);
-                tmem_wait_ld();
+            sweep_work(tl + T_WORK, cs, [&](const uint32_t (&v)[16], int j) {
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const float h = fmaxf(__uint_as_float(v[c]), 0.f);
@@ -220,32 +278,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                         z0 = fmaf(h, w3x[j * 16 + c].x, z0);
                     }
                 }
+            });
+            {   // the row's output-layer sums: combine the column slices (slice 0 + slice 1: same order in every warp)
+                float2 *zp = reinterpret_cast<float2 *>(smem + SM_ZP);
+                zp[cs * TM + r] = make_float2(z0, z1);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float2 pa = zp[r], pb = zp[TM + r];
+                z0 = pa.x + pb.x;
+                z1 = pa.y + pb.y;
             }
             float d0 = 0.f, d1 = 0.f;
             if (NET == NET_CRITIC) {
                 if (valid) {                              // loss "mse": mean over the global batch
-                    const float e = (z0 + b3[0]) - A.target[row];
+                    const float e = (z0 + b3[0]) - tgt;
                     stat += e * e;
                     d0 = 2.0f * e / (float)A.n_global;
                 }
             } else if (valid) {                           // through tanh, upstream = -dQ/da (SkillshotLearner.py:408-410)
                 const float a0 = tanhf(z0 + b3[0]), a1 = tanhf(z1 + b3[1]);
-                const float2 up = __ldg(reinterpret_cast<const float2 *>(A.up) + row);
-                d0 = up.x * (1.0f - a0 * a0);
-                d1 = up.y * (1.0f - a1 * a1);
+                d0 = side.x * (1.0f - a0 * a0);
+                d1 = side.y * (1.0f - a1 * a1);
             }
-            dsum0 += d0;
-            dsum1 += d1;
-            {
+            if (cs != 0) stat = 0.f;                      // statistics and db3 are kept by slice 0 only
+            else { dsum0 += d0; dsum1 += d1; }
+            if (cs == 0) {
                 const float h0 = bf16_round(d0), h1 = bf16_round(d1);
                 *reinterpret_cast<uint4 *>(smem + SM_DZ3 + r * 16) = make_uint4(pack_bf16(h0, h1), pack_bf16(d0 - h0, d1 - h1), 0u, 0u);
             }
             // ---- h2 and dz2 tiles (second sweep over z2) ----
-#pragma unroll 1
-            for (int j = 0; j < 8; ++j) {
-                uint32_t v[16];
-                tmem_ld16(tl + T_WORK + j * 16, v);
-                tmem_wait_ld();
+            sweep_work(tl + T_WORK, cs, [&](const uint32_t (&v)[16], int j) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     float gz[8];
@@ -268,23 +329,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                     *reinterpret_cast<uint4 *>(dz2row + (uint32_t)(j * 2 + c) * CHUNK_A) =
                         make_uint4(pack_bf16(gz[0], gz[1]), pack_bf16(gz[2], gz[3]), pack_bf16(gz[4], gz[5]), pack_bf16(gz[6], gz[7]));
                 }
-            }
+            });
             to_mma();                                     // -> G3, G2, BXa
+            make_keep(tile + gridDim.x, 1);               // ... and of the weight-gradient chains
             from_mma();
             back1(0);
             to_mma();                                     // -> BXb
             from_mma();
             back1(1);
-            store_obs_row(xin, dz2row);                   // X0 again (the DZ2 buffer is free: BXb has retired)
+            store_obs_half(xin, dz2row, cs);              // X0 again (the DZ2 buffer is free: BXb has retired)
             to_mma();                                     // -> G1
             from_mma();                                   // tiles free for the next round
         }
 
         // ======================= write this CTA's partial gradient =======================
-        // thread r = hidden-2 unit r for dW2'^T and dW3^T, = hidden-1 unit 128 h + r for dW1'^T
+        // thread r = hidden-2 unit r for dW2'^T and dW3^T, = hidden-1 unit 128 h + r for dW1'^T; columns split by slice
         {
 #pragma unroll 1
-            for (int j = 0; j < H1 / 16; ++j) {
+            for (int j = cs; j < H1 / 16; j += NSLICE) {
                 uint32_t v[16];
                 tmem_ld16(tl + T_W2T + j * 16, v);
                 tmem_wait_ld();
@@ -292,25 +354,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                 for (int c = 0; c < 16; ++c) __stcg(g + P_W2 + (j * 16 + c) * H2 + r, __uint_as_float(v[c]));
             }
             uint32_t t[16];
-            tmem_ld16(tl + T_W2T + H1, t);
-            tmem_wait_ld();
-            if (NET == NET_ACTOR) {
-                __stcg(g + A_B2 + r, __uint_as_float(t[0]));
-            } else {                                      // action rows (hi + lo parts of the action), then b2
-                __stcg(g + P_W2 + H1 * H2 + r, __uint_as_float(t[0]) + __uint_as_float(t[2]));
-                __stcg(g + P_W2 + (H1 + 1) * H2 + r, __uint_as_float(t[1]) + __uint_as_float(t[3]));
-                __stcg(g + C_B2 + r, __uint_as_float(t[4]));
+            if (cs == 0) {
+                tmem_ld16(tl + T_W2T + H1, t);
+                tmem_wait_ld();
+                if (NET == NET_ACTOR) {
+                    __stcg(g + A_B2 + r, __uint_as_float(t[0]));
+                } else {                                  // action rows (hi + lo parts of the action), then b2
+                    __stcg(g + P_W2 + H1 * H2 + r, __uint_as_float(t[0]) + __uint_as_float(t[2]));
+                    __stcg(g + P_W2 + (H1 + 1) * H2 + r, __uint_as_float(t[1]) + __uint_as_float(t[3]));
+                    __stcg(g + C_B2 + r, __uint_as_float(t[4]));
+                }
+                tmem_ld16(tl + T_W3T, t);
+                tmem_wait_ld();
+                if (NET == NET_ACTOR) {
+                    __stcg(g + A_W3 + r * DA + 0, __uint_as_float(t[0]) + __uint_as_float(t[2]));
+                    __stcg(g + A_W3 + r * DA + 1, __uint_as_float(t[1]) + __uint_as_float(t[3]));
+                } else {
+                    __stcg(g + C_W3 + r, __uint_as_float(t[0]) + __uint_as_float(t[2]));
+                }
             }
-            tmem_ld16(tl + T_W3T, t);
-            tmem_wait_ld();
-            if (NET == NET_ACTOR) {
-                __stcg(g + A_W3 + r * DA + 0, __uint_as_float(t[0]) + __uint_as_float(t[2]));
-                __stcg(g + A_W3 + r * DA + 1, __uint_as_float(t[1]) + __uint_as_float(t[3]));
-            } else {
-                __stcg(g + C_W3 + r, __uint_as_float(t[0]) + __uint_as_float(t[2]));
-            }
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
+            {
+                const int h = cs;                         // each slice dumps one half of dW1'^T
                 uint32_t a[16], b[16];
                 tmem_ld16(tl + T_W1T + h * 32, a);
                 tmem_ld16(tl + T_W1T + h * 32 + 16, b);
@@ -320,21 +384,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                     __stcg(g + P_W1 + i * H1 + h * 128 + r, __uint_as_float(a[i]) + __uint_as_float(b[i]));
                 __stcg(g + P_B1 + h * 128 + r, __uint_as_float(a[12]));
             }
-            // db3 and the loss statistic: sums over the rows
-            float s0 = dsum0, s1 = dsum1, s2 = stat;
-            for (int o = 16; o > 0; o >>= 1) {
-                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            }
-            float *red = reinterpret_cast<float *>(smem + SM_RED);
-            if (lane == 0) { red[warp * 4 + 0] = s0; red[warp * 4 + 1] = s1; red[warp * 4 + 2] = s2; }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (r == 0) {
-                const float t0 = (red[0] + red[4]) + (red[8] + red[12]), t1 = (red[1] + red[5]) + (red[9] + red[13]);
-                const float t2 = (red[2] + red[6]) + (red[10] + red[14]);
-                if (NET == NET_ACTOR) { g[A_B3] = t0; g[A_B3 + 1] = t1; g[PN] = 0.f; }
-                else { g[C_B3] = t0; g[PN] = t2; }
+            // db3 and the loss statistic: sums over the rows (slice 0 holds them)
+            if (cs == 0) {
+                float s0 = dsum0, s1 = dsum1, s2 = stat;
+                for (int o = 16; o > 0; o >>= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                float *red = reinterpret_cast<float *>(smem + SM_RED);
+                if (lane == 0) { red[warp * 4 + 0] = s0; red[warp * 4 + 1] = s1; red[warp * 4 + 2] = s2; }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (r == 0) {
+                    const float t0 = (red[0] + red[4]) + (red[8] + red[12]), t1 = (red[1] + red[5]) + (red[9] + red[13]);
+                    const float t2 = (red[2] + red[6]) + (red[10] + red[14]);
+                    if (NET == NET_ACTOR) { g[A_B3] = t0; g[A_B3 + 1] = t1; g[PN] = 0.f; }
+                    else { g[C_B3] = t0; g[PN] = t2; }
+                }
             }
         }
         tc_fence_before();
@@ -347,7 +413,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
         constexpr uint32_t kFwd = umma_idesc(TM, 128);                // K-major x K-major
         constexpr uint32_t kBx = umma_idesc(TM, 128, 0, 1);           // dz2 (K-major) x W2 image (MN-major)
         constexpr uint32_t kG256 = umma_idesc(TM, 256, 1, 1), kG16 = umma_idesc(TM, 16, 1, 1), kG32 = umma_idesc(TM, 32, 1, 1);
-        auto wait_epi = [&]() { mbar_wait(bar_mma, ph); ph ^= 1; tc_fence_after(); };
+        int ev = 0;
+        auto wait_epi = [&]() { mbar_wait(bar_mma, ph); ph ^= 1; tc_fence_after(); trace(1, 300 + ev); ++ev; };
         uint32_t acc = 0;                                             // 0 on the CTA's first tile: accumulators start fresh
         for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, acc = 1) {
             for (int half = 0; half < 2; ++half) {                    // L1a, L1b
@@ -360,6 +427,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                     umma_commit(bar_epi);
                 }
                 __syncwarp();
+                trace(1, 400 + ev);
             }
             wait_epi();                                               // L2
             if (lane == 0) {
@@ -479,6 +547,16 @@ int launch_grad(const GradArgs &A0, float *grad_out, float *aux_out, int64_t wor
 }  // namespace
 
 extern "C" {
+
+// development: the critic gradient kernel with an event trace of CTA 0 (tools/tc_grad_trace.py)
+int ss_debug_critic_grad_trace(const float *critic_params, const float *obs, const float *act, const float *target,
+                               int64_t n, float *grad_out, void *workspace, int64_t workspace_bytes, long long *trace,
+                               void *stream) {
+    GradArgs A{};
+    A.params = critic_params; A.obs = obs; A.act = act; A.target = target; A.rate = 0.2f; A.n = n; A.n_global = n;
+    A.work = (float *)workspace; A.trace = trace;
+    return launch_grad<NET_CRITIC>(A, grad_out, nullptr, workspace_bytes, stream);
+}
 
 int ss_critic_grad_tc(const float *critic_params, const float *obs, const float *act, const float *target,
                       const uint8_t *dropout_keep, float dropout_rate, uint64_t seed, uint64_t counter,

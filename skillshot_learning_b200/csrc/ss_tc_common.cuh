@@ -244,6 +244,21 @@ __device__ __forceinline__ void store_obs_row_f16(const float4 (&x)[3], uint8_t 
         make_uint4(pack_f16(x[0].x, x[0].y), pack_f16(x[0].z, x[0].w), pack_f16(x[1].x, x[1].y), pack_f16(x[1].z, x[1].w));
     *reinterpret_cast<uint4 *>(row + CHUNK_A) = make_uint4(pack_f16(x[2].x, x[2].y), pack_f16(x[2].z, x[2].w), 0x3C003C00u, 0u);
 }
+// the same, half of it: slice 0 writes the two high chunks, slice 1 the two low chunks (gradient kernel, two warps per row)
+__device__ __forceinline__ void store_obs_half(const float4 (&xin)[3], uint8_t *row, int slice) {
+    const float x[12] = {xin[0].x, xin[0].y, xin[0].z, xin[0].w, xin[1].x, xin[1].y,
+                         xin[1].z, xin[1].w, xin[2].x, xin[2].y, xin[2].z, xin[2].w};
+    float v[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+        const float hi = bf16_round(x[e]);
+        v[e] = slice == 0 ? hi : x[e] - hi;
+    }
+    *reinterpret_cast<uint4 *>(row + (2 * slice) * CHUNK_A) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4 *>(row + (2 * slice + 1) * CHUNK_A) =
+        make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), slice == 0 ? ONES : 0u, 0u);
+}
 // the constant / action chunk of the layer-2 tile (chunk 32): actor {1 1 0..}, critic {a0h a1h a0l a1l 1 1 0 0}
 __device__ __forceinline__ uint4 tail_chunk_actor() { return make_uint4(ONES, 0u, 0u, 0u); }
 __device__ __forceinline__ uint4 tail_chunk_critic(float a0, float a1) {

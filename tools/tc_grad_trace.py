@@ -1,0 +1,32 @@
+"""Development: event trace of the tensor-core critic gradient kernel (CTA 0): epilogue warp 0 and the MMA warp."""
+import os, sys, ctypes
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from skillshot_learning_b200 import ActorCritic, _lib
+ac = ActorCritic(device="cuda:0", seed=1, update_precision="bf16")
+n = 148 * 128 * 6
+s = torch.rand((n, 12), device="cuda"); a = torch.rand((n, 2), device="cuda") * 2 - 1; y = -torch.rand(n, device="cuda")
+g = torch.empty(36609, device="cuda")
+tr = torch.zeros((2, 256, 2), dtype=torch.int64, device="cuda")
+ws = ac._workspace_for(n)
+L = ctypes.CDLL(_lib.LIB_PATH)
+L.ss_debug_critic_grad_trace.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+for _ in range(3):
+    tr.zero_()
+    L.ss_debug_critic_grad_trace(ac.critic.data_ptr(), s.data_ptr(), a.data_ptr(), y.data_ptr(), n, g.data_ptr(), ws.data_ptr(), ws.numel(), tr.data_ptr(), None)
+torch.cuda.synchronize()
+t = tr.cpu().numpy()
+t0 = min(t[r, 0, 0] for r in range(2) if t[r, 0, 0] > 0)
+step = ["L1a", "L1b", "L2", "G3+G2+BXa", "BXb", "G1"]
+ev = []
+for r in range(2):
+    for k in range(256):
+        if t[r, k, 0] > 0:
+            code = int(t[r, k, 1]); kind, e = code // 100, code % 100
+            what = {1: "E handed over ->", 2: "E resumed after", 3: "M woke for", 4: "M issued"}[kind]
+            ev.append((int(t[r, k, 0] - t0), "%s %s (tile %d)" % (what, step[(e if kind in (1, 3) else e - 1) % 6], (e if kind in (1, 3) else e - 1) // 6)))
+ev.sort()
+prev = 0
+for c, what in ev[:110]:
+    print("%7d  (+%5d)  %s" % (c, c - prev, what)); prev = c
