@@ -501,3 +501,54 @@ def test_reference_surface_persistence_round_trip(tmp_path, capsys):
     assert torch.equal(other.networks.adam_m, skl.networks.adam_m) and other.networks.step_critic == skl.networks.step_critic
     state = skl.game_environment.get_state()
     assert np.array_equal(other.model_act(state, 1), skl.model_act(state, 1))
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json's full sizes (configs 3-4: 524,288 rows per tick / update) through size-independent properties
+# ---------------------------------------------------------------------------
+def test_full_size_actor_forward_properties(net):
+    """524,288 rows: (1) a sample of rows against the oracle, (2) row-permutation equivariance, bit for bit (a row's
+    action depends on that row only, whatever tile, CTA or lane it lands in), (3) repeatability."""
+    ac, theta, _ = net
+    n = 524288
+    g = torch.Generator(device="cuda").manual_seed(5)
+    obs = torch.rand((n, 12), device="cuda", generator=g)
+    obs[:, 4] *= 9.8
+    obs[:, 9] *= 9.8
+    for precision, tol in (("f32", 2e-5), ("bf16", 2e-2)):
+        act = ac.actor_forward(obs, precision=precision)
+        idx = torch.randint(0, n, (2000,), device="cuda", generator=g)
+        want = lo.actor_forward(theta, obs[idx].cpu().numpy())
+        np.testing.assert_allclose(act[idx].cpu().numpy(), want, rtol=0, atol=tol)
+        perm = torch.randperm(n, device="cuda", generator=g)
+        assert torch.equal(ac.actor_forward(obs[perm].contiguous(), precision=precision), act[perm])
+        assert torch.equal(ac.actor_forward(obs, precision=precision), act)
+
+
+def test_full_size_gradients_are_additive_over_shards(net):
+    """524,288 rows: the gradient of the whole batch equals the sum of the gradients of its two halves taken with the
+    global divisor (what the multi-GPU update relies on), for both kernel families."""
+    from skillshot_learning_b200 import ActorCritic
+    _, theta, phi = net
+    n = 524288
+    g = torch.Generator(device="cuda").manual_seed(6)
+    s = torch.rand((n, 12), device="cuda", generator=g)
+    a = torch.rand((n, 2), device="cuda", generator=g) * 2 - 1
+    y = -torch.rand(n, device="cuda", generator=g)
+    for precision, tol in (("bf16", 2e-4), ("f32", 2e-5)):
+        ac = ActorCritic(device="cuda:0", seed=13, update_precision=precision)
+        ac.set_weights(theta, phi)
+        h = n // 2
+        ac.counter = 50
+        full = ac.critic_grad(s, a, y).clone()
+        parts = []
+        for k in range(2):
+            ac.counter = 50
+            parts.append(ac.critic_grad(s[k * h:(k + 1) * h], a[k * h:(k + 1) * h], y[k * h:(k + 1) * h],
+                                        n_global=n, row_offset=k * h).clone())
+        scale = float(full.abs().max())
+        assert float((parts[0] + parts[1] - full).abs().max()) <= tol * scale
+        fa = ac.actor_grad(s).clone()
+        pa = [ac.actor_grad(s[k * h:(k + 1) * h]).clone() for k in range(2)]
+        assert float((pa[0] + pa[1] - fa).abs().max()) <= tol * float(fa.abs().max())
+        assert torch.isfinite(full).all() and torch.isfinite(fa).all()
