@@ -75,17 +75,6 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {      
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ bool mbar_probe(uint32_t bar, uint32_t parity) {     // non-blocking
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
 // Waits for the phase with the given parity.  try_wait parks the thread in hardware for a bounded
 // time per call; a barrier that never completes is a protocol bug, so give up after ~10^6 attempts
 // and trap instead of hanging the device.
@@ -210,41 +199,14 @@ __device__ __forceinline__ void relu_pack_store(const uint32_t (&v)[32], uint8_t
             pack_relu_bf16(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7])));
 }
 
-// 16 accumulator columns -> ReLU -> bf16 -> two chunks
-__device__ __forceinline__ void relu_pack_store16(const uint32_t (&v)[16], uint8_t *dst) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c)
-        *reinterpret_cast<uint4 *>(dst + c * CHUNK_A) = make_uint4(
-            pack_relu_bf16(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1])),
-            pack_relu_bf16(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3])),
-            pack_relu_bf16(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5])),
-            pack_relu_bf16(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7])));
-}
-
-// observation row -> the four layer-1 chunks [hi 0..7][hi 8..11, 1, 1, 0, 0][lo 0..7][lo 8..11, 0 x4] of its tile row
-__device__ __forceinline__ void store_obs_row(const float4 (&xin)[3], uint8_t *row) {
-    const float x[12] = {xin[0].x, xin[0].y, xin[0].z, xin[0].w, xin[1].x, xin[1].y,
-                         xin[1].z, xin[1].w, xin[2].x, xin[2].y, xin[2].z, xin[2].w};
-    float hi[12], lo[12];
-#pragma unroll
-    for (int e = 0; e < 12; ++e) {
-        hi[e] = bf16_round(x[e]);
-        lo[e] = x[e] - hi[e];
-    }
-    *reinterpret_cast<uint4 *>(row + 0 * CHUNK_A) =
-        make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
-    *reinterpret_cast<uint4 *>(row + 1 * CHUNK_A) = make_uint4(pack_bf16(hi[8], hi[9]), pack_bf16(hi[10], hi[11]), ONES, 0u);
-    *reinterpret_cast<uint4 *>(row + 2 * CHUNK_A) =
-        make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
-    *reinterpret_cast<uint4 *>(row + 3 * CHUNK_A) = make_uint4(pack_bf16(lo[8], lo[9]), pack_bf16(lo[10], lo[11]), 0u, 0u);
-}
 // observation row -> the two fp16 layer-1 chunks [x 0..7][x 8..11, 1, 1, 0, 0] of the forward kernels (K = 16)
 __device__ __forceinline__ void store_obs_row_f16(const float4 (&x)[3], uint8_t *row) {
     *reinterpret_cast<uint4 *>(row) =
         make_uint4(pack_f16(x[0].x, x[0].y), pack_f16(x[0].z, x[0].w), pack_f16(x[1].x, x[1].y), pack_f16(x[1].z, x[1].w));
     *reinterpret_cast<uint4 *>(row + CHUNK_A) = make_uint4(pack_f16(x[2].x, x[2].y), pack_f16(x[2].z, x[2].w), 0x3C003C00u, 0u);
 }
-// the same, half of it: slice 0 writes the two high chunks, slice 1 the two low chunks (gradient kernel, two warps per row)
+// observation row -> the bf16 layer-1 chunks [hi 0..7][hi 8..11, 1, 1, 0, 0][lo 0..7][lo 8..11, 0 x4] of its tile row
+// (K = 32, gradient kernel): slice 0 writes the two high chunks, slice 1 the two low ones (two warps share a row)
 __device__ __forceinline__ void store_obs_half(const float4 (&xin)[3], uint8_t *row, int slice) {
     const float x[12] = {xin[0].x, xin[0].y, xin[0].z, xin[0].w, xin[1].x, xin[1].y,
                          xin[1].z, xin[1].w, xin[2].x, xin[2].y, xin[2].z, xin[2].w};
