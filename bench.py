@@ -205,10 +205,30 @@ def learner_legs(dev, rank, world, seed, peaks, collective, ticks=64, updates=20
     obs, act = tr.obs.view(-1, 12), tr.actions.view(-1, 2)
     t_fwd = timed(lambda: tr.networks.actor_forward(obs, out=act, precision="bf16"), 50)
     tr.envs.check_status()
-    return t_roll, t_upd, t_fwd, t_upd32, t_upd_big
+
+    # ---- BASELINE.json configs[4]: 20-frame planning actor + randomised per-env game speeds ----
+    from skillshot_learning_b200 import FrameStackActor, SkillshotEnvs
+    E5, F5 = 65536, 20
+    envs5 = SkillshotEnvs(E5, device=dev, random_positions=True, seed=seed + 7, reward_mode="looking", tick_limit=TICK_LIMIT,
+                          auto_reset=True)
+    g5 = torch.Generator(device=dev).manual_seed(seed + 8)
+    scale = lambda: 0.5 + 1.5 * torch.rand(E5, device=dev, generator=g5)          # U(0.5, 2) x the reference constants
+    envs5.set_speeds(3.0 * scale(), 0.25 * scale(), 5.0 * scale(), (15.0 * scale()).round().clamp(min=1))
+    actor5 = FrameStackActor(2 * E5, frames=F5, device=dev, seed=seed)
+    actor5.push(envs5.observe().reshape(-1, 12))
+    act5 = torch.empty((E5, 2, 2), dtype=torch.float32, device=dev)
+
+    def tick5():
+        actor5.forward(param_noise_sd=0.5, noise_group=1024, out=act5.view(-1, 2))
+        out = envs5.step(act5)
+        actor5.push(out["obs"].reshape(-1, 12), out["done"], done_div=2)
+
+    t_cfg5 = timed(tick5, 32)
+    envs5.check_status()
+    return t_roll, t_upd, t_fwd, t_upd32, t_upd_big, t_cfg5
 
 
-def learner_report(t_roll, t_upd, t_fwd, t_upd32, t_upd_big, world, peaks, peak_kind, collective="nccl"):
+def learner_report(t_roll, t_upd, t_fwd, t_upd32, t_upd_big, t_cfg5, world, peaks, peak_kind, collective="nccl"):
     rows = 2 * ROLLOUT_ENVS
     tf = ACTOR_FLOP_PER_ROW * rows / (t_fwd * 1e-3) / 1e12
     return {
@@ -227,6 +247,12 @@ def learner_report(t_roll, t_upd, t_fwd, t_upd32, t_upd_big, world, peaks, peak_
                   "f32_path_samples_per_sec": world * TRAIN_BATCH / (t_upd32 * 1e-3),
                   "rows_524288_per_gpu": {"samples_per_sec": world * rows / (t_upd_big * 1e-3), "ms_per_update": t_upd_big,
                                           "algorithmic_tflops": world * rows * UPDATE_FLOP_PER_ROW / (t_upd_big * 1e-3) / 1e12}},
+        "planning_actor_speed_sweep": {
+            "workload": "BASELINE.json configs[4] (no reference code): 65,536 envs per GPU with per-env speed constants "
+                        "U(0.5, 2) x the reference's, 20-frame stacked-observation actor (240 -> 256 -> 128 -> 2, float32 "
+                        "kernels) with parameter noise (sd 0.5, one draw per 1,024 rows) + env step + frame-stack push",
+            "env_steps_per_sec": world * 65536 / (t_cfg5 * 1e-3), "samples_per_sec": world * 131072 / (t_cfg5 * 1e-3),
+            "ms_per_tick": t_cfg5},
         "actor_forward_roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                                    "frac": tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peak_kind,
                                    "kernel": "actor_fwd_tc_kernel", "rows_per_launch": rows,
@@ -353,7 +379,7 @@ def run_gpu_arm(args):
         e2e_s = time.perf_counter() - t0
 
     # ---- learner legs: rollout, DDPG update, tensor roofline of the actor forward ----
-    lt = (float("nan"),) * 5
+    lt = (float("nan"),) * 6
     if not args.no_learner:
         del actions
         torch.cuda.empty_cache()

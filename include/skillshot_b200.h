@@ -281,6 +281,27 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
                         uint64_t env_counter, uint64_t noise_seed, uint64_t noise_counter, const void *speeds,
                         uint32_t *status, void *stream);
 
+/* ---- frame-stacked ("planning") actor: readme.md:18-20, BASELINE.json configs[4]; no reference code ----
+ * The actor reads the last `frames` observations of a player: first layer 12 * frames -> 256, the rest as
+ * model_define_actor (SkillshotLearner.py:70-96); frames = 1 is the reference actor.  Parameters are one flat
+ * vector [W1[12 frames][256] b1[256] W2[256][128] b2[128] W3[128][2] b3[2]] (ss_actor_frames_params floats).
+ * The history is a ring per row, stack[n_rows][frames][12]; slot head % frames holds the newest frame, the
+ * network input is ordered oldest -> newest.  Exact float32 path only.
+ *   ss_obs_stack_push        newest observation -> slot head % frames; a row whose `done` flag is set (one flag
+ *                            per done_div rows, NULL = none) gets it in every slot (the game restarted)
+ *   ss_param_noise_groups    out[g][p] = params[p] + params[p] * sd * eps(p, g): one perturbed vector per noise group
+ *                            (SkillshotLearner.py:260-265), g < n_groups, rows of `stride` floats (stride % 4 == 0)
+ *   ss_actor_forward_frames  act_out[n][2]; param_stride = 0: every row uses `params`; else row i uses
+ *                            params + (i / noise_group) * param_stride */
+#define SS_MAX_FRAMES 20
+int64_t ss_actor_frames_params(int frames);
+int ss_obs_stack_push(float *stack, int64_t n_rows, int frames, int64_t head, const float *obs, const uint8_t *done,
+                      int done_div, void *stream);
+int ss_param_noise_groups(const float *params, float *out, int64_t n_params, int64_t n_groups, int64_t stride, float sd,
+                          uint64_t seed, uint64_t counter, void *stream);
+int ss_actor_forward_frames(const float *params, int64_t param_stride, int64_t noise_group, const float *stack, int frames,
+                            int64_t head, float *act_out, int64_t n, void *stream);
+
 /* ---- multi-GPU: the gradient all-reduce fused with its neighbours over NVLink peer memory ----
  * One exchange allocation per rank = flags[2][world] | inbox[2][world][capacity floats], made by
  * ss_peer_alloc and shared between the processes of one node through CUDA IPC (export on the owner,

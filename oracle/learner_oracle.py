@@ -110,6 +110,17 @@ def critic_forward(phi, s, a, keep=None, rate=0.2, dtype=torch.float32) -> np.nd
         return critic_forward_t(_t(phi, dtype), _t(s, dtype), _t(a, dtype), k, rate).numpy()
 
 
+def frames_actor_forward(theta, x, frames, dtype=torch.float32) -> np.ndarray:
+    """The frame-stacked actor (readme.md:18-20; no reference code): model_define_actor with a first Dense layer of
+    12 * frames inputs; x [n, 12 * frames] ordered oldest frame first.  frames = 1 is actor_forward."""
+    shapes = [(DIM_S * frames, H1), (H1,), (H1, H2), (H2,), (H2, DIM_A), (DIM_A,)]
+    with torch.no_grad():
+        w1, b1, w2, b2, w3, b3 = split(_t(theta, dtype), shapes)
+        h = torch.relu(_t(x, dtype) @ w1 + b1)
+        h = torch.relu(h @ w2 + b2)
+        return torch.tanh(h @ w3 + b3).numpy()
+
+
 def noisy_actor_params(theta: np.ndarray, eps: np.ndarray, sd: float) -> np.ndarray:
     """SkillshotLearner.py:260-265 with the normal draws injected: w += w * (sd * eps)."""
     theta = np.asarray(theta, np.float32)

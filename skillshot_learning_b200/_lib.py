@@ -63,6 +63,10 @@ SIGNATURES = {
                                 _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
     "ss_selfplay_rollout": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32,
                                     _f32, _i64, _f32, _i32, _i32, _i64, _i32, _u64, _u64, _u64, _u64, _vp, _vp, _vp]),
+    "ss_actor_frames_params": (_i64, [_i32]),
+    "ss_obs_stack_push": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _i32, _vp]),
+    "ss_param_noise_groups": (_i32, [_vp, _vp, _i64, _i64, _i64, _f32, _u64, _u64, _vp]),
+    "ss_actor_forward_frames": (_i32, [_vp, _i64, _i64, _vp, _i32, _i64, _vp, _i64, _vp]),
     "ss_param_noise": (_i32, [_vp, _vp, _i64, _f32, _u64, _u64, _u64, _vp]),
     "ss_critic_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "ss_ddpg_targets": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp]),

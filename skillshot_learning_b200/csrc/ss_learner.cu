@@ -251,6 +251,77 @@ __global__ void __launch_bounds__(NT) actor_fwd_kernel(const ActorFwdArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// frame-stacked ("planning") actor: readme.md:18-20 -- no reference code, parity unpinned
+// ---------------------------------------------------------------------------
+// The actor sees the last `frames` observations of a player instead of one: first layer 12 * frames -> 256, the rest
+// unchanged.  Parameters: one flat vector [W1[12 F][256] b1 W2 b2 W3 b3] in the same Keras order; frames = 1 IS the
+// reference actor.  The observation history is a ring per row, stack[row][slot][12]; `head` is the slot of the newest
+// frame and the network input is ordered oldest -> newest.  Parameter noise comes as ready-made vectors, one per
+// noise group (ss_param_noise_groups): group g of `group` consecutive rows uses theta + g * stride.
+struct FramesFwdArgs {
+    const float *theta, *stack;
+    float *act;
+    int64_t n, group, stride, head;
+    int frames;
+};
+
+__global__ void __launch_bounds__(NT) actor_frames_fwd_kernel(const FramesFwdArgs A) {
+    extern __shared__ __align__(16) float smem[];
+    const int dsf = DS * A.frames;
+    float *sT = smem, *h1T = sT + dsf * PITCH, *h2T = h1T + H1 * PITCH, *aT = h2T + H2 * PITCH;
+    const int w1 = 0, b1 = dsf * H1, w2 = b1 + H1, b2 = w2 + H1 * H2, w3 = b2 + H2, b3 = w3 + H2 * DA;
+    const int64_t upg = (A.group + TB - 1) / TB, n_groups = (A.n + A.group - 1) / A.group, units = n_groups * upg;
+    for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const int64_t g = u / upg, base = g * A.group + (u - g * upg) * TB;
+        const int64_t end = min(A.n, (g + 1) * A.group);
+        if (base >= end) continue;
+        const float *P = A.theta + g * A.stride;
+        __syncthreads();
+        for (int e = threadIdx.x; e < TB * dsf; e += NT) {
+            const int t = e / dsf, c = e - t * dsf, f = c / DS, j = c - f * DS;
+            const int slot = (int)((A.head + 1 + f) % A.frames);                  // oldest frame first
+            sT[c * PITCH + t] = (base + t < end) ? A.stack[((base + t) * A.frames + slot) * DS + j] : 0.f;
+        }
+        __syncthreads();
+        dense_fwd<H1, ACT_RELU>(P + w1, P + b1, sT, dsf, h1T);
+        __syncthreads();
+        dense_fwd<H2, ACT_RELU>(P + w2, P + b2, h1T, H1, h2T);
+        __syncthreads();
+        actor_out(P + w3, P + b3, h2T, aT);
+        __syncthreads();
+        if (threadIdx.x < TB && base + threadIdx.x < end)
+            reinterpret_cast<float2 *>(A.act)[base + threadIdx.x] = make_float2(aT[threadIdx.x], aT[PITCH + threadIdx.x]);
+    }
+}
+
+// stack[row][head % frames] = obs[row]; a row whose game has just restarted gets the new observation in every slot
+__global__ void obs_stack_push_kernel(float *stack, int64_t n_rows, int frames, int64_t head, const float *obs,
+                                      const uint8_t *done, int done_div) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 3 * n_rows) return;
+    const int64_t row = e / 3, part = e - row * 3;
+    const float4 v = reinterpret_cast<const float4 *>(obs)[e];
+    float4 *dst = reinterpret_cast<float4 *>(stack) + row * frames * 3 + part;
+    if (done && done[row / done_div]) {
+        for (int f = 0; f < frames; ++f) dst[f * 3] = v;
+    } else {
+        dst[(head % frames) * 3] = v;
+    }
+}
+
+__global__ void param_noise_groups_kernel(const float *theta, float *out, int64_t n_params, int64_t stride, float sd,
+                                          uint64_t seed, uint64_t counter) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (4 * q >= n_params) return;
+    float z[4];
+    normal4(seed, kTagParamNoise, (uint32_t)q, (uint32_t)blockIdx.y, counter, z);
+    for (int e = 0; e < 4; ++e) {
+        const int64_t p = 4 * q + e;
+        if (p < n_params) { const float w = theta[p]; out[(int64_t)blockIdx.y * stride + p] = w + w * (sd * z[e]); }
+    }
+}
+
 // The perturbed parameter vector itself (tests, and the host facade's introspection).
 __global__ void param_noise_kernel(const float *theta, float *out, int64_t n_params, float sd, uint64_t seed,
                                    uint64_t group, uint64_t counter) {
@@ -819,6 +890,41 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
         }
     }
     return SS_OK;
+}
+
+int64_t ss_actor_frames_params(int frames) { return frames < 1 ? -1 : (int64_t)DS * frames * H1 + H1 + H1 * H2 + H2 + H2 * DA + DA; }
+
+int ss_param_noise_groups(const float *params, float *out, int64_t n_params, int64_t n_groups, int64_t stride, float sd,
+                          uint64_t seed, uint64_t counter, void *stream) {
+    if (!params || !out || n_params <= 0 || n_groups <= 0 || n_groups > 65535 || stride < n_params) return SS_ERR_INVALID_ARG;
+    const int64_t quads = (n_params + 3) / 4;
+    param_noise_groups_kernel<<<dim3((unsigned)((quads + 127) / 128), (unsigned)n_groups), 128, 0, (cudaStream_t)stream>>>(
+        params, out, n_params, stride, sd, seed, counter);
+    return check_launch();
+}
+
+int ss_obs_stack_push(float *stack, int64_t n_rows, int frames, int64_t head, const float *obs, const uint8_t *done,
+                      int done_div, void *stream) {
+    if (!stack || !obs || n_rows <= 0 || frames < 1 || head < 0 || done_div < 1) return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)stack | (uintptr_t)obs) & 15) return SS_ERR_INVALID_ARG;
+    obs_stack_push_kernel<<<(unsigned)((3 * n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(stack, n_rows, frames, head, obs,
+                                                                                                 done, done_div);
+    return check_launch();
+}
+
+int ss_actor_forward_frames(const float *params, int64_t param_stride, int64_t noise_group, const float *stack, int frames,
+                            int64_t head, float *act_out, int64_t n, void *stream) {
+    if (!params || !stack || !act_out || n <= 0 || frames < 1 || frames > SS_MAX_FRAMES || head < 0 || param_stride < 0)
+        return SS_ERR_INVALID_ARG;
+    if (param_stride > 0 && noise_group <= 0) return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)params & 15) || (param_stride & 3) || ((uintptr_t)act_out & 7)) return SS_ERR_INVALID_ARG;
+    FramesFwdArgs A{params, stack, act_out, n, param_stride > 0 ? noise_group : n, param_stride, head, frames};
+    const size_t smem = (size_t)(DS * frames + H1 + H2 + DA) * PITCH * 4;
+    const int64_t units = ((n + A.group - 1) / A.group) * ((A.group + TB - 1) / TB);
+    const int grid = grid_for(actor_frames_fwd_kernel, smem, units, 0);
+    if (grid < 0) return SS_ERR_CUDA;
+    actor_frames_fwd_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(A);
+    return check_launch();
 }
 
 }  // extern "C"

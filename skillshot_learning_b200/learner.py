@@ -750,6 +750,77 @@ class SkillshotLearner:
             self.networks.load_state_dict(torch.load(full))
 
 
+class FrameStackActor:
+    """The "planning" actor of readme.md:18-20 (BASELINE.json configs[4]; no reference code, parity unpinned): the
+    actor of model_define_actor with a first layer that reads the last `frames` observations of its player,
+    12 * frames -> 256 relu -> 128 relu -> 2 tanh.  frames = 1 is the reference actor.  Exact float32 kernels;
+    exploration by parameter noise with one perturbed parameter vector per noise group.
+    """
+
+    def __init__(self, n_rows: int, frames: int = 20, device="cuda", seed: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("skillshot_learning_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device)
+        self.n_rows, self.frames, self.seed = int(n_rows), int(frames), int(seed)
+        self.n_params = int(lib.ss_actor_frames_params(self.frames))
+        if self.n_params < 0 or self.frames > 20:
+            raise ValueError("frames must be 1..20")
+        g = torch.Generator(device="cpu").manual_seed(self.seed)
+        shapes = [(12 * self.frames, 256), (256,), (256, 128), (128,), (128, 2), (2,)]
+        parts = [torch.randn(sh, generator=g) * 0.05 if len(sh) == 2 else torch.zeros(sh) for sh in shapes]   # RandomNormal(0, 0.05)
+        self.shapes = shapes
+        self.params = torch.cat([p.reshape(-1) for p in parts]).to(self.device)
+        self.stack = torch.zeros((self.n_rows, self.frames, 12), dtype=torch.float32, device=self.device)
+        self.head = -1                 # slot of the newest frame = head % frames
+        self.counter = 0
+        self._noisy = None
+
+    def push(self, obs, done=None, done_div: int = 2):
+        """Append the newest observation [n_rows,12]; rows whose game restarted (done, one flag per done_div rows)
+        are refilled with it.  The first push fills every slot."""
+        obs = _f32(obs, self.device).reshape(self.n_rows, 12)
+        first = self.head < 0
+        self.head += 1
+        if first:
+            done, done_div = torch.ones(self.n_rows, dtype=torch.uint8, device=self.device), 1
+        elif done is not None:
+            done = done.to(device=self.device, dtype=torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            check(lib.ss_obs_stack_push(self.stack.data_ptr(), self.n_rows, self.frames, self.head, obs.data_ptr(), _ptr(done),
+                                        int(done_div), _stream(self.device)), "ss_obs_stack_push")
+
+    def forward(self, param_noise_sd: float = 0.0, noise_group: int = 0, out: Optional[torch.Tensor] = None):
+        """actions [n_rows,2] from the current stack; param_noise_sd > 0: rows i share the perturbed parameters of
+        noise group i // noise_group (fresh draw per call)."""
+        if self.head < 0:
+            raise ValueError("push an observation first")
+        if out is None:
+            out = torch.empty((self.n_rows, 2), dtype=torch.float32, device=self.device)
+        params, stride = self.params, 0
+        with torch.cuda.device(self.device):
+            if param_noise_sd > 0:
+                if noise_group <= 0:
+                    raise ValueError("noise_group must be positive")
+                n_groups = (self.n_rows + noise_group - 1) // noise_group
+                stride = (self.n_params + 3) // 4 * 4
+                if self._noisy is None or self._noisy.numel() < n_groups * stride:
+                    self._noisy = torch.empty(n_groups * stride, dtype=torch.float32, device=self.device)
+                check(lib.ss_param_noise_groups(self.params.data_ptr(), self._noisy.data_ptr(), self.n_params, n_groups, stride,
+                                                float(param_noise_sd), self.seed, self.counter, _stream(self.device)),
+                      "ss_param_noise_groups")
+                self.counter += 1
+                params = self._noisy
+            check(lib.ss_actor_forward_frames(params.data_ptr(), stride, int(noise_group), self.stack.data_ptr(), self.frames,
+                                              self.head, out.data_ptr(), self.n_rows, _stream(self.device)),
+                  "ss_actor_forward_frames")
+        return out
+
+    def ordered_stack(self) -> torch.Tensor:
+        """[n_rows, frames * 12] network input, oldest frame first (introspection / tests)."""
+        order = [(self.head + 1 + f) % self.frames for f in range(self.frames)]
+        return self.stack[:, order, :].reshape(self.n_rows, self.frames * 12)
+
+
 class SelfPlayTrainer:
     """Batched self-play: E games stepped together, both players driven by the shared actor
     with parameter-noise exploration, transitions kept in a device replay ring, critic and

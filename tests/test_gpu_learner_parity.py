@@ -552,3 +552,48 @@ def test_full_size_gradients_are_additive_over_shards(net):
         pa = [ac.actor_grad(s[k * h:(k + 1) * h]).clone() for k in range(2)]
         assert float((pa[0] + pa[1] - fa).abs().max()) <= tol * float(fa.abs().max())
         assert torch.isfinite(full).all() and torch.isfinite(fa).all()
+
+
+# ---------------------------------------------------------------------------
+# frame-stacked planning actor (BASELINE.json configs[4]; no reference code: parity unpinned, reduction tested)
+# ---------------------------------------------------------------------------
+def test_frame_stack_actor_reduces_to_the_reference_actor(net):
+    from skillshot_learning_b200 import FrameStackActor
+    ac, theta, _ = net
+    n = 333
+    fa = FrameStackActor(n, frames=1, device="cuda:0", seed=1)
+    assert fa.n_params == lo.ACTOR_PARAMS
+    fa.params.copy_(torch.from_numpy(theta).cuda())
+    s, _, _ = _batch(n, 12)
+    fa.push(s)
+    assert torch.equal(fa.forward(), ac.actor_forward(s))                  # frames = 1 IS the reference actor
+
+
+def test_frame_stack_actor_ring_order_restarts_and_noise_groups():
+    from skillshot_learning_b200 import FrameStackActor
+    n, F = 301, 20
+    fa = FrameStackActor(n, frames=F, device="cuda:0", seed=3)
+    assert fa.n_params == 12 * F * 256 + 256 + 256 * 128 + 128 + 128 * 2 + 2
+    theta = fa.params.cpu().numpy()
+    rng = np.random.default_rng(0)
+    hist = np.zeros((n, F, 12), np.float32)                                # mirror, oldest -> newest
+    for t in range(27):                                                    # wraps the ring
+        s = rng.uniform(0, 1, (n, 12)).astype(np.float32)
+        done_env = (rng.uniform(size=(n + 1) // 2) < 0.1).astype(np.uint8)
+        restart = np.repeat(done_env, 2)[:n].astype(bool) if t > 0 else np.ones(n, bool)
+        fa.push(s, torch.from_numpy(done_env))
+        hist = np.concatenate([hist[:, 1:], s[:, None]], axis=1)
+        hist[restart] = s[restart][:, None, :]
+        np.testing.assert_array_equal(fa.ordered_stack().cpu().numpy(), hist.reshape(n, F * 12))
+        if t % 9 == 0:
+            got = fa.forward().cpu().numpy()
+            np.testing.assert_allclose(got, lo.frames_actor_forward(theta, hist.reshape(n, F * 12), F), rtol=2e-5, atol=2e-6)
+    group = 64
+    fa.counter = 5
+    got = fa.forward(param_noise_sd=0.5, noise_group=group).cpu().numpy()
+    x = hist.reshape(n, F * 12)
+    for g in range((n + group - 1) // group):
+        eps = philox_ref.param_noise_eps(fa.n_params, fa.seed, g, 5)
+        sl = slice(g * group, min(n, (g + 1) * group))
+        want = lo.frames_actor_forward(lo.noisy_actor_params(theta, eps, 0.5), x[sl], F)
+        np.testing.assert_allclose(got[sl], want, rtol=1e-4, atol=1e-5)
