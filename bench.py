@@ -214,7 +214,7 @@ def learner_legs(dev, rank, world, seed, peaks, collective, ticks=64, updates=20
     g5 = torch.Generator(device=dev).manual_seed(seed + 8)
     scale = lambda: 0.5 + 1.5 * torch.rand(E5, device=dev, generator=g5)          # U(0.5, 2) x the reference constants
     envs5.set_speeds(3.0 * scale(), 0.25 * scale(), 5.0 * scale(), (15.0 * scale()).round().clamp(min=1))
-    actor5 = FrameStackActor(2 * E5, frames=F5, device=dev, seed=seed)
+    actor5 = FrameStackActor(2 * E5, frames=F5, device=dev, seed=seed, precision="bf16")
     actor5.push(envs5.observe().reshape(-1, 12))
     act5 = torch.empty((E5, 2, 2), dtype=torch.float32, device=dev)
 
@@ -249,7 +249,7 @@ def learner_report(t_roll, t_upd, t_fwd, t_upd32, t_upd_big, t_cfg5, world, peak
                                           "algorithmic_tflops": world * rows * UPDATE_FLOP_PER_ROW / (t_upd_big * 1e-3) / 1e12}},
         "planning_actor_speed_sweep": {
             "workload": "BASELINE.json configs[4] (no reference code): 65,536 envs per GPU with per-env speed constants "
-                        "U(0.5, 2) x the reference's, 20-frame stacked-observation actor (240 -> 256 -> 128 -> 2, float32 "
+                        "U(0.5, 2) x the reference's, 20-frame stacked-observation actor (240 -> 256 -> 128 -> 2, tcgen05 "
                         "kernels) with parameter noise (sd 0.5, one draw per 1,024 rows) + env step + frame-stack push",
             "env_steps_per_sec": world * 65536 / (t_cfg5 * 1e-3), "samples_per_sec": world * 131072 / (t_cfg5 * 1e-3),
             "ms_per_tick": t_cfg5},

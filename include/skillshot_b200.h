@@ -286,13 +286,18 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
  * model_define_actor (SkillshotLearner.py:70-96); frames = 1 is the reference actor.  Parameters are one flat
  * vector [W1[12 frames][256] b1[256] W2[256][128] b2[128] W3[128][2] b3[2]] (ss_actor_frames_params floats).
  * The history is a ring per row, stack[n_rows][frames][12]; slot head % frames holds the newest frame, the
- * network input is ordered oldest -> newest.  Exact float32 path only.
+ * network input is ordered oldest -> newest.
  *   ss_obs_stack_push        newest observation -> slot head % frames; a row whose `done` flag is set (one flag
  *                            per done_div rows, NULL = none) gets it in every slot (the game restarted)
  *   ss_param_noise_groups    out[g][p] = params[p] + params[p] * sd * eps(p, g): one perturbed vector per noise group
  *                            (SkillshotLearner.py:260-265), g < n_groups, rows of `stride` floats (stride % 4 == 0)
  *   ss_actor_forward_frames  act_out[n][2]; param_stride = 0: every row uses `params`; else row i uses
- *                            params + (i / noise_group) * param_stride */
+ *                            params + (i / noise_group) * param_stride.  The exact float32 path.
+ *   ss_actor_forward_frames_tc  the same on the tensor cores (tcgen05.mma: layer 1 in fp16, layer 2 in bf16, fp32
+ *                            accumulation, the output layer and tanh in fp32): agrees with the float32 path to about
+ *                            1e-2 on the action.  noise_group must be a multiple of 128 when param_stride > 0;
+ *                            `workspace` (16-byte aligned) holds ss_actor_frames_tc_workspace_bytes(n, noise_group)
+ *                            bytes: hidden layer 1 of every 128-row tile between the two kernels of the call */
 #define SS_MAX_FRAMES 20
 int64_t ss_actor_frames_params(int frames);
 int ss_obs_stack_push(float *stack, int64_t n_rows, int frames, int64_t head, const float *obs, const uint8_t *done,
@@ -301,6 +306,10 @@ int ss_param_noise_groups(const float *params, float *out, int64_t n_params, int
                           uint64_t seed, uint64_t counter, void *stream);
 int ss_actor_forward_frames(const float *params, int64_t param_stride, int64_t noise_group, const float *stack, int frames,
                             int64_t head, float *act_out, int64_t n, void *stream);
+int64_t ss_actor_frames_tc_workspace_bytes(int64_t n, int64_t noise_group);
+int ss_actor_forward_frames_tc(const float *params, int64_t param_stride, int64_t noise_group, const float *stack, int frames,
+                               int64_t head, float *act_out, int64_t n, void *workspace, int64_t workspace_bytes,
+                               void *stream);
 
 /* ---- multi-GPU: the gradient all-reduce fused with its neighbours over NVLink peer memory ----
  * One exchange allocation per rank = flags[2][world] | inbox[2][world][capacity floats], made by
@@ -354,6 +363,48 @@ int ss_replay_sample(const float *ring_obs, const float *ring_act, const float *
                      const int64_t *indices, uint64_t seed, uint64_t counter, int64_t batch,
                      float *obs, float *act, float *reward, float *next_obs, uint8_t *done,
                      int64_t *indices_out, void *stream);
+
+/* One update step of the batched learner from a single host call: ss_replay_sample (Philox indices)
+ * -> TD target (skipped when gamma == 0: the critic regresses on the reward, SkillshotLearner.py:434)
+ * -> critic gradient -> [exchange] -> Adam + soft target update -> actor gradient with the UPDATED critic
+ * (model_actor_fit_step, SkillshotLearner.py:386-417, follows the critic fit, 434-443) -> [exchange] -> Adam.
+ * The same launches, in the same order and with the same arguments, as calling those entry points one by
+ * one; it exists because that sequence costs ~150 us of interpreter time per update from Python.
+ * All pointers are device pointers except peer_bases (host array, as for ss_peer_reduce_push).
+ *   tensor_cores != 0   the *_tc gradient / target kernels (workspace as they require)
+ *   peer_bases == NULL  single GPU: grad_actor / grad_critic receive the gradients
+ *   peer_bases != NULL  sharded batch with the fused NVLink exchange: the critic exchange is epoch
+ *                       `epoch`, the actor's `epoch + 1`; grad_* (may be NULL) receive the summed gradients
+ *   stats[2]            sum of squared errors of the critic batch, sum of Q of the actor batch (this shard's)
+ *   step_critic/actor   Adam step numbers of THIS update (>= 1) */
+typedef struct ss_ddpg_update_args {
+    const float *ring_obs, *ring_act, *ring_reward, *ring_next_obs;
+    const uint8_t *ring_done;
+    int64_t capacity, size;
+    uint64_t replay_seed, replay_counter;
+    int64_t batch;
+    float *obs, *act, *reward, *next_obs;      /* minibatch buffers of `batch` rows, filled by the call */
+    uint8_t *done;
+    int64_t *indices;                          /* may be NULL */
+    float *y;                                  /* TD targets [batch]; unused when gamma == 0 */
+    float *actor, *critic, *target_actor, *target_critic;    /* targets may be NULL when gamma == 0 (no soft update) */
+    float *m_actor, *v_actor, *m_critic, *v_critic;
+    float *grad_actor, *grad_critic;
+    float *stats;
+    float gamma, tau, lr_actor, lr_critic, beta1, beta2, eps, dropout_rate;
+    uint64_t seed, counter;                    /* dropout stream (ss_critic_grad) */
+    int64_t step_critic, step_actor;
+    int64_t n_global, row_offset;              /* as for ss_critic_grad */
+    void *workspace;
+    int64_t workspace_bytes;
+    int tensor_cores;
+    int world, rank;
+    void *const *peer_bases;
+    int64_t peer_capacity;
+    uint32_t epoch;
+    uint32_t *done_counter, *status;
+} ss_ddpg_update_args;
+int ss_ddpg_update(const ss_ddpg_update_args *args, void *stream);
 
 #ifdef __cplusplus
 }

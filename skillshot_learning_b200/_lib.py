@@ -32,6 +32,23 @@ DIM_STATE, DIM_ACTION, HIDDEN1, HIDDEN2 = 12, 2, 256, 128
 ACTOR_PARAMS, CRITIC_PARAMS = 36482, 36609
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 8, 64
 
+_u32 = ctypes.c_uint32
+
+
+class DdpgUpdateArgs(ctypes.Structure):
+    """struct ss_ddpg_update_args of include/skillshot_b200.h (same field order)."""
+    _fields_ = ([(k, _vp) for k in ("ring_obs", "ring_act", "ring_reward", "ring_next_obs", "ring_done")] +
+                [("capacity", _i64), ("size", _i64), ("replay_seed", _u64), ("replay_counter", _u64), ("batch", _i64)] +
+                [(k, _vp) for k in ("obs", "act", "reward", "next_obs", "done", "indices", "y", "actor", "critic",
+                                    "target_actor", "target_critic", "m_actor", "v_actor", "m_critic", "v_critic",
+                                    "grad_actor", "grad_critic", "stats")] +
+                [(k, _f32) for k in ("gamma", "tau", "lr_actor", "lr_critic", "beta1", "beta2", "eps", "dropout_rate")] +
+                [("seed", _u64), ("counter", _u64), ("step_critic", _i64), ("step_actor", _i64), ("n_global", _i64),
+                 ("row_offset", _i64), ("workspace", _vp), ("workspace_bytes", _i64), ("tensor_cores", _i32),
+                 ("world", _i32), ("rank", _i32), ("peer_bases", _vp), ("peer_capacity", _i64), ("epoch", _u32),
+                 ("done_counter", _vp), ("status", _vp)])
+
+
 # name -> (restype, argtypes); every symbol the header declares
 SIGNATURES = {
     "ss_version": (_i32, []),
@@ -67,6 +84,8 @@ SIGNATURES = {
     "ss_obs_stack_push": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _i32, _vp]),
     "ss_param_noise_groups": (_i32, [_vp, _vp, _i64, _i64, _i64, _f32, _u64, _u64, _vp]),
     "ss_actor_forward_frames": (_i32, [_vp, _i64, _i64, _vp, _i32, _i64, _vp, _i64, _vp]),
+    "ss_actor_frames_tc_workspace_bytes": (_i64, [_i64, _i64]),
+    "ss_actor_forward_frames_tc": (_i32, [_vp, _i64, _i64, _vp, _i32, _i64, _vp, _i64, _vp, _i64, _vp]),
     "ss_param_noise": (_i32, [_vp, _vp, _i64, _f32, _u64, _u64, _u64, _vp]),
     "ss_critic_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "ss_ddpg_targets": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp]),
@@ -74,6 +93,7 @@ SIGNATURES = {
     "ss_actor_grad": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "ss_adam_tf": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "ss_replay_push": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
+    "ss_ddpg_update": (_i32, [ctypes.POINTER(DdpgUpdateArgs), _vp]),
     "ss_replay_sample": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _u64, _u64, _i64,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -29,6 +29,8 @@ UNITS = {
     "ss_mlp_tc.cu": [],
     "ss_mlp_grad_tc.cu": [],
     "ss_peer.cu": [],
+    "ss_update.cu": [],
+    "ss_frames_tc.cu": [],
 }
 
 

@@ -1,0 +1,483 @@
+// ss_frames_tc.cu -- the frame-stacked planning actor on the tensor cores (tcgen05.mma, sm_100a).
+//
+// BASELINE.json configs[4] / readme.md:18-20 of the reference (no reference code): the actor of
+// model_define_actor (SkillshotLearner.py:70-96) fed the last `frames` observations of a player,
+// oldest first: 12 * frames -> 256 relu -> 128 relu -> 2 tanh.  With 20 frames layer 1 is a real
+// GEMM (K = 240, 76 % of the MACs) and its weight image alone takes 128 KB of shared memory, so the
+// three layers cannot share one resident CTA the way ss_mlp_tc.cu's do.  Two kernels:
+//
+//   frames_l1_kernel    H1[tile] = relu(X[128 x K1] . W1'[K1 x 256])      fp16 operands, fp32 accumulate
+//       W1' stays resident (K1 = 12 * frames + bias rows, padded to 16: 256 for 20 frames).  Eight loader
+//       warps gather the tile's rows from the observation ring (slot order rotated by `head`), convert
+//       to fp16 and fill a ring of four 64-column K stages; the MMA warp consumes a stage while the next
+//       ones are being filled, accumulating into one of two 256-column tensor-memory buffers; four epilogue warps
+//       drain the other buffer -> ReLU -> bf16 -> the tile's layer-2 operand image in global memory
+//       (64 KB per tile, the exact shared-memory layout of ss_tc_common.cuh).
+//   frames_l23_kernel   act = tanh(relu(H1 . W2') . W3 + b3)
+//       W2' resident; one thread streams the 64 KB operand images back with cp.async.bulk into a
+//       two-slot ring (they were written moments earlier and mostly still sit in the 126 MB L2), the MMA
+//       warp runs the 17-step layer-2 chain into one of two accumulators, four warps do the 128 -> 2
+//       layer and tanh in fp32 from the other.
+//
+// Parameter noise (SkillshotLearner.py:260-265): the caller passes one perturbed parameter vector per
+// noise group (ss_param_noise_groups); a CTA restages its weights when its tiles cross into the next
+// group, and the launch gives every CTA exactly one group when the groups fit the SMs.
+//
+// Precision as in ss_mlp_tc.cu: observations and W1 in fp16 (11-bit significands), hidden layer 1
+// and W2 in bf16, biases as high + low pairs against constant-one K columns, fp32 accumulation;
+// results agree with ss_actor_forward_frames (the exact float32 path) to about 1e-2 on the action.
+#include "ss_tc_common.cuh"
+
+namespace {
+
+using namespace sstc;
+
+constexpr int MAXF = SS_MAX_FRAMES;
+constexpr int K1MAX = (DS * MAXF + 2 + 15) / 16 * 16;       // 256
+constexpr int KSTAGE = 64, NSTAGE = K1MAX / KSTAGE;         // the X ring: four K stages of 64 columns
+constexpr uint32_t W1IMG_BYTES = (K1MAX / 8) * CHUNK_B1;    // 131,072
+constexpr uint32_t XSTAGE_BYTES = (KSTAGE / 8) * CHUNK_A;   // 16,384
+constexpr uint32_t H1TILE_BYTES = (H1 / 8) * CHUNK_A;       // 65,536: hidden layer 1 of one tile as a layer-2 operand
+
+struct FramesArgs {
+    const float *theta;          // [groups][stride] parameter vectors (stride 0: one vector)
+    const float *stack;          // [n][frames][12] observation ring
+    float *act;                  // [n][2]
+    uint8_t *h1;                 // [units][H1TILE_BYTES] scratch between the two kernels
+    int64_t n, group, stride, head;
+    int frames;
+    long long *trace;            // development: event timestamps of CTA 0 of the layer-1 kernel (NULL in production)
+    int dbg;                     // development: 1 = no proxy fence in the loaders, 2 = epilogue skips its work, 4 = no global loads
+};
+
+struct Units {                   // tiles as (noise group, tile in group) pairs, split evenly over the CTAs
+    int64_t upg, u0, u1;
+    int64_t group, n;
+    __device__ Units(const FramesArgs &A) : group(A.group), n(A.n) {
+        upg = (A.group + TM - 1) / TM;
+        const int64_t units = ((A.n + A.group - 1) / A.group) * upg;
+        u0 = units * blockIdx.x / gridDim.x;
+        u1 = units * (blockIdx.x + 1) / gridDim.x;
+    }
+    __device__ int64_t row0(int64_t u) const { const int64_t g = u / upg; return g * group + (u - g * upg) * TM; }
+    __device__ int64_t end(int64_t u) const { return min(n, (u / upg + 1) * group); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// layer 1
+// ---------------------------------------------------------------------------------------------
+namespace l1 {
+
+constexpr int LOAD_WARPS = 8, EPI_WARPS = 4, MMA_W = LOAD_WARPS + EPI_WARPS, NTH = 32 * (MMA_W + 1);
+constexpr uint32_t SM_W1 = 0;
+constexpr uint32_t SM_X = SM_W1 + W1IMG_BYTES;              // NSTAGE x [8][128][8] fp16
+constexpr uint32_t SM_BAR = SM_X + NSTAGE * XSTAGE_BYTES;
+constexpr int B_XFULL = 0, B_XFREE = NSTAGE, B_DFULL = 2 * NSTAGE, B_DFREE = 2 * NSTAGE + 2, B_COUNT = 2 * NSTAGE + 4;
+constexpr uint32_t SM_TMEM = SM_BAR + B_COUNT * 8;
+constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
+static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+
+// W1' image [k1 / 8][256][8] fp16 from W1 [kx][256], b1 [256]: rows kx, kx + 1 = b1 high, low
+__device__ __forceinline__ void stage_w1(const float *theta, int kx, int k1, uint8_t *img) {
+    const int tasks = (k1 / 8) * (H1 / 4);
+    for (int t = threadIdx.x; t < tasks; t += NTH) {
+        const int kc = t / (H1 / 4), n = (t % (H1 / 4)) * 4;
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = kc * 8 + i;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < kx) v[i] = __ldg(reinterpret_cast<const float4 *>(theta + (int64_t)k * H1 + n));
+            else if (k <= kx + 1) v[i] = __ldg(reinterpret_cast<const float4 *>(theta + (int64_t)kx * H1 + n));      // b1
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = kc * 8 + i;
+            if (k == kx || k == kx + 1) {                   // bias pair: hi at kx, lo at kx + 1
+                const float b[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float hi = __half2float(__float2half_rn(b[j]));
+                    o[j] = k == kx ? hi : b[j] - hi;
+                }
+                v[i] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        uint8_t *dst = img + (uint32_t)(kc * H1 + n) * 16;
+        *reinterpret_cast<uint4 *>(dst + 0) = make_uint4(pack_f16(v[0].x, v[1].x), pack_f16(v[2].x, v[3].x), pack_f16(v[4].x, v[5].x), pack_f16(v[6].x, v[7].x));
+        *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(pack_f16(v[0].y, v[1].y), pack_f16(v[2].y, v[3].y), pack_f16(v[4].y, v[5].y), pack_f16(v[6].y, v[7].y));
+        *reinterpret_cast<uint4 *>(dst + 32) = make_uint4(pack_f16(v[0].z, v[1].z), pack_f16(v[2].z, v[3].z), pack_f16(v[4].z, v[5].z), pack_f16(v[6].z, v[7].z));
+        *reinterpret_cast<uint4 *>(dst + 48) = make_uint4(pack_f16(v[0].w, v[1].w), pack_f16(v[2].w, v[3].w), pack_f16(v[4].w, v[5].w), pack_f16(v[6].w, v[7].w));
+    }
+}
+
+__global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto bar = [&](int idx) -> uint32_t { return sbase + SM_BAR + (uint32_t)idx * 8; };
+    int tr_n = 0;                // development trace: role 0 = loader warp 0, 1 = epilogue warp 8, 2 = MMA warp
+    auto trace = [&](int role, int code) {
+        if (A.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == LOAD_WARPS || warp == MMA_W) && tr_n < 256) {
+            A.trace[(role * 256 + tr_n) * 2] = clock64();
+            A.trace[(role * 256 + tr_n) * 2 + 1] = code;
+            ++tr_n;
+        }
+    };
+    trace(0, 900);
+    const int kx = DS * A.frames;                           // real input columns
+    const int k1 = (kx + 2 + 15) / 16 * 16;                 // + bias pair, padded to the MMA K step
+    const int nstages = (k1 + KSTAGE - 1) / KSTAGE;         // K stages in use (the last one may be partial)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(bar(B_XFULL + s), 32 * LOAD_WARPS);
+            mbar_init(bar(B_XFREE + s), 1);
+        }
+        for (int h = 0; h < 2; ++h) {
+            mbar_init(bar(B_DFULL + h), 1);
+            mbar_init(bar(B_DFREE + h), 32 * EPI_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == MMA_W) tmem_alloc(sbase + SM_TMEM, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<const volatile uint32_t *>(smem + SM_TMEM);
+
+    const Units U(A);
+    uint32_t tcount = 0;                                    // tiles this CTA has started: parities derive from it
+    for (int64_t u = U.u0; u < U.u1;) {
+        const int64_t g = u / U.upg;
+        const int64_t seg_end = min(U.u1, (g + 1) * U.upg);
+        const uint32_t ntiles = (uint32_t)(seg_end - u);
+        stage_w1(A.theta + g * A.stride, kx, k1, smem + SM_W1);
+        fence_proxy_async();
+        __syncthreads();
+        trace(0, 901);
+
+        if (warp < LOAD_WARPS) {
+            // ============ loaders ============
+            // A warp owns 16 rows of the tile; lane = (row in a group of 8, 16-byte column unit modulo 4).  One load
+            // instruction then reads 64 contiguous bytes of each of 8 rows (whole 32-byte sectors, each used once), and
+            // one store instruction writes 8 bytes per lane to two 128-byte runs of the operand image (no bank
+            // conflicts).  A stage is 64 columns = 16 units per row: 8 loads per thread, issued one stage AHEAD of the
+            // stage being converted so that global loads are always in flight.
+            const int rr = lane & 7, cg = lane >> 3;
+            const int oldest = (int)((A.head + 1) % A.frames);            // ring slot of the oldest frame
+            const int units_x = kx / 4;                                   // 16-byte units of real input per row
+            const uint32_t total = ntiles * (uint32_t)nstages;            // stages of this segment, tile-major
+            const int64_t seg_row = U.row0(u) + warp * 16 + rr, end = U.end(u);   // a segment stays inside one noise group
+            float4 va[8], vb[8];
+            uint32_t li = 0, lsg = 0;                                     // next stage to load: tile in segment, K stage
+            auto issue = [&](float4 (&v)[8]) {
+                const int64_t rbase = seg_row + (int64_t)li * TM;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int64_t row = rbase + (e >> 2) * 8;
+                    const int q = (int)lsg * 16 + cg + 4 * (e & 3);       // unit of the row: columns 4q .. 4q + 3
+                    v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q < units_x) {
+                        if (row < end && !(A.dbg & 4)) {
+                            const int f = q / 3;                          // 3 units per frame
+                            int slot = oldest + f;                        // oldest frame first
+                            if (slot >= A.frames) slot -= A.frames;
+                            v[e] = __ldg(reinterpret_cast<const float4 *>(A.stack + (row * A.frames + slot) * DS) + (q - f * 3));
+                        }
+                    } else if (q == units_x) {
+                        v[e] = make_float4(1.f, 1.f, 0.f, 0.f);           // against the bias pair
+                    }
+                }
+                if (++lsg == (uint32_t)nstages) { lsg = 0; ++li; }
+            };
+            uint32_t fi = 0, fsg = 0;                                     // next stage to convert and hand over
+            auto flush = [&](const float4 (&v)[8]) {
+                const uint32_t tc = tcount + fi;
+                trace(0, 100 + (int)(fi * 4 + fsg));
+                mbar_wait(bar(B_XFREE + fsg), (tc & 1) ^ 1);              // the previous tile's MMAs have read this stage
+                trace(0, 200 + (int)(fi * 4 + fsg));
+                uint8_t *dst = smem + SM_X + fsg * XSTAGE_BYTES + (uint32_t)(cg >> 1) * CHUNK_A + (warp * 16 + rr) * 16 + (cg & 1) * 8;
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    *reinterpret_cast<uint2 *>(dst + (uint32_t)(2 * (e & 3)) * CHUNK_A + (e >> 2) * 8 * 16) =
+                        make_uint2(pack_f16(v[e].x, v[e].y), pack_f16(v[e].z, v[e].w));
+                if (!(A.dbg & 1)) fence_proxy_async();
+                mbar_arrive(bar(B_XFULL + fsg));
+                trace(0, 300 + (int)(fi * 4 + fsg));
+                if (++fsg == (uint32_t)nstages) { fsg = 0; ++fi; }
+            };
+            issue(va);
+            for (uint32_t st = 0; st < total; st += 2) {
+                if (st + 1 < total) issue(vb);
+                flush(va);
+                if (st + 1 < total) {
+                    if (st + 2 < total) issue(va);
+                    flush(vb);
+                }
+            }
+        } else if (warp < MMA_W) {
+            // ============ epilogue: D[slot] -> ReLU -> bf16 -> the tile's layer-2 operand image ============
+            const int r = (warp & 3) * 32 + lane;
+            const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+            for (uint32_t i = 0; i < ntiles; ++i) {
+                const uint32_t tc = tcount + i, slot = tc & 1;
+                uint8_t *out = A.h1 + (u + i) * (int64_t)H1TILE_BYTES + r * 16;
+                trace(1, 100 + (int)i);
+                mbar_wait(bar(B_DFULL + slot), (tc >> 1) & 1);
+                tc_fence_after();
+                trace(1, 200 + (int)i);
+                if (A.dbg & 2) { tc_fence_before(); mbar_arrive(bar(B_DFREE + slot)); continue; }
+                uint32_t va[32], vb[32];
+                tmem_ld32(tl + slot * 256, va);
+#pragma unroll
+                for (int j = 0; j < H1 / 32; j += 2) {
+                    tmem_wait_ld();
+                    tmem_ld32(tl + slot * 256 + (j + 1) * 32, vb);
+                    relu_pack_store(va, out + (uint32_t)(j * 4) * CHUNK_A);
+                    tmem_wait_ld();
+                    if (j + 2 < H1 / 32) tmem_ld32(tl + slot * 256 + (j + 2) * 32, va);
+                    else { tc_fence_before(); mbar_arrive(bar(B_DFREE + slot)); }        // D[slot] fully read
+                    relu_pack_store(vb, out + (uint32_t)((j + 1) * 4) * CHUNK_A);
+                }
+                trace(1, 300 + (int)i);
+            }
+        } else {
+            // ============ the MMA-issuing warp ============
+            constexpr uint32_t kI = umma_idesc_f16(TM, H1);
+            const uint64_t xd = desc_kmajor(sbase + SM_X, CHUNK_A), wd = desc_kmajor(sbase + SM_W1, CHUNK_B1);
+            const uint32_t tc0 = __shfl_sync(0xffffffffu, tcount, 0);
+            for (uint32_t i = 0; i < ntiles; ++i) {
+                const uint32_t tc = tc0 + i, slot = tc & 1;
+                trace(2, 100 + (int)i);
+                mbar_wait(bar(B_DFREE + slot), ((tc >> 1) & 1) ^ 1);  // the epilogue has drained D[slot]
+                for (int sg = 0; sg < nstages; ++sg) {
+                    const int steps = min(KSTAGE, k1 - sg * KSTAGE) / 16;
+                    mbar_wait(bar(B_XFULL + sg), tc & 1);
+                    tc_fence_after();
+                    trace(2, 200 + (int)i * 4 + sg);
+                    if (lane == 0) {
+                        for (int ks = 0; ks < steps; ++ks)
+                            umma_bf16(tmem + slot * 256, desc_advance(xd, sg * XSTAGE_BYTES + 2 * CHUNK_A * ks),
+                                      desc_advance(wd, (uint32_t)(sg * (KSTAGE / 8) + 2 * ks) * CHUNK_B1), kI, (sg | ks) != 0);
+                        umma_commit(bar(B_XFREE + sg));
+                        if (sg == nstages - 1) umma_commit(bar(B_DFULL + slot));
+                    }
+                    __syncwarp();
+                    trace(2, 300 + (int)i * 4 + sg);
+                }
+            }
+        }
+        tcount += ntiles;
+        u = seg_end;
+        tc_fence_before();
+        __syncthreads();                   // every role has finished the segment: the weight image may be replaced
+        tc_fence_after();
+    }
+    if (warp == MMA_W) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace l1
+
+// ---------------------------------------------------------------------------------------------
+// layers 2 and 3
+// ---------------------------------------------------------------------------------------------
+namespace l23 {
+
+constexpr int Q_WARPS = 4, MMA_W = 4, NTH = 32 * 6;          // warp 5: the copy thread
+constexpr uint32_t SM_B2 = 0;
+constexpr uint32_t SM_A1 = SM_B2 + B2_BYTES;                // 2 x [K2/8][128][8] bf16: hidden layer 1 + constant tail
+constexpr uint32_t SM_W3 = SM_A1 + 2 * X2_BYTES;
+constexpr uint32_t SM_B3 = SM_W3 + H2 * 16;
+constexpr uint32_t SM_BAR = SM_B3 + 16;
+constexpr int B_AFULL = 0, B_AFREE = 2, B_DFULL = 4, B_DFREE = 6, B_COUNT = 8;
+constexpr uint32_t SM_TMEM = SM_BAR + B_COUNT * 8;
+constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
+static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(NTH, 1) frames_l23_kernel(const FramesArgs A) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto bar = [&](int idx) -> uint32_t { return sbase + SM_BAR + (uint32_t)idx * 8; };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar(B_AFULL + s), 1);
+            mbar_init(bar(B_AFREE + s), 1);
+            mbar_init(bar(B_DFULL + s), 1);
+            mbar_init(bar(B_DFREE + s), 32 * Q_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == MMA_W) tmem_alloc(sbase + SM_TMEM, 256);
+    for (uint32_t o = threadIdx.x * 16; o < SM_A1; o += NTH * 16) *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < TM) {                                 // constant tail chunks of both slots: {1 1 0 ..} | 0
+        for (int s = 0; s < 2; ++s) {
+            uint8_t *arow = smem + SM_A1 + s * X2_BYTES + threadIdx.x * 16;
+            *reinterpret_cast<uint4 *>(arow + (H1 / 8) * CHUNK_A) = tail_chunk_actor();
+            *reinterpret_cast<uint4 *>(arow + (H1 / 8 + 1) * CHUNK_A) = make_uint4(0, 0, 0, 0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<const volatile uint32_t *>(smem + SM_TMEM);
+    // the parameters after W1 are laid out as in the single-frame actor: shift the base so the shared offsets apply
+    const int64_t shift = (int64_t)(A.frames - 1) * DS * H1;
+
+    const Units U(A);
+    uint32_t tcount = 0;
+    for (int64_t u = U.u0; u < U.u1;) {
+        const int64_t g = u / U.upg;
+        const int64_t seg_end = min(U.u1, (g + 1) * U.upg);
+        const uint32_t ntiles = (uint32_t)(seg_end - u);
+        stage_weights<NET_ACTOR, NTH, true, false>(Stager{A.theta + g * A.stride + shift, nullptr, smem + SM_B2,
+                                                          reinterpret_cast<float4 *>(smem + SM_W3),
+                                                          reinterpret_cast<float *>(smem + SM_B3), false, 0.f, 0, 0, 0});
+        fence_proxy_async();
+        __syncthreads();
+
+        if (warp < Q_WARPS) {
+            // ============ output warps: layer 3 + tanh on D[slot] ============
+            const int r = warp * 32 + lane;
+            const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+            const float4 *w3x = reinterpret_cast<const float4 *>(smem + SM_W3);
+            const float *b3 = reinterpret_cast<const float *>(smem + SM_B3);
+            const int64_t seg_row = U.row0(u) + r, end = U.end(u);        // a segment stays inside one noise group
+            for (uint32_t i = 0; i < ntiles; ++i) {
+                const uint32_t tc = tcount + i, slot = tc & 1;
+                const int64_t row = seg_row + (int64_t)i * TM;
+                mbar_wait(bar(B_DFULL + slot), (tc >> 1) & 1);
+                tc_fence_after();
+                float acc[2][4] = {{b3[0], 0.f, 0.f, 0.f}, {b3[1], 0.f, 0.f, 0.f}};
+                uint32_t va[32], vb[32];
+                auto layer3 = [&](const uint32_t (&v)[32], const float4 *w) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float4 ww = w[c];                                  // W3[2c][0..1], W3[2c+1][0..1]
+                        const float ha = fmaxf(__uint_as_float(v[c * 2 + 0]), 0.f), hb = fmaxf(__uint_as_float(v[c * 2 + 1]), 0.f);
+                        acc[0][(c & 1) * 2 + 0] = fmaf(ha, ww.x, acc[0][(c & 1) * 2 + 0]);
+                        acc[1][(c & 1) * 2 + 0] = fmaf(ha, ww.y, acc[1][(c & 1) * 2 + 0]);
+                        acc[0][(c & 1) * 2 + 1] = fmaf(hb, ww.z, acc[0][(c & 1) * 2 + 1]);
+                        acc[1][(c & 1) * 2 + 1] = fmaf(hb, ww.w, acc[1][(c & 1) * 2 + 1]);
+                    }
+                };
+                tmem_ld32(tl + slot * 128, va);
+#pragma unroll
+                for (int j = 0; j < H2 / 32; j += 2) {
+                    tmem_wait_ld();
+                    tmem_ld32(tl + slot * 128 + (j + 1) * 32, vb);
+                    layer3(va, w3x + j * 16);
+                    tmem_wait_ld();
+                    if (j + 2 < H2 / 32) tmem_ld32(tl + slot * 128 + (j + 2) * 32, va);
+                    else { tc_fence_before(); mbar_arrive(bar(B_DFREE + slot)); }
+                    layer3(vb, w3x + (j + 1) * 16);
+                }
+                if (row < end)
+                    reinterpret_cast<float2 *>(A.act)[row] = make_float2(tanhf((acc[0][0] + acc[0][1]) + (acc[0][2] + acc[0][3])),
+                                                                         tanhf((acc[1][0] + acc[1][1]) + (acc[1][2] + acc[1][3])));
+            }
+        } else if (warp == MMA_W) {
+            constexpr uint32_t kI = umma_idesc(TM, H2);
+            const uint64_t ad = desc_kmajor(sbase + SM_A1, CHUNK_A), bd = desc_kmajor(sbase + SM_B2, CHUNK_B2);
+            const uint32_t tc0 = __shfl_sync(0xffffffffu, tcount, 0);
+            for (uint32_t i = 0; i < ntiles; ++i) {
+                const uint32_t tc = tc0 + i, slot = tc & 1;
+                mbar_wait(bar(B_DFREE + slot), ((tc >> 1) & 1) ^ 1);
+                mbar_wait(bar(B_AFULL + slot), (tc >> 1) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int ks = 0; ks < K2 / 16; ++ks)
+                        umma_bf16(tmem + slot * 128, desc_advance(ad, slot * X2_BYTES + 2 * CHUNK_A * ks),
+                                  desc_advance(bd, 2 * CHUNK_B2 * ks), kI, ks > 0);
+                    umma_commit(bar(B_AFREE + slot));
+                    umma_commit(bar(B_DFULL + slot));
+                }
+                __syncwarp();
+            }
+        } else if (lane == 0) {
+            // ============ the copy thread: operand images of the tiles -> A1 ring ============
+            for (uint32_t i = 0; i < ntiles; ++i) {
+                const uint32_t tc = tcount + i, slot = tc & 1;
+                mbar_wait(bar(B_AFREE + slot), ((tc >> 1) & 1) ^ 1);  // the MMAs that read this slot have retired
+                mbar_expect_tx(bar(B_AFULL + slot), H1TILE_BYTES);
+                const uint8_t *src = A.h1 + (u + i) * (int64_t)H1TILE_BYTES;
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    bulk_load(sbase + SM_A1 + slot * X2_BYTES + p * (H1TILE_BYTES / 4), src + p * (H1TILE_BYTES / 4), H1TILE_BYTES / 4,
+                              bar(B_AFULL + slot));
+            }
+        }
+        tcount += ntiles;
+        u = seg_end;
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    if (warp == MMA_W) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace l23
+
+int64_t frame_units(int64_t n, int64_t group) { return ((n + group - 1) / group) * ((group + TM - 1) / TM); }
+
+}  // namespace
+
+extern "C" int64_t ss_actor_frames_tc_workspace_bytes(int64_t n_rows, int64_t noise_group) {
+    if (n_rows <= 0) return -1;
+    const int64_t group = noise_group > 0 && noise_group < n_rows ? noise_group : n_rows;
+    return frame_units(n_rows, group) * (int64_t)H1TILE_BYTES;
+}
+
+static int frames_forward(const float *params, int64_t param_stride, int64_t noise_group, const float *stack, int frames,
+                          int64_t head, float *act_out, int64_t n_rows, void *workspace, int64_t workspace_bytes,
+                          long long *trace, void *stream, int dbg = 0) {
+    if (!params || !stack || !act_out || !workspace || n_rows <= 0 || frames < 1 || frames > MAXF || head < 0 || param_stride < 0)
+        return SS_ERR_INVALID_ARG;
+    if (param_stride > 0 && (noise_group <= 0 || noise_group % TM != 0)) return SS_ERR_INVALID_ARG;
+    if ((((uintptr_t)params | (uintptr_t)stack | (uintptr_t)workspace) & 15) || (param_stride & 3) || ((uintptr_t)act_out & 7))
+        return SS_ERR_INVALID_ARG;
+    FramesArgs A{params, stack, act_out, (uint8_t *)workspace, n_rows, param_stride > 0 ? noise_group : n_rows, param_stride, head, frames, trace, 0};
+    if (A.group > n_rows) A.group = n_rows;
+    A.dbg = dbg;
+    const int64_t units = frame_units(n_rows, A.group);
+    if (workspace_bytes < units * (int64_t)H1TILE_BYTES) return SS_ERR_INVALID_ARG;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return SS_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SS_ERR_CUDA;
+    const int64_t n_groups = (n_rows + A.group - 1) / A.group;
+    int grid = (int)(units < sms ? units : sms);
+    if (A.group < n_rows && n_groups <= sms) grid = (int)n_groups;       // one noise group per CTA: weights staged once
+    if (cudaFuncSetAttribute(l1::frames_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1::SM_TOTAL) != cudaSuccess ||
+        cudaFuncSetAttribute(l23::frames_l23_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l23::SM_TOTAL) != cudaSuccess)
+        return SS_ERR_CUDA;
+    l1::frames_l1_kernel<<<grid, l1::NTH, l1::SM_TOTAL, (cudaStream_t)stream>>>(A);
+    l23::frames_l23_kernel<<<grid, l23::NTH, l23::SM_TOTAL, (cudaStream_t)stream>>>(A);
+    return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
+}
+
+extern "C" int ss_actor_forward_frames_tc(const float *params, int64_t param_stride, int64_t noise_group, const float *stack,
+                                          int frames, int64_t head, float *act_out, int64_t n_rows, void *workspace,
+                                          int64_t workspace_bytes, void *stream) {
+    return frames_forward(params, param_stride, noise_group, stack, frames, head, act_out, n_rows, workspace, workspace_bytes,
+                          nullptr, stream);
+}
+
+// development: the same with an event trace of CTA 0 of the layer-1 kernel (3 roles x 256 events x {clock, code}); tools/frames_trace.py
+extern "C" int ss_debug_frames_trace(const float *params, const float *stack, int frames, int64_t head, float *act_out,
+                                     int64_t n_rows, void *workspace, int64_t workspace_bytes, long long *trace, void *stream,
+                                     int dbg) {
+    return frames_forward(params, 0, 0, stack, frames, head, act_out, n_rows, workspace, workspace_bytes, trace, stream, dbg);
+}

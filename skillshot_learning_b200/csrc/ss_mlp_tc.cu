@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
         }
     };
 
+    trace(0, 900);
     if (threadIdx.x == 0) {
         mbar_init(bar(B_X), 128);
         mbar_init(bar(B_Z), 1);
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<const volatile uint32_t *>(smem + SMP_TMEM);
+    trace(0, 901);
 
     const bool noisy = NET == NET_ACTOR && A.param_sd > 0.f;
     const int64_t group = noisy ? A.group : A.n;
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                                              (uint32_t)g});
         fence_proxy_async();
         __syncthreads();
+        trace(0, 902);
 
         if (warp < P_WARPS) {
             // ============ producer warps: observation staging and the layer-1 epilogue ============
@@ -328,6 +331,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
         tc_fence_before();
         __syncthreads();                   // pipeline drained: the output warps have read the last D2
         tc_fence_after();
+        trace(0, 903);
     }
 
     tc_fence_before();

@@ -270,9 +270,10 @@ struct Stager {
 // Weights are [k][n] with n contiguous in HBM and [k/8][n][k%8] bf16 in shared memory.  A task takes
 // one K chunk (8 rows) of four consecutive columns: 8 independent 16-byte loads (coalesced over the
 // lanes), 8 Philox quads if the weights are perturbed, then one 16-byte store per column.
-template <int NET, int NTHREADS, bool L1F16 = false>
+// WITH_L1 = false skips the layer-1 image (the frame-stacked actor builds its own wider one).
+template <int NET, int NTHREADS, bool L1F16 = false, bool WITH_L1 = true>
 __device__ __forceinline__ void stage_weights(const Stager &S) {
-    constexpr int T_W2 = (H1 / 8) * (H2 / 4), T_W1 = 2 * (H1 / 4), T_TAIL = H2 / 4;
+    constexpr int T_W2 = (H1 / 8) * (H2 / 4), T_W1 = WITH_L1 ? 2 * (H1 / 4) : 0, T_TAIL = H2 / 4;
     for (int t = threadIdx.x; t < T_W2 + T_W1 + T_TAIL + 1; t += NTHREADS) {
         if (t < T_W2) {
             const int kc = t / (H2 / 4), n = (t % (H2 / 4)) * 4;

@@ -1,0 +1,86 @@
+// ss_update.cu -- one DDPG update step enqueued by ONE host call.
+//
+// models_fit of the reference (SkillshotLearner.py:419-443) is, per minibatch, a critic fit
+// step followed by model_actor_fit_step (386-417).  The batched build draws the minibatch from
+// the device replay ring and may regress the critic on a TD target; every piece is its own
+// entry point of this library (ss_replay_sample, ss_ddpg_targets*, ss_critic_grad*,
+// ss_actor_grad*, ss_adam_tf, ss_peer_*).  Called one by one from Python they cost ~130-160 us
+// of interpreter and ctypes time per update, about as much as the kernels themselves at a
+// 65,536-row minibatch; this call issues the same launches, in the same order, with the same
+// arguments, from C.  Nothing here touches the device directly.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/skillshot_b200.h"
+
+extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
+    if (!a || !a->ring_obs || !a->ring_act || !a->ring_reward || !a->ring_next_obs || !a->ring_done || a->batch < 1 ||
+        a->size < 1 || a->size > a->capacity || !a->obs || !a->act || !a->reward || !a->next_obs || !a->done || !a->actor ||
+        !a->critic || !a->m_actor || !a->v_actor || !a->m_critic || !a->v_critic || !a->stats || !a->workspace ||
+        a->step_actor < 1 || a->step_critic < 1)
+        return SS_ERR_INVALID_ARG;
+    const bool peers = a->peer_bases != nullptr;
+    if (peers && (a->world < 1 || a->world > SS_PEER_MAX_WORLD || a->rank < 0 || a->rank >= a->world || a->epoch == 0 ||
+                  !a->done_counter))
+        return SS_ERR_INVALID_ARG;
+    if (!peers && (!a->grad_actor || !a->grad_critic)) return SS_ERR_INVALID_ARG;
+    if (a->gamma != 0.f && (!a->y || !a->target_actor || !a->target_critic)) return SS_ERR_INVALID_ARG;
+    const int64_t n = a->batch;
+    const bool tc = a->tensor_cores != 0;
+    int rc;
+
+    // minibatch (uniform with replacement from the filled part of the ring)
+    rc = ss_replay_sample(a->ring_obs, a->ring_act, a->ring_reward, a->ring_next_obs, a->ring_done, a->capacity, a->size,
+                          nullptr, a->replay_seed, a->replay_counter, n, a->obs, a->act, a->reward, a->next_obs, a->done,
+                          a->indices, stream);
+    if (rc != SS_OK) return rc;
+
+    // critic target: the reference regresses on the reward itself (gamma = 0, SkillshotLearner.py:434)
+    const float *y = a->reward;
+    if (a->gamma != 0.f) {
+        rc = tc ? ss_ddpg_targets_tc(a->target_actor, a->target_critic, a->reward, a->next_obs, a->done, a->gamma, a->y, n,
+                                     a->workspace, a->workspace_bytes, stream)
+                : ss_ddpg_targets(a->target_actor, a->target_critic, a->reward, a->next_obs, a->done, a->gamma, a->y, n, stream);
+        if (rc != SS_OK) return rc;
+        y = a->y;
+    }
+
+    // critic: gradient of the batch-mean squared error -> (exchange) -> Adam (+ soft target update)
+    auto critic_grad = tc ? ss_critic_grad_tc : ss_critic_grad;
+    rc = critic_grad(a->critic, a->obs, a->act, y, nullptr, a->dropout_rate, a->seed, a->counter, n, a->n_global, a->row_offset,
+                     peers ? nullptr : a->grad_critic, a->stats, a->workspace, a->workspace_bytes, stream);
+    if (peers) {
+        if (rc <= 0) return rc < 0 ? rc : SS_ERR_INVALID_ARG;
+        rc = ss_peer_reduce_push(a->workspace, rc, SS_CRITIC_PARAMS, a->stats, a->peer_bases, a->world, a->rank,
+                                 a->peer_capacity, a->epoch, a->done_counter, stream);
+        if (rc != SS_OK) return rc;
+        rc = ss_peer_adam_tf(a->peer_bases[a->rank], a->world, a->peer_capacity, a->epoch, a->critic, a->m_critic, a->v_critic,
+                             a->target_critic, a->grad_critic, SS_CRITIC_PARAMS, a->step_critic, a->lr_critic, a->beta1,
+                             a->beta2, a->eps, a->tau, 1.0f, a->status, stream);
+    } else {
+        if (rc != SS_OK) return rc;
+        rc = ss_adam_tf(a->critic, a->grad_critic, a->m_critic, a->v_critic, a->target_critic, SS_CRITIC_PARAMS, a->step_critic,
+                        a->lr_critic, a->beta1, a->beta2, a->eps, a->tau, 1.0f, stream);
+    }
+    if (rc != SS_OK) return rc;
+
+    // actor: model_actor_fit_step with the critic just updated (SkillshotLearner.py:440-443 follows 434)
+    auto actor_grad = tc ? ss_actor_grad_tc : ss_actor_grad;
+    rc = actor_grad(a->actor, a->critic, a->obs, n, peers ? nullptr : a->grad_actor, a->stats + 1, a->workspace,
+                    a->workspace_bytes, stream);
+    if (peers) {
+        if (rc <= 0) return rc < 0 ? rc : SS_ERR_INVALID_ARG;
+        // the tensor-core actor step sums Q with its own kernel; the float32 one through the slices' extra slot
+        rc = ss_peer_reduce_push(a->workspace, rc, SS_ACTOR_PARAMS, tc ? nullptr : a->stats + 1, a->peer_bases, a->world,
+                                 a->rank, a->peer_capacity, a->epoch + 1, a->done_counter, stream);
+        if (rc != SS_OK) return rc;
+        rc = ss_peer_adam_tf(a->peer_bases[a->rank], a->world, a->peer_capacity, a->epoch + 1, a->actor, a->m_actor, a->v_actor,
+                             a->target_actor, a->grad_actor, SS_ACTOR_PARAMS, a->step_actor, a->lr_actor, a->beta1, a->beta2,
+                             a->eps, a->tau, 1.0f, a->status, stream);
+    } else {
+        if (rc != SS_OK) return rc;
+        rc = ss_adam_tf(a->actor, a->grad_actor, a->m_actor, a->v_actor, a->target_actor, SS_ACTOR_PARAMS, a->step_actor,
+                        a->lr_actor, a->beta1, a->beta2, a->eps, a->tau, 1.0f, stream);
+    }
+    return rc;
+}

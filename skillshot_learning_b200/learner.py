@@ -188,6 +188,8 @@ class ActorCritic:
         self.step_actor = 0
         self.step_critic = 0
         self.counter = 0            # Philox counter: advances with every noisy call
+        self._update_args = None    # cached ss_ddpg_update argument block (pointers change rarely)
+        self._update_args_key = None
         self.init_weights(seed)
 
     # -- parameter views -----------------------------------------------------
@@ -417,6 +419,67 @@ class ActorCritic:
         self._allreduce(g)
         self.apply_adam("actor")
         return self.stats[1]
+
+    def update_from_ring(self, ring: "ReplayRing", batch: int, out: Optional[dict] = None):
+        """One whole update step from ONE library call (ss_ddpg_update): sample `batch` rows of `ring`,
+        TD target, critic step, actor step -- the launches critic_step / actor_step make, without the
+        interpreter time between them.  Single GPU or the fused peer exchange (an NCCL all-reduce needs
+        the host between the gradient and Adam: use the separate steps).  Returns the minibatch dict."""
+        if self.group is not None and self.peer is None:
+            raise ValueError("update_from_ring needs collective='peer' when the update is sharded")
+        if ring.size == 0:
+            raise ValueError("sampling from an empty ring")
+        dev = self.device
+        if out is None or out["reward"].shape[0] != batch or "y" not in out:
+            out = dict(obs=torch.empty((batch, 12), dtype=torch.float32, device=dev),
+                       act=torch.empty((batch, 2), dtype=torch.float32, device=dev),
+                       reward=torch.empty(batch, dtype=torch.float32, device=dev),
+                       next_obs=torch.empty((batch, 12), dtype=torch.float32, device=dev),
+                       done=torch.empty(batch, dtype=torch.uint8, device=dev),
+                       indices=torch.empty(batch, dtype=torch.int64, device=dev),
+                       y=torch.empty(batch, dtype=torch.float32, device=dev))
+        _, n_global, row_offset = shard_info(batch, self.group)
+        ws = self._workspace_for(batch)
+        a = self._update_args
+        if a is None or self._update_args_key != (id(ring), out["obs"].data_ptr(), ws.data_ptr()):
+            a = self._update_args = _lib.DdpgUpdateArgs()
+            self._update_args_key = (id(ring), out["obs"].data_ptr(), ws.data_ptr())
+            a.ring_obs, a.ring_act, a.ring_reward = ring.obs.data_ptr(), ring.act.data_ptr(), ring.reward.data_ptr()
+            a.ring_next_obs, a.ring_done, a.capacity = ring.next_obs.data_ptr(), ring.done.data_ptr(), ring.capacity
+            a.batch = batch
+            for k in ("obs", "act", "reward", "next_obs", "done", "indices", "y"):
+                setattr(a, k, out[k].data_ptr())
+            for k in ("actor", "critic"):
+                setattr(a, k, self._slice(self.params, k).data_ptr())
+                setattr(a, "target_" + k, self._slice(self.target, k).data_ptr())
+                setattr(a, "m_" + k, self._slice(self.adam_m, k).data_ptr())
+                setattr(a, "v_" + k, self._slice(self.adam_v, k).data_ptr())
+                setattr(a, "grad_" + k, self._slice(self.grads, k).data_ptr())
+            a.stats = self.stats.data_ptr()
+            a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+            if self.peer is not None:
+                px = self.peer
+                a.world, a.rank, a.peer_capacity = px.world, px.rank, px.capacity
+                a.peer_bases = ctypes.cast(px.bases, ctypes.c_void_p)
+                a.done_counter, a.status = px.done_counter.data_ptr(), px.status.data_ptr()
+        a.size, a.replay_seed, a.replay_counter = ring.size, ring.seed, ring.counter
+        a.gamma, a.tau, a.lr_actor, a.lr_critic = self.gamma, self.tau, self.lr_actor, self.lr_critic
+        a.beta1, a.beta2, a.eps, a.dropout_rate = self.beta1, self.beta2, self.eps, self.dropout
+        a.seed, a.counter = self.seed, self.counter
+        a.step_critic, a.step_actor = self.step_critic + 1, self.step_actor + 1
+        a.n_global, a.row_offset = n_global, row_offset
+        a.tensor_cores = 1 if self.update_precision == "bf16" else 0
+        if self.peer is not None:
+            a.epoch = self.peer.epoch + 1
+        with torch.cuda.device(dev):
+            check(lib.ss_ddpg_update(ctypes.byref(a), _stream(dev)), "ss_ddpg_update")
+        ring.counter += 1
+        self.counter += 1
+        self.step_critic += 1
+        self.step_actor += 1
+        if self.peer is not None:
+            self.peer.epoch += 2
+        return out
 
     # -- checkpoint ------------------------------------------------------------
     def state_dict(self):
@@ -753,11 +816,16 @@ class SkillshotLearner:
 class FrameStackActor:
     """The "planning" actor of readme.md:18-20 (BASELINE.json configs[4]; no reference code, parity unpinned): the
     actor of model_define_actor with a first layer that reads the last `frames` observations of its player,
-    12 * frames -> 256 relu -> 128 relu -> 2 tanh.  frames = 1 is the reference actor.  Exact float32 kernels;
-    exploration by parameter noise with one perturbed parameter vector per noise group.
+    12 * frames -> 256 relu -> 128 relu -> 2 tanh.  frames = 1 is the reference actor.  precision "f32": the exact
+    float32 kernels; "bf16": the tensor-core kernels (ss_frames_tc.cu).  Exploration by parameter noise with one
+    perturbed parameter vector per noise group.
     """
 
-    def __init__(self, n_rows: int, frames: int = 20, device="cuda", seed: int = 0):
+    def __init__(self, n_rows: int, frames: int = 20, device="cuda", seed: int = 0, precision: str = "f32"):
+        if precision not in ("f32", "bf16"):
+            raise ValueError("precision must be 'f32' (exact path) or 'bf16' (tensor cores)")
+        self.precision = precision
+        self._ws = None
         if not torch.cuda.is_available():
             raise RuntimeError("skillshot_learning_b200 needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device)
@@ -810,9 +878,17 @@ class FrameStackActor:
                       "ss_param_noise_groups")
                 self.counter += 1
                 params = self._noisy
-            check(lib.ss_actor_forward_frames(params.data_ptr(), stride, int(noise_group), self.stack.data_ptr(), self.frames,
-                                              self.head, out.data_ptr(), self.n_rows, _stream(self.device)),
-                  "ss_actor_forward_frames")
+            if self.precision == "bf16":
+                need = int(lib.ss_actor_frames_tc_workspace_bytes(self.n_rows, int(noise_group) if stride else 0))
+                if self._ws is None or self._ws.numel() < need:
+                    self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+                check(lib.ss_actor_forward_frames_tc(params.data_ptr(), stride, int(noise_group), self.stack.data_ptr(), self.frames,
+                                                     self.head, out.data_ptr(), self.n_rows, self._ws.data_ptr(), self._ws.numel(),
+                                                     _stream(self.device)), "ss_actor_forward_frames_tc")
+            else:
+                check(lib.ss_actor_forward_frames(params.data_ptr(), stride, int(noise_group), self.stack.data_ptr(), self.frames,
+                                                  self.head, out.data_ptr(), self.n_rows, _stream(self.device)),
+                      "ss_actor_forward_frames")
         return out
 
     def ordered_stack(self) -> torch.Tensor:
@@ -892,7 +968,16 @@ class SelfPlayTrainer:
         return dict(obs=self.obs, reward=out["reward"][0], done=out["done"][0], winner=out["winner"][0])
 
     def update(self):
-        """One critic step and one actor step on a sampled minibatch."""
+        """One critic step and one actor step on a sampled minibatch: a single library call on one GPU or
+        with the fused peer exchange, the separate steps (update_stepwise) around an NCCL all-reduce."""
+        net = self.networks
+        if net.group is not None and net.peer is None:
+            return self.update_stepwise()
+        self._batch = net.update_from_ring(self.replay, self.batch_size, out=self._batch)
+        return net.stats[0], net.stats[1]
+
+    def update_stepwise(self):
+        """The same update as one library call per step (sample, target, critic step, actor step)."""
         self._batch = b = self.replay.sample(self.batch_size, out=self._batch)
         net = self.networks
         y = net.td_targets(b["reward"], b["next_obs"], b["done"])

@@ -48,6 +48,25 @@ def test_learner_entry_points_reject_invalid_arguments_without_a_gpu():
     assert L.ss_replay_push(None, None, None, None, None, 10, 0, None, None, None, None, None, 1, 4, None) == -1
     assert L.ss_peer_bytes(9, 100) == -1 and L.ss_peer_bytes(2, 100) == 256 + 2 * 2 * 100 * 4
     assert L.ss_peer_reduce_push(None, 1, 10, None, None, 2, 0, 100, 1, None, None) == -1
+    assert L.ss_ddpg_update(None, None) == -1
+    blank = _lib.DdpgUpdateArgs()
+    blank.batch, blank.size, blank.capacity, blank.step_actor, blank.step_critic = 16, 16, 16, 1, 1
+    assert L.ss_ddpg_update(ctypes.byref(blank), None) == -1
+
+
+def test_update_argument_block_matches_the_header():
+    """The ctypes mirror of struct ss_ddpg_update_args lists the header's fields in the header's order."""
+    from skillshot_learning_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "skillshot_b200.h")).read()
+    body = re.search(r"typedef struct ss_ddpg_update_args \{(.*?)\} ss_ddpg_update_args;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [re.sub(r"[\s\*]|const", "", part.split()[-1] if i else part.split()[-1])
+                      for i, part in enumerate(decl.split(","))]
+    assert names == [f[0] for f in _lib.DdpgUpdateArgs._fields_]
 
 
 def test_product_package_does_not_touch_the_oracle():

@@ -477,6 +477,29 @@ def test_library_side_rollout_loop_equals_per_tick_calls(capacity):
         assert torch.equal(a.obs, b.obs) and a.replay.pos == b.replay.pos and a.replay.size == b.replay.size
 
 
+@pytest.mark.parametrize("precision,gamma,tau", [("f32", 0.0, 1.0), ("f32", 0.97, 0.01), ("bf16", 0.97, 0.01)])
+def test_single_call_update_equals_the_stepwise_update(precision, gamma, tau):
+    """ss_ddpg_update (the whole update enqueued by one host call) against sample / target / critic step /
+    actor step called one by one: same kernels, same arguments, same Philox counters -> identical weights,
+    optimiser state, targets, gradients, statistics and minibatch."""
+    from skillshot_learning_b200 import SelfPlayTrainer
+    a, b = [SelfPlayTrainer(1024, device="cuda:0", seed=5, batch_size=3000, noise_group=128, tick_limit=30, precision=precision,
+                            gamma=gamma, tau=tau) for _ in range(2)]
+    for tr in (a, b):
+        tr.rollout(5)
+    for it in range(4):
+        sa, qa = a.update()
+        sb, qb = b.update_stepwise()
+        assert float(sa) == float(sb) and float(qa) == float(qb), it
+        na, nb = a.networks, b.networks
+        for name in ("params", "target", "adam_m", "adam_v", "grads"):
+            assert torch.equal(getattr(na, name), getattr(nb, name)), (it, name)
+        for name in ("obs", "act", "reward", "next_obs", "done", "indices"):
+            assert torch.equal(a._batch[name], b._batch[name]), (it, name)
+        assert (na.counter, na.step_actor, na.step_critic, a.replay.counter) == (nb.counter, nb.step_actor, nb.step_critic, b.replay.counter)
+    assert not torch.equal(a.networks.params, SelfPlayTrainer(8, device="cuda:0", seed=5).networks.params)
+
+
 def test_reference_surface_persistence_round_trip(tmp_path, capsys):
     """save / load of models, progress CSV and board rasters in the reference's directory layout
     (SkillshotLearner.py:123-204), plus the full optimiser / Philox state for resuming."""
@@ -597,3 +620,67 @@ def test_frame_stack_actor_ring_order_restarts_and_noise_groups():
         sl = slice(g * group, min(n, (g + 1) * group))
         want = lo.frames_actor_forward(lo.noisy_actor_params(theta, eps, 0.5), x[sl], F)
         np.testing.assert_allclose(got[sl], want, rtol=1e-4, atol=1e-5)
+
+
+def frames_forward_tc_model(theta, x, frames):
+    """What ss_actor_forward_frames_tc computes, restated in numpy (ss_frames_tc.cu header): layer 1 with fp16
+    inputs and weights, hidden layer 1 rounded to bf16, bf16 W2, fp32 accumulation (float64 here), fp32 output layer."""
+    shapes = [(12 * frames, 256), (256,), (256, 128), (128,), (128, 2), (2,)]
+    w1, b1, w2, b2, w3, b3 = lo.split(np.asarray(theta, np.float32), shapes)
+    z1 = _f16(x) @ _f16(w1) + b1
+    h1 = _bf16(np.maximum(z1, 0).astype(np.float32)).astype(np.float64)
+    h2 = np.maximum(h1 @ _bf16(w2).astype(np.float64) + b2, 0)
+    return np.tanh(h2 @ w3.astype(np.float64) + b3).astype(np.float32)
+
+
+@pytest.mark.parametrize("frames,n", [(1, 77), (5, 300), (20, 1), (20, 128), (20, 1000), (11, 148 * 128 * 2 + 77)])
+def test_tensor_core_frame_stack_actor(frames, n):
+    from skillshot_learning_b200 import FrameStackActor
+    exact = FrameStackActor(n, frames=frames, device="cuda:0", seed=8)
+    fast = FrameStackActor(n, frames=frames, device="cuda:0", seed=8, precision="bf16")
+    assert torch.equal(exact.params, fast.params)
+    bias = torch.Generator(device="cpu").manual_seed(2)
+    with torch.no_grad():                                                  # non-zero biases: they ride through the MMA
+        o = 12 * frames * 256
+        exact.params[o:o + 256] = (torch.randn(256, generator=bias) * 0.05).cuda()
+        exact.params[-2:] = torch.tensor([0.01, -0.02]).cuda()
+        fast.params.copy_(exact.params)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for t in range(frames + 3):                                            # fills and wraps the ring
+        s = torch.rand((n, 12), device="cuda", generator=g)
+        s[:, 4] *= 9.87                                                    # the rotation term's range (prepare_states)
+        exact.push(s)
+        fast.push(s)
+    got = fast.forward().cpu().numpy()
+    ref = exact.forward().cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=3e-2)
+    assert np.abs(got - ref).mean() < 3e-3
+    rows = np.unique(np.concatenate([np.arange(min(n, 300)), np.arange(max(0, n - 300), n)]))
+    x = exact.ordered_stack().cpu().numpy()[rows]
+    np.testing.assert_allclose(got[rows], frames_forward_tc_model(fast.params.cpu().numpy(), x, frames), rtol=0, atol=2e-3)
+
+
+def test_tensor_core_frame_stack_actor_noise_groups():
+    from skillshot_learning_b200 import FrameStackActor
+    n, F, group = 1500, 20, 256
+    exact = FrameStackActor(n, frames=F, device="cuda:0", seed=3)
+    fast = FrameStackActor(n, frames=F, device="cuda:0", seed=3, precision="bf16")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(7):
+        s = torch.rand((n, 12), device="cuda", generator=g)
+        exact.push(s)
+        fast.push(s)
+    exact.counter = fast.counter = 9
+    ref = exact.forward(param_noise_sd=0.5, noise_group=group).cpu().numpy()
+    got = fast.forward(param_noise_sd=0.5, noise_group=group).cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=8e-2)                # same Philox vectors; bf16 / fp16 rounding only
+    assert np.abs(got - ref).mean() < 8e-3
+    theta, x = fast.params.cpu().numpy(), fast.ordered_stack().cpu().numpy()
+    for gi in range((n + group - 1) // group):
+        eps = philox_ref.param_noise_eps(fast.n_params, fast.seed, gi, 9)
+        sl = slice(gi * group, min(n, (gi + 1) * group))
+        want = frames_forward_tc_model(lo.noisy_actor_params(theta, eps, 0.5), x[sl], F)
+        np.testing.assert_allclose(got[sl], want, rtol=0, atol=3e-3)
+    with pytest.raises(Exception):
+        fast.forward(param_noise_sd=0.5, noise_group=100)                  # groups are whole tiles

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 from skillshot_learning_b200 import ActorCritic, _lib
 ac = ActorCritic(device="cuda:0", seed=1)
-n = 148 * 128 * 12
+n = 148 * 128 * int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 128 * 12
 obs = torch.rand((n, 12), device="cuda"); out = torch.empty((n, 2), device="cuda")
 tr = torch.zeros((3, 256, 2), dtype=torch.int64, device="cuda")
 L = ctypes.CDLL(_lib.LIB_PATH)
@@ -16,7 +16,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 t = tr.cpu().numpy()
 t0 = min(t[r, 0, 0] for r in range(3) if t[r, 0, 0] > 0)
-names = {0: {1: "P wait MMA1", 2: "P D1 ready", 3: "P epilogue1 done", 4: "P other tile free", 5: "P handed over"},
+names = {0: {9: "K 0 entry/1 init/2 staged/3 drained", 1: "P wait MMA1", 2: "P D1 ready", 3: "P epilogue1 done", 4: "P other tile free", 5: "P handed over"},
          1: {1: "Q wait MMA2", 2: "Q D2 ready"},
          2: {1: "M wait P", 2: "M woke", 3: "M MMA1 issued", 4: "M D2 free", 5: "M MMA2 issued"}}
 ev = []
@@ -25,5 +25,5 @@ for r in range(3):
         if t[r, k, 0] > 0:
             ev.append((int(t[r, k, 0] - t0), names[r][int(t[r, k, 1]) // 100], int(t[r, k, 1]) % 100))
 ev.sort()
-for c, what, tile in ev[:150]:
+for c, what, tile in (ev[:40] + [e for e in ev[40:] if e[1].startswith('K')]):
     print("%7d  %-22s tile %d" % (c, what, tile))
