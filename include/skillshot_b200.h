@@ -293,11 +293,16 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
  *                            (SkillshotLearner.py:260-265), g < n_groups, rows of `stride` floats (stride % 4 == 0)
  *   ss_actor_forward_frames  act_out[n][2]; param_stride = 0: every row uses `params`; else row i uses
  *                            params + (i / noise_group) * param_stride.  The exact float32 path.
- *   ss_actor_forward_frames_tc  the same on the tensor cores (tcgen05.mma: layer 1 in fp16, layer 2 in bf16, fp32
- *                            accumulation, the output layer and tanh in fp32): agrees with the float32 path to about
- *                            1e-2 on the action.  noise_group must be a multiple of 128 when param_stride > 0;
- *                            `workspace` (16-byte aligned) holds ss_actor_frames_tc_workspace_bytes(n, noise_group)
- *                            bytes: hidden layer 1 of every 128-row tile between the two kernels of the call */
+ * Tensor-core path (tcgen05.mma: layer 1 in fp16, layer 2 in bf16, fp32 accumulation, the output layer and
+ * tanh in fp32; agrees with the float32 path to about 1e-2 on the action).  Its history ring is a separate
+ * buffer of ss_obs_stack_tc_bytes(n_rows, frames) bytes, zero-initialised by the caller: fp16 tiles of 128 rows
+ * already in the tensor core's operand layout [tile][K / 8][128][8] with K = 12 frames + 2 padded to 16, columns
+ * in ring-slot order (column 12 slot + j), a constant {1, 1} pair behind them.
+ *   ss_obs_stack_push_tc        as ss_obs_stack_push, into that buffer (observations rounded to fp16)
+ *   ss_actor_forward_frames_tc  as ss_actor_forward_frames, from that buffer.  noise_group must be a multiple
+ *                            of 128 when param_stride > 0; `workspace` (16-byte aligned) holds
+ *                            ss_actor_frames_tc_workspace_bytes(n, noise_group) bytes: hidden layer 1 of every
+ *                            128-row tile between the two kernels of the call */
 #define SS_MAX_FRAMES 20
 int64_t ss_actor_frames_params(int frames);
 int ss_obs_stack_push(float *stack, int64_t n_rows, int frames, int64_t head, const float *obs, const uint8_t *done,
@@ -307,7 +312,10 @@ int ss_param_noise_groups(const float *params, float *out, int64_t n_params, int
 int ss_actor_forward_frames(const float *params, int64_t param_stride, int64_t noise_group, const float *stack, int frames,
                             int64_t head, float *act_out, int64_t n, void *stream);
 int64_t ss_actor_frames_tc_workspace_bytes(int64_t n, int64_t noise_group);
-int ss_actor_forward_frames_tc(const float *params, int64_t param_stride, int64_t noise_group, const float *stack, int frames,
+int64_t ss_obs_stack_tc_bytes(int64_t n_rows, int frames);
+int ss_obs_stack_push_tc(void *stack_tc, int64_t n_rows, int frames, int64_t head, const float *obs, const uint8_t *done,
+                         int done_div, void *stream);
+int ss_actor_forward_frames_tc(const float *params, int64_t param_stride, int64_t noise_group, const void *stack_tc, int frames,
                                int64_t head, float *act_out, int64_t n, void *workspace, int64_t workspace_bytes,
                                void *stream);
 

@@ -85,6 +85,8 @@ SIGNATURES = {
     "ss_param_noise_groups": (_i32, [_vp, _vp, _i64, _i64, _i64, _f32, _u64, _u64, _vp]),
     "ss_actor_forward_frames": (_i32, [_vp, _i64, _i64, _vp, _i32, _i64, _vp, _i64, _vp]),
     "ss_actor_frames_tc_workspace_bytes": (_i64, [_i64, _i64]),
+    "ss_obs_stack_tc_bytes": (_i64, [_i64, _i32]),
+    "ss_obs_stack_push_tc": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _i32, _vp]),
     "ss_actor_forward_frames_tc": (_i32, [_vp, _i64, _i64, _vp, _i32, _i64, _vp, _i64, _vp, _i64, _vp]),
     "ss_param_noise": (_i32, [_vp, _vp, _i64, _f32, _u64, _u64, _u64, _vp]),
     "ss_critic_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),

@@ -7,12 +7,16 @@
 // three layers cannot share one resident CTA the way ss_mlp_tc.cu's do.  Two kernels:
 //
 //   frames_l1_kernel    H1[tile] = relu(X[128 x K1] . W1'[K1 x 256])      fp16 operands, fp32 accumulate
-//       W1' stays resident (K1 = 12 * frames + bias rows, padded to 16: 256 for 20 frames).  Eight loader
-//       warps gather the tile's rows from the observation ring (slot order rotated by `head`), convert
-//       to fp16 and fill a ring of four 64-column K stages; the MMA warp consumes a stage while the next
-//       ones are being filled, accumulating into one of two 256-column tensor-memory buffers; four epilogue warps
-//       drain the other buffer -> ReLU -> bf16 -> the tile's layer-2 operand image in global memory
-//       (64 KB per tile, the exact shared-memory layout of ss_tc_common.cuh).
+//       W1' stays resident (K1 = 12 * frames + bias rows, padded to 16: 256 for 20 frames).  The history
+//       ring of this path is kept in HBM as fp16 tiles already in the tensor core's operand layout
+//       (ss_obs_stack_push_tc), columns in ring-slot order; the rotation that makes the network see the
+//       oldest frame first is applied to W1's rows while staging instead.  One thread streams each tile
+//       in with four 16 KB bulk copies (a ring of 64-column K stages), the MMA warp consumes a stage
+//       while the next ones land, accumulating into one of two 256-column tensor-memory buffers; four
+//       epilogue warps drain the other buffer -> ReLU -> bf16 -> the tile's layer-2 operand image in global
+//       memory (64 KB per tile, the exact shared-memory layout of ss_tc_common.cuh).
+//       (A first version gathered fp32 rows with eight loader warps and converted in registers: 55 us per
+//       131,072 rows, bound by the 64 KB of loads a CTA's registers can keep in flight.)
 //   frames_l23_kernel   act = tanh(relu(H1 . W2') . W3 + b3)
 //       W2' resident; one thread streams the 64 KB operand images back with cp.async.bulk into a
 //       two-slot ring (they were written moments earlier and mostly still sit in the 126 MB L2), the MMA
@@ -41,14 +45,23 @@ constexpr uint32_t H1TILE_BYTES = (H1 / 8) * CHUNK_A;       // 65,536: hidden la
 
 struct FramesArgs {
     const float *theta;          // [groups][stride] parameter vectors (stride 0: one vector)
-    const float *stack;          // [n][frames][12] observation ring
+    const uint8_t *xt;           // history tiles [tile][k1 / 8][128][8] fp16, columns in ring (slot-major) order
     float *act;                  // [n][2]
     uint8_t *h1;                 // [units][H1TILE_BYTES] scratch between the two kernels
     int64_t n, group, stride, head;
     int frames;
-    long long *trace;            // development: event timestamps of CTA 0 of the layer-1 kernel (NULL in production)
-    int dbg;                     // development: 1 = no proxy fence in the loaders, 2 = epilogue skips its work, 4 = no global loads
 };
+
+__host__ __device__ constexpr int frames_k1(int frames) { return (DS * frames + 2 + 15) / 16 * 16; }
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 
 struct Units {                   // tiles as (noise group, tile in group) pairs, split evenly over the CTAs
     int64_t upg, u0, u1;
@@ -68,7 +81,7 @@ struct Units {                   // tiles as (noise group, tile in group) pairs,
 // ---------------------------------------------------------------------------------------------
 namespace l1 {
 
-constexpr int LOAD_WARPS = 8, EPI_WARPS = 4, MMA_W = LOAD_WARPS + EPI_WARPS, NTH = 32 * (MMA_W + 1);
+constexpr int EPI_WARPS = 4, MMA_W = 4, NTH = 32 * 6;        // warp 5: the copy thread
 constexpr uint32_t SM_W1 = 0;
 constexpr uint32_t SM_X = SM_W1 + W1IMG_BYTES;              // NSTAGE x [8][128][8] fp16
 constexpr uint32_t SM_BAR = SM_X + NSTAGE * XSTAGE_BYTES;
@@ -77,9 +90,11 @@ constexpr uint32_t SM_TMEM = SM_BAR + B_COUNT * 8;
 constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 
-// W1' image [k1 / 8][256][8] fp16 from W1 [kx][256], b1 [256]: rows kx, kx + 1 = b1 high, low
-__device__ __forceinline__ void stage_w1(const float *theta, int kx, int k1, uint8_t *img) {
-    const int tasks = (k1 / 8) * (H1 / 4);
+// W1' image [k1 / 8][256][8] fp16.  The history tiles keep their columns in RING order (slot-major), so the
+// image's K rows are W1's rows rotated the same way: image row 12 slot + j = W1 row 12 f + j with
+// f = (slot - oldest) mod frames, the frame's age rank (0 = oldest).  Rows kx, kx + 1 = b1 high, low.
+__device__ __forceinline__ void stage_w1(const float *theta, int frames, int oldest, int k1, uint8_t *img) {
+    const int kx = DS * frames, tasks = (k1 / 8) * (H1 / 4);
     for (int t = threadIdx.x; t < tasks; t += NTH) {
         const int kc = t / (H1 / 4), n = (t % (H1 / 4)) * 4;
         float4 v[8];
@@ -87,8 +102,14 @@ __device__ __forceinline__ void stage_w1(const float *theta, int kx, int k1, uin
         for (int i = 0; i < 8; ++i) {
             const int k = kc * 8 + i;
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < kx) v[i] = __ldg(reinterpret_cast<const float4 *>(theta + (int64_t)k * H1 + n));
-            else if (k <= kx + 1) v[i] = __ldg(reinterpret_cast<const float4 *>(theta + (int64_t)kx * H1 + n));      // b1
+            if (k < kx) {
+                const int slot = k / DS, j = k - slot * DS;
+                int f = slot - oldest;
+                if (f < 0) f += frames;
+                v[i] = __ldg(reinterpret_cast<const float4 *>(theta + (int64_t)(f * DS + j) * H1 + n));
+            } else if (k <= kx + 1) {
+                v[i] = __ldg(reinterpret_cast<const float4 *>(theta + (int64_t)kx * H1 + n));      // b1
+            }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -117,22 +138,14 @@ __global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto bar = [&](int idx) -> uint32_t { return sbase + SM_BAR + (uint32_t)idx * 8; };
-    int tr_n = 0;                // development trace: role 0 = loader warp 0, 1 = epilogue warp 8, 2 = MMA warp
-    auto trace = [&](int role, int code) {
-        if (A.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == LOAD_WARPS || warp == MMA_W) && tr_n < 256) {
-            A.trace[(role * 256 + tr_n) * 2] = clock64();
-            A.trace[(role * 256 + tr_n) * 2 + 1] = code;
-            ++tr_n;
-        }
-    };
-    trace(0, 900);
-    const int kx = DS * A.frames;                           // real input columns
-    const int k1 = (kx + 2 + 15) / 16 * 16;                 // + bias pair, padded to the MMA K step
+    const int k1 = frames_k1(A.frames);                     // input columns + bias pair, padded to the MMA K step
     const int nstages = (k1 + KSTAGE - 1) / KSTAGE;         // K stages in use (the last one may be partial)
+    const uint32_t tile_bytes = (uint32_t)(k1 / 8) * CHUNK_A;
+    const int oldest = (int)((A.head + 1) % A.frames);      // ring slot of the oldest frame
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(bar(B_XFULL + s), 32 * LOAD_WARPS);
+            mbar_init(bar(B_XFULL + s), 1);
             mbar_init(bar(B_XFREE + s), 1);
         }
         for (int h = 0; h < 2; ++h) {
@@ -153,82 +166,19 @@ __global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
         const int64_t g = u / U.upg;
         const int64_t seg_end = min(U.u1, (g + 1) * U.upg);
         const uint32_t ntiles = (uint32_t)(seg_end - u);
-        stage_w1(A.theta + g * A.stride, kx, k1, smem + SM_W1);
+        stage_w1(A.theta + g * A.stride, A.frames, oldest, k1, smem + SM_W1);
         fence_proxy_async();
         __syncthreads();
-        trace(0, 901);
 
-        if (warp < LOAD_WARPS) {
-            // ============ loaders ============
-            // A warp owns 16 rows of the tile; lane = (row in a group of 8, 16-byte column unit modulo 4).  One load
-            // instruction then reads 64 contiguous bytes of each of 8 rows (whole 32-byte sectors, each used once), and
-            // one store instruction writes 8 bytes per lane to two 128-byte runs of the operand image (no bank
-            // conflicts).  A stage is 64 columns = 16 units per row: 8 loads per thread, issued one stage AHEAD of the
-            // stage being converted so that global loads are always in flight.
-            const int rr = lane & 7, cg = lane >> 3;
-            const int oldest = (int)((A.head + 1) % A.frames);            // ring slot of the oldest frame
-            const int units_x = kx / 4;                                   // 16-byte units of real input per row
-            const uint32_t total = ntiles * (uint32_t)nstages;            // stages of this segment, tile-major
-            const int64_t seg_row = U.row0(u) + warp * 16 + rr, end = U.end(u);   // a segment stays inside one noise group
-            float4 va[8], vb[8];
-            uint32_t li = 0, lsg = 0;                                     // next stage to load: tile in segment, K stage
-            auto issue = [&](float4 (&v)[8]) {
-                const int64_t rbase = seg_row + (int64_t)li * TM;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int64_t row = rbase + (e >> 2) * 8;
-                    const int q = (int)lsg * 16 + cg + 4 * (e & 3);       // unit of the row: columns 4q .. 4q + 3
-                    v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (q < units_x) {
-                        if (row < end && !(A.dbg & 4)) {
-                            const int f = q / 3;                          // 3 units per frame
-                            int slot = oldest + f;                        // oldest frame first
-                            if (slot >= A.frames) slot -= A.frames;
-                            v[e] = __ldg(reinterpret_cast<const float4 *>(A.stack + (row * A.frames + slot) * DS) + (q - f * 3));
-                        }
-                    } else if (q == units_x) {
-                        v[e] = make_float4(1.f, 1.f, 0.f, 0.f);           // against the bias pair
-                    }
-                }
-                if (++lsg == (uint32_t)nstages) { lsg = 0; ++li; }
-            };
-            uint32_t fi = 0, fsg = 0;                                     // next stage to convert and hand over
-            auto flush = [&](const float4 (&v)[8]) {
-                const uint32_t tc = tcount + fi;
-                trace(0, 100 + (int)(fi * 4 + fsg));
-                mbar_wait(bar(B_XFREE + fsg), (tc & 1) ^ 1);              // the previous tile's MMAs have read this stage
-                trace(0, 200 + (int)(fi * 4 + fsg));
-                uint8_t *dst = smem + SM_X + fsg * XSTAGE_BYTES + (uint32_t)(cg >> 1) * CHUNK_A + (warp * 16 + rr) * 16 + (cg & 1) * 8;
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    *reinterpret_cast<uint2 *>(dst + (uint32_t)(2 * (e & 3)) * CHUNK_A + (e >> 2) * 8 * 16) =
-                        make_uint2(pack_f16(v[e].x, v[e].y), pack_f16(v[e].z, v[e].w));
-                if (!(A.dbg & 1)) fence_proxy_async();
-                mbar_arrive(bar(B_XFULL + fsg));
-                trace(0, 300 + (int)(fi * 4 + fsg));
-                if (++fsg == (uint32_t)nstages) { fsg = 0; ++fi; }
-            };
-            issue(va);
-            for (uint32_t st = 0; st < total; st += 2) {
-                if (st + 1 < total) issue(vb);
-                flush(va);
-                if (st + 1 < total) {
-                    if (st + 2 < total) issue(va);
-                    flush(vb);
-                }
-            }
-        } else if (warp < MMA_W) {
+        if (warp < EPI_WARPS) {
             // ============ epilogue: D[slot] -> ReLU -> bf16 -> the tile's layer-2 operand image ============
-            const int r = (warp & 3) * 32 + lane;
-            const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+            const int r = warp * 32 + lane;
+            const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
             for (uint32_t i = 0; i < ntiles; ++i) {
                 const uint32_t tc = tcount + i, slot = tc & 1;
                 uint8_t *out = A.h1 + (u + i) * (int64_t)H1TILE_BYTES + r * 16;
-                trace(1, 100 + (int)i);
                 mbar_wait(bar(B_DFULL + slot), (tc >> 1) & 1);
                 tc_fence_after();
-                trace(1, 200 + (int)i);
-                if (A.dbg & 2) { tc_fence_before(); mbar_arrive(bar(B_DFREE + slot)); continue; }
                 uint32_t va[32], vb[32];
                 tmem_ld32(tl + slot * 256, va);
 #pragma unroll
@@ -241,22 +191,19 @@ __global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
                     else { tc_fence_before(); mbar_arrive(bar(B_DFREE + slot)); }        // D[slot] fully read
                     relu_pack_store(vb, out + (uint32_t)((j + 1) * 4) * CHUNK_A);
                 }
-                trace(1, 300 + (int)i);
             }
-        } else {
+        } else if (warp == MMA_W) {
             // ============ the MMA-issuing warp ============
             constexpr uint32_t kI = umma_idesc_f16(TM, H1);
             const uint64_t xd = desc_kmajor(sbase + SM_X, CHUNK_A), wd = desc_kmajor(sbase + SM_W1, CHUNK_B1);
             const uint32_t tc0 = __shfl_sync(0xffffffffu, tcount, 0);
             for (uint32_t i = 0; i < ntiles; ++i) {
                 const uint32_t tc = tc0 + i, slot = tc & 1;
-                trace(2, 100 + (int)i);
                 mbar_wait(bar(B_DFREE + slot), ((tc >> 1) & 1) ^ 1);  // the epilogue has drained D[slot]
                 for (int sg = 0; sg < nstages; ++sg) {
                     const int steps = min(KSTAGE, k1 - sg * KSTAGE) / 16;
                     mbar_wait(bar(B_XFULL + sg), tc & 1);
                     tc_fence_after();
-                    trace(2, 200 + (int)i * 4 + sg);
                     if (lane == 0) {
                         for (int ks = 0; ks < steps; ++ks)
                             umma_bf16(tmem + slot * 256, desc_advance(xd, sg * XSTAGE_BYTES + 2 * CHUNK_A * ks),
@@ -265,7 +212,18 @@ __global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
                         if (sg == nstages - 1) umma_commit(bar(B_DFULL + slot));
                     }
                     __syncwarp();
-                    trace(2, 300 + (int)i * 4 + sg);
+                }
+            }
+        } else if (lane == 0) {
+            // ============ the copy thread: K stages of the history tiles -> X ring ============
+            for (uint32_t i = 0; i < ntiles; ++i) {
+                const uint32_t tc = tcount + i;
+                const uint8_t *src = A.xt + (u + i) * (int64_t)tile_bytes;
+                for (int sg = 0; sg < nstages; ++sg) {
+                    const uint32_t bytes = (uint32_t)min(KSTAGE, k1 - sg * KSTAGE) / 8 * CHUNK_A;
+                    mbar_wait(bar(B_XFREE + sg), (tc & 1) ^ 1);       // the previous tile's MMAs have read this stage
+                    mbar_expect_tx(bar(B_XFULL + sg), bytes);
+                    bulk_load(sbase + SM_X + sg * XSTAGE_BYTES, src + sg * XSTAGE_BYTES, bytes, bar(B_XFULL + sg));
                 }
             }
         }
@@ -295,15 +253,6 @@ constexpr int B_AFULL = 0, B_AFREE = 2, B_DFULL = 4, B_DFREE = 6, B_COUNT = 8;
 constexpr uint32_t SM_TMEM = SM_BAR + B_COUNT * 8;
 constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
-
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
 
 __global__ void __launch_bounds__(NTH, 1) frames_l23_kernel(const FramesArgs A) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -433,7 +382,50 @@ __global__ void __launch_bounds__(NTH, 1) frames_l23_kernel(const FramesArgs A) 
 
 int64_t frame_units(int64_t n, int64_t group) { return ((n + group - 1) / group) * ((group + TM - 1) / TM); }
 
+// newest observation -> ring slot `slot` of every row's history (fp16, operand layout); a row whose game has just
+// restarted gets it in every slot.  Also (re)writes the constant-one pair that multiplies the bias rows.
+__global__ void obs_stack_push_tc_kernel(uint8_t *xt, int64_t n_rows, int frames, int slot, uint32_t tile_bytes, const float *obs,
+                                         const uint8_t *done, int done_div) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const float4 *src = reinterpret_cast<const float4 *>(obs + row * DS);
+    const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+    const uint32_t h[6] = {pack_f16(a.x, a.y), pack_f16(a.z, a.w), pack_f16(b.x, b.y), pack_f16(b.z, b.w), pack_f16(c.x, c.y), pack_f16(c.z, c.w)};
+    uint8_t *base = xt + (row / TM) * (int64_t)tile_bytes + (row % TM) * 16;
+    auto put = [&](int s) {                                 // columns 12 s .. 12 s + 11: 24 bytes starting 0 or 8 bytes into a chunk
+        uint8_t *p = base + (uint32_t)((DS * s) >> 3) * CHUNK_A;
+        if ((s & 1) == 0) {
+            *reinterpret_cast<uint4 *>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint2 *>(p + CHUNK_A) = make_uint2(h[4], h[5]);
+        } else {
+            *reinterpret_cast<uint2 *>(p + 8) = make_uint2(h[0], h[1]);
+            *reinterpret_cast<uint4 *>(p + CHUNK_A) = make_uint4(h[2], h[3], h[4], h[5]);
+        }
+    };
+    if (done && done[row / done_div]) {
+        for (int s = 0; s < frames; ++s) put(s);
+    } else {
+        put(slot);
+    }
+    const int kx = DS * frames;                             // {1, 1} at columns kx, kx + 1
+    *reinterpret_cast<uint32_t *>(base + (uint32_t)(kx >> 3) * CHUNK_A + (kx & 7) * 2) = 0x3C003C00u;
+}
+
 }  // namespace
+
+extern "C" int64_t ss_obs_stack_tc_bytes(int64_t n_rows, int frames) {
+    if (n_rows <= 0 || frames < 1 || frames > MAXF) return -1;
+    return (n_rows + TM - 1) / TM * (int64_t)(frames_k1(frames) / 8) * CHUNK_A;
+}
+
+extern "C" int ss_obs_stack_push_tc(void *stack_tc, int64_t n_rows, int frames, int64_t head, const float *obs, const uint8_t *done,
+                                    int done_div, void *stream) {
+    if (!stack_tc || !obs || n_rows <= 0 || frames < 1 || frames > MAXF || head < 0 || done_div < 1) return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)stack_tc | (uintptr_t)obs) & 15) return SS_ERR_INVALID_ARG;
+    obs_stack_push_tc_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (uint8_t *)stack_tc, n_rows, frames, (int)(head % frames), (uint32_t)(frames_k1(frames) / 8) * CHUNK_A, obs, done, done_div);
+    return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
+}
 
 extern "C" int64_t ss_actor_frames_tc_workspace_bytes(int64_t n_rows, int64_t noise_group) {
     if (n_rows <= 0) return -1;
@@ -441,17 +433,17 @@ extern "C" int64_t ss_actor_frames_tc_workspace_bytes(int64_t n_rows, int64_t no
     return frame_units(n_rows, group) * (int64_t)H1TILE_BYTES;
 }
 
-static int frames_forward(const float *params, int64_t param_stride, int64_t noise_group, const float *stack, int frames,
-                          int64_t head, float *act_out, int64_t n_rows, void *workspace, int64_t workspace_bytes,
-                          long long *trace, void *stream, int dbg = 0) {
-    if (!params || !stack || !act_out || !workspace || n_rows <= 0 || frames < 1 || frames > MAXF || head < 0 || param_stride < 0)
+extern "C" int ss_actor_forward_frames_tc(const float *params, int64_t param_stride, int64_t noise_group, const void *stack_tc,
+                                          int frames, int64_t head, float *act_out, int64_t n_rows, void *workspace,
+                                          int64_t workspace_bytes, void *stream) {
+    if (!params || !stack_tc || !act_out || !workspace || n_rows <= 0 || frames < 1 || frames > MAXF || head < 0 || param_stride < 0)
         return SS_ERR_INVALID_ARG;
     if (param_stride > 0 && (noise_group <= 0 || noise_group % TM != 0)) return SS_ERR_INVALID_ARG;
-    if ((((uintptr_t)params | (uintptr_t)stack | (uintptr_t)workspace) & 15) || (param_stride & 3) || ((uintptr_t)act_out & 7))
+    if ((((uintptr_t)params | (uintptr_t)stack_tc | (uintptr_t)workspace) & 15) || (param_stride & 3) || ((uintptr_t)act_out & 7))
         return SS_ERR_INVALID_ARG;
-    FramesArgs A{params, stack, act_out, (uint8_t *)workspace, n_rows, param_stride > 0 ? noise_group : n_rows, param_stride, head, frames, trace, 0};
+    FramesArgs A{params, (const uint8_t *)stack_tc, act_out, (uint8_t *)workspace, n_rows,
+                 param_stride > 0 ? noise_group : n_rows, param_stride, head, frames};
     if (A.group > n_rows) A.group = n_rows;
-    A.dbg = dbg;
     const int64_t units = frame_units(n_rows, A.group);
     if (workspace_bytes < units * (int64_t)H1TILE_BYTES) return SS_ERR_INVALID_ARG;
     int dev = 0, sms = 0;
@@ -466,18 +458,4 @@ static int frames_forward(const float *params, int64_t param_stride, int64_t noi
     l1::frames_l1_kernel<<<grid, l1::NTH, l1::SM_TOTAL, (cudaStream_t)stream>>>(A);
     l23::frames_l23_kernel<<<grid, l23::NTH, l23::SM_TOTAL, (cudaStream_t)stream>>>(A);
     return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
-}
-
-extern "C" int ss_actor_forward_frames_tc(const float *params, int64_t param_stride, int64_t noise_group, const float *stack,
-                                          int frames, int64_t head, float *act_out, int64_t n_rows, void *workspace,
-                                          int64_t workspace_bytes, void *stream) {
-    return frames_forward(params, param_stride, noise_group, stack, frames, head, act_out, n_rows, workspace, workspace_bytes,
-                          nullptr, stream);
-}
-
-// development: the same with an event trace of CTA 0 of the layer-1 kernel (3 roles x 256 events x {clock, code}); tools/frames_trace.py
-extern "C" int ss_debug_frames_trace(const float *params, const float *stack, int frames, int64_t head, float *act_out,
-                                     int64_t n_rows, void *workspace, int64_t workspace_bytes, long long *trace, void *stream,
-                                     int dbg) {
-    return frames_forward(params, 0, 0, stack, frames, head, act_out, n_rows, workspace, workspace_bytes, trace, stream, dbg);
 }

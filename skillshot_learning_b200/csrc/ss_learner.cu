@@ -315,10 +315,17 @@ __global__ void param_noise_groups_kernel(const float *theta, float *out, int64_
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (4 * q >= n_params) return;
     float z[4];
-    normal4(seed, kTagParamNoise, (uint32_t)q, (uint32_t)blockIdx.y, counter, z);
-    for (int e = 0; e < 4; ++e) {
-        const int64_t p = 4 * q + e;
-        if (p < n_params) { const float w = theta[p]; out[(int64_t)blockIdx.y * stride + p] = w + w * (sd * z[e]); }
+    normal4_fast(seed, kTagParamNoise, (uint32_t)q, (uint32_t)blockIdx.y, counter, z);
+    float *dst = out + (int64_t)blockIdx.y * stride;
+    if (4 * q + 3 < n_params) {          // parameter vectors are 16-byte aligned and stride % 4 == 0
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(theta) + q);
+        reinterpret_cast<float4 *>(dst)[q] = make_float4(w.x + w.x * (sd * z[0]), w.y + w.y * (sd * z[1]), w.z + w.z * (sd * z[2]),
+                                                         w.w + w.w * (sd * z[3]));
+    } else {
+        for (int e = 0; e < 4; ++e) {
+            const int64_t p = 4 * q + e;
+            if (p < n_params) { const float w = theta[p]; dst[p] = w + w * (sd * z[e]); }
+        }
     }
 }
 
@@ -897,6 +904,7 @@ int64_t ss_actor_frames_params(int frames) { return frames < 1 ? -1 : (int64_t)D
 int ss_param_noise_groups(const float *params, float *out, int64_t n_params, int64_t n_groups, int64_t stride, float sd,
                           uint64_t seed, uint64_t counter, void *stream) {
     if (!params || !out || n_params <= 0 || n_groups <= 0 || n_groups > 65535 || stride < n_params) return SS_ERR_INVALID_ARG;
+    if ((((uintptr_t)params | (uintptr_t)out) & 15) || (stride & 3)) return SS_ERR_INVALID_ARG;
     const int64_t quads = (n_params + 3) / 4;
     param_noise_groups_kernel<<<dim3((unsigned)((quads + 127) / 128), (unsigned)n_groups), 128, 0, (cudaStream_t)stream>>>(
         params, out, n_params, stride, sd, seed, counter);

@@ -237,17 +237,6 @@ __device__ __forceinline__ void load_obs(const float *obs, int64_t row, int64_t 
 }
 
 // ---- weight staging ------------------------------------------------------------
-// fast N(0,1) quad for the staging loop (same Philox draw as normal4; intrinsic log / sincos:
-// differs from the float32 path's draw by ~1e-6, far below the bf16 rounding that follows)
-__device__ __forceinline__ void normal4_fast(uint64_t seed, uint32_t q, uint32_t g, uint64_t counter, float *z) {
-    const U4 u = draw4(seed, kTagParamNoise, q, g, counter);
-    const float r0 = sqrtf(-2.0f * __logf(unit_open(u.x))), r1 = sqrtf(-2.0f * __logf(unit_open(u.z)));
-    float s0, c0, s1, c1;
-    __sincosf(6.283185307179586f * unit_open(u.y), &s0, &c0);
-    __sincosf(6.283185307179586f * unit_open(u.w), &s1, &c1);
-    z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
-}
-
 struct Stager {
     const float *theta;      // flat parameter vector of the network
     uint8_t *b1, *b2;        // weight images in shared memory (zero-filled beforehand)
@@ -261,7 +250,7 @@ struct Stager {
     __device__ __forceinline__ void perturb(int p, float4 &v) const {
         if (!noisy) return;
         float z[4];
-        normal4_fast(seed, (uint32_t)(p >> 2), group, counter, z);
+        normal4_fast(seed, kTagParamNoise, (uint32_t)(p >> 2), group, counter, z);   // ~3e-6 off the float32 path's draw
         v.x += v.x * (sd * z[0]); v.y += v.y * (sd * z[1]); v.z += v.z * (sd * z[2]); v.w += v.w * (sd * z[3]);
     }
     __device__ __forceinline__ float4 load(int p) const { return __ldg(reinterpret_cast<const float4 *>(theta + p)); }

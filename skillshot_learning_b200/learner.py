@@ -838,7 +838,11 @@ class FrameStackActor:
         parts = [torch.randn(sh, generator=g) * 0.05 if len(sh) == 2 else torch.zeros(sh) for sh in shapes]   # RandomNormal(0, 0.05)
         self.shapes = shapes
         self.params = torch.cat([p.reshape(-1) for p in parts]).to(self.device)
-        self.stack = torch.zeros((self.n_rows, self.frames, 12), dtype=torch.float32, device=self.device)
+        if precision == "bf16":
+            # the tensor-core path keeps the history as fp16 tiles in the MMA operand layout (ss_obs_stack_push_tc)
+            self.stack = torch.zeros(int(lib.ss_obs_stack_tc_bytes(self.n_rows, self.frames)), dtype=torch.uint8, device=self.device)
+        else:
+            self.stack = torch.zeros((self.n_rows, self.frames, 12), dtype=torch.float32, device=self.device)
         self.head = -1                 # slot of the newest frame = head % frames
         self.counter = 0
         self._noisy = None
@@ -853,9 +857,10 @@ class FrameStackActor:
             done, done_div = torch.ones(self.n_rows, dtype=torch.uint8, device=self.device), 1
         elif done is not None:
             done = done.to(device=self.device, dtype=torch.uint8).contiguous()
+        fn = lib.ss_obs_stack_push_tc if self.precision == "bf16" else lib.ss_obs_stack_push
         with torch.cuda.device(self.device):
-            check(lib.ss_obs_stack_push(self.stack.data_ptr(), self.n_rows, self.frames, self.head, obs.data_ptr(), _ptr(done),
-                                        int(done_div), _stream(self.device)), "ss_obs_stack_push")
+            check(fn(self.stack.data_ptr(), self.n_rows, self.frames, self.head, obs.data_ptr(), _ptr(done), int(done_div),
+                     _stream(self.device)), "ss_obs_stack_push")
 
     def forward(self, param_noise_sd: float = 0.0, noise_group: int = 0, out: Optional[torch.Tensor] = None):
         """actions [n_rows,2] from the current stack; param_noise_sd > 0: rows i share the perturbed parameters of
@@ -894,7 +899,12 @@ class FrameStackActor:
     def ordered_stack(self) -> torch.Tensor:
         """[n_rows, frames * 12] network input, oldest frame first (introspection / tests)."""
         order = [(self.head + 1 + f) % self.frames for f in range(self.frames)]
-        return self.stack[:, order, :].reshape(self.n_rows, self.frames * 12)
+        stack = self.stack
+        if self.precision == "bf16":      # [tile][K / 8][128][8] fp16 -> [row][slot][12]
+            tiles = (self.n_rows + 127) // 128
+            x = stack.view(torch.float16).view(tiles, -1, 128, 8).permute(0, 2, 1, 3).reshape(tiles * 128, -1)
+            stack = x[:self.n_rows, :self.frames * 12].float().reshape(self.n_rows, self.frames, 12)
+        return stack[:, order, :].reshape(self.n_rows, self.frames * 12)
 
 
 class SelfPlayTrainer:

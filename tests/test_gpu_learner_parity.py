@@ -651,6 +651,8 @@ def test_tensor_core_frame_stack_actor(frames, n):
         s[:, 4] *= 9.87                                                    # the rotation term's range (prepare_states)
         exact.push(s)
         fast.push(s)
+    # the tensor-core path keeps its history as fp16 operand tiles: same frames, same order, rounded once
+    assert torch.equal(fast.ordered_stack(), exact.ordered_stack().half().float())
     got = fast.forward().cpu().numpy()
     ref = exact.forward().cpu().numpy()
     assert np.isfinite(got).all()
@@ -667,10 +669,12 @@ def test_tensor_core_frame_stack_actor_noise_groups():
     exact = FrameStackActor(n, frames=F, device="cuda:0", seed=3)
     fast = FrameStackActor(n, frames=F, device="cuda:0", seed=3, precision="bf16")
     g = torch.Generator(device="cuda").manual_seed(5)
-    for t in range(7):
+    for t in range(27):                                                    # wraps the ring, with restarts
         s = torch.rand((n, 12), device="cuda", generator=g)
-        exact.push(s)
-        fast.push(s)
+        done = (torch.rand(n // 2, device="cuda", generator=g) < 0.1).to(torch.uint8)
+        exact.push(s, done)
+        fast.push(s, done)
+    assert torch.equal(fast.ordered_stack(), exact.ordered_stack().half().float())
     exact.counter = fast.counter = 9
     ref = exact.forward(param_noise_sd=0.5, noise_group=group).cpu().numpy()
     got = fast.forward(param_noise_sd=0.5, noise_group=group).cpu().numpy()
