@@ -50,6 +50,7 @@ struct FramesArgs {
     uint8_t *h1;                 // [units][H1TILE_BYTES] scratch between the two kernels
     int64_t n, group, stride, head;
     int frames;
+    long long *trace;            // development: event timestamps of CTA 0 of the layer-1 kernel (NULL in production)
 };
 
 __host__ __device__ constexpr int frames_k1(int frames) { return (DS * frames + 2 + 15) / 16 * 16; }
@@ -81,7 +82,7 @@ struct Units {                   // tiles as (noise group, tile in group) pairs,
 // ---------------------------------------------------------------------------------------------
 namespace l1 {
 
-constexpr int EPI_WARPS = 4, MMA_W = 4, NTH = 32 * 6;        // warp 5: the copy thread
+constexpr int EPI_WARPS = 4, MMA_W = 4, COPY_W = 5, NTH = 32 * 12;    // warps 6..11 only help to stage the weights
 constexpr uint32_t SM_W1 = 0;
 constexpr uint32_t SM_X = SM_W1 + W1IMG_BYTES;              // NSTAGE x [8][128][8] fp16
 constexpr uint32_t SM_BAR = SM_X + NSTAGE * XSTAGE_BYTES;
@@ -95,9 +96,9 @@ static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 // f = (slot - oldest) mod frames, the frame's age rank (0 = oldest).  Rows kx, kx + 1 = b1 high, low.
 __device__ __forceinline__ void stage_w1(const float *theta, int frames, int oldest, int k1, uint8_t *img) {
     const int kx = DS * frames, tasks = (k1 / 8) * (H1 / 4);
-    for (int t = threadIdx.x; t < tasks; t += NTH) {
+    // a task = one K chunk (8 rows) of four consecutive units: 8 independent 16-byte loads; two tasks are kept in flight
+    auto load = [&](int t, float4 (&v)[8]) {
         const int kc = t / (H1 / 4), n = (t % (H1 / 4)) * 4;
-        float4 v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int k = kc * 8 + i;
@@ -111,6 +112,9 @@ __device__ __forceinline__ void stage_w1(const float *theta, int frames, int old
                 v[i] = __ldg(reinterpret_cast<const float4 *>(theta + (int64_t)kx * H1 + n));      // b1
             }
         }
+    };
+    auto store = [&](int t, float4 (&v)[8]) {
+        const int kc = t / (H1 / 4), n = (t % (H1 / 4)) * 4;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int k = kc * 8 + i;
@@ -130,6 +134,13 @@ __device__ __forceinline__ void stage_w1(const float *theta, int frames, int old
         *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(pack_f16(v[0].y, v[1].y), pack_f16(v[2].y, v[3].y), pack_f16(v[4].y, v[5].y), pack_f16(v[6].y, v[7].y));
         *reinterpret_cast<uint4 *>(dst + 32) = make_uint4(pack_f16(v[0].z, v[1].z), pack_f16(v[2].z, v[3].z), pack_f16(v[4].z, v[5].z), pack_f16(v[6].z, v[7].z));
         *reinterpret_cast<uint4 *>(dst + 48) = make_uint4(pack_f16(v[0].w, v[1].w), pack_f16(v[2].w, v[3].w), pack_f16(v[4].w, v[5].w), pack_f16(v[6].w, v[7].w));
+    };
+    for (int t = threadIdx.x; t < tasks; t += 2 * NTH) {
+        float4 va[8], vb[8];
+        load(t, va);
+        if (t + NTH < tasks) load(t + NTH, vb);
+        store(t, va);
+        if (t + NTH < tasks) store(t + NTH, vb);
     }
 }
 
@@ -138,6 +149,15 @@ __global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto bar = [&](int idx) -> uint32_t { return sbase + SM_BAR + (uint32_t)idx * 8; };
+    int tr_n = 0;                // development trace: role 0 = epilogue warp 0, 1 = MMA warp, 2 = copy thread
+    auto trace = [&](int role, int code) {
+        if (A.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == MMA_W || warp == COPY_W) && tr_n < 256) {
+            A.trace[(role * 256 + tr_n) * 2] = clock64();
+            A.trace[(role * 256 + tr_n) * 2 + 1] = code;
+            ++tr_n;
+        }
+    };
+    trace(0, 900);
     const int k1 = frames_k1(A.frames);                     // input columns + bias pair, padded to the MMA K step
     const int nstages = (k1 + KSTAGE - 1) / KSTAGE;         // K stages in use (the last one may be partial)
     const uint32_t tile_bytes = (uint32_t)(k1 / 8) * CHUNK_A;
@@ -169,6 +189,7 @@ __global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
         stage_w1(A.theta + g * A.stride, A.frames, oldest, k1, smem + SM_W1);
         fence_proxy_async();
         __syncthreads();
+        trace(0, 901);
 
         if (warp < EPI_WARPS) {
             // ============ epilogue: D[slot] -> ReLU -> bf16 -> the tile's layer-2 operand image ============
@@ -177,8 +198,10 @@ __global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
             for (uint32_t i = 0; i < ntiles; ++i) {
                 const uint32_t tc = tcount + i, slot = tc & 1;
                 uint8_t *out = A.h1 + (u + i) * (int64_t)H1TILE_BYTES + r * 16;
+                trace(0, 100 + (int)i);
                 mbar_wait(bar(B_DFULL + slot), (tc >> 1) & 1);
                 tc_fence_after();
+                trace(0, 200 + (int)i);
                 uint32_t va[32], vb[32];
                 tmem_ld32(tl + slot * 256, va);
 #pragma unroll
@@ -191,30 +214,57 @@ __global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
                     else { tc_fence_before(); mbar_arrive(bar(B_DFREE + slot)); }        // D[slot] fully read
                     relu_pack_store(vb, out + (uint32_t)((j + 1) * 4) * CHUNK_A);
                 }
+                trace(0, 300 + (int)i);
             }
         } else if (warp == MMA_W) {
             // ============ the MMA-issuing warp ============
             constexpr uint32_t kI = umma_idesc_f16(TM, H1);
             const uint64_t xd = desc_kmajor(sbase + SM_X, CHUNK_A), wd = desc_kmajor(sbase + SM_W1, CHUNK_B1);
             const uint32_t tc0 = __shfl_sync(0xffffffffu, tcount, 0);
+            // The tensor pipe queues only a couple of MMAs, so the issuing thread cannot run ahead: whatever it waits for
+            // idles the pipe unless MMAs are queued behind it.  Every wait (next stage landed, next accumulator drained) is
+            // therefore placed BETWEEN the two halves of a stage's MMAs, and the commits after them.
+            trace(1, 100);
+            mbar_wait(bar(B_DFREE + (tc0 & 1)), ((tc0 >> 1) & 1) ^ 1);
+            mbar_wait(bar(B_XFULL + 0), tc0 & 1);
+            tc_fence_after();
             for (uint32_t i = 0; i < ntiles; ++i) {
                 const uint32_t tc = tc0 + i, slot = tc & 1;
-                mbar_wait(bar(B_DFREE + slot), ((tc >> 1) & 1) ^ 1);  // the epilogue has drained D[slot]
-                for (int sg = 0; sg < nstages; ++sg) {
+                const uint32_t d = tmem + slot * 256;
+#pragma unroll
+                for (int sg = 0; sg < NSTAGE; ++sg) {             // unrolled: descriptor offsets and flags fold to constants --
+                    if (sg >= nstages) break;                     // a single thread's issue loop must stay a few instructions per MMA
                     const int steps = min(KSTAGE, k1 - sg * KSTAGE) / 16;
-                    mbar_wait(bar(B_XFULL + sg), tc & 1);
+                    trace(1, 200 + (int)i * 4 + sg);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks)
+                            if (ks < steps)
+                                umma_bf16(d, desc_advance(xd, sg * XSTAGE_BYTES + 2 * CHUNK_A * ks),
+                                          desc_advance(wd, (uint32_t)(sg * (KSTAGE / 8) + 2 * ks) * CHUNK_B1), kI, (sg | ks) != 0);
+                    }
+                    __syncwarp();
+                    if (sg + 1 < nstages) {
+                        mbar_wait(bar(B_XFULL + sg + 1), tc & 1);
+                    } else if (i + 1 < ntiles) {
+                        mbar_wait(bar(B_DFREE + (slot ^ 1)), (((tc + 1) >> 1) & 1) ^ 1);      // the epilogue has drained the other D
+                        mbar_wait(bar(B_XFULL + 0), (tc + 1) & 1);
+                    }
                     tc_fence_after();
                     if (lane == 0) {
-                        for (int ks = 0; ks < steps; ++ks)
-                            umma_bf16(tmem + slot * 256, desc_advance(xd, sg * XSTAGE_BYTES + 2 * CHUNK_A * ks),
-                                      desc_advance(wd, (uint32_t)(sg * (KSTAGE / 8) + 2 * ks) * CHUNK_B1), kI, (sg | ks) != 0);
+#pragma unroll
+                        for (int ks = 2; ks < KSTAGE / 16; ++ks)
+                            if (ks < steps)
+                                umma_bf16(d, desc_advance(xd, sg * XSTAGE_BYTES + 2 * CHUNK_A * ks),
+                                          desc_advance(wd, (uint32_t)(sg * (KSTAGE / 8) + 2 * ks) * CHUNK_B1), kI, 1);
                         umma_commit(bar(B_XFREE + sg));
                         if (sg == nstages - 1) umma_commit(bar(B_DFULL + slot));
                     }
                     __syncwarp();
+                    trace(1, 300 + (int)i * 4 + sg);
                 }
             }
-        } else if (lane == 0) {
+        } else if (warp == COPY_W && lane == 0) {
             // ============ the copy thread: K stages of the history tiles -> X ring ============
             for (uint32_t i = 0; i < ntiles; ++i) {
                 const uint32_t tc = tcount + i;
@@ -222,6 +272,7 @@ __global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
                 for (int sg = 0; sg < nstages; ++sg) {
                     const uint32_t bytes = (uint32_t)min(KSTAGE, k1 - sg * KSTAGE) / 8 * CHUNK_A;
                     mbar_wait(bar(B_XFREE + sg), (tc & 1) ^ 1);       // the previous tile's MMAs have read this stage
+                    trace(2, 100 + (int)i * 4 + sg);
                     mbar_expect_tx(bar(B_XFULL + sg), bytes);
                     bulk_load(sbase + SM_X + sg * XSTAGE_BYTES, src + sg * XSTAGE_BYTES, bytes, bar(B_XFULL + sg));
                 }
@@ -433,16 +484,16 @@ extern "C" int64_t ss_actor_frames_tc_workspace_bytes(int64_t n_rows, int64_t no
     return frame_units(n_rows, group) * (int64_t)H1TILE_BYTES;
 }
 
-extern "C" int ss_actor_forward_frames_tc(const float *params, int64_t param_stride, int64_t noise_group, const void *stack_tc,
-                                          int frames, int64_t head, float *act_out, int64_t n_rows, void *workspace,
-                                          int64_t workspace_bytes, void *stream) {
+static int frames_forward(const float *params, int64_t param_stride, int64_t noise_group, const void *stack_tc, int frames,
+                          int64_t head, float *act_out, int64_t n_rows, void *workspace, int64_t workspace_bytes,
+                          long long *trace, void *stream) {
     if (!params || !stack_tc || !act_out || !workspace || n_rows <= 0 || frames < 1 || frames > MAXF || head < 0 || param_stride < 0)
         return SS_ERR_INVALID_ARG;
     if (param_stride > 0 && (noise_group <= 0 || noise_group % TM != 0)) return SS_ERR_INVALID_ARG;
     if ((((uintptr_t)params | (uintptr_t)stack_tc | (uintptr_t)workspace) & 15) || (param_stride & 3) || ((uintptr_t)act_out & 7))
         return SS_ERR_INVALID_ARG;
     FramesArgs A{params, (const uint8_t *)stack_tc, act_out, (uint8_t *)workspace, n_rows,
-                 param_stride > 0 ? noise_group : n_rows, param_stride, head, frames};
+                 param_stride > 0 ? noise_group : n_rows, param_stride, head, frames, trace};
     if (A.group > n_rows) A.group = n_rows;
     const int64_t units = frame_units(n_rows, A.group);
     if (workspace_bytes < units * (int64_t)H1TILE_BYTES) return SS_ERR_INVALID_ARG;
@@ -458,4 +509,17 @@ extern "C" int ss_actor_forward_frames_tc(const float *params, int64_t param_str
     l1::frames_l1_kernel<<<grid, l1::NTH, l1::SM_TOTAL, (cudaStream_t)stream>>>(A);
     l23::frames_l23_kernel<<<grid, l23::NTH, l23::SM_TOTAL, (cudaStream_t)stream>>>(A);
     return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
+}
+
+extern "C" int ss_actor_forward_frames_tc(const float *params, int64_t param_stride, int64_t noise_group, const void *stack_tc,
+                                          int frames, int64_t head, float *act_out, int64_t n_rows, void *workspace,
+                                          int64_t workspace_bytes, void *stream) {
+    return frames_forward(params, param_stride, noise_group, stack_tc, frames, head, act_out, n_rows, workspace, workspace_bytes,
+                          nullptr, stream);
+}
+
+// development: the same with an event trace of CTA 0 of the layer-1 kernel (3 roles x 256 events x {clock, code}); tools/frames_trace.py
+extern "C" int ss_debug_frames_trace(const float *params, const void *stack_tc, int frames, int64_t head, float *act_out,
+                                     int64_t n_rows, void *workspace, int64_t workspace_bytes, long long *trace, void *stream) {
+    return frames_forward(params, 0, 0, stack_tc, frames, head, act_out, n_rows, workspace, workspace_bytes, trace, stream);
 }
