@@ -60,6 +60,39 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+// L2 policies.  The hidden tiles written by the layer-1 kernel are read back by the layer-2/3 kernel moments later: at
+// 131,072 rows they are 67 MB and fit the 126 MB L2 if the 67 MB of history that streams through beside them does not
+// push them out, which saves their round trip to HBM (two thirds of the traffic of the pair of kernels).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_load_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void st_global_hint(void *p, uint4 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
+                 : "memory");
+}
+// 32 accumulator columns -> ReLU -> bf16 -> four 16-byte chunks of this thread's row of a 128-row tile in global memory
+__device__ __forceinline__ void relu_pack_store_global(const uint32_t (&v)[32], uint8_t *dst, uint64_t policy) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        st_global_hint(dst + c * CHUNK_A,
+                       make_uint4(pack_relu_bf16(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1])),
+                                  pack_relu_bf16(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3])),
+                                  pack_relu_bf16(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5])),
+                                  pack_relu_bf16(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]))),
+                       policy);
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -195,6 +228,7 @@ __global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
             // ============ epilogue: D[slot] -> ReLU -> bf16 -> the tile's layer-2 operand image ============
             const int r = warp * 32 + lane;
             const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+            const uint64_t keep = l2_policy_evict_last();
             for (uint32_t i = 0; i < ntiles; ++i) {
                 const uint32_t tc = tcount + i, slot = tc & 1;
                 uint8_t *out = A.h1 + (u + i) * (int64_t)H1TILE_BYTES + r * 16;
@@ -208,11 +242,11 @@ __global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
                 for (int j = 0; j < H1 / 32; j += 2) {
                     tmem_wait_ld();
                     tmem_ld32(tl + slot * 256 + (j + 1) * 32, vb);
-                    relu_pack_store(va, out + (uint32_t)(j * 4) * CHUNK_A);
+                    relu_pack_store_global(va, out + (uint32_t)(j * 4) * CHUNK_A, keep);
                     tmem_wait_ld();
                     if (j + 2 < H1 / 32) tmem_ld32(tl + slot * 256 + (j + 2) * 32, va);
                     else { tc_fence_before(); mbar_arrive(bar(B_DFREE + slot)); }        // D[slot] fully read
-                    relu_pack_store(vb, out + (uint32_t)((j + 1) * 4) * CHUNK_A);
+                    relu_pack_store_global(vb, out + (uint32_t)((j + 1) * 4) * CHUNK_A, keep);
                 }
                 trace(0, 300 + (int)i);
             }
@@ -266,6 +300,7 @@ __global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
             }
         } else if (warp == COPY_W && lane == 0) {
             // ============ the copy thread: K stages of the history tiles -> X ring ============
+            const uint64_t stream_through = l2_policy_evict_first();
             for (uint32_t i = 0; i < ntiles; ++i) {
                 const uint32_t tc = tcount + i;
                 const uint8_t *src = A.xt + (u + i) * (int64_t)tile_bytes;
@@ -274,7 +309,7 @@ __global__ void __launch_bounds__(NTH, 1) frames_l1_kernel(const FramesArgs A) {
                     mbar_wait(bar(B_XFREE + sg), (tc & 1) ^ 1);       // the previous tile's MMAs have read this stage
                     trace(2, 100 + (int)i * 4 + sg);
                     mbar_expect_tx(bar(B_XFULL + sg), bytes);
-                    bulk_load(sbase + SM_X + sg * XSTAGE_BYTES, src + sg * XSTAGE_BYTES, bytes, bar(B_XFULL + sg));
+                    bulk_load_hint(sbase + SM_X + sg * XSTAGE_BYTES, src + sg * XSTAGE_BYTES, bytes, bar(B_XFULL + sg), stream_through);
                 }
             }
         }
@@ -409,6 +444,7 @@ __global__ void __launch_bounds__(NTH, 1) frames_l23_kernel(const FramesArgs A) 
             }
         } else if (lane == 0) {
             // ============ the copy thread: operand images of the tiles -> A1 ring ============
+            const uint64_t last_use = l2_policy_evict_first();
             for (uint32_t i = 0; i < ntiles; ++i) {
                 const uint32_t tc = tcount + i, slot = tc & 1;
                 mbar_wait(bar(B_AFREE + slot), ((tc >> 1) & 1) ^ 1);  // the MMAs that read this slot have retired
@@ -416,8 +452,8 @@ __global__ void __launch_bounds__(NTH, 1) frames_l23_kernel(const FramesArgs A) 
                 const uint8_t *src = A.h1 + (u + i) * (int64_t)H1TILE_BYTES;
 #pragma unroll
                 for (int p = 0; p < 4; ++p)
-                    bulk_load(sbase + SM_A1 + slot * X2_BYTES + p * (H1TILE_BYTES / 4), src + p * (H1TILE_BYTES / 4), H1TILE_BYTES / 4,
-                              bar(B_AFULL + slot));
+                    bulk_load_hint(sbase + SM_A1 + slot * X2_BYTES + p * (H1TILE_BYTES / 4), src + p * (H1TILE_BYTES / 4), H1TILE_BYTES / 4,
+                                   bar(B_AFULL + slot), last_use);
             }
         }
         tcount += ntiles;
