@@ -49,6 +49,15 @@ def test_learner_entry_points_reject_invalid_arguments_without_a_gpu():
     assert L.ss_peer_bytes(9, 100) == -1 and L.ss_peer_bytes(2, 100) == 256 + 2 * 2 * 100 * 4
     assert L.ss_peer_reduce_push(None, 1, 10, None, None, 2, 0, 100, 1, None, None) == -1
     assert L.ss_ddpg_update(None, None) == -1
+    assert L.ss_actor_frames_params(20) == 240 * 256 + 256 + 256 * 128 + 128 + 128 * 2 + 2 and L.ss_actor_frames_params(0) == -1
+    assert L.ss_obs_stack_tc_bytes(131072, 20) == 1024 * 32 * 2048 and L.ss_obs_stack_tc_bytes(1, 1) == 2 * 2048
+    assert L.ss_obs_stack_tc_bytes(16, 21) == -1
+    assert L.ss_actor_frames_tc_workspace_bytes(131072, 1024) == 1024 * 65536 and L.ss_actor_frames_tc_workspace_bytes(300, 0) == 3 * 65536
+    assert L.ss_obs_stack_push(None, 16, 20, 0, None, None, 1, None) == -1
+    assert L.ss_obs_stack_push_tc(None, 16, 20, 0, None, None, 1, None) == -1
+    assert L.ss_param_noise_groups(None, None, 100, 2, 100, 0.5, 0, 0, None) == -1
+    assert L.ss_actor_forward_frames(None, 0, 0, None, 20, 0, None, 16, None) == -1
+    assert L.ss_actor_forward_frames_tc(None, 0, 0, None, 20, 0, None, 16, None, 0, None) == -1
     blank = _lib.DdpgUpdateArgs()
     blank.batch, blank.size, blank.capacity, blank.step_actor, blank.step_critic = 16, 16, 16, 1, 1
     assert L.ss_ddpg_update(ctypes.byref(blank), None) == -1

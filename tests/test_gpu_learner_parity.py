@@ -688,3 +688,41 @@ def test_tensor_core_frame_stack_actor_noise_groups():
         np.testing.assert_allclose(got[sl], want, rtol=0, atol=3e-3)
     with pytest.raises(Exception):
         fast.forward(param_noise_sd=0.5, noise_group=100)                  # groups are whole tiles
+
+
+def test_full_size_frame_stack_actor_is_invariant_to_the_ring_phase():
+    """BASELINE.json configs[4] size (131,072 rows x 20 frames).  Two actors see the same last 20 frames but their rings
+    are at different phases (one has been pushed 7 more times before): the network input is the same history, so the
+    float32 path must give identical actions and the tensor-core path -- which rotates W1's rows instead of the data --
+    the same up to the order of its fp32 sums.  Also the tensor-core path against the float32 path at this size."""
+    from skillshot_learning_b200 import FrameStackActor
+    n, F = 131072, 20
+    g = torch.Generator(device="cuda").manual_seed(11)
+    outs = {}
+    for precision in ("f32", "bf16"):
+        a = FrameStackActor(n, frames=F, device="cuda:0", seed=2, precision=precision)
+        b = FrameStackActor(n, frames=F, device="cuda:0", seed=2, precision=precision)
+        g.manual_seed(11)
+        for _ in range(7):
+            b.push(torch.rand((n, 12), device="cuda", generator=g))
+        for _ in range(F + 4):
+            s = torch.rand((n, 12), device="cuda", generator=g)
+            a.push(s)
+            b.push(s)
+        assert a.head % F != b.head % F
+        assert torch.equal(a.ordered_stack(), b.ordered_stack())
+        oa, ob = a.forward(), b.forward()
+        if precision == "f32":
+            assert torch.equal(oa, ob)
+        else:
+            # a different order of the fp32 sums moves a hidden unit across a bf16 rounding boundary now and then
+            assert float((oa - ob).abs().max()) < 2e-3 and float((oa - ob).abs().mean()) < 1e-5
+        a.counter = b.counter = 3
+        na, nb = a.forward(param_noise_sd=0.5, noise_group=1024), b.forward(param_noise_sd=0.5, noise_group=1024)
+        assert float((na - nb).abs().max()) < (1e-6 if precision == "f32" else 5e-3)
+        assert float((na - nb).abs().mean()) < (1e-7 if precision == "f32" else 5e-5)
+        assert torch.isfinite(na).all() and float((na - oa).abs().mean()) > 1e-3          # the noise does something
+        outs[precision] = (oa, na)
+    for k in range(2):
+        d = (outs["bf16"][k] - outs["f32"][k]).abs()
+        assert float(d.max()) < (3e-2, 1e-1)[k] and float(d.mean()) < (3e-3, 8e-3)[k]
