@@ -261,6 +261,14 @@ int ss_adam_tf(float *params, const float *grads, float *m, float *v, float *tar
                int64_t step, float lr, float beta1, float beta2, float eps, float tau, float grad_scale,
                void *stream);
 
+/* The fixed-order sum of the per-CTA gradient slices a gradient entry point left in `workspace` (called with
+ * grad_out == NULL; `parts` = its return value) and ss_adam_tf on the result, in one kernel: the single-GPU form of
+ * ss_peer_reduce_push + ss_peer_adam_tf.  aux_out[0] (may be NULL) = sum of the slices' extra slot (squared error /
+ * Q sum); grad_out (may be NULL) receives the summed gradient. */
+int ss_reduce_adam_tf(const void *workspace, int parts, int n_params, float *aux_out, float *grad_out, float *params,
+                      float *m, float *v, float *target_params, int64_t step, float lr, float beta1, float beta2,
+                      float eps, float tau, float grad_scale, void *stream);
+
 /* n_ticks iterations of the rollout loop of model_train (SkillshotLearner.py:302-315) for n_envs games,
  * enqueued back to back from one host call: actor forward on both players' observations (2 n_envs rows;
  * tensor_cores != 0: ss_actor_forward_tc) -> ss_env_step with auto-reset -> ss_replay_push (skipped when
@@ -380,7 +388,7 @@ int ss_replay_sample(const float *ring_obs, const float *ring_act, const float *
  * one; it exists because that sequence costs ~150 us of interpreter time per update from Python.
  * All pointers are device pointers except peer_bases (host array, as for ss_peer_reduce_push).
  *   tensor_cores != 0   the *_tc gradient / target kernels (workspace as they require)
- *   peer_bases == NULL  single GPU: grad_actor / grad_critic receive the gradients
+ *   peer_bases == NULL  single GPU (ss_reduce_adam_tf): grad_actor / grad_critic (may be NULL) receive the gradients
  *   peer_bases != NULL  sharded batch with the fused NVLink exchange: the critic exchange is epoch
  *                       `epoch`, the actor's `epoch + 1`; grad_* (may be NULL) receive the summed gradients
  *   stats[2]            sum of squared errors of the critic batch, sum of Q of the actor batch (this shard's)

@@ -614,6 +614,37 @@ __global__ void adam_kernel(float *params, const float *grads, float *m, float *
     if (target) target[p] = tau * w + (1.0f - tau) * target[p];
 }
 
+// reduce_kernel and adam_kernel in one pass (single GPU: nothing sits between the two): the thread that holds a
+// parameter's summed gradient applies Adam and the soft target update to it.
+__global__ void reduce_adam_kernel(const float *work, int parts, int n_params, float *aux, float *grad_out, float *params,
+                                   float *m, float *v, float *target, float lr_t, float beta1, float beta2, float eps, float tau,
+                                   float grad_scale) {
+    __shared__ float red[4][64];
+    const int p = blockIdx.x * 64 + threadIdx.x, q = threadIdx.y;
+    float s = 0.f;
+    if (p <= n_params) {
+#pragma unroll 4
+        for (int c = q; c < parts; c += 4) s += __ldcg(work + (int64_t)c * (n_params + 1) + p);
+    }
+    red[q][threadIdx.x] = s;
+    __syncthreads();
+    if (q != 0 || p > n_params) return;
+    const float t = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
+    if (p == n_params) {
+        if (aux) aux[0] = t;
+        return;
+    }
+    if (grad_out) grad_out[p] = t;
+    const float gr = t * grad_scale;
+    const float mm = beta1 * m[p] + (1.0f - beta1) * gr;
+    const float vv = beta2 * v[p] + (1.0f - beta2) * gr * gr;
+    m[p] = mm;
+    v[p] = vv;
+    const float w = params[p] - lr_t * mm / (sqrtf(vv) + eps);
+    params[p] = w;
+    if (target) target[p] = tau * w + (1.0f - tau) * target[p];
+}
+
 // ---------------------------------------------------------------------------
 // replay ring: SoA of (s[12], a[2], r, s'[12], done) rows
 // ---------------------------------------------------------------------------
@@ -801,6 +832,17 @@ int ss_adam_tf(float *params, const float *grads, float *m, float *v, float *tar
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, target_params, n,
                                                                                (float)lr_t, beta1, beta2, eps, tau,
                                                                                grad_scale);
+    return check_launch();
+}
+
+int ss_reduce_adam_tf(const void *workspace, int parts, int n_params, float *aux_out, float *grad_out, float *params, float *m,
+                      float *v, float *target_params, int64_t step, float lr, float beta1, float beta2, float eps, float tau,
+                      float grad_scale, void *stream) {
+    if (!workspace || parts < 1 || n_params < 1 || !params || !m || !v || step < 1) return SS_ERR_INVALID_ARG;
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+    reduce_adam_kernel<<<(n_params + 1 + 63) / 64, dim3(64, 4), 0, (cudaStream_t)stream>>>(
+        (const float *)workspace, parts, n_params, aux_out, grad_out, params, m, v, target_params, (float)lr_t, beta1, beta2, eps,
+        tau, grad_scale);
     return check_launch();
 }
 

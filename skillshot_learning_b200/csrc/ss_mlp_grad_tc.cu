@@ -61,6 +61,7 @@ struct GradArgs {
     const float *params, *obs;
     const float *act, *target;       // critic: actions [n][2], regression target [n]
     const float *up;                 // actor: upstream gradient on the action [n][2] (= -dQ/da)
+    const float *q;                  // actor: Q(s, actor(s)) per row [n] or NULL; its sum goes out through the slices' extra slot
     const uint8_t *keep;             // critic: injected dropout mask [n][256] or NULL (Philox)
     float rate;
     uint64_t seed, counter;
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
             if (tile < tiles && row < A.n) {
                 side_next = __ldg(reinterpret_cast<const float2 *>(NET == NET_CRITIC ? A.act : A.up) + row);
                 if (NET == NET_CRITIC) tgt_next = __ldg(A.target + row);
+                else if (A.q) tgt_next = __ldg(A.q + row);
             }
         };
         fetch(blockIdx.x);
@@ -295,6 +297,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                     d0 = 2.0f * e / (float)A.n_global;
                 }
             } else if (valid) {                           // through tanh, upstream = -dQ/da (SkillshotLearner.py:408-410)
+                stat += tgt;                              // Q of the row (reported sum)
                 const float a0 = tanhf(z0 + b3[0]), a1 = tanhf(z1 + b3[1]);
                 d0 = side.x * (1.0f - a0 * a0);
                 d1 = side.y * (1.0f - a1 * a1);
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                 if (r == 0) {
                     const float t0 = (red[0] + red[4]) + (red[8] + red[12]), t1 = (red[1] + red[5]) + (red[9] + red[13]);
                     const float t2 = (red[2] + red[6]) + (red[10] + red[14]);
-                    if (NET == NET_ACTOR) { g[A_B3] = t0; g[A_B3 + 1] = t1; g[PN] = 0.f; }
+                    if (NET == NET_ACTOR) { g[A_B3] = t0; g[A_B3 + 1] = t1; g[PN] = t2; }
                     else { g[C_B3] = t0; g[PN] = t2; }
                 }
             }
@@ -510,20 +513,6 @@ __global__ void reduce_parts_kernel(const float *work, int parts, int n_params, 
     }
 }
 
-// out[0] = sum of x[0..n) in a fixed order (one CTA)
-__global__ void sum_f32_kernel(const float *x, int64_t n, float *out) {
-    __shared__ float red[1024];
-    float s = 0.f;
-    for (int64_t i = threadIdx.x; i < n; i += 1024) s += x[i];
-    red[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 512; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[0] = red[0];
-}
-
 template <int NET>
 int launch_grad(const GradArgs &A0, float *grad_out, float *aux_out, int64_t workspace_bytes, void *stream) {
     constexpr int PN = NET == NET_ACTOR ? A_N : C_N;
@@ -588,14 +577,13 @@ int ss_actor_grad_tc(const float *actor_params, const float *critic_params, cons
     // a = actor(s);  q, -dq/da = critic([s, a]) with Dropout off;  then the actor's backward pass
     int rc = ss_actor_forward_tc(actor_params, obs, act, n, 0.f, 0, 0.f, 0, 0, stream);
     if (rc != SS_OK) return rc;
-    rc = ss_critic_forward_tc(critic_params, obs, act, n, q_sum_out ? q : nullptr, up, nullptr, nullptr, 0.f, nullptr, stream);
+    rc = ss_critic_forward_tc(critic_params, obs, act, n, q, up, nullptr, nullptr, 0.f, nullptr, stream);
     if (rc != SS_OK) return rc;
     GradArgs A{};
-    A.params = actor_params; A.obs = obs; A.up = up; A.n = n; A.n_global = n; A.work = (float *)workspace;
-    rc = launch_grad<NET_ACTOR>(A, grad_out, nullptr, slice_bytes / 16 * 16, stream);
-    if (rc < 0) return rc;
-    if (q_sum_out) sum_f32_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(q, n, q_sum_out);
-    return cudaGetLastError() == cudaSuccess ? rc : SS_ERR_CUDA;
+    A.params = actor_params; A.obs = obs; A.up = up; A.q = q; A.n = n; A.n_global = n; A.work = (float *)workspace;
+    // the rows' Q values are summed by the gradient kernel's row owners into the slices' extra slot: the fixed-order
+    // reduction that follows (here or in ss_peer_reduce_push / ss_reduce_adam_tf) delivers sum Q without a kernel of its own
+    return launch_grad<NET_ACTOR>(A, grad_out, q_sum_out, slice_bytes / 16 * 16, stream);
 }
 
 int ss_ddpg_targets_tc(const float *target_actor_params, const float *target_critic_params, const float *reward,

@@ -23,7 +23,6 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
     if (peers && (a->world < 1 || a->world > SS_PEER_MAX_WORLD || a->rank < 0 || a->rank >= a->world || a->epoch == 0 ||
                   !a->done_counter))
         return SS_ERR_INVALID_ARG;
-    if (!peers && (!a->grad_actor || !a->grad_critic)) return SS_ERR_INVALID_ARG;
     if (a->gamma != 0.f && (!a->y || !a->target_actor || !a->target_critic)) return SS_ERR_INVALID_ARG;
     const int64_t n = a->batch;
     const bool tc = a->tensor_cores != 0;
@@ -45,12 +44,14 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
         y = a->y;
     }
 
-    // critic: gradient of the batch-mean squared error -> (exchange) -> Adam (+ soft target update)
+    // critic: gradient of the batch-mean squared error -> (exchange) -> Adam (+ soft target update).  The gradient
+    // kernels leave per-CTA slices; one more kernel sums them in a fixed order and applies Adam (ss_reduce_adam_tf), or
+    // pushes the sum to every rank's inbox (ss_peer_reduce_push) for the peers' Adam kernel.
     auto critic_grad = tc ? ss_critic_grad_tc : ss_critic_grad;
     rc = critic_grad(a->critic, a->obs, a->act, y, nullptr, a->dropout_rate, a->seed, a->counter, n, a->n_global, a->row_offset,
-                     peers ? nullptr : a->grad_critic, a->stats, a->workspace, a->workspace_bytes, stream);
+                     nullptr, a->stats, a->workspace, a->workspace_bytes, stream);
+    if (rc <= 0) return rc < 0 ? rc : SS_ERR_INVALID_ARG;
     if (peers) {
-        if (rc <= 0) return rc < 0 ? rc : SS_ERR_INVALID_ARG;
         rc = ss_peer_reduce_push(a->workspace, rc, SS_CRITIC_PARAMS, a->stats, a->peer_bases, a->world, a->rank,
                                  a->peer_capacity, a->epoch, a->done_counter, stream);
         if (rc != SS_OK) return rc;
@@ -58,29 +59,25 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
                              a->target_critic, a->grad_critic, SS_CRITIC_PARAMS, a->step_critic, a->lr_critic, a->beta1,
                              a->beta2, a->eps, a->tau, 1.0f, a->status, stream);
     } else {
-        if (rc != SS_OK) return rc;
-        rc = ss_adam_tf(a->critic, a->grad_critic, a->m_critic, a->v_critic, a->target_critic, SS_CRITIC_PARAMS, a->step_critic,
-                        a->lr_critic, a->beta1, a->beta2, a->eps, a->tau, 1.0f, stream);
+        rc = ss_reduce_adam_tf(a->workspace, rc, SS_CRITIC_PARAMS, a->stats, a->grad_critic, a->critic, a->m_critic, a->v_critic,
+                               a->target_critic, a->step_critic, a->lr_critic, a->beta1, a->beta2, a->eps, a->tau, 1.0f, stream);
     }
     if (rc != SS_OK) return rc;
 
     // actor: model_actor_fit_step with the critic just updated (SkillshotLearner.py:440-443 follows 434)
     auto actor_grad = tc ? ss_actor_grad_tc : ss_actor_grad;
-    rc = actor_grad(a->actor, a->critic, a->obs, n, peers ? nullptr : a->grad_actor, a->stats + 1, a->workspace,
-                    a->workspace_bytes, stream);
+    rc = actor_grad(a->actor, a->critic, a->obs, n, nullptr, a->stats + 1, a->workspace, a->workspace_bytes, stream);
+    if (rc <= 0) return rc < 0 ? rc : SS_ERR_INVALID_ARG;
     if (peers) {
-        if (rc <= 0) return rc < 0 ? rc : SS_ERR_INVALID_ARG;
-        // the tensor-core actor step sums Q with its own kernel; the float32 one through the slices' extra slot
-        rc = ss_peer_reduce_push(a->workspace, rc, SS_ACTOR_PARAMS, tc ? nullptr : a->stats + 1, a->peer_bases, a->world,
-                                 a->rank, a->peer_capacity, a->epoch + 1, a->done_counter, stream);
+        rc = ss_peer_reduce_push(a->workspace, rc, SS_ACTOR_PARAMS, a->stats + 1, a->peer_bases, a->world, a->rank,
+                                 a->peer_capacity, a->epoch + 1, a->done_counter, stream);
         if (rc != SS_OK) return rc;
         rc = ss_peer_adam_tf(a->peer_bases[a->rank], a->world, a->peer_capacity, a->epoch + 1, a->actor, a->m_actor, a->v_actor,
                              a->target_actor, a->grad_actor, SS_ACTOR_PARAMS, a->step_actor, a->lr_actor, a->beta1, a->beta2,
                              a->eps, a->tau, 1.0f, a->status, stream);
     } else {
-        if (rc != SS_OK) return rc;
-        rc = ss_adam_tf(a->actor, a->grad_actor, a->m_actor, a->v_actor, a->target_actor, SS_ACTOR_PARAMS, a->step_actor,
-                        a->lr_actor, a->beta1, a->beta2, a->eps, a->tau, 1.0f, stream);
+        rc = ss_reduce_adam_tf(a->workspace, rc, SS_ACTOR_PARAMS, a->stats + 1, a->grad_actor, a->actor, a->m_actor, a->v_actor,
+                               a->target_actor, a->step_actor, a->lr_actor, a->beta1, a->beta2, a->eps, a->tau, 1.0f, stream);
     }
     return rc;
 }

@@ -393,31 +393,54 @@ class ActorCritic:
                                  self._slice(self.target, which).data_ptr(), n, step, lr, self.beta1, self.beta2,
                                  self.eps, self.tau, float(grad_scale), _stream(self.device)), "ss_adam_tf")
 
+    def reduce_adam(self, which: str, parts: int, aux: Optional[torch.Tensor], grad_scale: float = 1.0):
+        """Single GPU: fixed-order sum of the `parts` gradient slices in the workspace + Adam + soft update, one kernel."""
+        n = A_N if which == "actor" else C_N
+        if which == "actor":
+            self.step_actor += 1
+            step, lr = self.step_actor, self.lr_actor
+        else:
+            self.step_critic += 1
+            step, lr = self.step_critic, self.lr_critic
+        with torch.cuda.device(self.device):
+            check(lib.ss_reduce_adam_tf(self.workspace.data_ptr(), int(parts), n, _ptr(aux), self._slice(self.grads, which).data_ptr(),
+                                        self._slice(self.params, which).data_ptr(), self._slice(self.adam_m, which).data_ptr(),
+                                        self._slice(self.adam_v, which).data_ptr(), self._slice(self.target, which).data_ptr(),
+                                        step, lr, self.beta1, self.beta2, self.eps, self.tau, float(grad_scale),
+                                        _stream(self.device)), "ss_reduce_adam_tf")
+
     def critic_step(self, obs, act, y, keep=None):
         """One batch of model_critic.fit (SkillshotLearner.py:434): gradient of the batch-mean
-        squared error, all-reduced when sharded, then Adam.  Returns the (device) sum of squared errors."""
+        squared error, summed over the ranks when sharded, then Adam.  Returns the (device) sum of squared errors."""
         _, n_global, row_offset = shard_info(int(np.prod(y.shape)), self.group)
-        if self.peer is not None:      # slices -> every rank's inbox -> Adam on the rank-ordered sum
-            parts = self.critic_grad(obs, act, y, keep, n_global=n_global, row_offset=row_offset, slices_only=True)
+        if self.group is not None and self.peer is None:      # NCCL: gradient -> all-reduce -> Adam
+            g = self.critic_grad(obs, act, y, keep, n_global=n_global, row_offset=row_offset)
+            self._allreduce(g)
+            self.apply_adam("critic")
+            return self.stats[0]
+        # per-CTA slices -> one kernel that sums them and applies Adam (single GPU), or pushes the sum into every
+        # rank's inbox for the peers' Adam kernel (fused exchange)
+        parts = self.critic_grad(obs, act, y, keep, n_global=n_global, row_offset=row_offset, slices_only=True)
+        if self.peer is not None:
             self.peer.reduce_push(self.workspace, parts, C_N, self.stats[0:1])
             self.apply_adam("critic", from_peers=True)
-            return self.stats[0]
-        g = self.critic_grad(obs, act, y, keep, n_global=n_global, row_offset=row_offset)
-        self._allreduce(g)
-        self.apply_adam("critic")
+        else:
+            self.reduce_adam("critic", parts, self.stats[0:1])
         return self.stats[0]
 
     def actor_step(self, obs):
         """model_actor_fit_step (SkillshotLearner.py:386-417).  Returns the (device) sum of q."""
-        if self.peer is not None:
-            parts = self.actor_grad(obs, slices_only=True)
-            # the tensor-core actor step sums Q with its own kernel; the float32 one through the slices' extra slot
-            self.peer.reduce_push(self.workspace, parts, A_N, None if self.update_precision == "bf16" else self.stats[1:2])
-            self.apply_adam("actor", from_peers=True)
+        if self.group is not None and self.peer is None:
+            g = self.actor_grad(obs)
+            self._allreduce(g)
+            self.apply_adam("actor")
             return self.stats[1]
-        g = self.actor_grad(obs)
-        self._allreduce(g)
-        self.apply_adam("actor")
+        parts = self.actor_grad(obs, slices_only=True)
+        if self.peer is not None:
+            self.peer.reduce_push(self.workspace, parts, A_N, self.stats[1:2])
+            self.apply_adam("actor", from_peers=True)
+        else:
+            self.reduce_adam("actor", parts, self.stats[1:2])
         return self.stats[1]
 
     def update_from_ring(self, ring: "ReplayRing", batch: int, out: Optional[dict] = None):
