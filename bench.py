@@ -161,6 +161,7 @@ def cpu_baseline(target_seconds: float = 4.0):
 
 ROLLOUT_ENVS = 262144          # BASELINE.json configs[2]
 TRAIN_BATCH = 65536            # update rows per GPU per step
+SM_BATCH = 148 * 512           # the same sized to the machine: 4 tiles of 128 rows per SM, no partial round
 ACTOR_FLOP_PER_ROW = 72192     # 2 * (12*256 + 256*128 + 128*2)
 UPDATE_FLOP_PER_ROW = 638976   # full DDPG update with target actor + critic forward on s'
 
@@ -201,6 +202,8 @@ def learner_legs(dev, rank, world, seed, peaks, collective, ticks=64, updates=20
     tr.networks.update_precision = "bf16"
     tr.batch_size, tr._batch = 2 * E, None            # one update on as many rows as one rollout tick produces
     t_upd_big = timed(tr.update, max(3, updates // 2))
+    tr.batch_size, tr._batch = SM_BATCH, None         # a whole number of 128-row tiles on every SM
+    t_upd_sm = timed(tr.update, updates)
     tr.batch_size, tr._batch = TRAIN_BATCH, None
     obs, act = tr.obs.view(-1, 12), tr.actions.view(-1, 2)
     t_fwd = timed(lambda: tr.networks.actor_forward(obs, out=act, precision="bf16"), 50)
@@ -225,10 +228,10 @@ def learner_legs(dev, rank, world, seed, peaks, collective, ticks=64, updates=20
 
     t_cfg5 = timed(tick5, 32)
     envs5.check_status()
-    return t_roll, t_upd, t_fwd, t_upd32, t_upd_big, t_cfg5
+    return t_roll, t_upd, t_fwd, t_upd32, t_upd_big, t_cfg5, t_upd_sm
 
 
-def learner_report(t_roll, t_upd, t_fwd, t_upd32, t_upd_big, t_cfg5, world, peaks, peak_kind, collective="nccl"):
+def learner_report(t_roll, t_upd, t_fwd, t_upd32, t_upd_big, t_cfg5, t_upd_sm, world, peaks, peak_kind, collective="nccl"):
     rows = 2 * ROLLOUT_ENVS
     tf = ACTOR_FLOP_PER_ROW * rows / (t_fwd * 1e-3) / 1e12
     return {
@@ -245,6 +248,10 @@ def learner_report(t_roll, t_upd, t_fwd, t_upd32, t_upd_big, t_cfg5, world, peak
                   "dtype": "bf16 operands, f32 accumulate (tcgen05); Adam and parameters f32",
                   "algorithmic_tflops": world * TRAIN_BATCH * UPDATE_FLOP_PER_ROW / (t_upd * 1e-3) / 1e12,
                   "f32_path_samples_per_sec": world * TRAIN_BATCH / (t_upd32 * 1e-3),
+                  "rows_75776_per_gpu": {"note": "148 SMs x 512 rows: every SM gets 4 whole tiles (65,536 rows are 3.46 per SM, "
+                                                 "i.e. 4 rounds with a partial one)",
+                                         "samples_per_sec": world * SM_BATCH / (t_upd_sm * 1e-3), "ms_per_update": t_upd_sm,
+                                         "algorithmic_tflops": world * SM_BATCH * UPDATE_FLOP_PER_ROW / (t_upd_sm * 1e-3) / 1e12},
                   "rows_524288_per_gpu": {"samples_per_sec": world * rows / (t_upd_big * 1e-3), "ms_per_update": t_upd_big,
                                           "algorithmic_tflops": world * rows * UPDATE_FLOP_PER_ROW / (t_upd_big * 1e-3) / 1e12}},
         "planning_actor_speed_sweep": {
@@ -379,7 +386,7 @@ def run_gpu_arm(args):
         e2e_s = time.perf_counter() - t0
 
     # ---- learner legs: rollout, DDPG update, tensor roofline of the actor forward ----
-    lt = (float("nan"),) * 6
+    lt = (float("nan"),) * 7
     if not args.no_learner:
         del actions
         torch.cuda.empty_cache()

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
         }
     };
 
+    trace(0, 900);
     if (threadIdx.x == 0) {
         mbar_init(bar_mma, 32 * EPI_WARPS);
         mbar_init(bar_epi, 1);
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<const volatile uint32_t *>(smem + SM_TMEM);
+    trace(0, 901);
 
     const int64_t tiles = (A.n + TM - 1) / TM;
     float *g = A.work + (int64_t)blockIdx.x * (PN + 1);
@@ -345,6 +347,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
             from_mma();                                   // tiles free for the next round
         }
 
+        trace(0, 902);
         // ======================= write this CTA's partial gradient =======================
         // thread r = hidden-2 unit r for dW2'^T and dW3^T, = hidden-1 unit 128 h + r for dW1'^T; columns split by slice
         {
@@ -406,6 +409,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                 }
             }
         }
+        trace(0, 903);
         tc_fence_before();
     } else {
         // ======================= the MMA-issuing warp =======================

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 from skillshot_learning_b200 import ActorCritic, _lib
 ac = ActorCritic(device="cuda:0", seed=1, update_precision="bf16")
-n = 148 * 128 * 6
+n = 148 * 128 * (int(sys.argv[1]) if len(sys.argv) > 1 else 6)
 s = torch.rand((n, 12), device="cuda"); a = torch.rand((n, 2), device="cuda") * 2 - 1; y = -torch.rand(n, device="cuda")
 g = torch.empty(36609, device="cuda")
 tr = torch.zeros((2, 256, 2), dtype=torch.int64, device="cuda")
@@ -24,9 +24,13 @@ for r in range(2):
     for k in range(256):
         if t[r, k, 0] > 0:
             code = int(t[r, k, 1]); kind, e = code // 100, code % 100
+            if kind == 9:
+                ev.append((int(t[r, k, 0] - t0), "K " + ["entry", "set up + weights staged", "tiles done", "gradient slice written"][e]))
+                continue
             what = {1: "E handed over ->", 2: "E resumed after", 3: "M woke for", 4: "M issued"}[kind]
             ev.append((int(t[r, k, 0] - t0), "%s %s (tile %d)" % (what, step[(e if kind in (1, 3) else e - 1) % 6], (e if kind in (1, 3) else e - 1) // 6)))
 ev.sort()
 prev = 0
-for c, what in ev[:110]:
+show = ev[:110] if len(sys.argv) <= 2 else [x for x in ev if x[1].startswith("K")]
+for c, what in show:
     print("%7d  (+%5d)  %s" % (c, c - prev, what)); prev = c
