@@ -154,9 +154,41 @@ def cpu_baseline(target_seconds: float = 4.0):
     dt, envs, actions = cpu_port_run(ENVS_PER_GPU, 4, cores)            # warm-up + calibration
     ticks = int(max(8, min(4096, target_seconds / max(dt / 4, 1e-6))))
     dt, _, _ = cpu_port_run(ENVS_PER_GPU, ticks, cores, envs=envs, actions=actions)
-    return {"value": ENVS_PER_GPU * ticks / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d envs x %d ticks (%.1f s wall, %d OpenMP threads) of the same workload, C port of the "
-                      "Python reference (oracle/skillshot_oracle.c)" % (ENVS_PER_GPU, ticks, dt, cores)}
+    out = {"value": ENVS_PER_GPU * ticks / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "%d envs x %d ticks (%.1f s wall, %d OpenMP threads) of the same workload, C port of the "
+                     "Python reference (oracle/skillshot_oracle.c)" % (ENVS_PER_GPU, ticks, dt, cores)}
+    # SURVEY.md 8(d) config 1, second figure: tick + get_state + prepare_states (the rollout's env side)
+    rng = np.random.default_rng(1)
+    t_obs = max(4, ticks // 8)
+    t0 = time.perf_counter()
+    for t in range(t_obs):
+        envs.step(actions[t % actions.shape[0]], want_obs=True, reward_mode=1, tick_limit=TICK_LIMIT, auto_reset=True, nthreads=cores)
+    out["with_observations_env_steps_per_sec"] = ENVS_PER_GPU * t_obs / (time.perf_counter() - t0)
+    out["learner_update_batch16"] = cpu_learner_baseline()
+    return out
+
+
+def cpu_learner_baseline(target_seconds: float = 3.0):
+    """The reference's own update on the host: Keras-semantics restatement in torch-CPU (oracle/learner_oracle.py; TensorFlow is
+    not installable here), batches of 16 as model_param_batch_size (SkillshotLearner.py:61): critic fit step + actor fit step."""
+    import torch
+    from oracle import learner_oracle as lo
+    rng = np.random.default_rng(0)
+    L = lo.LearnerOracle(lo.init_actor(rng), lo.init_critic(rng))
+    n = 16 * 64
+    s = rng.uniform(0, 1, (n, 12)).astype(np.float32); a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    y = -rng.uniform(0, 1, n).astype(np.float32); keep = (rng.uniform(size=(n, 256)) >= 0.2).astype(np.float32)
+    order = np.arange(n)
+    L.critic_fit(s[:32], a[:32], y[:32], order[:32], keep[:32]); L.actor_fit(s[:32])          # warm-up
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < target_seconds:
+        L.critic_fit(s, a, y, order, keep)
+        L.actor_fit(s)
+        done += n
+    dt = time.perf_counter() - t0
+    return {"samples_per_sec": done / dt, "threads": int(torch.get_num_threads()),
+            "sample": "%d rows in batches of 16 (%.1f s): critic fit step + actor fit step per batch, torch-CPU restatement of "
+                      "the Keras update (the reference's TensorFlow is not installable here)" % (done, dt)}
 
 
 ROLLOUT_ENVS = 262144          # BASELINE.json configs[2]
