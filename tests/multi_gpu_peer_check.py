@@ -76,6 +76,30 @@ def main():
         if rank == 0:
             print("%s: 512-row critic step  nccl %.1f us   peer %.1f us" % (precision, res["nccl"], res["peer"]), flush=True)
         nets["peer"].peer.close()
+
+    # the whole sharded update from one library call (ss_ddpg_update with the peer exchange inside) against the same
+    # update made of separate calls: two trainers per rank with the same seeds must stay bit-identical
+    from skillshot_learning_b200 import SelfPlayTrainer
+    for precision in ("f32", "bf16"):
+        a, b = [SelfPlayTrainer(1024, device=dev, seed=40 + rank, batch_size=3000, noise_group=128, tick_limit=30, gamma=0.95,
+                                tau=0.05, precision=precision, process_group=True, collective="peer") for _ in range(2)]
+        for tr in (a, b):
+            tr.rollout(5)
+        for it in range(4):
+            sa, qa = a.update()
+            sb, qb = b.update_stepwise()
+            torch.cuda.synchronize()
+            for name in ("params", "target", "adam_m", "adam_v", "grads", "stats"):
+                assert torch.equal(getattr(a.networks, name), getattr(b.networks, name)), (precision, it, name)
+        for tr in (a, b):
+            tr.networks.peer.check_status()
+        gathered = [torch.empty_like(a.networks.params) for _ in range(world)]
+        dist.all_gather(gathered, a.networks.params)
+        assert all(torch.equal(gathered[0], g) for g in gathered), "ranks diverged"
+        if rank == 0:
+            print("%s: single-call sharded update == stepwise, ranks identical" % precision, flush=True)
+        for tr in (a, b):
+            tr.networks.peer.close()
     if rank == 0:
         print("PEER OK", flush=True)
     dist.destroy_process_group()
