@@ -281,7 +281,10 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
             //    reading tensor memory at the same time the MMAs retire at ~95 cycles apiece and the issue stream is
             //    never far ahead of the pipe;
             //  * two issuing warps alternating tiles -- the tensor pipe is one in-order queue, so MMA1(t+1), which the
-            //    producers wait for, lands behind the other warp's 17-step MMA2 chain;
+            //    producers wait for, lands behind the other warp's 17-step MMA2 chain; and two issuing warps split by
+            //    LAYER (one issues every MMA1 the moment a tile is handed over, the other the MMA2 chains back to back,
+            //    producers waiting explicitly for MMA2(t-2)) -- correct, 5 % slower: the output warps' ~1.8 k cycles per
+            //    tile and the producers' ~1.2 k are then the pace, not the issuing thread;
             //  * eight producer warps (two per tensor-memory lane quadrant) -- 12 % SLOWER: more concurrent tcgen05.ld
             //    traffic slows the MMAs' accumulator updates further;
             //  * cta_group::2 (a cluster of two CTAs, one thread issuing M = 256 pair MMAs for both, each CTA holding
@@ -301,18 +304,18 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                     umma_commit(bar(B_Z));
                 }
             };
-            mbar_wait(bar(B_X), xph); xph ^= 1;
+            mbar_wait_likely_done(bar(B_X), xph); xph ^= 1;
             tc_fence_after();
             mma1(tc0);
             for (int64_t i = 0; i < ntiles; ++i) {
                 const uint32_t tc = __shfl_sync(0xffffffffu, tc0 + (uint32_t)i, 0), slot = tc & 1;
                 trace(2, 100 + (int)i);
-                mbar_wait(bar(B_X), xph); xph ^= 1;               // A1[tile] full, D1 free, X0(tile + 1) staged
+                mbar_wait_likely_done(bar(B_X), xph); xph ^= 1;   // A1[tile] full, D1 free, X0(tile + 1) staged
                 tc_fence_after();
                 trace(2, 200 + (int)i);
                 if (i + 1 < ntiles) mma1(tc + 1);
                 trace(2, 300 + (int)i);
-                mbar_wait(bar(B_D2E + slot), ((tc >> 1) & 1) ^ 1);    // the output warps have drained D2[slot]
+                mbar_wait_likely_done(bar(B_D2E + slot), ((tc >> 1) & 1) ^ 1);    // the output warps have drained D2[slot]
                 tc_fence_after();
                 trace(2, 400 + (int)i);
                 if (lane == 0) {

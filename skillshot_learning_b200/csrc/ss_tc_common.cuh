@@ -84,6 +84,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 22)) __trap();
     }
 }
+// For a barrier that has usually completed by the time it is looked at (the MMA-issuing thread's waits): one
+// non-suspending test first -- try_wait costs ~170 cycles even on a completed phase, test_wait a fraction of that --
+// and the parking wait only if the phase is still open.
+__device__ __forceinline__ bool mbar_poll(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_likely_done(uint32_t bar, uint32_t parity) {
+    if (!mbar_poll(bar, parity)) mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

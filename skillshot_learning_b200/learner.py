@@ -464,9 +464,11 @@ class ActorCritic:
         _, n_global, row_offset = shard_info(batch, self.group)
         ws = self._workspace_for(batch)
         a = self._update_args
-        if a is None or self._update_args_key != (id(ring), out["obs"].data_ptr(), ws.data_ptr()):
+        key = (ring.obs.data_ptr(), ring.next_obs.data_ptr(), ring.capacity, out["obs"].data_ptr(), out["y"].data_ptr(), ws.data_ptr(),
+               ws.numel(), batch, id(self.peer))
+        if a is None or self._update_args_key != key:
             a = self._update_args = _lib.DdpgUpdateArgs()
-            self._update_args_key = (id(ring), out["obs"].data_ptr(), ws.data_ptr())
+            self._update_args_key = key
             a.ring_obs, a.ring_act, a.ring_reward = ring.obs.data_ptr(), ring.act.data_ptr(), ring.reward.data_ptr()
             a.ring_next_obs, a.ring_done, a.capacity = ring.next_obs.data_ptr(), ring.done.data_ptr(), ring.capacity
             a.batch = batch
