@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                         if (j + 2 < H2 / 32) tmem_ld32(tl + slot * 128 + (j + 2) * 32, va);
                         else { tc_fence_before(); mbar_arrive(bar(B_D2E + slot)); }     // D2[slot] fully read
                         layer3<NET>(vb, w3x + (j + 1) * kW3Step, acc);
+                        trace(1, (j == 0 ? 600 : 700) + (int)i);
                     }
                 }
                 const float out0 = (acc[0][0] + acc[0][1]) + (acc[0][2] + acc[0][3]);
@@ -271,6 +272,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                         if (A.y_out) A.y_out[row] = A.reward[row] + A.gamma * ((A.done && A.done[row]) ? 0.f : 1.f) * out0;
                     }
                 }
+                trace(1, 800 + (int)i);
             }
         } else {
             // ============ the MMA-issuing warp ============
@@ -285,6 +287,8 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
             //    LAYER (one issues every MMA1 the moment a tile is handed over, the other the MMA2 chains back to back,
             //    producers waiting explicitly for MMA2(t-2)) -- correct, 5 % slower: the output warps' ~1.8 k cycles per
             //    tile and the producers' ~1.2 k are then the pace, not the issuing thread;
+            //  * fetching the output warps' layer-3 weights eight loads ahead of their FMAs -- their pass over D2 drops
+            //    from ~1.6 k to ~1.2 k cycles per tile (trace events 600 / 700 / 800) and the KERNEL gets 6 % slower;
             //  * eight producer warps (two per tensor-memory lane quadrant) -- 12 % SLOWER: more concurrent tcgen05.ld
             //    traffic slows the MMAs' accumulator updates further;
             //  * cta_group::2 (a cluster of two CTAs, one thread issuing M = 256 pair MMAs for both, each CTA holding

@@ -17,7 +17,7 @@ torch.cuda.synchronize()
 t = tr.cpu().numpy()
 t0 = min(t[r, 0, 0] for r in range(3) if t[r, 0, 0] > 0)
 names = {0: {9: "K 0 entry/1 init/2 staged/3 drained", 1: "P wait MMA1", 2: "P D1 ready", 3: "P epilogue1 done", 4: "P other tile free", 5: "P handed over"},
-         1: {1: "Q wait MMA2", 2: "Q D2 ready"},
+         1: {1: "Q wait MMA2", 2: "Q D2 ready", 6: "Q half of D2 done", 7: "Q D2 done", 8: "Q stored"},
          2: {1: "M wait P", 2: "M woke", 3: "M MMA1 issued", 4: "M D2 free", 5: "M MMA2 issued"}}
 ev = []
 for r in range(3):
