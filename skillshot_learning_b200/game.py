@@ -93,6 +93,23 @@ class SkillshotEnvs:
         buf[16 * n:].view(torch.int64).view(n, 2)[:, 1] = torch.as_tensor(cooldown_max, dtype=torch.int64, device=self.device)
         self.speeds = buf
 
+    # -- checkpoint --------------------------------------------------------
+    def state_dict(self):
+        """Everything a resumed run needs to continue bit-identically: the packed env state, the Philox counter, the
+        per-env speed constants and the configuration."""
+        return dict(n_envs=self.n_envs, state=self.state.cpu(), counter=self.counter, seed=self.seed,
+                    speeds=None if self.speeds is None else self.speeds.cpu(), random_positions=self.random_positions,
+                    reward_mode=self.reward_mode, tick_limit=self.tick_limit, auto_reset=self.auto_reset)
+
+    def load_state_dict(self, sd):
+        if int(sd["n_envs"]) != self.n_envs:
+            raise ValueError("checkpoint holds %d envs, this batch %d" % (sd["n_envs"], self.n_envs))
+        self.state.copy_(sd["state"].to(self.device))
+        self.counter, self.seed = int(sd["counter"]), int(sd["seed"])
+        self.speeds = None if sd["speeds"] is None else sd["speeds"].to(self.device)
+        self.random_positions, self.reward_mode = bool(sd["random_positions"]), sd["reward_mode"]
+        self.tick_limit, self.auto_reset = int(sd["tick_limit"]), bool(sd["auto_reset"])
+
     # -- reset -------------------------------------------------------------
     def reset(self, mask: Optional[torch.Tensor] = None, positions=None, random_positions: Optional[bool] = None):
         """SkillshotGame.game_reset for the envs selected by `mask` (all by default)."""

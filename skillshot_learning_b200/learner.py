@@ -552,6 +552,17 @@ class ReplayRing:
         self.pos = (self.pos + n) % self.capacity
         self.size = min(self.capacity, self.size + n)
 
+    def state_dict(self):
+        return dict(capacity=self.capacity, seed=self.seed, pos=self.pos, size=self.size, counter=self.counter,
+                    **{k: getattr(self, k).cpu() for k in ("obs", "act", "reward", "next_obs", "done")})
+
+    def load_state_dict(self, sd):
+        if int(sd["capacity"]) != self.capacity:
+            raise ValueError("checkpoint ring holds %d rows, this ring %d" % (sd["capacity"], self.capacity))
+        for k in ("obs", "act", "reward", "next_obs", "done"):
+            getattr(self, k).copy_(sd[k].to(self.device))
+        self.seed, self.pos, self.size, self.counter = int(sd["seed"]), int(sd["pos"]), int(sd["size"]), int(sd["counter"])
+
     def sample(self, batch: int, indices=None, out: Optional[dict] = None):
         """dict(obs, act, reward, next_obs, done, indices) of `batch` rows: the rows `indices` or a
         uniform draw with replacement from the filled part of the ring."""
@@ -1001,6 +1012,32 @@ class SelfPlayTrainer:
             self.obs, self.prev_obs = b, a
         self.ticks += n_ticks
         return dict(obs=self.obs, reward=out["reward"][0], done=out["done"][0], winner=out["winner"][0])
+
+    # -- checkpoint / resume (SkillshotLearner.py:123-162 keeps the two Keras models; a batched run also needs the
+    #    optimiser moments, the targets, the games in flight, the replay ring and every Philox counter) ---------------
+    def state_dict(self):
+        return dict(envs=self.envs.state_dict(), networks=self.networks.state_dict(), replay=self.replay.state_dict(),
+                    obs=self.obs.cpu(), actions=self.actions.cpu(), ticks=self.ticks, batch_size=self.batch_size,
+                    param_noise_sd=self.param_noise_sd, noise_group=self.noise_group, precision=self.precision)
+
+    def load_state_dict(self, sd):
+        self.envs.load_state_dict(sd["envs"])
+        self.networks.load_state_dict(sd["networks"])
+        self.replay.load_state_dict(sd["replay"])
+        self.obs.copy_(sd["obs"].to(self.device))
+        self.actions.copy_(sd["actions"].to(self.device))
+        self.ticks, self.batch_size = int(sd["ticks"]), int(sd["batch_size"])
+        self.param_noise_sd, self.noise_group = float(sd["param_noise_sd"]), int(sd["noise_group"])
+        self._batch = None
+
+    def save(self, path: str):
+        """Write a checkpoint the run can be resumed from bit-identically (one file per rank when sharded)."""
+        torch.cuda.synchronize(self.device)
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        torch.save(self.state_dict(), path)
+
+    def load(self, path: str):
+        self.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
 
     def update(self):
         """One critic step and one actor step on a sampled minibatch: a single library call on one GPU or

@@ -726,3 +726,30 @@ def test_full_size_frame_stack_actor_is_invariant_to_the_ring_phase():
     for k in range(2):
         d = (outs["bf16"][k] - outs["f32"][k]).abs()
         assert float(d.max()) < (3e-2, 1e-1)[k] and float(d.mean()) < (3e-3, 8e-3)[k]
+
+
+@pytest.mark.parametrize("precision", ["f32", "bf16"])
+def test_trainer_checkpoint_resumes_bit_identically(tmp_path, precision):
+    """a batched run saved and resumed (games in flight, replay ring, weights, Adam moments, targets,
+    every Philox counter) continues exactly as the uninterrupted run does."""
+    from skillshot_learning_b200 import SelfPlayTrainer
+    kw = dict(device="cuda:0", seed=17, batch_size=2000, noise_group=128, tick_limit=25, gamma=0.9, tau=0.05, precision=precision,
+              replay_capacity=2048 * 6)
+    a = SelfPlayTrainer(1024, **kw)
+    for _ in range(3):
+        a.rollout(3)
+        a.update()
+    a.save(str(tmp_path / "ckpt" / "trainer.pt"))
+    b = SelfPlayTrainer(1024, **dict(kw, seed=99))                       # different seeds: everything must come from the file
+    b.load(str(tmp_path / "ckpt" / "trainer.pt"))
+    for tr in (a, b):
+        for _ in range(3):
+            tr.rollout(4)                                                # wraps the ring
+            tr.update()
+    for name in ("params", "target", "adam_m", "adam_v", "grads"):
+        assert torch.equal(getattr(a.networks, name), getattr(b.networks, name)), name
+    for name in ("obs", "act", "reward", "next_obs", "done"):
+        assert torch.equal(getattr(a.replay, name), getattr(b.replay, name)), name
+    assert torch.equal(a.envs.state, b.envs.state) and torch.equal(a.obs, b.obs)
+    assert (a.ticks, a.replay.pos, a.replay.size, a.networks.counter, a.envs.counter) == (
+        b.ticks, b.replay.pos, b.replay.size, b.networks.counter, b.envs.counter)
