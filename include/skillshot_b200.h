@@ -57,6 +57,13 @@ extern "C" {
 
 /* flags of ss_env_step */
 #define SS_STEP_OBS_EVERY_TICK 1  /* obs_out is [n_ticks][n][2][12] instead of last tick only */
+#define SS_STEP_EPISODE_STATS 2   /* `status` is the head of a block {uint32 status, uint32 pad, uint64 stats[SS_EPISODE_STATS]}:
+                                   * every game that ENDS in this call is counted there (the per-episode ticks / winner log of
+                                   * SkillshotLearner.py:164-180, 365-366, reduced on the device) */
+/* stats[]: 0 episodes, 1 ended by a hit on player 1 (winner_id 1), 2 by a hit on player 2, 3 by the tick limit,
+ * 4 sum of the episodes' tick counts, 5..7 reserved, 8..71 histogram of the tick counts in 64 bins of
+ * ceil(tick_limit / 64) ticks (32 ticks when tick_limit <= 0; the last bin is open) */
+#define SS_EPISODE_STATS 72
 
 /* status bits OR-ed into *status by the kernels */
 #define SS_STATUS_NAN 1       /* where the reference raises ValueError: int(round(nan)), Player.py:63 */
@@ -104,7 +111,7 @@ int ss_env_reset(void *state, int64_t n_envs, const uint8_t *mask, int reset_mod
  *   speeds      NULL (reference constants) or per-env constants, two 16-byte planes:
  *               plane 0 double2 {Player.speed_move, Player.speed_look},
  *               plane 1 {double Projectile.speed_move, int64 cooldown_max}
- *   status      NULL or uint32[1], SS_STATUS_* bits are OR-ed in
+ *   status      NULL or uint32[1], SS_STATUS_* bits are OR-ed in (a larger block with SS_STEP_EPISODE_STATS)
  */
 int ss_env_step(void *state, int64_t n_envs, const float *actions, float *obs_out,
                 float *reward_out, uint8_t *done_out, uint8_t *winner_out,
@@ -279,7 +286,8 @@ int ss_reduce_adam_tf(const void *workspace, int parts, int n_params, float *aux
  * When capacity and write_pos are multiples of 2 n_envs the transitions are produced IN the ring (the actor
  * reads its observations from and writes its actions to the ring's rows, ss_env_step_ring writes reward, done
  * and both copies of the next observation there): no copy kernel runs, and the current observation is left
- * in obs_a whatever the parity of n_ticks.  Otherwise ss_replay_push copies each tick's rows. */
+ * in obs_a whatever the parity of n_ticks.  Otherwise ss_replay_push copies each tick's rows.
+ * step_flags: SS_STEP_EPISODE_STATS or 0, passed to every env step of the loop. */
 int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_params, float *obs_a, float *obs_b,
                         float *actions, float *reward, uint8_t *done, uint8_t *winner,
                         float *ring_obs, float *ring_act, float *ring_reward, float *ring_next_obs,
@@ -287,7 +295,7 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
                         float param_noise_sd, int64_t noise_group, float action_noise_sd, int tensor_cores,
                         int reward_mode, int64_t tick_limit, int reset_mode, uint64_t env_seed,
                         uint64_t env_counter, uint64_t noise_seed, uint64_t noise_counter, const void *speeds,
-                        uint32_t *status, void *stream);
+                        uint32_t *status, int step_flags, void *stream);
 
 /* ---- frame-stacked ("planning") actor: readme.md:18-20, BASELINE.json configs[4]; no reference code ----
  * The actor reads the last `frames` observations of a player: first layer 12 * frames -> 256, the rest as

@@ -19,6 +19,8 @@ EXPORT_INTS = 17
 REWARD_NONE, REWARD_LOOKING, REWARD_TERMINAL, REWARD_SIMPLE = 0, 1, 2, 3
 RESET_FIXED, RESET_RANDOM, RESET_GIVEN = 0, 1, 2
 STEP_OBS_EVERY_TICK = 1
+STEP_EPISODE_STATS = 2
+EPISODE_STATS = 72
 STATUS_NAN = 1
 STATUS_PEER_TIMEOUT = 2
 (OP_MOVE_DIRECTION_FLOAT, OP_MOVE_LOOK_FLOAT, OP_SHOOT, OP_MOVE_FORWARDS, OP_MOVE_BACKWARDS,
@@ -79,7 +81,8 @@ SIGNATURES = {
     "ss_peer_adam_tf": (_i32, [_vp, _i32, _i64, ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
                                 _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
     "ss_selfplay_rollout": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32,
-                                    _f32, _i64, _f32, _i32, _i32, _i64, _i32, _u64, _u64, _u64, _u64, _vp, _vp, _vp]),
+                                    _f32, _i64, _f32, _i32, _i32, _i64, _i32, _u64, _u64, _u64, _u64, _vp, _vp, _i32,
+                                    _vp]),
     "ss_actor_frames_params": (_i64, [_i32]),
     "ss_obs_stack_push": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _i32, _vp]),
     "ss_param_noise_groups": (_i32, [_vp, _vp, _i64, _i64, _i64, _f32, _u64, _u64, _vp]),

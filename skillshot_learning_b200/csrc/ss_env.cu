@@ -64,6 +64,16 @@ struct NoSink {
     __device__ __forceinline__ void put(int, float, float, float, float) {}
 };
 
+// One finished game into the episode statistics (SS_STEP_EPISODE_STATS).  Kept out of line: it runs once per game,
+// and inlined it cost the step kernels 30-40 registers.
+__device__ __noinline__ void count_episode(unsigned long long *stats, int len, int winner, int tick_limit) {
+    const int width = tick_limit > 0 ? (tick_limit + 63) / 64 : 32;
+    atomicAdd(stats + 0, 1ull);
+    atomicAdd(stats + (winner == 1 ? 1 : winner == 2 ? 2 : 3), 1ull);
+    atomicAdd(stats + 4, (unsigned long long)len);
+    atomicAdd(stats + 8 + min(63, len / width), 1ull);
+}
+
 struct StepArgs {
     void *state;
     int64_t n;
@@ -76,6 +86,7 @@ struct StepArgs {
     uint16_t *done_rows_out;   // done flag once per player row ([n][2] bytes, the replay ring's layout), or NULL
     const void *speeds;
     uint32_t *status;
+    unsigned long long *stats;  // episode statistics (SS_STEP_EPISODE_STATS) or NULL
     TickParams P;
     int n_ticks, obs_every_tick;
 };
@@ -83,7 +94,7 @@ struct StepArgs {
 // OBS: write observations.  CARRY: keep sin/cos of the rotations in registers across
 // ticks (fused ticks, observations, shaped rewards); !CARRY is the lean one-tick
 // physics-only kernel.
-template <bool OBS, bool CARRY, bool SPEEDS, int MINB = 1>
+template <bool OBS, bool CARRY, bool SPEEDS, int MINB = 1, bool STATS = false>
 __global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
     __shared__ float4 tile[OBS ? kWarps : 1][OBS ? 32 * kRowF4 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -115,7 +126,11 @@ __global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
         float r[2];
         int done, winner;
         SmemSink sink{&tile[OBS ? warp : 0][OBS ? lane * kRowF4 : 0]};
+        // a game that is over before the tick (no auto-reset) stays "done" and is not an episode end again
+        const int ticks_before = !STATS ? 0 : (!e.live || (A.P.tick_limit > 0 && e.ticks >= A.P.tick_limit)) ? -1 : e.ticks;
         tick_env<OBS, CARRY>(e, a.x, a.y, a.z, a.w, k, A.P, (uint64_t)i, t, want_obs, status, tr, r, done, winner, sink);
+        if (STATS && active && done && ticks_before >= 0)          // rare: a few atomics per finished game
+            count_episode(A.stats, ticks_before + 1, winner, (int)A.P.tick_limit);
         if (active) {
             if (write_reward) A.reward_out[row] = make_float2(r[0], r[1]);
             if (A.done_out) A.done_out[row] = (uint8_t)done;
@@ -308,6 +323,8 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
     A.reward_out = (float2 *)reward_out; A.done_out = done_out; A.winner_out = winner_out;
     A.obs_out2 = (float4 *)obs_out2; A.done_rows_out = (uint16_t *)done_rows_out;
     A.speeds = speeds; A.status = status;
+    A.stats = (status && (flags & SS_STEP_EPISODE_STATS)) ? reinterpret_cast<unsigned long long *>(status) + 1 : nullptr;
+    if (A.stats && ((uintptr_t)status & 7)) return SS_ERR_INVALID_ARG;
     A.P.seed = seed; A.P.counter = counter; A.P.tick_limit = tick_limit;
     A.P.reward_mode = reward_mode; A.P.auto_reset = auto_reset ? 1 : 0; A.P.reset_mode = reset_mode;
     A.n_ticks = n_ticks; A.obs_every_tick = (flags & SS_STEP_OBS_EVERY_TICK) ? 1 : 0;
@@ -320,19 +337,38 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
     if (!configured) {
         cudaFuncSetAttribute(step_kernel<true, true, false, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
         cudaFuncSetAttribute(step_kernel<true, true, true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        cudaFuncSetAttribute(step_kernel<true, true, false, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        cudaFuncSetAttribute(step_kernel<true, true, true, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
         configured = true;
     }
+    // (the statistics variants are separate instantiations: the bookkeeping costs the physics-only kernels a few
+    //  registers and ~5 % when compiled in)
     if (obs_out) {
         // 8 CTAs (16 warps) per SM: capping the observation kernel at 128 registers measured
         // 83 us vs 100 us uncapped at 1M envs (profiles/README.md)
-        if (speeds) step_kernel<true, true, true, 8><<<grid, block, 0, st>>>(A);
-        else step_kernel<true, true, false, 8><<<grid, block, 0, st>>>(A);
+        if (A.stats) {
+            if (speeds) step_kernel<true, true, true, 8, true><<<grid, block, 0, st>>>(A);
+            else step_kernel<true, true, false, 8, true><<<grid, block, 0, st>>>(A);
+        } else {
+            if (speeds) step_kernel<true, true, true, 8><<<grid, block, 0, st>>>(A);
+            else step_kernel<true, true, false, 8><<<grid, block, 0, st>>>(A);
+        }
     } else if (carry) {
-        if (speeds) step_kernel<false, true, true><<<grid, block, 0, st>>>(A);
-        else step_kernel<false, true, false><<<grid, block, 0, st>>>(A);
+        if (A.stats) {
+            if (speeds) step_kernel<false, true, true, 1, true><<<grid, block, 0, st>>>(A);
+            else step_kernel<false, true, false, 1, true><<<grid, block, 0, st>>>(A);
+        } else {
+            if (speeds) step_kernel<false, true, true><<<grid, block, 0, st>>>(A);
+            else step_kernel<false, true, false><<<grid, block, 0, st>>>(A);
+        }
     } else {
-        if (speeds) step_kernel<false, false, true><<<grid, block, 0, st>>>(A);
-        else step_kernel<false, false, false><<<grid, block, 0, st>>>(A);
+        if (A.stats) {
+            if (speeds) step_kernel<false, false, true, 1, true><<<grid, block, 0, st>>>(A);
+            else step_kernel<false, false, false, 1, true><<<grid, block, 0, st>>>(A);
+        } else {
+            if (speeds) step_kernel<false, false, true><<<grid, block, 0, st>>>(A);
+            else step_kernel<false, false, false><<<grid, block, 0, st>>>(A);
+        }
     }
     return check_launch();
 }

@@ -883,7 +883,7 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
                         int64_t capacity, int64_t write_pos, int n_ticks, float param_noise_sd, int64_t noise_group,
                         float action_noise_sd, int tensor_cores, int reward_mode, int64_t tick_limit, int reset_mode,
                         uint64_t env_seed, uint64_t env_counter, uint64_t noise_seed, uint64_t noise_counter,
-                        const void *speeds, uint32_t *status, void *stream) {
+                        const void *speeds, uint32_t *status, int step_flags, void *stream) {
     if (!env_state || !actor_params || !obs_a || !obs_b || !actions || !reward || !done || n_envs <= 0 || n_ticks <= 0)
         return SS_ERR_INVALID_ARG;
     const bool store = ring_obs != nullptr;
@@ -908,7 +908,7 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
             if (rc != SS_OK) return rc;
             rc = ss_env_step_ring(env_state, n_envs, a, ring_next_obs + seg * rows * 12, o_next, ring_reward + seg * rows, done,
                                   ring_done + seg * rows, winner, 1, reward_mode, tick_limit, 1, reset_mode, env_seed,
-                                  env_counter + (uint64_t)t, speeds, status, 0, stream);
+                                  env_counter + (uint64_t)t, speeds, status, step_flags, stream);
             if (rc != SS_OK) return rc;
         }
         // the last tick's actions and rewards for the caller's scratch tensors
@@ -929,7 +929,7 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
         if (rc != SS_OK) return rc;
         // game_tick, reward of the post-tick state, next observation; finished games restart (SkillshotLearner.py:312-315)
         rc = ss_env_step(env_state, n_envs, actions, next, reward, done, winner, 1, reward_mode, tick_limit, 1, reset_mode,
-                         env_seed, env_counter + (uint64_t)t, speeds, status, 0, stream);
+                         env_seed, env_counter + (uint64_t)t, speeds, status, step_flags, stream);
         if (rc != SS_OK) return rc;
         if (store) {
             rc = ss_replay_push(ring_obs, ring_act, ring_reward, ring_next_obs, ring_done, capacity,

@@ -75,7 +75,11 @@ class SkillshotEnvs:
         self.counter = 0           # Philox counter base: advances with every tick / reset
         n = self.n_envs
         self.state = torch.zeros(_lib.STATE_BYTES_PER_ENV * n, dtype=torch.uint8, device=self.device)
-        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # {uint32 status, pad, uint64 episode statistics[72]}: the block SS_STEP_EPISODE_STATS describes
+        self._status_block = torch.zeros(2 + 2 * _lib.EPISODE_STATS, dtype=torch.int32, device=self.device)
+        self.status = self._status_block[0:1]
+        self.episode_stats = self._status_block[2:].view(torch.int64)
+        self.collect_episode_stats = False     # count every finished game on the device (episode_summary); opt-in
         self.speeds: Optional[torch.Tensor] = None
         self._obs = torch.empty((n, 2, _lib.NUM_OBS), dtype=torch.float32, device=self.device)
         self._out = {}
@@ -98,6 +102,7 @@ class SkillshotEnvs:
         """Everything a resumed run needs to continue bit-identically: the packed env state, the Philox counter, the
         per-env speed constants and the configuration."""
         return dict(n_envs=self.n_envs, state=self.state.cpu(), counter=self.counter, seed=self.seed,
+                    episode_stats=self.episode_stats.cpu(),
                     speeds=None if self.speeds is None else self.speeds.cpu(), random_positions=self.random_positions,
                     reward_mode=self.reward_mode, tick_limit=self.tick_limit, auto_reset=self.auto_reset)
 
@@ -106,6 +111,8 @@ class SkillshotEnvs:
             raise ValueError("checkpoint holds %d envs, this batch %d" % (sd["n_envs"], self.n_envs))
         self.state.copy_(sd["state"].to(self.device))
         self.counter, self.seed = int(sd["counter"]), int(sd["seed"])
+        if sd.get("episode_stats") is not None:
+            self.episode_stats.copy_(sd["episode_stats"].to(self.device))
         self.speeds = None if sd["speeds"] is None else sd["speeds"].to(self.device)
         self.random_positions, self.reward_mode = bool(sd["random_positions"]), sd["reward_mode"]
         self.tick_limit, self.auto_reset = int(sd["tick_limit"]), bool(sd["auto_reset"])
@@ -145,8 +152,21 @@ class SkillshotEnvs:
                                   K, REWARD_MODES[self.reward_mode], self.tick_limit, int(self.auto_reset),
                                   _lib.RESET_RANDOM if self.random_positions else _lib.RESET_FIXED,
                                   self.seed, self.counter, _ptr(self.speeds), self.status.data_ptr(),
-                                  flags, _stream(self.device)), "ss_env_step")
+                                  flags | (_lib.STEP_EPISODE_STATS if self.collect_episode_stats else 0), _stream(self.device)),
+                  "ss_env_step")
         self.counter += K
+
+    def episode_summary(self, reset: bool = False) -> dict:
+        """(with collect_episode_stats = True)  The per-episode log of the reference (ticks and winner of every finished
+        game, SkillshotLearner.py:164-180, 365-366) reduced on the device: counts of the games that ended since the last reset of the statistics, by how
+        they ended, their mean length and a 64-bin histogram of their lengths."""
+        st = self.episode_stats.cpu().numpy()
+        if reset:
+            self.episode_stats.zero_()
+        n = int(st[0])
+        width = (self.tick_limit + 63) // 64 if self.tick_limit > 0 else 32
+        return dict(episodes=n, player1_hit=int(st[1]), player2_hit=int(st[2]), tick_limit=int(st[3]),
+                    mean_ticks=float(st[4]) / n if n else float("nan"), histogram=st[8:72].copy(), bin_ticks=width)
 
     def step(self, actions: torch.Tensor, want_obs: bool = True, obs_every_tick: bool = False,
              obs_out: Optional[torch.Tensor] = None):

@@ -957,6 +957,7 @@ class SelfPlayTrainer:
         self.device = torch.device(device)
         self.envs = SkillshotEnvs(n_envs, device=device, random_positions=random_positions, seed=seed,
                                   reward_mode=reward_mode, tick_limit=tick_limit, auto_reset=True)
+        self.envs.collect_episode_stats = True     # the reference's per-episode ticks / winner log, reduced on the device
         self.networks = ActorCritic(device=device, seed=seed if process_group is None else 0, gamma=gamma, tau=tau,
                                     process_group=process_group, update_precision=precision, collective=collective)
         self.networks.seed = seed          # exploration / dropout streams differ per rank, weights do not
@@ -1001,7 +1002,8 @@ class SelfPlayTrainer:
                 rp.done.data_ptr(), rp.capacity, rp.pos, int(n_ticks), self.param_noise_sd, self.noise_group, 0.0,
                 1 if self.precision == "bf16" else 0, REWARD_MODES[envs.reward_mode], envs.tick_limit,
                 _lib.RESET_RANDOM if envs.random_positions else _lib.RESET_FIXED, envs.seed, envs.counter, net.seed,
-                net.counter, _ptr(envs.speeds), envs.status.data_ptr(), _stream(self.device)), "ss_selfplay_rollout")
+                net.counter, _ptr(envs.speeds), envs.status.data_ptr(), _lib.STEP_EPISODE_STATS if envs.collect_episode_stats else 0, _stream(self.device)),
+                  "ss_selfplay_rollout")
         envs.counter += n_ticks
         net.counter += n_ticks
         if store:
@@ -1029,6 +1031,11 @@ class SelfPlayTrainer:
         self.ticks, self.batch_size = int(sd["ticks"]), int(sd["batch_size"])
         self.param_noise_sd, self.noise_group = float(sd["param_noise_sd"]), int(sd["noise_group"])
         self._batch = None
+
+    def progress(self, reset: bool = False) -> dict:
+        """The training-progress log of the reference (per-episode ticks and winner, SkillshotLearner.py:164-180,
+        365-366) for the games finished so far, reduced on the device by the step kernel (SkillshotEnvs.episode_summary)."""
+        return self.envs.episode_summary(reset=reset)
 
     def save(self, path: str):
         """Write a checkpoint the run can be resumed from bit-identically (one file per rank when sharded)."""

@@ -128,3 +128,44 @@ def test_facade_matches_reference_surface():
     assert board.shape == (250, 250) and board[4, 103] == 1
     g.game_reset()
     assert g.ticks == 0 and list(g.player1.pos) == [50, 50]
+
+
+@pytest.mark.parametrize("auto_reset,fused", [(True, 1), (True, 8), (False, 4)])
+def test_episode_statistics_match_the_per_tick_done_log(auto_reset, fused):
+    """SS_STEP_EPISODE_STATS: the device-side reduction of the reference's per-episode log (ticks and winner of every
+    finished game, SkillshotLearner.py:164-180) against the same figures rebuilt on the host from the per-tick done /
+    winner outputs.  Without auto-reset a finished game stays done and must be counted once."""
+    import torch
+    n, T, limit = 3000, 96, 40
+    envs = make(n, random_positions=True, seed=3, reward_mode="terminal", tick_limit=limit, auto_reset=auto_reset)
+    envs.collect_episode_stats = True
+    g = torch.Generator(device="cuda").manual_seed(1)
+    age = np.zeros(n, np.int64)
+    over = np.zeros(n, bool)
+    want = dict(episodes=0, hit1=0, hit2=0, limit=0, ticks=0, hist=np.zeros(64, np.int64))
+    width = (limit + 63) // 64
+    for _ in range(T // fused):
+        a = torch.rand((fused, n, 2, 2), device="cuda", generator=g) * 2.4 - 1.2
+        out = envs.step(a, want_obs=False)
+        done, winner = out["done"].cpu().numpy().reshape(fused, n), out["winner"].cpu().numpy().reshape(fused, n)
+        for t in range(fused):
+            age += ~over
+            ended = (done[t] != 0) & ~over
+            want["episodes"] += int(ended.sum())
+            want["hit1"] += int((ended & (winner[t] == 1)).sum())
+            want["hit2"] += int((ended & (winner[t] == 2)).sum())
+            want["limit"] += int((ended & (winner[t] == 0)).sum())
+            want["ticks"] += int(age[ended].sum())
+            np.add.at(want["hist"], np.minimum(63, age[ended] // width), 1)
+            if auto_reset:
+                age[ended] = 0
+            else:
+                over |= ended
+    got = envs.episode_summary()
+    assert want["episodes"] > n // 2
+    assert (got["episodes"], got["player1_hit"], got["player2_hit"], got["tick_limit"]) == (
+        want["episodes"], want["hit1"], want["hit2"], want["limit"])
+    assert abs(got["mean_ticks"] * got["episodes"] - want["ticks"]) < 0.5
+    assert np.array_equal(got["histogram"], want["hist"]) and got["bin_ticks"] == width
+    envs.episode_summary(reset=True)
+    assert envs.episode_summary()["episodes"] == 0
