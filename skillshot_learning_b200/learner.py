@@ -1032,6 +1032,24 @@ class SelfPlayTrainer:
         self.param_noise_sd, self.noise_group = float(sd["param_noise_sd"]), int(sd["noise_group"])
         self._batch = None
 
+    def record_boards(self, env: int, n_ticks: int, path: Optional[str] = None, store: bool = True):
+        """Play n_ticks rollout ticks and return the 250 x 250 rasters of game `env` after each of them
+        (SkillshotGame.get_board, SkillshotGame.py:36-56, rebuilt on the host from the exported state row): the frames
+        SkillshotGameDisplay.display_sequence shows.  With `path`, also written as training_boards.npy in the shape
+        save_training_boards uses (one object-array entry = one sequence, SkillshotLearner.py:182-204)."""
+        from .game import render_board
+        boards = []
+        for _ in range(int(n_ticks)):
+            self.rollout_tick(store=store)
+            boards.append(render_board(self.envs.export_state(int(env), 1), 0))
+        boards = np.asarray(boards)
+        if path is not None:
+            os.makedirs(path, exist_ok=True)
+            arr = np.empty(1, dtype=object)
+            arr[0] = boards
+            np.save(os.path.join(path, "training_boards"), arr, allow_pickle=True)
+        return boards
+
     def progress(self, reset: bool = False) -> dict:
         """The training-progress log of the reference (per-episode ticks and winner, SkillshotLearner.py:164-180,
         365-366) for the games finished so far, reduced on the device by the step kernel (SkillshotEnvs.episode_summary)."""

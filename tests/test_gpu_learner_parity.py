@@ -753,3 +753,20 @@ def test_trainer_checkpoint_resumes_bit_identically(tmp_path, precision):
     assert torch.equal(a.envs.state, b.envs.state) and torch.equal(a.obs, b.obs)
     assert (a.ticks, a.replay.pos, a.replay.size, a.networks.counter, a.envs.counter) == (
         b.ticks, b.replay.pos, b.replay.size, b.networks.counter, b.envs.counter)
+
+
+def test_trainer_board_export_and_progress(tmp_path):
+    """SURVEY.md 8(f) ranks 2-3 for batched runs: board rasters of one game of the batch for the host display tools, and
+    the per-episode log reduced on the device."""
+    from skillshot_learning_b200 import SelfPlayTrainer
+    tr = SelfPlayTrainer(512, device="cuda:0", seed=2, batch_size=256, noise_group=128, tick_limit=12, replay_capacity=1024 * 40)
+    boards = tr.record_boards(7, 30, path=str(tmp_path / "training_boards"))
+    assert boards.shape == (30, 250, 250) and set(np.unique(boards)) <= {0, 1, 2, 3, 4}
+    st = tr.envs.export_state(7, 1)
+    body = np.argwhere(boards[-1] == 1)                                   # player 1's 3 x 3 body sits at pos + 1
+    assert body.min(axis=0).tolist() == [int(st["px"][0, 0]) + 1, int(st["py"][0, 0]) + 1] and len(body) >= 8
+    saved = np.load(str(tmp_path / "training_boards" / "training_boards.npy"), allow_pickle=True)
+    assert saved.shape == (1,) and np.array_equal(saved[0], boards)
+    p = tr.progress()
+    assert p["episodes"] >= 2 * 512 and p["episodes"] == p["player1_hit"] + p["player2_hit"] + p["tick_limit"]
+    assert 1 <= p["mean_ticks"] <= 12 and int(p["histogram"].sum()) == p["episodes"]
