@@ -770,3 +770,20 @@ def test_trainer_board_export_and_progress(tmp_path):
     p = tr.progress()
     assert p["episodes"] >= 2 * 512 and p["episodes"] == p["player1_hit"] + p["player2_hit"] + p["tick_limit"]
     assert 1 <= p["mean_ticks"] <= 12 and int(p["histogram"].sum()) == p["episodes"]
+
+
+@pytest.mark.parametrize("precision", ["f32", "bf16"])
+@pytest.mark.parametrize("batch", [1, 127, 129])
+def test_single_call_update_at_ragged_batch_sizes(precision, batch):
+    """ss_ddpg_update at batch sizes around the 128-row tile (and a single row) against the stepwise update."""
+    from skillshot_learning_b200 import SelfPlayTrainer
+    a, b = [SelfPlayTrainer(64, device="cuda:0", seed=8, batch_size=batch, noise_group=128, tick_limit=20, precision=precision,
+                            gamma=0.9, tau=0.1) for _ in range(2)]
+    for tr in (a, b):
+        tr.rollout(3)
+    for _ in range(3):
+        a.update()
+        b.update_stepwise()
+    for name in ("params", "target", "adam_m", "adam_v", "grads", "stats"):
+        assert torch.equal(getattr(a.networks, name), getattr(b.networks, name)), name
+    assert torch.isfinite(a.networks.params).all()
