@@ -260,10 +260,25 @@ def learner_legs(dev, rank, world, seed, peaks, collective, ticks=64, updates=20
 
     t_cfg5 = timed(tick5, 32)
     envs5.check_status()
-    return t_roll, t_upd, t_fwd, t_upd32, t_upd_big, t_cfg5, t_upd_sm
+
+    # ---- BASELINE.json configs[3]: full self-play training, 1,048,576 envs in total sharded over the GPUs ----
+    del tr, envs5, actor5
+    torch.cuda.empty_cache()
+    E4 = 1048576 // world
+    tr4 = SelfPlayTrainer(E4, device=dev, seed=seed + 11, replay_capacity=2 * E4 * 2, batch_size=TRAIN_BATCH, process_group=True if world > 1 else None,
+                          gamma=0.99, tau=0.005, param_noise_sd=0.5, noise_group=-(-(2 * E4 // 128) // 148) * 128,
+                          reward_mode="looking", tick_limit=TICK_LIMIT, precision="bf16", collective=collective)
+
+    def iteration():
+        tr4.rollout(1)
+        tr4.update()
+
+    t_cfg4 = timed(iteration, 16)
+    tr4.envs.check_status()
+    return t_roll, t_upd, t_fwd, t_upd32, t_upd_big, t_cfg5, t_upd_sm, t_cfg4
 
 
-def learner_report(t_roll, t_upd, t_fwd, t_upd32, t_upd_big, t_cfg5, t_upd_sm, world, peaks, peak_kind, collective="nccl"):
+def learner_report(t_roll, t_upd, t_fwd, t_upd32, t_upd_big, t_cfg5, t_upd_sm, t_cfg4, world, peaks, peak_kind, collective="nccl"):
     rows = 2 * ROLLOUT_ENVS
     tf = ACTOR_FLOP_PER_ROW * rows / (t_fwd * 1e-3) / 1e12
     return {
@@ -286,6 +301,12 @@ def learner_report(t_roll, t_upd, t_fwd, t_upd32, t_upd_big, t_cfg5, t_upd_sm, w
                                          "algorithmic_tflops": world * SM_BATCH * UPDATE_FLOP_PER_ROW / (t_upd_sm * 1e-3) / 1e12},
                   "rows_524288_per_gpu": {"samples_per_sec": world * rows / (t_upd_big * 1e-3), "ms_per_update": t_upd_big,
                                           "algorithmic_tflops": world * rows * UPDATE_FLOP_PER_ROW / (t_upd_big * 1e-3) / 1e12}},
+        "selfplay_training": {
+            "workload": "BASELINE.json configs[3]: 1,048,576 envs in total (%d per GPU), one iteration = one rollout tick of every env "
+                        "(tensor-core actor, parameter noise, transitions into the replay ring) + one %d-row-per-GPU DDPG update; "
+                        "strong scaling (the total is fixed)" % (1048576 // world, TRAIN_BATCH),
+            "env_steps_per_sec": 1048576 / (t_cfg4 * 1e-3), "update_samples_per_sec": world * TRAIN_BATCH / (t_cfg4 * 1e-3),
+            "ms_per_iteration": t_cfg4},
         "planning_actor_speed_sweep": {
             "workload": "BASELINE.json configs[4] (no reference code): 65,536 envs per GPU with per-env speed constants "
                         "U(0.5, 2) x the reference's, 20-frame stacked-observation actor (240 -> 256 -> 128 -> 2, tcgen05 "
@@ -418,7 +439,7 @@ def run_gpu_arm(args):
         e2e_s = time.perf_counter() - t0
 
     # ---- learner legs: rollout, DDPG update, tensor roofline of the actor forward ----
-    lt = (float("nan"),) * 7
+    lt = (float("nan"),) * 8
     if not args.no_learner:
         del actions
         torch.cuda.empty_cache()
