@@ -279,9 +279,9 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
             // Measured on B200 (tools/umma_probe.cu): ~54 cycles to issue one tcgen05.mma, ~50 per commit and ~170 for a
             // wait even on a completed barrier, against 68 cycles of execution for a 128 x 128 x 16 MMA: per tile this
             // warp can afford two waits and two commits, not more.  Tried and measured, none of them a gain:
-            //  * slotting the next tile's hand-off into the middle of the layer-2 chain -- with the epilogue warps
-            //    reading tensor memory at the same time the MMAs retire at ~95 cycles apiece and the issue stream is
-            //    never far ahead of the pipe;
+            //  * slotting the next tile's hand-off into the middle of the layer-2 chain -- no change (the pipe queues
+            //    only a couple of MMAs: the issue stream is never far ahead of it; tools/umma_probe3.cu shows that
+            //    tcgen05.ld, shared-memory and bulk-copy traffic beside an MMA stream do not slow it);
             //  * two issuing warps alternating tiles -- the tensor pipe is one in-order queue, so MMA1(t+1), which the
             //    producers wait for, lands behind the other warp's 17-step MMA2 chain; and two issuing warps split by
             //    LAYER (one issues every MMA1 the moment a tile is handed over, the other the MMA2 chains back to back,
@@ -289,8 +289,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
             //    tile and the producers' ~1.2 k are then the pace, not the issuing thread;
             //  * fetching the output warps' layer-3 weights eight loads ahead of their FMAs -- their pass over D2 drops
             //    from ~1.6 k to ~1.2 k cycles per tile (trace events 600 / 700 / 800) and the KERNEL gets 6 % slower;
-            //  * eight producer warps (two per tensor-memory lane quadrant) -- 12 % SLOWER: more concurrent tcgen05.ld
-            //    traffic slows the MMAs' accumulator updates further;
+            //  * eight producer warps (two per tensor-memory lane quadrant) -- 12 % SLOWER;
             //  * cta_group::2 (a cluster of two CTAs, one thread issuing M = 256 pair MMAs for both, each CTA holding
             //    half of the weight images, hand-offs through the cluster address window, multicast commits) --
             //    correct on the first run and 13 % SLOWER: halving the issue overhead does not help because the
