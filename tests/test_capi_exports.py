@@ -86,3 +86,18 @@ def test_product_package_does_not_touch_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle-free", ""), os.path.join(dirpath, f)
                 assert "hostsim" not in src or f == "ss_env_core.cuh", os.path.join(dirpath, f)
+
+
+def test_binding_arity_matches_the_header():
+    """Every ctypes signature in _lib.SIGNATURES has as many parameters as the header's prototype."""
+    from skillshot_learning_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "skillshot_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"typedef struct.*?\}\s*\w+;", "", text, flags=re.S)
+    protos = dict(re.findall(r"\b(ss_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert len(protos) >= 40
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert name in _lib.SIGNATURES, name
+        assert len(_lib.SIGNATURES[name][1]) == n, (name, len(_lib.SIGNATURES[name][1]), n)
