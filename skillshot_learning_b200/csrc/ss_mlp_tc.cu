@@ -54,6 +54,7 @@ struct FwdArgs {
     const uint8_t *done;
     float gamma;
     long long *trace;        // development: event timestamps of CTA 0 (NULL in production)
+    int dbg;                 // development ablations: 1 = output warps skip layer 3, 2 = producers skip the conversion
 };
 
 // 32 accumulator columns (hidden-2 units) -> ReLU -> layer 3, four split accumulators per output.
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                 tc_fence_after();
                 trace(0, 200 + (int)i);
                 if (NET == NET_CRITIC) *reinterpret_cast<uint4 *>(arow + (H1 / 8) * CHUNK_A) = tail_chunk_critic(act.x, act.y);
-                {
+                if (!(A.dbg & 2)) {
                     uint32_t va[32], vb[32];
                     tmem_ld32(tl, va);
 #pragma unroll
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                 mbar_wait(bar(B_Y + slot), (tc >> 1) & 1);
                 tc_fence_after();
                 trace(1, 200 + (int)i);
+                if (A.dbg & 1) { tc_fence_before(); mbar_arrive(bar(B_D2E + slot)); continue; }
                 float acc[3][4] = {{b3[0], 0.f, 0.f, 0.f}, {NET == NET_ACTOR ? b3[1] : 0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
                 {
                     constexpr int kW3Step = NET == NET_ACTOR ? 16 : 32;
@@ -287,6 +289,10 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
             //    LAYER (one issues every MMA1 the moment a tile is handed over, the other the MMA2 chains back to back,
             //    producers waiting explicitly for MMA2(t-2)) -- correct, 5 % slower: the output warps' ~1.8 k cycles per
             //    tile and the producers' ~1.2 k are then the pace, not the issuing thread;
+            //  * both waits first, then MMA1(t+1) and the MMA2(t) chain back to back with one fence -- no change;
+            //  * ablations (tools/tc_ablate.py, 524,288 rows): 44.5 us whole, 37.4 with the output warps' layer 3 switched
+            //    off, 40.2 with the producers' conversion off, 35.3 with both off -- the issuing loop alone (two waits,
+            //    MMA1, 17 x MMA2, two commits per tile) already takes ~1.9 k cycles per tile against 1.29 k of MMA execution;
             //  * fetching the output warps' layer-3 weights eight loads ahead of their FMAs -- their pass over D2 drops
             //    from ~1.6 k to ~1.2 k cycles per tile (trace events 600 / 700 / 800) and the KERNEL gets 6 % slower;
             //  * eight producer warps (two per tensor-memory lane quadrant) -- 12 % SLOWER;
@@ -386,9 +392,9 @@ extern "C" int ss_actor_forward_tc(const float *actor_params, const float *obs, 
 
 // development: the actor forward with an event trace of CTA 0 (3 roles x 256 events x {clock, code}); tools/tc_trace.py
 extern "C" int ss_debug_actor_forward_trace(const float *actor_params, const float *obs, float *act_out, int64_t n,
-                                            long long *trace, void *stream) {
+                                            long long *trace, void *stream, int dbg) {
     FwdArgs A{};
-    A.params = actor_params; A.obs = obs; A.n = n; A.group = n; A.act_out = act_out; A.trace = trace;
+    A.params = actor_params; A.obs = obs; A.n = n; A.group = n; A.act_out = act_out; A.trace = trace; A.dbg = dbg;
     return launch_fwd<NET_ACTOR>(A, stream);
 }
 

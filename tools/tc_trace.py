@@ -9,10 +9,10 @@ n = 148 * 128 * int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 128 * 12
 obs = torch.rand((n, 12), device="cuda"); out = torch.empty((n, 2), device="cuda")
 tr = torch.zeros((3, 256, 2), dtype=torch.int64, device="cuda")
 L = ctypes.CDLL(_lib.LIB_PATH)
-L.ss_debug_actor_forward_trace.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+L.ss_debug_actor_forward_trace.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 for _ in range(3):
     tr.zero_()
-    L.ss_debug_actor_forward_trace(ac.actor.data_ptr(), obs.data_ptr(), out.data_ptr(), n, tr.data_ptr(), None)
+    L.ss_debug_actor_forward_trace(ac.actor.data_ptr(), obs.data_ptr(), out.data_ptr(), n, tr.data_ptr(), None, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 torch.cuda.synchronize()
 t = tr.cpu().numpy()
 t0 = min(t[r, 0, 0] for r in range(3) if t[r, 0, 0] > 0)
