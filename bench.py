@@ -47,7 +47,8 @@ import numpy as np
 
 ENVS_PER_GPU = 65536
 TICKS = 2048                # ticks per bench step (one full 2,000-tick episode plus the auto-reset)
-TICKS_PER_LAUNCH = 32       # fused ticks per ss_env_step launch
+TICKS_PER_LAUNCH = 128      # fused ticks per ss_env_step launch (32: 4.33e10, 64: 4.54e10, 128: 4.69e10 env-steps/s)
+E2E_TICKS_PER_LAUNCH = 32   # the host-buffer leg pipelines copy in / kernel / copy out per chunk: finer chunks overlap better
 TICK_LIMIT = 2000           # SkillshotLearner.py:62
 ALGO_BYTES_PER_ENV_STEP = 202   # SURVEY.md 8(d), physics-only
 METRIC = "env_steps_per_sec"
@@ -65,12 +66,15 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+def ncu_traffic(ticks_per_launch=None):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (taken at the default number of fused
+    ticks per launch), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("step_kernel_physics_bytes_per_launch")
+            t = json.load(open(p))
+            if ticks_per_launch is None or t.get("ticks_per_launch", ticks_per_launch) == ticks_per_launch:
+                return t.get("step_kernel_physics_bytes_per_launch")
         except Exception:
             pass
     return None
@@ -429,12 +433,13 @@ def run_gpu_arm(args):
         host_actions = torch.empty((T, E, 2, 2), dtype=torch.float32, pin_memory=True)
         host_actions.copy_(actions)
         host_out = envs.alloc_host_outputs(T)
+        KE = E2E_TICKS_PER_LAUNCH if T % E2E_TICKS_PER_LAUNCH == 0 else KF
         for _ in range(2):
-            envs.step_host(host_actions, host_out, ticks_per_launch=KF)
+            envs.step_host(host_actions, host_out, ticks_per_launch=KE)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            envs.step_host(host_actions, host_out, ticks_per_launch=KF)   # synchronises before returning
+            envs.step_host(host_actions, host_out, ticks_per_launch=KE)   # synchronises before returning
         barrier()
         e2e_s = time.perf_counter() - t0
 
@@ -464,13 +469,14 @@ def run_gpu_arm(args):
                        "l2": "action stream per step (%.0f MB) exceeds the 126 MB L2; game state (4 MB) is L2-resident by design"
                              % (T * E * 16 / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(), "peak_source": peak_kind,
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(KF), "peak_source": peak_kind,
                          "kernel": "step_kernel<OBS=false,SPEEDS=false>",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
                          "moved_bytes_per_env_step": 16 + 8 + 2 + 128.0 / KF,
                          "launch_us": launch_s * 1e6},
             "e2e": {"value": None if args.no_e2e else world * E * T * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": T * E * 16, "d2h_bytes_per_step": T * E * 10,
+                    "ticks_per_launch": E2E_TICKS_PER_LAUNCH if T % E2E_TICKS_PER_LAUNCH == 0 else KF,
                     "note": "PCIe-bound: 26 B per env-step cross the bus (float32 actions in; reward, done, winner out); "
                             "rank processes pinned to their GPU's NUMA node (%d CPUs) before the pinned buffers are allocated"
                             % numa_cpus},
