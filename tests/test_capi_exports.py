@@ -101,3 +101,21 @@ def test_binding_arity_matches_the_header():
         n = 0 if params in ("", "void") else params.count(",") + 1
         assert name in _lib.SIGNATURES, name
         assert len(_lib.SIGNATURES[name][1]) == n, (name, len(_lib.SIGNATURES[name][1]), n)
+
+
+def test_bench_report_assembles_without_a_gpu():
+    """bench.py's learner report is plain arithmetic on the measured times: build it from made-up times for 1 and 8
+    ranks so that a typo in a key or a format string shows up here and not at the end of a GPU run."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    peaks = {"hbm_gbs": 6556.5, "bf16_tflops": 1631.0}
+    for world, collective in ((1, "peer"), (8, "peer"), (2, "nccl")):
+        rep = bench.learner_report(0.08, 0.19, 0.044, 2.1, 0.79, 0.094, 0.188, 0.49, world, peaks, "measured", collective)
+        json.dumps(rep)
+        assert set(rep) == {"rollout", "train", "selfplay_training", "planning_actor_speed_sweep", "actor_forward_roofline"}
+        assert rep["train"]["samples_per_sec"] == world * bench.TRAIN_BATCH / 0.19e-3
+        assert 0 < rep["actor_forward_roofline"]["frac"] < 1
+    assert bench.ncu_traffic(bench.TICKS_PER_LAUNCH) is not None and bench.ncu_traffic(7) is None
