@@ -306,7 +306,8 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
  *   ss_obs_stack_push        newest observation -> slot head % frames; a row whose `done` flag is set (one flag
  *                            per done_div rows, NULL = none) gets it in every slot (the game restarted)
  *   ss_param_noise_groups    out[g][p] = params[p] + params[p] * sd * eps(p, g): one perturbed vector per noise group
- *                            (SkillshotLearner.py:260-265), g < n_groups, rows of `stride` floats (stride % 4 == 0)
+ *                            (SkillshotLearner.py:260-265), g < n_groups, rows of `stride` floats (stride % 4 == 0);
+ *                            the normals come from the hardware log / sincos units: within ~3e-6 of ss_param_noise's
  *   ss_actor_forward_frames  act_out[n][2]; param_stride = 0: every row uses `params`; else row i uses
  *                            params + (i / noise_group) * param_stride.  The exact float32 path.
  * Tensor-core path (tcgen05.mma: layer 1 in fp16, layer 2 in bf16, fp32 accumulation, the output layer and
