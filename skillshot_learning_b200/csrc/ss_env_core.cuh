@@ -103,27 +103,48 @@ SS_HD double flip_sign_if(double v, int cond) {    // v or -v without a branch
 // arithmetic with explicit FMAs, so host and device builds return identical bits.
 // About a third of the instructions of the CUDA library sincos (no slow-path call,
 // no local-memory out-parameters), which is what the step kernel's issue rate needs.
+// The 17 float64 constants live in constant memory on the device: an FMA can take one of its operands straight from
+// the constant bank, whereas a literal costs two uniform-register moves in front of every use (345 UMOVs of the 2,112
+// instructions of the physics kernel before this, profiles/r1_sass_mnemonics.txt).
+#define SS_SINCOS_CONSTANTS                                                                                            \
+    6755399441055744.0,          /* 0  1.5 * 2^52: round-to-nearest-int trick */                                      \
+    0.6366197723675814,          /* 1  2/pi */                                                                        \
+    -1.5707963267948966, -6.123233995736766e-17, 1.4973849048591698e-33,       /* 2..4  -pi/2 in three parts */        \
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,  /* 5..10  sin kernel */      \
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,                              \
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,  /* 11..16  cos kernel */    \
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02
+#ifdef __CUDACC__
+static __constant__ double kSinCosDev[17] = {SS_SINCOS_CONSTANTS};
+#endif
+static const double kSinCosHost[17] = {SS_SINCOS_CONSTANTS};
+#ifdef __CUDA_ARCH__
+#define SS_SC(i) kSinCosDev[i]
+#else
+#define SS_SC(i) kSinCosHost[i]
+#endif
+
 SS_HD void sincos_d(double x, double *sp, double *cp) {
     if (!(fabs(x) < 1.0e5)) { sincos_lib(x, sp, cp); return; }
-    const double kMagic = 6755399441055744.0;                  // 1.5 * 2^52: round-to-nearest-int trick
-    double q = fma(x, 0.6366197723675814, kMagic);             // x * 2/pi
+    const double kMagic = SS_SC(0);
+    double q = fma(x, SS_SC(1), kMagic);                       // x * 2/pi
     const int k = lo_word(q);
     q -= kMagic;
-    double t = fma(q, -1.5707963267948966, x);
-    t = fma(q, -6.123233995736766e-17, t);
-    t = fma(q, 1.4973849048591698e-33, t);
+    double t = fma(q, SS_SC(2), x);
+    t = fma(q, SS_SC(3), t);
+    t = fma(q, SS_SC(4), t);
     const double t2 = t * t;
-    double ps = fma(1.58969099521155010221e-10, t2, -2.50507602534068634195e-08);
-    ps = fma(ps, t2, 2.75573137070700676789e-06);
-    ps = fma(ps, t2, -1.98412698298579493134e-04);
-    ps = fma(ps, t2, 8.33333333332248946124e-03);
-    ps = fma(ps, t2, -1.66666666666666324348e-01);
+    double ps = fma(SS_SC(5), t2, SS_SC(6));
+    ps = fma(ps, t2, SS_SC(7));
+    ps = fma(ps, t2, SS_SC(8));
+    ps = fma(ps, t2, SS_SC(9));
+    ps = fma(ps, t2, SS_SC(10));
     const double sn = fma(t * t2, ps, t);
-    double pc = fma(-1.13596475577881948265e-11, t2, 2.08757232129817482790e-09);
-    pc = fma(pc, t2, -2.75573143513906633035e-07);
-    pc = fma(pc, t2, 2.48015872894767294178e-05);
-    pc = fma(pc, t2, -1.38888888888741095749e-03);
-    pc = fma(pc, t2, 4.16666666666666019037e-02);
+    double pc = fma(SS_SC(11), t2, SS_SC(12));
+    pc = fma(pc, t2, SS_SC(13));
+    pc = fma(pc, t2, SS_SC(14));
+    pc = fma(pc, t2, SS_SC(15));
+    pc = fma(pc, t2, SS_SC(16));
     // 1 - t2/2 + t2^2*pc with the rounding error of (1 - t2/2) fed back (fdlibm/musl __cos form)
     const double hz = 0.5 * t2, w = 1.0 - hz;
     const double cs = w + (((1.0 - w) - hz) + (t2 * t2) * pc);
