@@ -47,7 +47,7 @@ import numpy as np
 
 ENVS_PER_GPU = 65536
 TICKS = 2048                # ticks per bench step (one full 2,000-tick episode plus the auto-reset)
-TICKS_PER_LAUNCH = 128      # fused ticks per ss_env_step launch (32: 4.33e10, 64: 4.54e10, 128: 4.69e10 env-steps/s)
+TICKS_PER_LAUNCH = 128      # fused ticks per ss_env_step launch (32: 4.8e10, 128: 5.1e10 env-steps/s)
 E2E_TICKS_PER_LAUNCH = 32   # the host-buffer leg pipelines copy in / kernel / copy out per chunk: finer chunks overlap better
 TICK_LIMIT = 2000           # SkillshotLearner.py:62
 ALGO_BYTES_PER_ENV_STEP = 202   # SURVEY.md 8(d), physics-only

@@ -103,57 +103,73 @@ SS_HD double flip_sign_if(double v, int cond) {    // v or -v without a branch
 // arithmetic with explicit FMAs, so host and device builds return identical bits.
 // About a third of the instructions of the CUDA library sincos (no slow-path call,
 // no local-memory out-parameters), which is what the step kernel's issue rate needs.
-// The 17 float64 constants live in constant memory on the device: an FMA can take one of its operands straight from
-// the constant bank, whereas a literal costs two uniform-register moves in front of every use (345 UMOVs of the 2,112
-// instructions of the physics kernel before this, profiles/r1_sass_mnemonics.txt).
-#define SS_SINCOS_CONSTANTS                                                                                            \
-    6755399441055744.0,          /* 0  1.5 * 2^52: round-to-nearest-int trick */                                      \
-    0.6366197723675814,          /* 1  2/pi */                                                                        \
-    -1.5707963267948966, -6.123233995736766e-17, 1.4973849048591698e-33,       /* 2..4  -pi/2 in three parts */        \
-    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,  /* 5..10  sin kernel */      \
-    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,                              \
-    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,  /* 11..16  cos kernel */    \
-    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02
+// The 17 float64 constants.  On the device the multi-tick kernels read them from constant memory: an FMA can take
+// one operand straight from the constant bank, whereas a literal costs two uniform-register moves in front of every use
+// (345 UMOVs of the physics kernel's 2,112 instructions before this): +7.6 % on the issue-bound fused kernels.  The
+// one-tick physics kernel keeps the literals (sincos_d_lit): it is memory-bound and short, and the constant-cache
+// latency in front of each thread's only tick cost it 14 %.
+#define SS_C0 6755399441055744.0           /* 1.5 * 2^52: round-to-nearest-int trick */
+#define SS_C1 0.6366197723675814           /* 2/pi */
+#define SS_C2 -1.5707963267948966          /* -pi/2 in three parts */
+#define SS_C3 -6.123233995736766e-17
+#define SS_C4 1.4973849048591698e-33
+#define SS_C5 1.58969099521155010221e-10   /* sin kernel */
+#define SS_C6 -2.50507602534068634195e-08
+#define SS_C7 2.75573137070700676789e-06
+#define SS_C8 -1.98412698298579493134e-04
+#define SS_C9 8.33333333332248946124e-03
+#define SS_C10 -1.66666666666666324348e-01
+#define SS_C11 -1.13596475577881948265e-11  /* cos kernel */
+#define SS_C12 2.08757232129817482790e-09
+#define SS_C13 -2.75573143513906633035e-07
+#define SS_C14 2.48015872894767294178e-05
+#define SS_C15 -1.38888888888741095749e-03
+#define SS_C16 4.16666666666666019037e-02
+#define SS_SINCOS_CONSTANTS SS_C0, SS_C1, SS_C2, SS_C3, SS_C4, SS_C5, SS_C6, SS_C7, SS_C8, SS_C9, SS_C10, SS_C11, SS_C12, SS_C13, \
+                            SS_C14, SS_C15, SS_C16
 #ifdef __CUDACC__
 static __constant__ double kSinCosDev[17] = {SS_SINCOS_CONSTANTS};
 #endif
-static const double kSinCosHost[17] = {SS_SINCOS_CONSTANTS};
 #ifdef __CUDA_ARCH__
 #define SS_SC(i) kSinCosDev[i]
 #else
-#define SS_SC(i) kSinCosHost[i]
+#define SS_SC(i) SS_C##i
 #endif
+#define SS_LIT(i) SS_C##i
 
-SS_HD void sincos_d(double x, double *sp, double *cp) {
-    if (!(fabs(x) < 1.0e5)) { sincos_lib(x, sp, cp); return; }
-    const double kMagic = SS_SC(0);
-    double q = fma(x, SS_SC(1), kMagic);                       // x * 2/pi
-    const int k = lo_word(q);
-    q -= kMagic;
-    double t = fma(q, SS_SC(2), x);
-    t = fma(q, SS_SC(3), t);
-    t = fma(q, SS_SC(4), t);
-    const double t2 = t * t;
-    double ps = fma(SS_SC(5), t2, SS_SC(6));
-    ps = fma(ps, t2, SS_SC(7));
-    ps = fma(ps, t2, SS_SC(8));
-    ps = fma(ps, t2, SS_SC(9));
-    ps = fma(ps, t2, SS_SC(10));
-    const double sn = fma(t * t2, ps, t);
-    double pc = fma(SS_SC(11), t2, SS_SC(12));
-    pc = fma(pc, t2, SS_SC(13));
-    pc = fma(pc, t2, SS_SC(14));
-    pc = fma(pc, t2, SS_SC(15));
-    pc = fma(pc, t2, SS_SC(16));
-    // 1 - t2/2 + t2^2*pc with the rounding error of (1 - t2/2) fed back (fdlibm/musl __cos form)
-    const double hz = 0.5 * t2, w = 1.0 - hz;
-    const double cs = w + (((1.0 - w) - hz) + (t2 * t2) * pc);
-    // quadrant k mod 4: (s,c) = (sn,cs), (cs,-sn), (-sn,-cs), (-cs,sn)
-    const int swap = k & 1;
-    const double a = swap ? cs : sn, b = swap ? sn : cs;
-    *sp = flip_sign_if(a, (k & 2) != 0);
-    *cp = flip_sign_if(b, ((k + 1) & 2) != 0);
-}
+#define SS_SINCOS_BODY(C)                                                                                   \
+    {                                                                                                       \
+        if (!(fabs(x) < 1.0e5)) { sincos_lib(x, sp, cp); return; }                                          \
+        const double kMagic = C(0);                                                                         \
+        double q = fma(x, C(1), kMagic); /* x * 2/pi */                                                     \
+        const int k = lo_word(q);                                                                           \
+        q -= kMagic;                                                                                        \
+        double t = fma(q, C(2), x);                                                                         \
+        t = fma(q, C(3), t);                                                                                \
+        t = fma(q, C(4), t);                                                                                \
+        const double t2 = t * t;                                                                            \
+        double ps = fma(C(5), t2, C(6));                                                                    \
+        ps = fma(ps, t2, C(7));                                                                             \
+        ps = fma(ps, t2, C(8));                                                                             \
+        ps = fma(ps, t2, C(9));                                                                             \
+        ps = fma(ps, t2, C(10));                                                                            \
+        const double sn = fma(t * t2, ps, t);                                                               \
+        double pc = fma(C(11), t2, C(12));                                                                  \
+        pc = fma(pc, t2, C(13));                                                                            \
+        pc = fma(pc, t2, C(14));                                                                            \
+        pc = fma(pc, t2, C(15));                                                                            \
+        pc = fma(pc, t2, C(16));                                                                            \
+        /* 1 - t2/2 + t2^2*pc with the rounding error of (1 - t2/2) fed back (fdlibm/musl __cos form) */    \
+        const double hz = 0.5 * t2, w = 1.0 - hz;                                                           \
+        const double cs = w + (((1.0 - w) - hz) + (t2 * t2) * pc);                                          \
+        /* quadrant k mod 4: (s,c) = (sn,cs), (cs,-sn), (-sn,-cs), (-cs,sn) */                              \
+        const int swap = k & 1;                                                                             \
+        const double a = swap ? cs : sn, b = swap ? sn : cs;                                                \
+        *sp = flip_sign_if(a, (k & 2) != 0);                                                                \
+        *cp = flip_sign_if(b, ((k + 1) & 2) != 0);                                                          \
+    }
+SS_HD void sincos_d(double x, double *sp, double *cp) SS_SINCOS_BODY(SS_SC)
+SS_HD void sincos_d_lit(double x, double *sp, double *cp) SS_SINCOS_BODY(SS_LIT)
 SS_HD bool finite_d(double v) { return v - v == 0.0; }
 
 // Python float % 2 (Objects/floatobject.c float_rem): fmod, result takes the
@@ -455,19 +471,19 @@ SS_HD void act_and_tick_carry(Env &e, float a0, float a1, float a2, float a3, co
 // The same without carried state (one physics-only tick per launch): 4 sincos.
 SS_HD void act_and_tick(Env &e, float a0, float a1, float a2, float a3, const Speeds &k, uint32_t &status) {
     double s, c;
-    sincos_d(e.prot[0], &s, &c);
+    sincos_d_lit(e.prot[0], &s, &c);
     move_direction_float<0>(e, (double)a0, s, c, k, status);
     move_look_float<0>(e, (double)a1, k);
     move_shoot<0>(e, k);
-    sincos_d(e.prot[1], &s, &c);
+    sincos_d_lit(e.prot[1], &s, &c);
     move_direction_float<1>(e, (double)a2, s, c, k, status);
     move_look_float<1>(e, (double)a3, k);
     move_shoot<1>(e, k);
     if (e.live) {
         e.ticks += 1;
-        sincos_d(e.qrot[0], &s, &c);
+        sincos_d_lit(e.qrot[0], &s, &c);
         proj_tick<0>(e, s, c, k, status);
-        sincos_d(e.qrot[1], &s, &c);
+        sincos_d_lit(e.qrot[1], &s, &c);
         proj_tick<1>(e, s, c, k, status);
         check_collision(e);
     }
