@@ -123,7 +123,9 @@ int ss_env_step(void *state, int64_t n_envs, const float *actions, float *obs_ou
  * replay ring instead of copying them there afterwards (one tick per call when obs_out2 is given):
  *   obs_out2       second copy of the observation, float32 [n_envs][2][12] (the ring's NEXT segment:
  *                  the next tick's "obs" rows are this tick's "next_obs" rows), or NULL
- *   done_rows_out  the done flag once per player row, uint8 [n_envs][2], or NULL */
+ *   done_rows_out  the TERMINAL flag once per player row, uint8 [n_envs][2], or NULL: 1 when the game ended by a hit
+ *                  (winner_id != 0), 0 otherwise -- a tick-limit restart is a truncation, not a termination, and must not
+ *                  zero the TD bootstrap of r + gamma (1 - done) Q' (the reference itself has gamma = 0) */
 int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *obs_out, float *obs_out2,
                      float *reward_out, uint8_t *done_out, uint8_t *done_rows_out, uint8_t *winner_out,
                      int n_ticks, int reward_mode, int64_t tick_limit, int auto_reset,
@@ -283,7 +285,9 @@ int ss_reduce_adam_tf(const void *workspace, int parts, int n_params, float *aux
  * observation on entry, and after the call it is in obs_a if n_ticks is even, in obs_b otherwise (but see below).
  * actions [n_envs][2][2], reward [n_envs][2], done / winner [n_envs] hold the last tick's values on return.
  * Tick t uses Philox counters env_counter + t and noise_counter + t; ring rows advance by 2 n_envs per tick.
- * When capacity and write_pos are multiples of 2 n_envs the transitions are produced IN the ring (the actor
+ * The ring's done flag is the TERMINAL flag (a hit, winner != 0; see ss_env_step_ring), so `winner` is required with a ring.
+ * When capacity and write_pos are multiples of 2 n_envs (and the ring has at least two such segments, or n_ticks == 1)
+ * the transitions are produced IN the ring (the actor
  * reads its observations from and writes its actions to the ring's rows, ss_env_step_ring writes reward, done
  * and both copies of the next observation there): no copy kernel runs, and the current observation is left
  * in obs_a whatever the parity of n_ticks.  Otherwise ss_replay_push copies each tick's rows.
@@ -430,6 +434,15 @@ typedef struct ss_ddpg_update_args {
     uint32_t *done_counter, *status;
 } ss_ddpg_update_args;
 int ss_ddpg_update(const ss_ddpg_update_args *args, void *stream);
+
+/* Measurement aid (no reference counterpart): instruction-rate ceilings of this GPU for the roofline record of the fused
+ * step kernel, which is bound by the warp schedulers and the float64 pipe rather than by HBM once K ticks are played per
+ * launch.  Runs two register-only kernels, times them with CUDA events and SYNCHRONISES (the one entry point that does).
+ *   out_host[0]  warp-instructions per second of an FFMA stream (the issue ceiling: SMs x 4 schedulers x clock)
+ *   out_host[1]  warp-instructions per second of a DFMA stream (the float64 pipe)
+ *   out_host[2]  number of SMs;  out_host[3] reserved
+ *   scratch      any device buffer of >= 8 bytes (never written in practice) */
+int ss_probe_rates(double *out_host, void *scratch, void *stream);
 
 #ifdef __cplusplus
 }

@@ -25,8 +25,9 @@ def _stack(recs):
     return {k: np.stack([r[k] for r in recs]) for k in recs[0]}
 
 
-def _save(name, actions, positions, rotations, recs, np_pos):
+def _save(name, actions, positions, rotations, recs, np_pos, extra=None):
     d = _stack(recs)
+    d.update(extra or {})
     # 1 where Player.pos was a numpy int64 row (as after a random start), 0 where it
     # was the fixed start's Python list: selects sqrt vs pow in get_dist_point_point
     d["np_pos"] = np.asarray(np_pos, np.int32)
@@ -71,6 +72,41 @@ def scenario(name, n, T, seed, start="fixed", action_scale=1.0, close=False):
     _save(name, actions, positions, rotations, recs, [0 if fixed else 1] * n)
 
 
+def speeds_scenario(name, n, T, seed):
+    """Per-env game-speed constants (the readme.md:22-23 sweep): Player.speed_move / speed_look and
+    Projectile.speed_move / cooldown_max (class attributes, Player.py:14-15, Projectile.py:9-10) overridden per game,
+    U(0.5, 2) x the defaults; close random starts so that projectiles of every speed get to hit."""
+    rng = np.random.default_rng(seed)
+    actions = (rng.uniform(-1, 1, size=(n, T, 2, 2)) * 1.2).astype(np.float32)
+    p1 = rng.integers(40, 200, size=(n, 2))
+    positions = np.concatenate([p1, np.clip(p1 + rng.integers(-60, 61, size=(n, 2)), 0, 245)], axis=1)
+    d = (positions[:, 2:] - positions[:, :2]).astype(np.float64)
+    aim = np.arctan2(-d[:, 0], -d[:, 1])
+    rotations = np.stack([aim, aim + np.pi], axis=1) + rng.normal(0, 0.3, size=(n, 2))
+    actions[:, :, :, 1] *= 0.3
+    scale = lambda: rng.uniform(0.5, 2.0, n)
+    sm, sl, ps = 3.0 * scale(), 0.25 * scale(), 5.0 * scale()
+    cm = np.maximum(1, np.rint(15.0 * scale())).astype(np.int64)
+    recs = [ref_harness.run_episode(actions[i], tuple(int(v) for v in positions[i]), rotations[i],
+                                    speeds=(float(sm[i]), float(sl[i]), float(ps[i]), int(cm[i]))) for i in range(n)]
+    _save(name, actions, positions, rotations, recs, [1] * n,
+          extra=dict(speed_move=sm, speed_look=sl, proj_speed=ps, cooldown_max=cm))
+
+
+def boards_scenario(name, n, T, seed):
+    """get_board() rasters per tick (SkillshotGame.py:36-56) as sparse cell lists, with the state they were drawn from:
+    random starts and turning players (the direction pointer visits every cell it can), shots fired throughout."""
+    rng = np.random.default_rng(seed)
+    actions = (rng.uniform(-1, 1, size=(n, T, 2, 2)) * 1.2).astype(np.float32)
+    positions = rng.integers(25, 225, size=(n, 4))
+    positions[0] = (0, 0, 245, 245)            # corners of the board: the raster's edges
+    rotations = rng.uniform(-np.pi, np.pi, size=(n, 2))
+    rotations[1] = (np.pi / 2, -np.pi / 2)     # pointer index at the extremes of floor(-sin * 2.5 + 2.5)
+    recs = [ref_harness.run_episode(actions[i], tuple(int(v) for v in positions[i]), rotations[i], boards=True, features=False)
+            for i in range(n)]
+    _save(name, actions, positions, rotations, recs, [1] * n)
+
+
 def kats():
     """KAT-A..E of SURVEY.md section 4 as one file (zero/explicit actions)."""
     T = 20
@@ -100,6 +136,8 @@ def main():
     scenario("lockstep_fixed", 24, 64, seed=1)
     scenario("lockstep_random", 24, 64, seed=2, start="random", action_scale=1.3)
     scenario("close_hits", 48, 40, seed=3, close=True)
+    speeds_scenario("speeds", 32, 48, seed=4)
+    boards_scenario("boards", 12, 40, seed=5)
 
 
 if __name__ == "__main__":

@@ -1,7 +1,9 @@
-"""Runs the UNMODIFIED reference (imported from /root/reference) -- only usable
-in the authoring container, where /root/reference is mounted.  Used by
-oracle/gen_golden.py to produce tests/golden/*.npz and by the
-`requires_reference` tests that cross-check the C oracle live.
+"""Runs the UNMODIFIED reference: imported from /root/reference where that is
+mounted (the authoring container), else from the sourceless byte-code that
+oracle/build_ref.py compiled from it into oracle/_ref/ (a git-ignored build
+output that travels to the GPU box).  Used by oracle/gen_golden.py to produce
+tests/golden/*.npz, by the `requires_reference` tests that cross-check the C
+oracle and the device facade live, and by bench.py's CPU legs.
 
 TEST INFRASTRUCTURE ONLY.  Never imported by the product package.
 
@@ -22,11 +24,25 @@ import warnings
 
 import numpy as np
 
-REFERENCE_DIR = os.environ.get("SKILLSHOT_REFERENCE_DIR", "/root/reference")
+SOURCE_DIR = os.environ.get("SKILLSHOT_REFERENCE_DIR", "/root/reference")
+COMPILED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def source() -> str | None:
+    """"source" (the mounted reference), "compiled" (oracle/_ref byte-code of it) or None."""
+    if os.path.exists(os.path.join(SOURCE_DIR, "SkillshotGame.py")):
+        return "source"
+    if all(os.path.exists(os.path.join(COMPILED_DIR, m + ".pyc")) for m in ("Projectile", "Player", "SkillshotGame", "SkillshotLearner")):
+        return "compiled"
+    return None
 
 
 def available() -> bool:
-    return os.path.exists(os.path.join(REFERENCE_DIR, "SkillshotGame.py"))
+    return source() is not None
+
+
+def reference_dir() -> str:
+    return SOURCE_DIR if source() == "source" else COMPILED_DIR
 
 
 def _install_tf_stub():
@@ -50,6 +66,39 @@ def _install_tf_stub():
     })
 
 
+KEYS = dict(K_w=119, K_s=115, K_a=97, K_d=100, K_SPACE=32, K_UP=1073741906, K_DOWN=1073741905, K_LEFT=1073741904,
+            K_RIGHT=1073741903, K_PERIOD=46, K_0=48)
+
+
+def _install_pygame_stub():
+    """InputHandler.py imports pygame for its key constants only (InputHandler.py:1, 10-52); pygame is not installed."""
+    if "pygame" not in sys.modules:
+        pg = types.ModuleType("pygame")
+        for k, v in KEYS.items():
+            setattr(pg, k, v)
+        sys.modules["pygame"] = pg
+    return sys.modules["pygame"]
+
+
+def input_handler():
+    """A reference InputHandler (InputHandler.py) driven through input_start / input_stop with the stub's key codes."""
+    modules()
+    _install_pygame_stub()
+    from InputHandler import InputHandler
+    return InputHandler()
+
+
+def playable_tick():
+    """Code object of skillshot_playable.py:51-64 (key states -> Player.move_* calls -> game_tick), to be exec'd with the
+    globals `inputHandler` and `skillshotGame`: cut from the mounted source, or loaded from oracle/_ref."""
+    from oracle import build_ref
+    if source() == "source":
+        return build_ref.playable_tick_code(SOURCE_DIR)
+    import marshal
+    with open(os.path.join(COMPILED_DIR, build_ref.PLAYABLE_TICK), "rb") as f:
+        return marshal.load(f)
+
+
 _mods = None
 
 
@@ -58,9 +107,9 @@ def modules():
     global _mods
     if _mods is None:
         if not available():
-            raise RuntimeError("reference not mounted at %s" % REFERENCE_DIR)
-        if REFERENCE_DIR not in sys.path:
-            sys.path.insert(0, REFERENCE_DIR)
+            raise RuntimeError("reference neither mounted at %s nor compiled into %s" % (SOURCE_DIR, COMPILED_DIR))
+        if reference_dir() not in sys.path:
+            sys.path.insert(0, reference_dir())
         _install_tf_stub()
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")  # `is not 0` SyntaxWarning, SkillshotGame.py:44,54
@@ -121,35 +170,67 @@ def features_of(state_dict):
     return out
 
 
-def run_episode(actions, positions=None, rotations=None):
+def set_speeds(g, speed_move, speed_look, proj_speed, cooldown_max):
+    """Per-game speed constants: the reference keeps them as class attributes (Player.py:14-15, Projectile.py:9-10);
+    instance attributes of one game's objects shadow them for that game only."""
+    for p in (g.player1, g.player2):
+        p.speed_move, p.speed_look = speed_move, speed_look
+        p.projectile.speed_move, p.projectile.cooldown_max = proj_speed, cooldown_max
+
+
+BOARD_CELLS = 32      # a board holds at most 2 x (9 body cells incl. pointer) + 2 x 5 projectile cells non-zero
+
+
+def sparse_board(board):
+    """get_board() raster (SkillshotGame.py:36-56) as its non-zero cells: int16 [BOARD_CELLS, 3] = (x, y, value), -1 padded,
+    in row-major order of the raster."""
+    xs, ys = np.nonzero(board)
+    assert len(xs) <= BOARD_CELLS
+    out = np.full((BOARD_CELLS, 3), -1, np.int16)
+    out[:len(xs), 0], out[:len(xs), 1], out[:len(xs), 2] = xs, ys, board[xs, ys]
+    return out
+
+
+def run_episode(actions, positions=None, rotations=None, speeds=None, boards=False, features=True):
     """Step one reference game through `actions` (float32 [T,2,2]) exactly as
     model_train does per tick (SkillshotLearner.py:304-315), continuing past the
-    terminal tick.  Returns per-tick records, index 0 = initial state."""
+    terminal tick.  Returns per-tick records, index 0 = initial state.
+    speeds: (speed_move, speed_look, proj_speed, cooldown_max) of this game, or None (class constants);
+    boards: also record get_board() per tick (sparse_board); features=False records the raw state only."""
     g = make_game(positions, rotations)
+    if speeds is not None:
+        set_speeds(g, *speeds)
     skl = make_learner(g)
     T = actions.shape[0]
     rec = dict((k, np.zeros((T + 1, 2), np.int64)) for k in STATE_INT_FIELDS)
     rec.update(prot=np.zeros((T + 1, 2)), qrot=np.zeros((T + 1, 2)),
                ticks=np.zeros(T + 1, np.int64), live=np.zeros(T + 1, np.int64),
-               winner=np.zeros(T + 1, np.int64),
-               feat=np.zeros((T + 1, 2, 18)), obs=np.zeros((T + 1, 2, 12)),
-               rew_looking=np.zeros((T + 1, 2)), rew_simple=np.zeros((T + 1, 2)))
+               winner=np.zeros(T + 1, np.int64))
+    if features:
+        rec.update(feat=np.zeros((T + 1, 2, 18)), obs=np.zeros((T + 1, 2, 12)),
+                   rew_looking=np.zeros((T + 1, 2)), rew_simple=np.zeros((T + 1, 2)))
+    if boards:
+        rec["board"] = np.full((T + 1, BOARD_CELLS, 3), -1, np.int16)
     sink = io.StringIO()
 
     def record(t):
-        with contextlib.redirect_stdout(sink):
-            sd = g.get_state()
+        with contextlib.redirect_stdout(sink), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
             st = read_state(g)
             for k in STATE_INT_FIELDS + ("prot", "qrot"):
                 rec[k][t] = st[k]
             rec["ticks"][t], rec["live"][t], rec["winner"][t] = st["ticks"], st["live"], st["winner"]
-            rec["feat"][t] = features_of(sd)
-            for p in (1, 2):
-                rec["obs"][t, p - 1] = np.array(skl.prepare_states([sd], p)[0], dtype=np.float64)
-            rl = skl.calculate_rewards_looking([sd])[0]
-            rs = skl.calculate_rewards_simple([sd])[0]
-            rec["rew_looking"][t] = [rl[1], rl[2]]
-            rec["rew_simple"][t] = [rs[1], rs[2]]
+            if features:
+                sd = g.get_state()
+                rec["feat"][t] = features_of(sd)
+                for p in (1, 2):
+                    rec["obs"][t, p - 1] = np.array(skl.prepare_states([sd], p)[0], dtype=np.float64)
+                rl = skl.calculate_rewards_looking([sd])[0]
+                rs = skl.calculate_rewards_simple([sd])[0]
+                rec["rew_looking"][t] = [rl[1], rl[2]]
+                rec["rew_simple"][t] = [rs[1], rs[2]]
+            if boards:
+                rec["board"][t] = sparse_board(g.get_board())
 
     record(0)
     for t in range(T):
@@ -158,5 +239,6 @@ def run_episode(actions, positions=None, rotations=None):
                 # float32 values handed over as Python floats (SURVEY hard part 1)
                 skl.do_actions(p, (float(actions[t, p - 1, 0]), float(actions[t, p - 1, 1])))
             g.game_tick()
+        sink.seek(0); sink.truncate(0)
         record(t + 1)
     return rec

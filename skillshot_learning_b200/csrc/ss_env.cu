@@ -83,7 +83,7 @@ struct StepArgs {
     uint8_t *done_out;
     uint8_t *winner_out;
     float4 *obs_out2;          // second copy of the observation (the replay ring's next segment), or NULL
-    uint16_t *done_rows_out;   // done flag once per player row ([n][2] bytes, the replay ring's layout), or NULL
+    uint16_t *done_rows_out;   // terminal (hit) flag once per player row ([n][2] bytes, the replay ring's layout), or NULL
     const void *speeds;
     uint32_t *status;
     unsigned long long *stats;  // episode statistics (SS_STEP_EPISODE_STATS) or NULL
@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
         if (active) {
             if (write_reward) A.reward_out[row] = make_float2(r[0], r[1]);
             if (A.done_out) A.done_out[row] = (uint8_t)done;
-            if (A.done_rows_out) A.done_rows_out[row] = (uint16_t)(done ? 0x0101 : 0);
+            // the replay ring's flag masks the TD bootstrap: a hit is a true termination, a tick-limit restart is not
+            if (A.done_rows_out) A.done_rows_out[row] = (uint16_t)(winner ? 0x0101 : 0);
             if (A.winner_out) A.winner_out[row] = (uint8_t)winner;
         }
         if (OBS && want_obs) {

@@ -889,7 +889,10 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
     const bool store = ring_obs != nullptr;
     if (store && (2 * n_envs > capacity || write_pos < 0 || write_pos >= capacity)) return SS_ERR_INVALID_ARG;
     const int64_t rows = 2 * n_envs;
-    if (store && capacity % rows == 0 && write_pos % rows == 0) {
+    if (store && !winner) return SS_ERR_INVALID_ARG;      // the ring's done flag is the hit flag (winner != 0)
+    // (with a single segment the step kernel's second observation copy would land in the very rows the actor has just read
+    //  and overwrite the stored transition's obs with its next_obs: the in-place form needs two segments or a single tick)
+    if (store && capacity % rows == 0 && write_pos % rows == 0 && (capacity / rows >= 2 || n_ticks == 1)) {
         // transitions produced in place: tick t owns ring rows [seg_t * rows, (seg_t + 1) * rows)
         const int64_t segs = capacity / rows;
         cudaStream_t st = (cudaStream_t)stream;
@@ -933,8 +936,8 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
         if (rc != SS_OK) return rc;
         if (store) {
             rc = ss_replay_push(ring_obs, ring_act, ring_reward, ring_next_obs, ring_done, capacity,
-                                (write_pos + (int64_t)t * 2 * n_envs) % capacity, cur, actions, reward, next, done, 2,
-                                2 * n_envs, stream);
+                                (write_pos + (int64_t)t * 2 * n_envs) % capacity, cur, actions, reward, next, winner, 2,
+                                2 * n_envs, stream);     // terminal = a hit (winner != 0); a tick-limit restart keeps its bootstrap
             if (rc != SS_OK) return rc;
         }
     }

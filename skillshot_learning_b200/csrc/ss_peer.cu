@@ -88,6 +88,12 @@ __global__ void peer_adam_kernel(void *base, int world, int64_t capacity, uint32
                                  float *target, float *grad_out, int64_t n, float lr_t, float beta1, float beta2, float eps,
                                  float tau, float grad_scale, uint32_t *status) {
     const int parity = (int)(epoch & 1u);
+    __shared__ int timed_out;
+    // A timeout is sticky: once a rank's gradient has failed to arrive, no later step is applied either (the ranks would no
+    // longer hold the same weights) until the host has seen the status word and decided what to do (PeerExchange.check_status).
+    if (threadIdx.x == 0) timed_out = (status && (*(volatile uint32_t *)status & SS_STATUS_PEER_TIMEOUT)) ? 1 : 0;
+    __syncthreads();
+    if (timed_out) return;
     if (threadIdx.x < world) {
         const uint32_t *f = flag_ptr(base, world, parity, threadIdx.x);
         uint32_t seen = 0, spins = 0;
@@ -96,12 +102,14 @@ __global__ void peer_adam_kernel(void *base, int world, int64_t capacity, uint32
             if (seen == epoch) break;
             if (++spins > (1u << 26)) {                        // a peer never arrived: report instead of hanging
                 if (status) atomicOr(status, SS_STATUS_PEER_TIMEOUT);
+                *(volatile int *)&timed_out = 1;
                 break;
             }
             __nanosleep(64);
         }
     }
     __syncthreads();
+    if (timed_out) return;     // never sum a stale or partial inbox into Adam and the targets
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     float g = 0.f;

@@ -798,14 +798,20 @@ class SkillshotLearner:
     # -- persistence (SkillshotLearner.py:123-162, naming kept, bugs not) ------------------
     def save_actor_critic_models(self, epochs):
         """training_models/{actor,critic}/{start}_{end}_model.npz (the reference writes .h5 through
-        Keras; same directory layout and epoch-range naming, arrays in get_weights() order)."""
+        Keras; same directory layout and epoch-range naming, arrays in get_weights() order), and next to them
+        training_models/learner_state/{start}_{end}_state.pt: targets, Adam moments and step counters of THAT range."""
+        name = None
         for which, dir_name in (("actor", self.actor_dir_name), ("critic", self.critic_dir_name)):
             d = os.path.join(self.save_location, dir_name)
             os.makedirs(d, exist_ok=True)
             ends = [int(f.split("_")[1]) for f in os.listdir(d) if f.endswith("_model.npz")]
             start = max(ends) + 1 if ends else 0                  # SkillshotLearner.py:153-157
-            np.savez(os.path.join(d, "%d_%d_model.npz" % (start, start + epochs)), *self.networks.get_weights(which))
-        torch.save(self.networks.state_dict(), os.path.join(self.save_location, "learner_state.pt"))
+            name = "%d_%d" % (start, start + epochs)
+            np.savez(os.path.join(d, name + "_model.npz"), *self.networks.get_weights(which))
+        d = os.path.join(self.save_location, "learner_state")
+        os.makedirs(d, exist_ok=True)
+        torch.save(self.networks.state_dict(), os.path.join(d, name + "_state.pt"))
+        print("Actor and Critic Saved.")
 
     def save_training_progress(self, total_progress):
         """training_models/training_progress/training_progress.csv, appended (SkillshotLearner.py:164-173):
@@ -837,16 +843,34 @@ class SkillshotLearner:
         return np.load(os.path.join(self.save_location, self.training_boards_dir_name, "training_boards.npy"), allow_pickle=True)
 
     def load_actor_critic_models(self, load_index=-1):
-        flat = {}
+        """Loads the `load_index`-th saved actor and critic (sorted by their end epoch, SkillshotLearner.py:123-137) and, when
+        it exists, the optimiser state saved WITH THAT epoch range.  Returns True, or False when a directory holds no model
+        (as the reference does; its assignment to a loop variable, which loaded nothing, is not reproduced)."""
+        flat, names = {}, {}
         for which, dir_name in (("actor", self.actor_dir_name), ("critic", self.critic_dir_name)):
             d = os.path.join(self.save_location, dir_name)
-            files = sorted((f for f in os.listdir(d) if f.endswith("_model.npz")), key=lambda x: int(x.split("_")[1]))
-            z = np.load(os.path.join(d, files[load_index]))
+            files = sorted((f for f in os.listdir(d) if f.endswith("_model.npz")), key=lambda x: int(x.split("_")[1])) if os.path.isdir(d) else []
+            if len(files) == 0:
+                print("Failed to load: ", d)
+                return False
+            try:
+                chosen = files[load_index]
+            except IndexError:
+                print("Failed to load: ", d)
+                return False
+            z = np.load(os.path.join(d, chosen))
             flat[which] = np.concatenate([z[k].ravel() for k in z.files])
+            names[which] = chosen[:-len("_model.npz")]
         self.networks.set_weights(flat["actor"], flat["critic"])
-        full = os.path.join(self.save_location, "learner_state.pt")
-        if os.path.exists(full):
-            self.networks.load_state_dict(torch.load(full))
+        state = os.path.join(self.save_location, "learner_state", names["actor"] + "_state.pt")
+        if names["actor"] == names["critic"] and os.path.exists(state):
+            sd = torch.load(state, map_location="cpu", weights_only=False)
+            # the weights of the chosen files stay; the optimiser moments, targets and counters of the same range come back
+            for k in ("target", "adam_m", "adam_v"):
+                getattr(self.networks, k).copy_(sd[k].to(self.networks.device))
+            self.networks.step_actor, self.networks.step_critic = int(sd["step_actor"]), int(sd["step_critic"])
+            self.networks.counter = int(sd["counter"])
+        return True
 
 
 class FrameStackActor:
@@ -970,6 +994,8 @@ class SelfPlayTrainer:
         self.actions = torch.empty((n, 2, 2), dtype=torch.float32, device=self.device)
         self._batch = None
         self.ticks = 0
+        self.updates = 0
+        self.exchange_check_every = 256     # updates between looks at the peer exchange's status word
 
     def rollout_tick(self, store: bool = True):
         """One tick of every env: actor forward on both players' observations (fresh parameter
@@ -979,7 +1005,8 @@ class SelfPlayTrainer:
                                     out=self.actions.view(-1, 2), precision=self.precision)
         out = self.envs.step(self.actions, obs_out=self.obs)
         if store:
-            self.replay.push(self.prev_obs, self.actions, out["reward"], self.obs, out["done"], done_div=2)
+            # the ring's flag masks the TD bootstrap: only a hit (winner != 0) is a termination, a tick-limit restart is not
+            self.replay.push(self.prev_obs, self.actions, out["reward"], self.obs, out["winner"], done_div=2)
         self.ticks += 1
         return out
 
@@ -1009,7 +1036,9 @@ class SelfPlayTrainer:
         if store:
             rp.pos = (rp.pos + 2 * envs.n_envs * n_ticks) % rp.capacity
             rp.size = min(rp.capacity, rp.size + 2 * envs.n_envs * n_ticks)
-        in_place = store and rp.capacity % (2 * envs.n_envs) == 0 and (rp.pos - 2 * envs.n_envs * n_ticks) % (2 * envs.n_envs) == 0
+        rows = 2 * envs.n_envs
+        in_place = (store and rp.capacity % rows == 0 and (rp.pos - rows * n_ticks) % rows == 0
+                    and (rp.capacity // rows >= 2 or n_ticks == 1))       # the library's own condition (ss_selfplay_rollout)
         if (n_ticks & 1) and not in_place:        # (in place, the library leaves the current observation in buffer A)
             self.obs, self.prev_obs = b, a
         self.ticks += n_ticks
@@ -1055,8 +1084,15 @@ class SelfPlayTrainer:
         365-366) for the games finished so far, reduced on the device by the step kernel (SkillshotEnvs.episode_summary)."""
         return self.envs.episode_summary(reset=reset)
 
+    def check_exchange(self):
+        """Raises if a rank's gradient failed to arrive in the fused peer exchange (the Adam kernels skip their writes from
+        that point on, so the ranks still hold identical weights: reload or stop)."""
+        if self.networks.peer is not None:
+            self.networks.peer.check_status()
+
     def save(self, path: str):
         """Write a checkpoint the run can be resumed from bit-identically (one file per rank when sharded)."""
+        self.check_exchange()
         torch.cuda.synchronize(self.device)
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
         torch.save(self.state_dict(), path)
@@ -1071,6 +1107,9 @@ class SelfPlayTrainer:
         if net.group is not None and net.peer is None:
             return self.update_stepwise()
         self._batch = net.update_from_ring(self.replay, self.batch_size, out=self._batch)
+        self.updates += 1
+        if net.peer is not None and self.updates % self.exchange_check_every == 0:
+            net.peer.check_status()         # one device-to-host read every few hundred updates
         return net.stats[0], net.stats[1]
 
     def update_stepwise(self):

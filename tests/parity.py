@@ -33,29 +33,60 @@ def start_from_golden(make, g, **kw):
     st = envs.export_state()
     st["prot"] = g["rotations"].copy()
     envs.import_state(st)
+    if "speed_move" in g:
+        envs.set_speeds(g["speed_move"], g["speed_look"], g["proj_speed"], g["cooldown_max"])
     return envs
 
 
-def ambiguous_future_collision(st, proj_grad):
-    """bool [n,2]: views whose check_future_collision (SkillshotGame.py:96-113) is decided by
-    rounding noise in the reference itself: the line value g*x + (y - g*x) lands on a box
-    bound (typically projectile x == opponent bound x and projectile y == a y bound, an
-    integer coincidence), so the comparison's outcome depends on the last bits of the host
-    libm's tan().  No independent implementation can reproduce those bits; the flag is
-    compared exactly everywhere else.  proj_grad = reference projectile_grad, float64 [n,2]."""
+AMBIGUOUS_ULPS = 8.0      # see ambiguous_future_collision
+AMBIGUITY = {"views": 0, "ambiguous": 0}     # running totals over a test session (asserted by the callers)
+
+
+def ambiguous_future_collision(st, proj_grad, count=True):
+    """bool [n,2]: views whose check_future_collision (SkillshotGame.py:96-113) is decided by the reference's own rounding
+    noise.  The reference evaluates g*x_b + (y - g*x) in absolute board coordinates: three roundings at magnitude
+    |g| * 250, so where the line passes EXACTLY through a corner of the opponent's box (an integer coincidence: projectile
+    x == a box bound x and projectile y == a box bound y, or a vertical shot with x == bound x) its value is the residue
+    of a cancellation and the comparison with the bound depends on the last bits of the host libm's tan().  No independent
+    implementation can reproduce those bits.  Excused is exactly that set and nothing wider:
+      * the line value lies within AMBIGUOUS_ULPS * 2^-52 * 250 * (1 + |g|) of a bound ("a few ulp of g*x"), AND
+      * the projectile's x equals one of the opponent's two x bounds, or its y one of the y bounds (asserted below: a
+        kernel that is wrong NEAR corners, rather than exactly on them, fails), AND
+      * the projectile has been turned: an unturned shot (rotation exactly 0) has g = tan(fl(pi/2)) = 1.633123935319537e16,
+        a constant both sides evaluate identically (test_tan_half_pi_matches_libm), so it is always compared exactly.
+    The callers bound the excused fraction (ambiguity_fraction).  proj_grad = reference projectile_grad, float64 [n,2]."""
     out = np.zeros(st["qx"].shape, bool)
+    eps = 2.0 ** -52
     for p in range(2):
         o = 1 - p
-        g = proj_grad[:, p]
+        g = np.abs(proj_grad[:, p])
         qx, qy = st["qx"][:, p].astype(float), st["qy"][:, p].astype(float)
         ox, oy = st["px"][:, o].astype(float), st["py"][:, o].astype(float)
-        tol = 1e-9 * (1.0 + np.abs(g) * 250.0)
-        d = np.full(len(g), np.inf)
-        for xb in (ox, ox + 5):
-            v = qy + g * (xb - qx)
-            d = np.minimum(d, np.minimum(np.abs(v - oy), np.abs(v - (oy + 5))))
-        out[:, p] = (st["valid"][:, p] == 1) & (d <= tol)
+        with np.errstate(over="ignore", invalid="ignore"):
+            tol = AMBIGUOUS_ULPS * eps * 250.0 * (1.0 + g)
+            d = np.full(len(g), np.inf)
+            for xb in (ox, ox + 5):
+                v = qy + proj_grad[:, p] * (xb - qx)
+                d = np.minimum(d, np.minimum(np.abs(v - oy), np.abs(v - (oy + 5))))
+        near = (st["valid"][:, p] == 1) & (d <= tol)
+        if "qrot" in st:
+            near &= np.asarray(st["qrot"])[:, p] != 0.0
+        # ... or, for a (near-)horizontal shot, the projectile's y equals a y bound
+        coincidence = (qx == ox) | (qx == ox + 5) | (qy == oy) | (qy == oy + 5)
+        assert not (near & ~coincidence).any(), "a future-collision view near a box bound is not an integer coincidence"
+        out[:, p] = near
+    if count:
+        AMBIGUITY["views"] += int((st["valid"] == 1).sum())
+        AMBIGUITY["ambiguous"] += int(out.sum())
     return out
+
+
+def ambiguity_fraction(reset=False):
+    """Fraction of the valid-projectile views compared so far whose future-collision flag was excused."""
+    f = AMBIGUITY["ambiguous"] / max(1, AMBIGUITY["views"])
+    if reset:
+        AMBIGUITY["views"] = AMBIGUITY["ambiguous"] = 0
+    return f
 
 
 def assert_obs_close(obs, ref_obs, st, proj_grad, msg):
@@ -103,7 +134,7 @@ def check_golden_lockstep(make, name):
                                    rtol=OBS_RTOL, atol=OBS_ATOL, err_msg=f"{name} reward t={t + 1}")
         if t % 8 == 0 or t == T - 1:
             feat, obs64, gen = (to_np(x) for x in envs.features())
-            amb = ambiguous_future_collision(st, g["feat"][:, t + 1, :, 8])
+            amb = ambiguous_future_collision(st, g["feat"][:, t + 1, :, 8], count=False)
             feat[..., 17] = np.where(amb, g["feat"][:, t + 1, :, 17], feat[..., 17])
             obs64[..., 11] = np.where(amb, g["obs"][:, t + 1, :, 11], obs64[..., 11])
             assert_features_close(feat, g["feat"][:, t + 1], f"{name} t={t + 1}")
@@ -125,7 +156,7 @@ def check_golden_fused(make, name, K=8):
         assert_state_equal(envs.export_state(), ref, f"{name} fused t={t0 + K}")
         obs = to_np(out["obs"])
         for c in range(K):
-            stc = {k: g[k][:, t0 + c + 1] for k in ("qx", "qy", "px", "py", "valid")}
+            stc = {k: g[k][:, t0 + c + 1] for k in ("qx", "qy", "px", "py", "valid", "qrot")}
             assert_obs_close(obs[c], g["obs"][:, t0 + c + 1], stc, g["feat"][:, t0 + c + 1, :, 8], f"{name} fused obs t={t0 + c + 1}")
         want_rew = np.swapaxes(g["rew_simple"][:, t0 + 1:t0 + K + 1], 0, 1).astype(np.float32)
         np.testing.assert_allclose(to_np(out["reward"]), want_rew, rtol=OBS_RTOL, atol=1e-4)
@@ -150,7 +181,7 @@ def check_oracle_lockstep(make, n, T, seed, close=False, reward_mode="looking", 
     orc = OracleEnvs(n, pos)
     envs = make(n, reward_mode=reward_mode)
     envs.reset(positions=pos)
-    hits = ambiguous = 0
+    hits = ambiguous = views = 0
     for t0 in range(0, T, chunk):
         a = random_actions(rng, (chunk, n, 2, 2))
         if close:
@@ -171,8 +202,13 @@ def check_oracle_lockstep(make, n, T, seed, close=False, reward_mode="looking", 
             snap = orc.snapshot()
             assert_state_equal(envs.export_state(), snap, f"t={t0 + chunk}")
             ambiguous += assert_obs_close(to_np(out["obs"]), ro["obs"], snap, orc.features()[0][..., 8], f"obs t={t0 + chunk}")
+            views += int((snap["valid"] == 1).sum())
         hits = int((orc.envs["live"] == 0).sum())
     assert_state_equal(envs.export_state(), orc.snapshot(), "final")
+    # the excused set is bounded: exact corner coincidences only (asserted in ambiguous_future_collision), about 5e-4 of the
+    # views of random play and 2.5e-3 of close combat (finished games whose last projectile rests on the loser's corner)
+    if views >= 20000:
+        assert ambiguous <= views * (5e-3 if close else 1e-3), (ambiguous, views)
     return hits
 
 
@@ -227,3 +263,34 @@ def check_speeds(make, n=32, T=48, seed=9):
         snap = orc.snapshot()
         assert_state_equal(envs.export_state(), snap, f"speeds t={t}")
         assert_obs_close(to_np(out["obs"]), ro["obs"], snap, orc.features()[0][..., 8], f"speeds obs t={t}")
+
+
+def check_bench_shape(make, n, T, K, seed=1234, tick_limit=2000, nthreads=0, action_source=None):
+    """The timed configuration of bench.py as a parity case: `n` envs, Philox random starts, U(-1.2, 1.2) actions, terminal
+    +1 / -1 / 0 reward, `tick_limit` with Philox random auto-reset, K fused ticks per launch, T ticks in all.  The oracle is
+    stepped tick by tick with the reset positions of tests/philox_ref.py (the library's counter: one per reset() call, then
+    one per tick).  Every winner, done flag and reward of every tick and the final state must be EQUAL."""
+    from tests import philox_ref
+    envs = make(n, random_positions=True, seed=seed, reward_mode="terminal", tick_limit=tick_limit, auto_reset=True)
+    counter = 1                                    # the constructor's reset() used counter 0
+    orc = OracleEnvs(n, philox_ref.reset_positions(n, seed, 0))
+    assert_state_equal(envs.export_state(), orc.snapshot(), "start")
+    rng = np.random.default_rng(seed + 1)
+    episodes = hits = 0
+    for t0 in range(0, T, K):
+        a = action_source(K) if action_source else (rng.uniform(-1.2, 1.2, size=(K, n, 2, 2))).astype(np.float32)
+        out = envs.step(a, want_obs=False)
+        a_np = to_np(a)
+        rew, done, win = to_np(out["reward"]), to_np(out["done"]), to_np(out["winner"])
+        for c in range(K):
+            ro = orc.step(a_np[c], want_obs=False, reward_mode=2, tick_limit=tick_limit, auto_reset=True,
+                          reset_pos=philox_ref.reset_positions(n, seed, counter + c), nthreads=nthreads)
+            assert ro["errors"] == 0
+            np.testing.assert_array_equal(done[c], ro["done"], err_msg=f"done t={t0 + c}")
+            np.testing.assert_array_equal(win[c], ro["winner"], err_msg=f"winner t={t0 + c}")
+            np.testing.assert_array_equal(rew[c], ro["reward"], err_msg=f"reward t={t0 + c}")
+            episodes += int(ro["done"].sum())
+            hits += int((ro["winner"] != 0).sum())
+        counter += K
+        assert_state_equal(envs.export_state(), orc.snapshot(), f"t={t0 + K}")
+    return episodes, hits

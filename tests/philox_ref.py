@@ -70,3 +70,13 @@ def replay_indices(batch, size, seed, counter):
     lane = b % 4
     x = np.where(lane == 0, u[0], np.where(lane == 1, u[1], np.where(lane == 2, u[2], u[3]))).astype(np.uint64)
     return ((x * np.uint64(size)) >> np.uint64(32)).astype(np.int64)
+
+
+def reset_positions(n_envs, seed, counter):
+    """int64 [n_envs, 4] = (p1x, p1y, p2x, p2y) of SS_RESET_RANDOM for Philox counter `counter` (ss_env_core.cuh
+    reset_random: counter words (env lo, env hi, counter lo, counter hi), key = seed; coordinate = 25 + mulhi(u, 200),
+    the library's draw for np.random.randint(25, 225), SkillshotGame.py:15)."""
+    env = np.arange(n_envs, dtype=np.uint64)
+    seed, counter = int(seed), int(counter)
+    u = philox4x32_10(env & MASK, env >> np.uint64(32), counter & 0xFFFFFFFF, counter >> 32, seed & 0xFFFFFFFF, seed >> 32)
+    return np.stack([25 + ((x.astype(np.uint64) * np.uint64(200)) >> np.uint64(32)).astype(np.int64) for x in u], axis=1)

@@ -112,10 +112,35 @@ def test_bench_report_assembles_without_a_gpu():
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     peaks = {"hbm_gbs": 6556.5, "bf16_tflops": 1631.0}
+    times = dict(zip(bench.LEG_KEYS, (0.08, 0.19, 0.044, 2.1, 0.79, 0.094, 0.188, 0.49, 0.17, 0.52)))
     for world, collective in ((1, "peer"), (8, "peer"), (2, "nccl")):
-        rep = bench.learner_report(0.08, 0.19, 0.044, 2.1, 0.79, 0.094, 0.188, 0.49, world, peaks, "measured", collective)
+        rep = bench.learner_report(times, world, peaks, "measured", collective, dict(times, roll=0.079, cfg5=0.09))
         json.dumps(rep)
-        assert set(rep) == {"rollout", "train", "selfplay_training", "planning_actor_speed_sweep", "actor_forward_roofline"}
+        want = {"rollout", "train", "selfplay_training", "planning_actor_speed_sweep", "actor_forward_roofline"}
+        assert set(rep) == (want | {"scaling_in_run"} if world > 1 else want)
         assert rep["train"]["samples_per_sec"] == world * bench.TRAIN_BATCH / 0.19e-3
         assert 0 < rep["actor_forward_roofline"]["frac"] < 1
+        if world > 1:
+            sc = rep["scaling_in_run"]
+            assert abs(sc["update_weak_efficiency"] - 0.17 / 0.19) < 1e-12
+            assert abs(sc["config4_strong_efficiency"] - 0.52 / 0.49 / world) < 1e-12
     assert bench.ncu_traffic(bench.TICKS_PER_LAUNCH) is not None and bench.ncu_traffic(7) is None
+    prof = bench.ncu_profile(bench.TICKS_PER_LAUNCH)
+    assert prof["step_kernel_physics_warp_inst_per_launch"] > prof["step_kernel_physics_fp64_warp_inst_per_launch"] > 0
+    # both arms print the same config object (the driver compares them)
+    cfg = bench.bench_config(bench.TICKS, bench.TICKS_PER_LAUNCH)
+    assert set(cfg) == {"workload", "envs_per_gpu", "ticks_per_step", "ticks_per_launch", "l2"}
+
+
+def test_cpu_legs_ignore_omp_num_threads(monkeypatch):
+    """torch.distributed.run exports OMP_NUM_THREADS=1: the CPU legs size themselves from the CPU affinity instead."""
+    import importlib.util
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    spec = importlib.util.spec_from_file_location("_bench2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.host_cores() == len(os.sched_getaffinity(0))
+    if bench.host_cores() > 1:
+        from oracle.oracle import lib as olib
+        dt, envs, actions = bench.cpu_port_run(4096, 4, bench.host_cores())
+        assert olib().ss_oracle_max_threads() == bench.host_cores()      # omp_set_num_threads took effect

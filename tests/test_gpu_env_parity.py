@@ -101,6 +101,26 @@ def test_full_size_physics_matches_oracle_256_ticks():
     parity.assert_state_equal(envs.export_state(), orc.snapshot(), "65536 envs")
 
 
+def test_bench_shape_full_size_matches_oracle():
+    """bench.py's timed configuration as it is timed: 65,536 envs x 2,048 ticks in launches of 128 fused ticks, Philox
+    random starts and auto-reset at the 2,000-tick limit, terminal reward.  Every winner, done flag and reward of all
+    1.3e8 env-steps and the state after every launch are compared with the oracle for equality."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(99)
+
+    def actions(K):
+        return (torch.rand((K, 65536, 2, 2), device="cuda", generator=g) * 2.4 - 1.2).contiguous()
+
+    episodes, hits = parity.check_bench_shape(make, n=65536, T=2048, K=128, action_source=actions)
+    assert episodes >= 65536 and hits > 1000          # every env restarts at least once (the 2,000-tick limit), many by a hit
+
+
+def test_bench_shape_short_episodes():
+    """The same shape with a 40-tick limit: ~50 Philox restarts per env inside the fused launches."""
+    episodes, hits = parity.check_bench_shape(make, n=8192, T=256, K=128, tick_limit=40, seed=77)
+    assert episodes > 8192 * 5
+
+
 def test_facade_matches_reference_surface():
     """The SkillshotGame / Player / Projectile object surface on one device env (KAT-A, KAT-D)."""
     from skillshot_learning_b200.game import SkillshotGame

@@ -517,13 +517,26 @@ def test_reference_surface_persistence_round_trip(tmp_path, capsys):
     skl.model_train(epochs=1, save_progress=True, save_boards=False)
     assert sorted(os.listdir(os.path.join(skl.save_location, "critic"))) == ["0_2_model.npz", "3_4_model.npz"]
     assert len(skl.load_training_progress()) == 3
+    first = {k: v.copy() for k, v in np.load(os.path.join(skl.save_location, "actor", "0_2_model.npz")).items()}
     other = SkillshotLearner(device="cuda:0", seed=99)
     other.save_location = skl.save_location
-    other.load_actor_critic_models()
+    assert other.load_actor_critic_models() is True              # SkillshotLearner.py:123-137 returns True / False
     assert torch.equal(other.networks.params, skl.networks.params)
     assert torch.equal(other.networks.adam_m, skl.networks.adam_m) and other.networks.step_critic == skl.networks.step_critic
     state = skl.game_environment.get_state()
     assert np.array_equal(other.model_act(state, 1), skl.model_act(state, 1))
+    # load_index selects the epoch range, weights AND optimiser state: the first save is not the latest one
+    steps_latest = other.networks.step_critic
+    assert other.load_actor_critic_models(load_index=0) is True
+    assert np.array_equal(np.concatenate([w.ravel() for w in other.networks.get_weights("actor")]),
+                          np.concatenate([first[k].ravel() for k in first]))
+    assert not torch.equal(other.networks.params, skl.networks.params) and 0 < other.networks.step_critic < steps_latest
+    # nothing saved: False, like the reference
+    empty = SkillshotLearner(device="cuda:0", seed=1)
+    empty.save_location = str(tmp_path / "nothing_here")
+    assert empty.load_actor_critic_models() is False
+    os.makedirs(os.path.join(empty.save_location, "actor"))
+    assert empty.load_actor_critic_models() is False
 
 
 # ---------------------------------------------------------------------------

@@ -56,3 +56,10 @@ def test_nan_action_sets_status():
     a[2, 1, 0] = np.nan
     e.step(a)
     assert e.status_bits() & 1
+
+
+def test_bench_shape_small():
+    """bench.py's timed shape (fused ticks, Philox auto-reset, terminal reward) at a size the host simulation finishes in
+    seconds; the GPU run of the same check is at the full 65,536 envs x 2,048 ticks x K = 128."""
+    episodes, hits = parity.check_bench_shape(make, n=512, T=192, K=32, tick_limit=50)
+    assert episodes > 512 * 2 and hits > 10
