@@ -1,6 +1,7 @@
 """Recipe for oracle/_ref/: byte-compiles the UNMODIFIED reference modules where they lie under
-/root/reference into sourceless .pyc files (build outputs only -- no reference source enters the
-repository; oracle/_ref/ is git-ignored but travels to the GPU box with the snapshot).
+/root/reference into marshalled code objects, <Module>.code (build outputs only -- no reference source
+enters the repository; oracle/_ref/ is git-ignored but travels to the GPU box with the snapshot; the
+files are not named .pyc because snapshot tools commonly drop those).
 
     python -m oracle.build_ref
 
@@ -10,8 +11,8 @@ on the host cores.  Rendering modules (pygame) are not compiled: they stay off t
 """
 from __future__ import annotations
 
+import marshal
 import os
-import py_compile
 import sys
 import warnings
 
@@ -42,24 +43,47 @@ def playable_tick_code(source_dir: str = None):
     return compile(ast.Module(body=keep, type_ignores=[]), "skillshot_playable.py", "exec")
 
 
+def built() -> bool:
+    return all(os.path.exists(os.path.join(OUT, m + ".code")) for m in MODULES) and os.path.exists(os.path.join(OUT, PLAYABLE_TICK))
+
+
 def build(force: bool = False) -> bool:
     """True when oracle/_ref holds the compiled reference (built now or earlier)."""
     if not os.path.exists(os.path.join(SOURCE_DIR, "SkillshotGame.py")):
-        return all(os.path.exists(os.path.join(OUT, m + ".pyc")) for m in MODULES)
+        return built()
     os.makedirs(OUT, exist_ok=True)
     for m in MODULES:
-        src, dst = os.path.join(SOURCE_DIR, m + ".py"), os.path.join(OUT, m + ".pyc")
+        src, dst = os.path.join(SOURCE_DIR, m + ".py"), os.path.join(OUT, m + ".code")
         if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")      # `is not 0` SyntaxWarning, SkillshotGame.py:44,54
-                py_compile.compile(src, cfile=dst, dfile=m + ".py", doraise=True,
-                                   invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
-    import marshal
+                code = compile(open(src).read(), m + ".py", "exec")
+            with open(dst, "wb") as f:
+                marshal.dump(code, f)
     with open(os.path.join(OUT, PLAYABLE_TICK), "wb") as f:
         marshal.dump(playable_tick_code(), f)
     with open(os.path.join(OUT, "BUILT_FROM"), "w") as f:
         f.write("%s, python %s\n" % (SOURCE_DIR, sys.version.split()[0]))
     return True
+
+
+def load_module(name: str):
+    """Import reference module `name` from its marshalled code object (its own imports of sibling reference modules
+    resolve through sys.modules, so load in the order of MODULES)."""
+    import types
+    if name in sys.modules:
+        return sys.modules[name]
+    with open(os.path.join(OUT, name + ".code"), "rb") as f:
+        code = marshal.load(f)
+    mod = types.ModuleType(name)
+    mod.__file__ = os.path.join(OUT, name + ".code")
+    sys.modules[name] = mod
+    try:
+        exec(code, mod.__dict__)
+    except BaseException:
+        del sys.modules[name]
+        raise
+    return mod
 
 
 if __name__ == "__main__":

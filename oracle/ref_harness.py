@@ -32,7 +32,8 @@ def source() -> str | None:
     """"source" (the mounted reference), "compiled" (oracle/_ref byte-code of it) or None."""
     if os.path.exists(os.path.join(SOURCE_DIR, "SkillshotGame.py")):
         return "source"
-    if all(os.path.exists(os.path.join(COMPILED_DIR, m + ".pyc")) for m in ("Projectile", "Player", "SkillshotGame", "SkillshotLearner")):
+    from oracle import build_ref
+    if build_ref.built():
         return "compiled"
     return None
 
@@ -108,9 +109,15 @@ def modules():
     if _mods is None:
         if not available():
             raise RuntimeError("reference neither mounted at %s nor compiled into %s" % (SOURCE_DIR, COMPILED_DIR))
-        if reference_dir() not in sys.path:
-            sys.path.insert(0, reference_dir())
         _install_tf_stub()
+        _install_pygame_stub()
+        if source() == "source":
+            if SOURCE_DIR not in sys.path:
+                sys.path.insert(0, SOURCE_DIR)
+        else:
+            from oracle import build_ref
+            for m in build_ref.MODULES:
+                build_ref.load_module(m)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")  # `is not 0` SyntaxWarning, SkillshotGame.py:44,54
             from SkillshotGame import SkillshotGame

@@ -160,6 +160,184 @@ __global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
     if (status && A.status) atomicOr(A.status, status);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// step_pp_kernel -- the fused physics-only step with ONE THREAD PER PLAYER.
+//
+// Lanes 2i and 2i+1 of a warp are players 1 and 2 of env i: each lane owns its player (position, rotation) and that
+// player's projectile, the env's three scalars (ticks, live, winner) are replicated in both lanes.  Everything a tick
+// does is per player except the hit test, which needs the OTHER player's projectile: one __shfl_xor of the packed
+// (x, y, valid) word, and one warp ballot that gives both lanes the pair's two hit bits (SkillshotGame.check_collision's
+// "player 1 first, first hit wins" is then a bit test).  Compared with one thread per env (step_kernel) a 65,536-env
+// launch has twice the warps (6.9 instead of 3.5 per scheduler, which was latency-bound: ncu round 1, 36 % of cycles
+// without an eligible warp) and each thread half the dependent chain.
+//
+// The arithmetic is the core's (ss_env_core.cuh), restated without the conversion instructions, which ncu and
+// tools/op_probe.cu showed to be the scarce pipe (I2F.F64 / F2I.F64 issue once per 8-9 cycles and take 18-19, a DADD once
+// per 2 and 8):
+//   int -> double   (2^52 + x) - 2^52 with x placed in the low word of 2^52's bit pattern: exact for 0 <= x < 2^32
+//   double -> int   low word of v + 1.5 * 2^52: the add rounds v to an integer, half-to-even, exactly Python's
+//                   int(round(v)) and cvt.rni (|v| < 2^31)
+// so positions stay integers in registers and both conversions are one DADD.  The float32 -> float64 conversion of the
+// two actions stays (2 per lane and tick).  The clip keeps the reference's NaN behaviour (a NaN falls through both
+// compares, Player.py:36-37, 60-61): min.NaN / max.NaN.  Where the reference raises (int(round(nan)), Player.py:63,
+// Projectile.py:40) SS_STATUS_NAN is set from ONE unordered compare of the two candidate x coordinates per tick.
+//
+// Physics-only: reward modes none / terminal, reference speed constants, no observations, no episode statistics; the
+// other combinations stay on step_kernel.  Same HBM layout, same outputs, bit-identical results (tests: every fused
+// physics test of tests/test_gpu_env_parity.py runs through it, bench shape included).
+constexpr int kBlockPP = 64;        // 32 envs per CTA: a 65,536-env launch is 2,048 CTAs, 13.8 per SM, all resident at once
+constexpr double kRound = 6755399441055744.0;      // 1.5 * 2^52
+
+// A position coordinate x (0 ... 250) is carried as the double kRound + x: its low word IS the integer (hit test, bounds,
+// packing read it for free), kRound + x - kRound is the exact double (one DADD), and rounding a candidate v to the nearest
+// integer, half to even, is v + kRound, already in this form.  A commit replaces the low word only (the high word is
+// 0x43380000 for every committed value).
+__device__ __forceinline__ double coord(int x) { return __hiloint2double(0x43380000, x); }
+__device__ __forceinline__ int icoord(double w) { return __double2loint(w); }
+__device__ __forceinline__ double with_low(double w, int lo) { return __hiloint2double(__double2hiint(w), lo); }
+
+struct Lane {
+    double rot, qrot;               // Player.rotation, Projectile.rotation
+    double s3, c3;                  // sin / cos of rot times Player.speed_move (3)
+    double qs5, qc5;                // sin / cos of qrot times Projectile.speed_move (5)
+    double wx, wy, ux, uy;          // player and projectile position in coord() form
+    int cd, age, valid, live, winner, ticks;
+};
+
+__device__ __forceinline__ float clip_unit_nan(float v) {        // Player.py:36-37, 60-61; NaN falls through
+    float r;
+    asm("max.NaN.f32 %0, %1, 0fBF800000;" : "=f"(r) : "f"(v));
+    asm("min.NaN.f32 %0, %1, 0f3F800000;" : "=f"(r) : "f"(r));
+    return r;
+}
+__device__ __forceinline__ bool either_nan(double a, double b) {
+    int p;
+    asm("{ .reg .pred q; setp.nan.f64 q, %1, %2; selp.s32 %0, 1, 0, q; }" : "=r"(p) : "d"(a), "d"(b));
+    return p != 0;
+}
+
+__device__ __forceinline__ void lane_reset(Lane &L, int x, int y) {      // SkillshotGame.__init__, this player's half
+    L.wx = coord(x); L.wy = coord(y); L.rot = 0.0;
+    L.ux = coord(0); L.uy = coord(0); L.qrot = 0.0; L.cd = 0; L.age = 0; L.valid = 0;
+    L.ticks = 0; L.live = 1; L.winner = 0;
+    L.s3 = 0.0; L.c3 = 3.0; L.qs5 = 0.0; L.qc5 = 5.0;                     // sin 0 = 0, cos 0 = 1
+}
+
+// TERMINAL: write the +1 / -1 / 0 reward (readme.md:10); otherwise rewards are not written (reward_mode none) or zero.
+template <bool TERMINAL>
+__global__ void __launch_bounds__(kBlockPP, 14) step_pp_kernel(const StepArgs A) {
+    const int lane = threadIdx.x & 31, P = lane & 1;
+    // global lane = 2 * env + player.  Lanes past the end replay the last env (same inputs, same values stored twice):
+    // no lane of the warp is ever inactive, so the shuffle and the ballot need no guards and the loop no predicates.
+    int64_t gl = (int64_t)blockIdx.x * kBlockPP + threadIdx.x;
+    gl = min(gl, 2 * A.n - 2 + P);
+    const int64_t env = gl >> 1;
+    char *const base = (char *)A.state;
+    Lane L;
+    {
+        L.rot = ((const double *)base)[gl];                               // plane 0 is double2 per env: this lane's half
+        L.qrot = ((const double *)(base + 16 * A.n))[gl];
+        const int4 a = ((const int4 *)(base + 32 * A.n))[env], b = ((const int4 *)(base + 48 * A.n))[env];
+        const uint32_t pp = (uint32_t)a.x >> (16 * P), qq = (uint32_t)a.y >> (16 * P), f = (uint32_t)b.w;
+        L.wx = coord(pp & 255); L.wy = coord((pp >> 8) & 255); L.ux = coord(qq & 255); L.uy = coord((qq >> 8) & 255);
+        L.cd = P ? a.w : a.z; L.age = P ? b.y : b.x; L.ticks = b.z;
+        L.valid = (f >> P) & 1; L.live = (f >> 2) & 1; L.winner = (f >> 4) & 3;
+        double s, c;
+        sincos_d(L.rot, &s, &c);
+        L.s3 = mul(s, 3.0); L.c3 = mul(c, 3.0);
+        sincos_d(L.qrot, &s, &c);
+        L.qs5 = mul(s, 5.0); L.qc5 = mul(c, 5.0);
+    }
+    bool nan_seen = false;
+    const int64_t n2 = 2 * A.n;
+    const float2 *ap = (const float2 *)A.actions + gl;
+    float *rp = (float *)A.reward_out + gl;
+    uint8_t *fp = (P ? A.winner_out : A.done_out);
+    const bool write_flag = fp != nullptr;
+    const bool write_zero = !TERMINAL && A.reward_out && A.P.reward_mode != SS_REWARD_NONE;
+    fp += env;
+    const int limit = A.P.tick_limit > 0 ? (int)min((int64_t)0x7fffffff, A.P.tick_limit) : 0x7fffffff;
+    const bool auto_reset = A.P.auto_reset != 0;
+
+    float2 a_next = __ldg(ap);
+    for (int t = A.n_ticks; t > 0; --t) {
+        const float2 a = a_next;
+        ap += n2;
+        if (t > 1) a_next = __ldg(ap);                                    // prefetch: hide the load behind this tick
+        // ---- do_actions (SkillshotLearner.py:206-213): move with the rotation BEFORE the turn, turn, shoot ----
+        const double speed = (double)clip_unit_nan(a.x), angle = (double)clip_unit_nan(a.y);
+        const double vx = sub(sub(L.wx, kRound), mul(L.s3, speed));       // Player.py:63
+        const double vy = sub(sub(L.wy, kRound), mul(L.c3, speed));       // Player.py:64
+        const double cx = add(vx, kRound), cy = add(vy, kRound);          // int(round(.)), in coord() form
+        const bool ok = (unsigned)icoord(cx) <= (unsigned)(kBoard - kPlayerSize) &&
+                        (unsigned)icoord(cy) <= (unsigned)(kBoard - kPlayerSize);
+        L.wx = with_low(L.wx, ok ? icoord(cx) : icoord(L.wx));            // Player.py:66-68: both or neither
+        L.wy = with_low(L.wy, ok ? icoord(cy) : icoord(L.wy));
+        L.rot = fma(angle, 0.25, L.rot);                                  // rot + angle * 0.25: the product is exact
+        double s, c;
+        sincos_d(L.rot, &s, &c);
+        L.s3 = mul(s, 3.0); L.c3 = mul(c, 3.0);
+        if (L.cd <= 0) {                                                  // Player.move_shoot_projectile, Player.py:78-89
+            L.ux = L.wx; L.uy = L.wy; L.qrot = L.rot;
+            L.qs5 = mul(s, 5.0); L.qc5 = mul(c, 5.0);
+            L.valid = 1; L.cd = 15; L.age = 0;
+        }
+        // ---- game_tick (SkillshotGame.py:115-122), gated on game_live ----
+        const int lv = L.live;
+        const double zx = sub(sub(L.ux, kRound), L.qs5);                  // Projectile.py:40
+        const double zy = sub(sub(L.uy, kRound), L.qc5);                  // Projectile.py:41
+        if (either_nan(vx, zx)) nan_seen = true;                          // int(round(nan)) raises
+        const double dx = add(zx, kRound), dy = add(zy, kRound);
+        const bool inb = (unsigned)icoord(dx) <= (unsigned)(kBoard - kProjSize) &&
+                         (unsigned)icoord(dy) <= (unsigned)(kBoard - kProjSize);
+        const bool fly = lv && L.valid && inb;                            // Projectile.py:43-47
+        L.ux = with_low(L.ux, fly ? icoord(dx) : icoord(L.ux));
+        L.uy = with_low(L.uy, fly ? icoord(dy) : icoord(L.uy));
+        L.valid = lv ? (int)fly : L.valid;
+        L.ticks += lv; L.cd -= lv; L.age += lv;                           // SkillshotGame.py:118, Projectile.py:52-53
+        // check_collision (SkillshotGame.py:58-94): my player against the OTHER player's projectile
+        const uint32_t mine = (uint32_t)icoord(L.ux) | ((uint32_t)icoord(L.uy) << 8) | ((uint32_t)L.valid << 16);
+        const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
+        const int jx = theirs & 255, jy = (theirs >> 8) & 255, px = icoord(L.wx), py = icoord(L.wy);
+        const bool in_x = (unsigned)(jx + kProjSize - px) <= (unsigned)kPlayerSize || (unsigned)(jx - px) <= (unsigned)kPlayerSize;
+        const bool in_y = (unsigned)(jy - py) <= (unsigned)kPlayerSize || (unsigned)(jy - kProjSize - py) <= (unsigned)kPlayerSize;  // :72 minus
+        const bool hit = lv && (theirs >> 16) && in_x && in_y;
+        const uint32_t pair = (__ballot_sync(0xffffffffu, hit) >> (lane & 30)) & 3u;     // bit 0: player 1 hit, bit 1: player 2 hit
+        float r = 0.f;
+        if (pair) {                                                       // the pair with player 1 first; the first hit breaks
+            L.winner = (pair & 1u) ? 1 : 2;                               // winner_id = the player that was HIT (:77)
+            L.live = 0;
+            r = (L.winner - 1 == P) ? -1.f : 1.f;                         // readme.md:10: -1 for the hit player, +1 for the shooter
+        }
+        const bool done = !L.live || L.ticks >= limit;
+        if (TERMINAL) *rp = r;
+        else if (write_zero) *rp = 0.f;
+        if (write_flag) *fp = (uint8_t)(P ? L.winner : (int)done);
+        rp += n2; fp += A.n;
+        if (auto_reset && done) {                                         // game_reset (SkillshotGame.py:168-169)
+            int x = P ? 200 : 50, y = x;
+            if (A.P.reset_mode == SS_RESET_RANDOM) {
+                const uint64_t ctr = A.P.counter + (uint64_t)(A.n_ticks - t);
+                const U4 u = philox4x32_10(U4{(uint32_t)env, (uint32_t)((uint64_t)env >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32)},
+                                           (uint32_t)A.P.seed, (uint32_t)(A.P.seed >> 32));
+                x = rand_coord(P ? u.z : u.x); y = rand_coord(P ? u.w : u.y);
+            }
+            lane_reset(L, x, y);
+        }
+    }
+    // the partner's valid bit for the env's flag word
+    const int v_other = __shfl_xor_sync(0xffffffffu, L.valid, 1);
+    ((double *)base)[gl] = L.rot;
+    ((double *)(base + 16 * A.n))[gl] = L.qrot;
+    char *ia = base + 32 * A.n + env * 16, *ib = base + 48 * A.n + env * 16;
+    ((uint16_t *)ia)[P] = (uint16_t)(icoord(L.wx) | (icoord(L.wy) << 8));
+    ((uint16_t *)ia)[2 + P] = (uint16_t)(icoord(L.ux) | (icoord(L.uy) << 8));
+    ((int *)ia)[2 + P] = L.cd;
+    ((int *)ib)[P] = L.age;
+    if (!P) ((int2 *)ib)[1] = make_int2(L.ticks, L.valid | (v_other << 1) | (L.live << 2) | (L.winner << 4));
+    if (nan_seen && A.status) atomicOr(A.status, kStatusNaN);
+}
+
 __global__ void reset_kernel(void *state, int64_t n, const uint8_t *mask, int reset_mode,
                              const int32_t *positions, uint64_t seed, uint64_t counter) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -287,6 +465,12 @@ __global__ void apply_kernel(void *state, int64_t n, int64_t env, int player, in
     if (status && status_out) atomicOr(status_out, status);
 }
 
+// SS_STEP_PP=0 sends the physics-only fused step back to the one-thread-per-env kernel (A/B measurements only)
+inline bool getenv_pp() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SS_STEP_PP"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
 inline int check_launch() { return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA; }
 inline unsigned blocks_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
@@ -354,6 +538,12 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
             if (speeds) step_kernel<true, true, true, 8><<<grid, block, 0, st>>>(A);
             else step_kernel<true, true, false, 8><<<grid, block, 0, st>>>(A);
         }
+    } else if (n_ticks > 1 && !A.stats && !speeds && !shaped && !done_rows_out && getenv_pp()) {
+        // physics-only fused ticks (bench.py's timed shape): one thread per player.  (A single tick per launch stays on
+        // the one-thread-per-env kernel: a launch then pays 3 sincos per lane to set up what it carries, measured 4.1 vs 3.9 us.)
+        const dim3 grid_pp(blocks_for(2 * n_envs, kBlockPP));
+        if (reward_out && reward_mode == SS_REWARD_TERMINAL) step_pp_kernel<true><<<grid_pp, kBlockPP, 0, st>>>(A);
+        else step_pp_kernel<false><<<grid_pp, kBlockPP, 0, st>>>(A);
     } else if (carry) {
         if (A.stats) {
             if (speeds) step_kernel<false, true, true, 1, true><<<grid, block, 0, st>>>(A);

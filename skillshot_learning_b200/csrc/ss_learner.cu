@@ -665,7 +665,7 @@ __global__ void replay_push_kernel(Ring R, int64_t pos, const float *s, const fl
     if (part == 0) {
         reinterpret_cast<float2 *>(R.a)[dst] = reinterpret_cast<const float2 *>(a)[row];
         R.r[dst] = r[row];
-        R.done[dst] = done ? done[row / done_div] : 0;
+        R.done[dst] = (done && done[row / done_div]) ? 1 : 0;      // any non-zero flag (e.g. winner_id 1 / 2) is stored as 1
     }
 }
 

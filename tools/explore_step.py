@@ -16,7 +16,10 @@ def main():
     print("envs ticks obs reward us_per_launch env_steps_per_s algo_GBs frac_of_6556 moved_GBs")
     for E in Es:
         for K in Ks:
-            for obs, reward in ((False, "terminal"), (True, "looking"), (False, "looking"), (True, "terminal")):
+            combos = ((False, "terminal"), (True, "looking"), (False, "looking"), (True, "terminal"))
+            if os.environ.get("SS_ONLY") == "physics":
+                combos = ((False, "terminal"),)
+            for obs, reward in combos:
                 envs = SkillshotEnvs(E, device=dev, random_positions=True, seed=1, reward_mode=reward,
                                      tick_limit=2000, auto_reset=True)
                 nbuf = max(1, min(PER_GRAPH, int(4e8 // (E * K * 16))))
