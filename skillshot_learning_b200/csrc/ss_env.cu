@@ -197,9 +197,9 @@ __device__ __forceinline__ int icoord(double w) { return __double2loint(w); }
 __device__ __forceinline__ double with_low(double w, int lo) { return __hiloint2double(__double2hiint(w), lo); }
 
 struct Lane {
-    double rot, qrot;               // Player.rotation, Projectile.rotation
+    double rot;                     // Player.rotation (Projectile.rotation is parked in shared memory: only a spawn writes it)
     double s3, c3;                  // sin / cos of rot times Player.speed_move (3)
-    double qs5, qc5;                // sin / cos of qrot times Projectile.speed_move (5)
+    double qs5, qc5;                // sin / cos of the projectile's rotation times Projectile.speed_move (5)
     double wx, wy, ux, uy;          // player and projectile position in coord() form
     int cd, age, valid, live, winner, ticks;
 };
@@ -216,16 +216,138 @@ __device__ __forceinline__ bool either_nan(double a, double b) {
     return p != 0;
 }
 
-__device__ __forceinline__ void lane_reset(Lane &L, int x, int y) {      // SkillshotGame.__init__, this player's half
+__device__ __forceinline__ void lane_reset(Lane &L, double *qrot, int x, int y) {      // SkillshotGame.__init__, this player's half
     L.wx = coord(x); L.wy = coord(y); L.rot = 0.0;
-    L.ux = coord(0); L.uy = coord(0); L.qrot = 0.0; L.cd = 0; L.age = 0; L.valid = 0;
+    L.ux = coord(0); L.uy = coord(0); *qrot = 0.0; L.cd = 0; L.age = 0; L.valid = 0;
     L.ticks = 0; L.live = 1; L.winner = 0;
-    L.s3 = 0.0; L.c3 = 3.0; L.qs5 = 0.0; L.qc5 = 5.0;                     // sin 0 = 0, cos 0 = 1
+    L.s3 = 0.0; L.c3 = 3.0; L.qs5 = 0.0; L.qc5 = 5.0;                                   // sin 0 = 0, cos 0 = 1
+}
+
+struct LaneIo {                     // per-lane cursor into the per-tick tensors: ONE 32-bit element index, advanced once per tick
+    uint32_t idx;                   // tick * 2n + global lane: this lane's float2 action, its float reward; idx >> 1 = its env's flag byte
+    uint32_t n2;                    // 2n: lanes per tick
+    const float2 *actions;
+    float *reward;
+    uint8_t *flags;                 // done_out (player-1 lanes) or winner_out (player-2 lanes)
+};
+
+// sin / cos of the player's rotation, computed one tick AHEAD of its use.  rot(t) = rot(t-1) + clip(look(t)) * 0.25
+// depends on the actions alone (Player.py:33-39), not on anything the tick computes, so the longest dependent chain of a
+// tick -- argument reduction and the two polynomial evaluations, ~150 cycles -- is taken off the tick's critical path: tick
+// t runs beside the sin / cos of tick t + 1, two independent instruction streams the scheduler interleaves.  Only a game
+// reset (rotation back to 0) invalidates the speculation; the reset path redoes it.
+struct Turn {
+    double rot, s, c;               // post-turn rotation of a tick and its sin / cos
+};
+
+template <bool CHECKED>
+__device__ __forceinline__ void turn_from(Turn &out, double rot_before, float look) {
+    out.rot = fma((double)clip_unit_nan(look), 0.25, rot_before);    // rot + angle * 0.25: the product is exact (Player.py:39)
+    if (CHECKED) sincos_d(out.rot, &out.s, &out.c);
+    else sincos_d_unchecked(out.rot, &out.s, &out.c);
+}
+
+// One tick of one player.  `now` = this tick's post-turn rotation with its sin / cos (computed during the previous tick),
+// `next` = the next tick's, computed here from `look_next`.  CHECKED: sin / cos with the |rot| < 1e5 range check.
+template <bool TERMINAL, bool CHECKED>
+__device__ __forceinline__ void lane_tick(Lane &L, double *qrot, const float move, const float look_next, const Turn &now, Turn &next,
+                                          const StepArgs &A, LaneIo &io, int lane, int P, int64_t env, int tick, int limit,
+                                          bool write_zero, bool &nan_seen) {
+    turn_from<CHECKED>(next, now.rot, look_next);
+    // ---- do_actions (SkillshotLearner.py:206-213): move with the rotation BEFORE the turn, turn, shoot ----
+    const double speed = (double)clip_unit_nan(move);
+    const double vx = sub(sub(L.wx, kRound), mul(L.s3, speed));       // Player.py:63
+    const double vy = sub(sub(L.wy, kRound), mul(L.c3, speed));       // Player.py:64
+    const double cx = add(vx, kRound), cy = add(vy, kRound);          // int(round(.)), in coord() form
+    const bool ok = (unsigned)icoord(cx) <= (unsigned)(kBoard - kPlayerSize) &&
+                    (unsigned)icoord(cy) <= (unsigned)(kBoard - kPlayerSize);
+    L.wx = with_low(L.wx, ok ? icoord(cx) : icoord(L.wx));            // Player.py:66-68: both or neither
+    L.wy = with_low(L.wy, ok ? icoord(cy) : icoord(L.wy));
+    L.rot = now.rot;
+    L.s3 = mul(now.s, 3.0); L.c3 = mul(now.c, 3.0);
+    if (L.cd <= 0) {                                                  // Player.move_shoot_projectile, Player.py:78-89
+        L.ux = with_low(L.ux, icoord(L.wx)); L.uy = with_low(L.uy, icoord(L.wy));
+        *qrot = now.rot;
+        L.qs5 = mul(now.s, 5.0); L.qc5 = mul(now.c, 5.0);
+        L.valid = 1; L.cd = 15; L.age = 0;
+    }
+    // ---- game_tick (SkillshotGame.py:115-122), gated on game_live ----
+    const int lv = L.live;
+    const double zx = sub(sub(L.ux, kRound), L.qs5);                  // Projectile.py:40
+    const double zy = sub(sub(L.uy, kRound), L.qc5);                  // Projectile.py:41
+    if (either_nan(vx, zx)) nan_seen = true;                          // int(round(nan)) raises
+    const double dx = add(zx, kRound), dy = add(zy, kRound);
+    const bool inb = (unsigned)icoord(dx) <= (unsigned)(kBoard - kProjSize) &&
+                     (unsigned)icoord(dy) <= (unsigned)(kBoard - kProjSize);
+    const bool fly = lv && L.valid && inb;                            // Projectile.py:43-47
+    L.ux = with_low(L.ux, fly ? icoord(dx) : icoord(L.ux));
+    L.uy = with_low(L.uy, fly ? icoord(dy) : icoord(L.uy));
+    L.valid = lv ? (int)fly : L.valid;
+    L.ticks += lv; L.cd -= lv; L.age += lv;                           // SkillshotGame.py:118, Projectile.py:52-53
+    // check_collision (SkillshotGame.py:58-94): my player against the OTHER player's projectile
+    const uint32_t mine = (uint32_t)icoord(L.ux) | ((uint32_t)icoord(L.uy) << 8) | ((uint32_t)L.valid << 16);
+    const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
+    const int jx = theirs & 255, jy = (theirs >> 8) & 255, px = icoord(L.wx), py = icoord(L.wy);
+    const bool in_x = (unsigned)(jx + kProjSize - px) <= (unsigned)kPlayerSize || (unsigned)(jx - px) <= (unsigned)kPlayerSize;
+    const bool in_y = (unsigned)(jy - py) <= (unsigned)kPlayerSize || (unsigned)(jy - kProjSize - py) <= (unsigned)kPlayerSize;  // :72 minus
+    const bool hit = lv && (theirs >> 16) && in_x && in_y;
+    const uint32_t pair = (__ballot_sync(0xffffffffu, hit) >> (lane & 30)) & 3u;     // bit 0: player 1 hit, bit 1: player 2 hit
+    float r = 0.f;
+    if (pair) {                                                       // the pair with player 1 first; the first hit breaks
+        L.winner = (pair & 1u) ? 1 : 2;                               // winner_id = the player that was HIT (:77)
+        L.live = 0;
+        r = (L.winner - 1 == P) ? -1.f : 1.f;                         // readme.md:10: -1 for the hit player, +1 for the shooter
+    }
+    const bool done = !L.live || L.ticks >= limit;
+    if (TERMINAL) io.reward[io.idx] = r;
+    else if (write_zero) io.reward[io.idx] = 0.f;
+    io.flags[io.idx >> 1] = (uint8_t)(P ? L.winner : (int)done);
+    io.idx += io.n2;
+    if (A.P.auto_reset && done) {                                     // game_reset (SkillshotGame.py:168-169)
+        int x = P ? 200 : 50, y = x;
+        if (A.P.reset_mode == SS_RESET_RANDOM) {
+            const uint64_t ctr = A.P.counter + (uint64_t)tick;
+            const U4 u = philox4x32_10(U4{(uint32_t)env, (uint32_t)((uint64_t)env >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32)},
+                                       (uint32_t)A.P.seed, (uint32_t)(A.P.seed >> 32));
+            x = rand_coord(P ? u.z : u.x); y = rand_coord(P ? u.w : u.y);
+        }
+        lane_reset(L, qrot, x, y);
+        turn_from<CHECKED>(next, 0.0, look_next);                     // the next tick turns from rotation 0
+    }
+}
+
+template <bool TERMINAL, bool CHECKED>
+__device__ __forceinline__ void lane_loop(Lane &L, double *qrot, const StepArgs &A, LaneIo &io, int lane, int P, int64_t env,
+                                          bool &nan_seen) {
+    const int limit = A.P.tick_limit > 0 ? (int)min((int64_t)0x7fffffff, A.P.tick_limit) : 0x7fffffff;
+    const bool write_zero = !TERMINAL && A.reward_out && A.P.reward_mode != SS_REWARD_NONE;
+    const int T = A.n_ticks;
+    const float2 zero = make_float2(0.f, 0.f);
+    // tick t needs move(t) and look(t + 1): the action of tick t + 1 is consumed during tick t (its look half now, its
+    // move half one tick later) and the action of tick t + 2 is in flight.  The loop is unrolled by two so that the two
+    // action registers and the two Turn records alternate by renaming.
+    float2 a0 = __ldg(io.actions + io.idx);
+    float2 qa = T > 1 ? __ldg(io.actions + (io.idx + io.n2)) : zero;          // action of tick 1
+    float2 qb = T > 2 ? __ldg(io.actions + (io.idx + 2 * io.n2)) : zero;      // action of tick 2
+    Turn ta, tb;
+    turn_from<CHECKED>(ta, L.rot, a0.y);
+    float move = a0.x;
+    for (int t = 0; t < T; t += 2) {
+        lane_tick<TERMINAL, CHECKED>(L, qrot, move, qa.y, ta, tb, A, io, lane, P, env, t, limit, write_zero, nan_seen);
+        move = qa.x;
+        qa = (t + 3 < T) ? __ldg(io.actions + (io.idx + 2 * io.n2)) : zero;      // action of tick t + 3 (idx is at tick t + 1 now)
+        if (t + 1 < T) {
+            lane_tick<TERMINAL, CHECKED>(L, qrot, move, qb.y, tb, ta, A, io, lane, P, env, t + 1, limit, write_zero, nan_seen);
+            move = qb.x;
+            qb = (t + 4 < T) ? __ldg(io.actions + (io.idx + 2 * io.n2)) : zero;  // action of tick t + 4 (idx is at tick t + 2 now)
+        }
+    }
 }
 
 // TERMINAL: write the +1 / -1 / 0 reward (readme.md:10); otherwise rewards are not written (reward_mode none) or zero.
 template <bool TERMINAL>
 __global__ void __launch_bounds__(kBlockPP, 14) step_pp_kernel(const StepArgs A) {
+    __shared__ double qrot_sh[kBlockPP];
     const int lane = threadIdx.x & 31, P = lane & 1;
     // global lane = 2 * env + player.  Lanes past the end replay the last env (same inputs, same values stored twice):
     // no lane of the warp is ever inactive, so the shuffle and the ballot need no guards and the loop no predicates.
@@ -233,10 +355,11 @@ __global__ void __launch_bounds__(kBlockPP, 14) step_pp_kernel(const StepArgs A)
     gl = min(gl, 2 * A.n - 2 + P);
     const int64_t env = gl >> 1;
     char *const base = (char *)A.state;
+    double *const qrot = &qrot_sh[threadIdx.x];
     Lane L;
     {
         L.rot = ((const double *)base)[gl];                               // plane 0 is double2 per env: this lane's half
-        L.qrot = ((const double *)(base + 16 * A.n))[gl];
+        *qrot = ((const double *)(base + 16 * A.n))[gl];
         const int4 a = ((const int4 *)(base + 32 * A.n))[env], b = ((const int4 *)(base + 48 * A.n))[env];
         const uint32_t pp = (uint32_t)a.x >> (16 * P), qq = (uint32_t)a.y >> (16 * P), f = (uint32_t)b.w;
         L.wx = coord(pp & 255); L.wy = coord((pp >> 8) & 255); L.ux = coord(qq & 255); L.uy = coord((qq >> 8) & 255);
@@ -245,90 +368,26 @@ __global__ void __launch_bounds__(kBlockPP, 14) step_pp_kernel(const StepArgs A)
         double s, c;
         sincos_d(L.rot, &s, &c);
         L.s3 = mul(s, 3.0); L.c3 = mul(c, 3.0);
-        sincos_d(L.qrot, &s, &c);
+        sincos_d(*qrot, &s, &c);
         L.qs5 = mul(s, 5.0); L.qc5 = mul(c, 5.0);
     }
     bool nan_seen = false;
-    const int64_t n2 = 2 * A.n;
-    const float2 *ap = (const float2 *)A.actions + gl;
-    float *rp = (float *)A.reward_out + gl;
-    uint8_t *fp = (P ? A.winner_out : A.done_out);
-    const bool write_flag = fp != nullptr;
-    const bool write_zero = !TERMINAL && A.reward_out && A.P.reward_mode != SS_REWARD_NONE;
-    fp += env;
-    const int limit = A.P.tick_limit > 0 ? (int)min((int64_t)0x7fffffff, A.P.tick_limit) : 0x7fffffff;
-    const bool auto_reset = A.P.auto_reset != 0;
-
-    float2 a_next = __ldg(ap);
-    for (int t = A.n_ticks; t > 0; --t) {
-        const float2 a = a_next;
-        ap += n2;
-        if (t > 1) a_next = __ldg(ap);                                    // prefetch: hide the load behind this tick
-        // ---- do_actions (SkillshotLearner.py:206-213): move with the rotation BEFORE the turn, turn, shoot ----
-        const double speed = (double)clip_unit_nan(a.x), angle = (double)clip_unit_nan(a.y);
-        const double vx = sub(sub(L.wx, kRound), mul(L.s3, speed));       // Player.py:63
-        const double vy = sub(sub(L.wy, kRound), mul(L.c3, speed));       // Player.py:64
-        const double cx = add(vx, kRound), cy = add(vy, kRound);          // int(round(.)), in coord() form
-        const bool ok = (unsigned)icoord(cx) <= (unsigned)(kBoard - kPlayerSize) &&
-                        (unsigned)icoord(cy) <= (unsigned)(kBoard - kPlayerSize);
-        L.wx = with_low(L.wx, ok ? icoord(cx) : icoord(L.wx));            // Player.py:66-68: both or neither
-        L.wy = with_low(L.wy, ok ? icoord(cy) : icoord(L.wy));
-        L.rot = fma(angle, 0.25, L.rot);                                  // rot + angle * 0.25: the product is exact
-        double s, c;
-        sincos_d(L.rot, &s, &c);
-        L.s3 = mul(s, 3.0); L.c3 = mul(c, 3.0);
-        if (L.cd <= 0) {                                                  // Player.move_shoot_projectile, Player.py:78-89
-            L.ux = L.wx; L.uy = L.wy; L.qrot = L.rot;
-            L.qs5 = mul(s, 5.0); L.qc5 = mul(c, 5.0);
-            L.valid = 1; L.cd = 15; L.age = 0;
-        }
-        // ---- game_tick (SkillshotGame.py:115-122), gated on game_live ----
-        const int lv = L.live;
-        const double zx = sub(sub(L.ux, kRound), L.qs5);                  // Projectile.py:40
-        const double zy = sub(sub(L.uy, kRound), L.qc5);                  // Projectile.py:41
-        if (either_nan(vx, zx)) nan_seen = true;                          // int(round(nan)) raises
-        const double dx = add(zx, kRound), dy = add(zy, kRound);
-        const bool inb = (unsigned)icoord(dx) <= (unsigned)(kBoard - kProjSize) &&
-                         (unsigned)icoord(dy) <= (unsigned)(kBoard - kProjSize);
-        const bool fly = lv && L.valid && inb;                            // Projectile.py:43-47
-        L.ux = with_low(L.ux, fly ? icoord(dx) : icoord(L.ux));
-        L.uy = with_low(L.uy, fly ? icoord(dy) : icoord(L.uy));
-        L.valid = lv ? (int)fly : L.valid;
-        L.ticks += lv; L.cd -= lv; L.age += lv;                           // SkillshotGame.py:118, Projectile.py:52-53
-        // check_collision (SkillshotGame.py:58-94): my player against the OTHER player's projectile
-        const uint32_t mine = (uint32_t)icoord(L.ux) | ((uint32_t)icoord(L.uy) << 8) | ((uint32_t)L.valid << 16);
-        const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
-        const int jx = theirs & 255, jy = (theirs >> 8) & 255, px = icoord(L.wx), py = icoord(L.wy);
-        const bool in_x = (unsigned)(jx + kProjSize - px) <= (unsigned)kPlayerSize || (unsigned)(jx - px) <= (unsigned)kPlayerSize;
-        const bool in_y = (unsigned)(jy - py) <= (unsigned)kPlayerSize || (unsigned)(jy - kProjSize - py) <= (unsigned)kPlayerSize;  // :72 minus
-        const bool hit = lv && (theirs >> 16) && in_x && in_y;
-        const uint32_t pair = (__ballot_sync(0xffffffffu, hit) >> (lane & 30)) & 3u;     // bit 0: player 1 hit, bit 1: player 2 hit
-        float r = 0.f;
-        if (pair) {                                                       // the pair with player 1 first; the first hit breaks
-            L.winner = (pair & 1u) ? 1 : 2;                               // winner_id = the player that was HIT (:77)
-            L.live = 0;
-            r = (L.winner - 1 == P) ? -1.f : 1.f;                         // readme.md:10: -1 for the hit player, +1 for the shooter
-        }
-        const bool done = !L.live || L.ticks >= limit;
-        if (TERMINAL) *rp = r;
-        else if (write_zero) *rp = 0.f;
-        if (write_flag) *fp = (uint8_t)(P ? L.winner : (int)done);
-        rp += n2; fp += A.n;
-        if (auto_reset && done) {                                         // game_reset (SkillshotGame.py:168-169)
-            int x = P ? 200 : 50, y = x;
-            if (A.P.reset_mode == SS_RESET_RANDOM) {
-                const uint64_t ctr = A.P.counter + (uint64_t)(A.n_ticks - t);
-                const U4 u = philox4x32_10(U4{(uint32_t)env, (uint32_t)((uint64_t)env >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32)},
-                                           (uint32_t)A.P.seed, (uint32_t)(A.P.seed >> 32));
-                x = rand_coord(P ? u.z : u.x); y = rand_coord(P ? u.w : u.y);
-            }
-            lane_reset(L, x, y);
-        }
-    }
+    LaneIo io;
+    io.idx = (uint32_t)gl; io.n2 = (uint32_t)(2 * A.n);               // (the launch checks that 2n * (n_ticks + 2) fits 32 bits)
+    io.actions = (const float2 *)A.actions;
+    io.reward = (float *)A.reward_out;
+    io.flags = P ? A.winner_out : A.done_out;
+    // A rotation moves by at most 0.25 per tick and a reset zeroes it, so |rot| + 0.25 * n_ticks < 1e5 at the start keeps
+    // every rotation of this launch inside the range of the fast sin / cos: the per-tick range check (and the basic-block
+    // boundary it puts in the middle of the tick) then goes.  Otherwise (400,000 ticks of one-sided turning without a
+    // reset, or a NaN) the warp runs the checked loop.
+    const bool in_range = fabs(L.rot) + 0.25 * (double)A.n_ticks + 1.0 < 1.0e5;
+    if (__all_sync(0xffffffffu, in_range)) lane_loop<TERMINAL, false>(L, qrot, A, io, lane, P, env, nan_seen);
+    else lane_loop<TERMINAL, true>(L, qrot, A, io, lane, P, env, nan_seen);
     // the partner's valid bit for the env's flag word
     const int v_other = __shfl_xor_sync(0xffffffffu, L.valid, 1);
     ((double *)base)[gl] = L.rot;
-    ((double *)(base + 16 * A.n))[gl] = L.qrot;
+    ((double *)(base + 16 * A.n))[gl] = *qrot;
     char *ia = base + 32 * A.n + env * 16, *ib = base + 48 * A.n + env * 16;
     ((uint16_t *)ia)[P] = (uint16_t)(icoord(L.wx) | (icoord(L.wy) << 8));
     ((uint16_t *)ia)[2 + P] = (uint16_t)(icoord(L.ux) | (icoord(L.uy) << 8));
@@ -538,7 +597,8 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
             if (speeds) step_kernel<true, true, true, 8><<<grid, block, 0, st>>>(A);
             else step_kernel<true, true, false, 8><<<grid, block, 0, st>>>(A);
         }
-    } else if (n_ticks > 1 && !A.stats && !speeds && !shaped && !done_rows_out && getenv_pp()) {
+    } else if (n_ticks > 1 && !A.stats && !speeds && !shaped && !done_rows_out && done_out && winner_out &&
+               2 * n_envs * ((int64_t)n_ticks + 2) < (int64_t)0x7fffffff && getenv_pp()) {
         // physics-only fused ticks (bench.py's timed shape): one thread per player.  (A single tick per launch stays on
         // the one-thread-per-env kernel: a launch then pays 3 sincos per lane to set up what it carries, measured 4.1 vs 3.9 us.)
         const dim3 grid_pp(blocks_for(2 * n_envs, kBlockPP));

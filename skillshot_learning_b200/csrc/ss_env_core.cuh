@@ -137,9 +137,9 @@ static __constant__ double kSinCosDev[17] = {SS_SINCOS_CONSTANTS};
 #endif
 #define SS_LIT(i) SS_C##i
 
-#define SS_SINCOS_BODY(C)                                                                                   \
+#define SS_SINCOS_BODY(C, CHECKED)                                                                          \
     {                                                                                                       \
-        if (!(fabs(x) < 1.0e5)) { sincos_lib(x, sp, cp); return; }                                          \
+        if (CHECKED && !(fabs(x) < 1.0e5)) { sincos_lib(x, sp, cp); return; }                               \
         const double kMagic = C(0);                                                                         \
         double q = fma(x, C(1), kMagic); /* x * 2/pi */                                                     \
         const int k = lo_word(q);                                                                           \
@@ -168,8 +168,11 @@ static __constant__ double kSinCosDev[17] = {SS_SINCOS_CONSTANTS};
         *sp = flip_sign_if(a, (k & 2) != 0);                                                                \
         *cp = flip_sign_if(b, ((k + 1) & 2) != 0);                                                          \
     }
-SS_HD void sincos_d(double x, double *sp, double *cp) SS_SINCOS_BODY(SS_SC)
-SS_HD void sincos_d_lit(double x, double *sp, double *cp) SS_SINCOS_BODY(SS_LIT)
+SS_HD void sincos_d(double x, double *sp, double *cp) SS_SINCOS_BODY(SS_SC, true)
+SS_HD void sincos_d_lit(double x, double *sp, double *cp) SS_SINCOS_BODY(SS_LIT, true)
+// the same without the range check, for callers that have established |x| < 1e5 themselves (the per-player step kernel
+// checks once per launch: a rotation moves by at most 0.25 per tick)
+SS_HD void sincos_d_unchecked(double x, double *sp, double *cp) SS_SINCOS_BODY(SS_SC, false)
 SS_HD bool finite_d(double v) { return v - v == 0.0; }
 
 // Python float % 2 (Objects/floatobject.c float_rem): fmod, result takes the
