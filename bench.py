@@ -122,8 +122,9 @@ def ncu_traffic(ticks_per_launch=None):
 
 
 def probe_rates(dev):
-    """Measured instruction-rate ceilings of this GPU (ss_probe_rates): warp-instructions/s of an FFMA stream (the warp
-    schedulers' issue ceiling) and of a DFMA stream (the float64 pipe)."""
+    """Measured instruction-rate ceilings of this GPU (ss_probe_rates): warp-instructions/s of an alternating LOP3 / IMAD
+    stream (the warp schedulers' issue ceiling: two half-rate pipes fed in alternate cycles) and of a DFMA stream (the
+    float64 pipe)."""
     import ctypes
     import torch
     from skillshot_learning_b200._lib import lib, check
@@ -308,7 +309,12 @@ ACTOR_FLOP_PER_ROW = 72192     # 2 * (12*256 + 256*128 + 128*2)
 UPDATE_FLOP_PER_ROW = 638976   # full DDPG update with target actor + critic forward on s'
 
 
-LEG_KEYS = ("roll", "upd", "fwd", "upd32", "upd_big", "cfg5", "upd_sm", "cfg4", "upd_local", "cfg4_solo")
+LEG_KEYS = ("roll", "upd", "fwd", "upd32", "upd_big", "cfg5", "upd_sm", "cfg4", "upd_local", "cfg4_solo", "cfg5_upd")
+FRAMES5, FRAMES5_BATCH = 20, 65536
+# algorithmic FLOP per row of a full DDPG update of the frame-stacked networks: SURVEY.md 8(d)'s 638,976 for 12 inputs plus
+# the wider first layers: 12 (F - 1) x 256 more MACs in each of 7 GEMMs (critic forward + dW1; actor-step actor forward,
+# critic forward, actor dW1; target actor and critic forward), 2 FLOP per MAC
+FRAMES5_UPDATE_FLOP_PER_ROW = UPDATE_FLOP_PER_ROW + 14 * 12 * (FRAMES5 - 1) * 256
 
 
 def peer_check(dev, rank, world):
@@ -436,11 +442,25 @@ def learner_legs(dev, rank, world, seed, peaks, collective, ticks=64, updates=20
 
     t["cfg5"] = timed(tick5, 32)
     envs5.check_status()
+    # ... and its learner: the DDPG update of the 240-input actor and critic (float32 kernels, separate steps) on a
+    # minibatch drawn from a ring of stacked observations that a short self-play rollout has filled
+    del envs5, actor5
+    torch.cuda.empty_cache()
+    tr5 = SelfPlayTrainer(16384, device=dev, seed=seed + 9, frames=F5, batch_size=FRAMES5_BATCH, replay_capacity=2 * 16384 * 4,
+                          gamma=0.99, tau=0.005, param_noise_sd=0.5, noise_group=1024, reward_mode="looking",
+                          tick_limit=TICK_LIMIT, precision="bf16", process_group=True if world > 1 else None, collective=collective)
+    tr5.rollout(4)
+    t["cfg5_upd"] = timed(tr5.update, 4, warm=1)
+    tr5.envs.check_status()
+    if tr5.networks.peer is not None:
+        tr5.networks.peer.check_status()
+        tr5.networks.peer.close()
+    del tr5
 
     # ---- BASELINE.json configs[3]: full self-play training, 1,048,576 envs in total sharded over the GPUs ----
     if tr.networks.peer is not None:
         tr.networks.peer.close()
-    del tr, envs5, actor5
+    del tr
     torch.cuda.empty_cache()
 
     def config4(n_envs, group, coll):
@@ -523,7 +543,19 @@ def learner_report(t, world, peaks, peak_kind, collective="nccl", t_min=None):
                         "U(0.5, 2) x the reference's, 20-frame stacked-observation actor (240 -> 256 -> 128 -> 2, tcgen05 "
                         "kernels) with parameter noise (sd 0.5, one draw per 1,024 rows) + env step + frame-stack push",
             "env_steps_per_sec": world * 65536 / (t_cfg5 * 1e-3), "samples_per_sec": world * 131072 / (t_cfg5 * 1e-3),
-            "ms_per_tick": t_cfg5},
+            "ms_per_tick": t_cfg5,
+            "train": {"workload": "DDPG update of the 20-frame networks (actor 240 -> 256 -> 128 -> 2, critic 240 -> 256 -> (+2) -> "
+                                  "128 -> 1), %d rows per GPU drawn from a ring of stacked observations: TD targets, critic step "
+                                  "(dropout 0.2), actor step, Adam + soft update; exact float32 kernels (CUDA cores), separate steps"
+                                  % FRAMES5_BATCH,
+                      "samples_per_sec": world * FRAMES5_BATCH / (t["cfg5_upd"] * 1e-3) if t.get("cfg5_upd") else None,
+                      "ms_per_update": t.get("cfg5_upd"),
+                      "algorithmic_flop_per_row": FRAMES5_UPDATE_FLOP_PER_ROW,
+                      "algorithmic_tflops": (world * FRAMES5_BATCH * FRAMES5_UPDATE_FLOP_PER_ROW / (t["cfg5_upd"] * 1e-3) / 1e12
+                                             if t.get("cfg5_upd") else None),
+                      "tensor_frac": (FRAMES5_BATCH * FRAMES5_UPDATE_FLOP_PER_ROW / (t["cfg5_upd"] * 1e-3) / 1e12 / peaks["bf16_tflops"]
+                                      if t.get("cfg5_upd") else None),
+                      "dtype": "f32 (no tensor cores on this leg: the fraction is against the bf16 tensor peak for comparison)"}},
         "actor_forward_roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                                    "frac": tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peak_kind,
                                    "kernel": "actor_fwd_tc_kernel", "rows_per_launch": rows,
@@ -757,7 +789,7 @@ def run_gpu_arm(args):
                              "fp64": {"achieved": None if fp64_inst is None else fp64_inst / launch_s,
                                       "peak": rates["fp64_warp_inst_per_sec"],
                                       "frac": None if fp64_inst is None else fp64_inst / launch_s / rates["fp64_warp_inst_per_sec"]},
-                             "peak_source": "ss_probe_rates in this run: register-only FFMA / DFMA streams (csrc/ss_probe.cu); "
+                             "peak_source": "ss_probe_rates in this run: register-only LOP3+IMAD / DFMA streams (csrc/ss_probe.cu); "
                                             "instruction counts per launch from the committed ncu capture (profiles/traffic.json)"}},
             "e2e": {"value": None if args.no_e2e else world * E * T * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": T * E * 16, "d2h_bytes_per_step": T * E * 10,

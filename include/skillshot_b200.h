@@ -340,6 +340,39 @@ int ss_actor_forward_frames_tc(const float *params, int64_t param_stride, int64_
                                int64_t head, float *act_out, int64_t n, void *workspace, int64_t workspace_bytes,
                                void *stream);
 
+/* ---- the learner of the frame-stacked networks (readme.md:18-20; no reference code, parity unpinned) ----
+ * The update of SkillshotLearner.py:386-443 (critic fit step, model_actor_fit_step) for an actor and a critic whose first
+ * Dense layer reads 12 * frames inputs: actor as above, critic [W1[12 frames][256] b1 W2[258][128] b2 W3[128][1] b3]
+ * (ss_critic_frames_params floats).  Observations are dense float32 rows [n][12 frames], oldest frame first
+ * (ss_obs_stack_ordered writes them from the history ring).  The exact float32 kernels of the 12-input entry points with
+ * a run-time input width: frames = 1 IS ss_critic_forward / ss_ddpg_targets / ss_critic_grad / ss_actor_grad, argument
+ * for argument.  Workspace: ss_learner_frames_workspace_bytes(frames) bytes hold SS_LEARNER_MAX_PARTS gradient slices
+ * (fewer bytes = fewer CTAs).  The replay ring of these transitions is ss_replay_push_frames / ss_replay_sample_frames:
+ * ss_replay_push / ss_replay_sample with observation rows of 12 * frames floats. */
+int64_t ss_critic_frames_params(int frames);
+int64_t ss_learner_frames_workspace_bytes(int frames);
+int ss_obs_stack_ordered(const float *stack, int64_t n_rows, int frames, int64_t head, float *out, void *stream);
+int ss_critic_forward_frames(const float *critic_params, int frames, const float *obs, const float *act, float *q_out,
+                             int64_t n, void *stream);
+int ss_ddpg_targets_frames(const float *target_actor_params, const float *target_critic_params, int frames,
+                           const float *reward, const float *next_obs, const uint8_t *done, float gamma, float *y_out,
+                           int64_t n, void *stream);
+int ss_critic_grad_frames(const float *critic_params, int frames, const float *obs, const float *act, const float *target,
+                          const uint8_t *dropout_keep, float dropout_rate, uint64_t seed, uint64_t counter,
+                          int64_t n, int64_t n_global, int64_t row_offset, float *grad_out, float *sse_out,
+                          void *workspace, int64_t workspace_bytes, void *stream);
+int ss_actor_grad_frames(const float *actor_params, const float *critic_params, int frames, const float *obs, int64_t n,
+                         float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, void *stream);
+int ss_replay_push_frames(float *ring_obs, float *ring_act, float *ring_reward, float *ring_next_obs, uint8_t *ring_done,
+                          int64_t capacity, int64_t write_pos, int frames, const float *obs, const float *act,
+                          const float *reward, const float *next_obs, const uint8_t *done, int done_div, int64_t n,
+                          void *stream);
+int ss_replay_sample_frames(const float *ring_obs, const float *ring_act, const float *ring_reward,
+                            const float *ring_next_obs, const uint8_t *ring_done, int64_t capacity, int64_t size, int frames,
+                            const int64_t *indices, uint64_t seed, uint64_t counter, int64_t batch,
+                            float *obs, float *act, float *reward, float *next_obs, uint8_t *done, int64_t *indices_out,
+                            void *stream);
+
 /* ---- multi-GPU: the gradient all-reduce fused with its neighbours over NVLink peer memory ----
  * One exchange allocation per rank = flags[2][world] | inbox[2][world][capacity floats], made by
  * ss_peer_alloc and shared between the processes of one node through CUDA IPC (export on the owner,
@@ -438,7 +471,7 @@ int ss_ddpg_update(const ss_ddpg_update_args *args, void *stream);
 /* Measurement aid (no reference counterpart): instruction-rate ceilings of this GPU for the roofline record of the fused
  * step kernel, which is bound by the warp schedulers and the float64 pipe rather than by HBM once K ticks are played per
  * launch.  Runs two register-only kernels, times them with CUDA events and SYNCHRONISES (the one entry point that does).
- *   out_host[0]  warp-instructions per second of an FFMA stream (the issue ceiling: SMs x 4 schedulers x clock)
+ *   out_host[0]  warp-instructions per second of an alternating LOP3 / IMAD stream (the issue ceiling: SMs x 4 schedulers x clock)
  *   out_host[1]  warp-instructions per second of a DFMA stream (the float64 pipe)
  *   out_host[2]  number of SMs;  out_host[3] reserved
  *   scratch      any device buffer of >= 8 bytes (never written in practice) */

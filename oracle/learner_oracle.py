@@ -46,6 +46,15 @@ ACTOR_PARAMS = sum(int(np.prod(s)) for s in ACTOR_SHAPES)      # 36,482
 CRITIC_PARAMS = sum(int(np.prod(s)) for s in CRITIC_SHAPES)    # 36,609
 
 
+def actor_shapes(frames=1):
+    """model_define_actor with a first Dense layer of 12 * frames inputs (readme.md:18-20; frames = 1: the reference)."""
+    return [(DIM_S * frames, H1), (H1,), (H1, H2), (H2,), (H2, DIM_A), (DIM_A,)]
+
+
+def critic_shapes(frames=1):
+    return [(DIM_S * frames, H1), (H1,), (H1 + DIM_A, H2), (H2,), (H2, 1), (1,)]
+
+
 def split(flat, shapes):
     out, o = [], 0
     for s in shapes:
@@ -55,18 +64,18 @@ def split(flat, shapes):
     return out
 
 
-def init_actor(rng: np.random.Generator) -> np.ndarray:
+def init_actor(rng: np.random.Generator, frames=1) -> np.ndarray:
     """SkillshotLearner.py:74-89: every kernel N(0, 0.05), biases zero."""
     parts = []
-    for s in ACTOR_SHAPES:
+    for s in actor_shapes(frames):
         parts.append(rng.normal(0.0, 0.05, size=s) if len(s) == 2 else np.zeros(s))
     return np.concatenate([p.ravel() for p in parts]).astype(np.float32)
 
 
-def init_critic(rng: np.random.Generator) -> np.ndarray:
+def init_critic(rng: np.random.Generator, frames=1) -> np.ndarray:
     """SkillshotLearner.py:104-114: glorot-uniform hidden kernels, N(0, 0.05) output kernel."""
     parts = []
-    for idx, s in enumerate(CRITIC_SHAPES):
+    for idx, s in enumerate(critic_shapes(frames)):
         if len(s) == 1:
             parts.append(np.zeros(s))
         elif idx == 4:
@@ -82,7 +91,7 @@ def _t(x, dtype):
 
 
 def actor_forward_t(theta: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
-    w1, b1, w2, b2, w3, b3 = split(theta, ACTOR_SHAPES)
+    w1, b1, w2, b2, w3, b3 = split(theta, actor_shapes(s.shape[1] // DIM_S))       # input width 12 * frames
     h = torch.relu(s @ w1 + b1)
     h = torch.relu(h @ w2 + b2)
     return torch.tanh(h @ w3 + b3)
@@ -91,7 +100,7 @@ def actor_forward_t(theta: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
 def critic_forward_t(phi: torch.Tensor, s: torch.Tensor, a: torch.Tensor, keep=None, rate: float = 0.2):
     """keep: None = Dropout off (model(x) call / predict); else a {0,1} mask [n,256]
     applied with the inverted scaling 1 / (1 - rate) as Keras does during fit."""
-    w1, b1, w2, b2, w3, b3 = split(phi, CRITIC_SHAPES)
+    w1, b1, w2, b2, w3, b3 = split(phi, critic_shapes(s.shape[1] // DIM_S))        # input width 12 * frames
     h = torch.relu(s @ w1 + b1)
     if keep is not None:
         h = h * keep * (1.0 / (1.0 - rate))

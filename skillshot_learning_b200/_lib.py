@@ -91,6 +91,16 @@ SIGNATURES = {
     "ss_obs_stack_tc_bytes": (_i64, [_i64, _i32]),
     "ss_obs_stack_push_tc": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _i32, _vp]),
     "ss_actor_forward_frames_tc": (_i32, [_vp, _i64, _i64, _vp, _i32, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "ss_critic_frames_params": (_i64, [_i32]),
+    "ss_learner_frames_workspace_bytes": (_i64, [_i32]),
+    "ss_obs_stack_ordered": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp]),
+    "ss_critic_forward_frames": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "ss_ddpg_targets_frames": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _vp]),
+    "ss_critic_grad_frames": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _f32, _u64, _u64, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "ss_actor_grad_frames": (_i32, [_vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "ss_replay_push_frames": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
+    "ss_replay_sample_frames": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _u64, _u64, _i64,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ss_param_noise": (_i32, [_vp, _vp, _i64, _f32, _u64, _u64, _u64, _vp]),
     "ss_critic_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "ss_ddpg_targets": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp]),

@@ -39,6 +39,23 @@ constexpr int C_W1 = 0, C_B1 = C_W1 + DS * H1, C_W2 = C_B1 + H1, C_B2 = C_W2 + (
               C_W3 = C_B2 + H2, C_B3 = C_W3 + H2, C_N = C_B3 + 1;
 static_assert(A_N == SS_ACTOR_PARAMS && C_N == SS_CRITIC_PARAMS, "parameter counts");
 
+// The same two networks with a first layer of `ds` inputs instead of 12 (the frame-stacked "planning" networks of
+// readme.md:18-20, ds = 12 * frames; ds = 12 is the reference): offsets of the six Keras arrays in the flat vectors.
+struct Lay {
+    int ds;
+    int a_b1, a_w2, a_b2, a_w3, a_b3, a_n;       // actor:  W1[ds][256] b1 W2[256][128] b2 W3[128][2] b3
+    int c_b1, c_w2, c_b2, c_w3, c_b3, c_n;       // critic: W1[ds][256] b1 W2[258][128] b2 W3[128][1] b3
+};
+__host__ __device__ inline Lay lay_of(int ds) {
+    Lay L;
+    L.ds = ds;
+    L.a_b1 = ds * H1; L.a_w2 = L.a_b1 + H1; L.a_b2 = L.a_w2 + H1 * H2; L.a_w3 = L.a_b2 + H2; L.a_b3 = L.a_w3 + H2 * DA;
+    L.a_n = L.a_b3 + DA;
+    L.c_b1 = ds * H1; L.c_w2 = L.c_b1 + H1; L.c_b2 = L.c_w2 + (H1 + DA) * H2; L.c_w3 = L.c_b2 + H2; L.c_b3 = L.c_w3 + H2;
+    L.c_n = L.c_b3 + 1;
+    return L;
+}
+
 enum { ACT_NONE = 0, ACT_RELU = 1 };
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
@@ -157,6 +174,14 @@ __device__ __forceinline__ void load_tile_T(const float *src, int64_t base, int6
     for (int e = threadIdx.x; e < TB * W; e += NT) {
         const int t = e / W, c = e - t * W;
         dstT[c * PITCH + t] = (base + t < n) ? src[(base + t) * W + c] : 0.f;
+    }
+}
+
+// the same with a run-time row width (frame-stacked inputs)
+__device__ __forceinline__ void load_tile_rt(const float *src, int64_t base, int64_t n, float *dstT, int w) {
+    for (int e = threadIdx.x; e < TB * w; e += NT) {
+        const int t = e / w, c = e - t * w;
+        dstT[c * PITCH + t] = (base + t < n) ? src[(base + t) * w + c] : 0.f;
     }
 }
 
@@ -310,6 +335,17 @@ __global__ void obs_stack_push_kernel(float *stack, int64_t n_rows, int frames, 
     }
 }
 
+// out[row][f][12] = stack[row][(head + 1 + f) % frames][12]: the network input, oldest frame first, as dense rows
+__global__ void obs_stack_ordered_kernel(const float *stack, int64_t n_rows, int frames, int64_t head, float *out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w4 = 3 * frames;
+    if (e >= w4 * n_rows) return;
+    const int64_t row = e / w4;
+    const int q = (int)(e - row * w4), f = q / 3, part = q - 3 * f;
+    const int slot = (int)((head + 1 + f) % frames);
+    reinterpret_cast<float4 *>(out)[e] = reinterpret_cast<const float4 *>(stack)[(row * frames + slot) * 3 + part];
+}
+
 __global__ void param_noise_groups_kernel(const float *theta, float *out, int64_t n_params, int64_t stride, float sd,
                                           uint64_t seed, uint64_t counter) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -353,32 +389,34 @@ struct CriticFwdArgs {
     float gamma;
     float *out;
     int64_t n;
+    int ds;                  // input width: 12 (reference) or 12 * frames
 };
 
 template <bool WITH_ACTOR>
 __global__ void __launch_bounds__(NT) critic_fwd_kernel(const CriticFwdArgs A) {
     extern __shared__ __align__(16) float smem[];
-    float *sT = smem, *x2T = sT + DS * PITCH, *c2T = x2T + (H1 + DA) * PITCH, *qv = c2T + H2 * PITCH;
+    const Lay L = lay_of(A.ds);
+    float *sT = smem, *x2T = sT + L.ds * PITCH, *c2T = x2T + (H1 + DA) * PITCH, *qv = c2T + H2 * PITCH;
     float *h1T = qv + TB, *h2T = h1T + H1 * PITCH;       // WITH_ACTOR only
     const int64_t tiles = (A.n + TB - 1) / TB;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t base = tile * TB;
         __syncthreads();
-        load_tile_T<DS>(A.obs, base, A.n, sT);
+        load_tile_rt(A.obs, base, A.n, sT, L.ds);
         if (!WITH_ACTOR) load_tile_T<DA>(A.act, base, A.n, x2T + H1 * PITCH);
         __syncthreads();
         if (WITH_ACTOR) {
-            dense_fwd<H1, ACT_RELU>(A.theta + A_W1, A.theta + A_B1, sT, DS, h1T);
+            dense_fwd<H1, ACT_RELU>(A.theta, A.theta + L.a_b1, sT, L.ds, h1T);
             __syncthreads();
-            dense_fwd<H2, ACT_RELU>(A.theta + A_W2, A.theta + A_B2, h1T, H1, h2T);
+            dense_fwd<H2, ACT_RELU>(A.theta + L.a_w2, A.theta + L.a_b2, h1T, H1, h2T);
             __syncthreads();
-            actor_out(A.theta + A_W3, A.theta + A_B3, h2T, x2T + H1 * PITCH);
+            actor_out(A.theta + L.a_w3, A.theta + L.a_b3, h2T, x2T + H1 * PITCH);
         }
-        dense_fwd<H1, ACT_RELU>(A.phi + C_W1, A.phi + C_B1, sT, DS, x2T);
+        dense_fwd<H1, ACT_RELU>(A.phi, A.phi + L.c_b1, sT, L.ds, x2T);
         __syncthreads();
-        dense_fwd<H2, ACT_RELU>(A.phi + C_W2, A.phi + C_B2, x2T, H1 + DA, c2T);
+        dense_fwd<H2, ACT_RELU>(A.phi + L.c_w2, A.phi + L.c_b2, x2T, H1 + DA, c2T);
         __syncthreads();
-        critic_out(A.phi + C_W3, A.phi + C_B3, c2T, qv);
+        critic_out(A.phi + L.c_w3, A.phi + L.c_b3, c2T, qv);
         __syncthreads();
         if (threadIdx.x < TB && base + threadIdx.x < A.n) {
             const int64_t row = base + threadIdx.x;
@@ -398,12 +436,15 @@ struct CriticGradArgs {
     float rate;              // dropout rate (0 = off)
     uint64_t seed, counter;
     int64_t n, n_global, row_offset;   // row_offset: global index of row 0 (Philox dropout of a shard)
-    float *work;             // [gridDim.x][C_N + 1]
+    float *work;             // [gridDim.x][c_n + 1]
+    int ds;                  // input width: 12 (reference) or 12 * frames
 };
 
 __global__ void __launch_bounds__(NT) critic_grad_kernel(const CriticGradArgs A) {
     extern __shared__ __align__(16) float smem[];
-    float *sT = smem, *x2T = sT + DS * PITCH, *h2T = x2T + (H1 + DA) * PITCH, *qv = h2T + H2 * PITCH, *dq = qv + TB;
+    const Lay L = lay_of(A.ds);
+    const int C_B1 = L.c_b1, C_W2 = L.c_w2, C_B2 = L.c_b2, C_W3 = L.c_w3, C_B3 = L.c_b3, C_N = L.c_n, C_W1 = 0;
+    float *sT = smem, *x2T = sT + L.ds * PITCH, *h2T = x2T + (H1 + DA) * PITCH, *qv = h2T + H2 * PITCH, *dq = qv + TB;
     float *g = A.work + (int64_t)blockIdx.x * (C_N + 1);
     const float inv_keep = A.rate > 0.f ? 1.0f / (1.0f - A.rate) : 1.0f;
     const int64_t tiles = (A.n + TB - 1) / TB;
@@ -412,10 +453,10 @@ __global__ void __launch_bounds__(NT) critic_grad_kernel(const CriticGradArgs A)
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
         const int64_t base = tile * TB;
         __syncthreads();
-        load_tile_T<DS>(A.obs, base, A.n, sT);
+        load_tile_rt(A.obs, base, A.n, sT, L.ds);
         load_tile_T<DA>(A.act, base, A.n, x2T + H1 * PITCH);
         __syncthreads();
-        dense_fwd<H1, ACT_RELU>(A.phi + C_W1, A.phi + C_B1, sT, DS, x2T);
+        dense_fwd<H1, ACT_RELU>(A.phi + C_W1, A.phi + C_B1, sT, L.ds, x2T);
         if (A.rate > 0.f) {                                 // Dropout(0.2), training=True: h * keep / (1 - rate)
             const int j = threadIdx.x;                      // this thread wrote row j
             float *row = x2T + j * PITCH;
@@ -475,7 +516,7 @@ __global__ void __launch_bounds__(NT) critic_grad_kernel(const CriticGradArgs A)
         __syncthreads();
         dense_bwd_input(A.phi + C_W2, h2T, x2T, inv_keep);
         __syncthreads();
-        dense_bwd_weight<H1>(sT, DS, x2T, g + C_W1, g + C_B1, first);
+        dense_bwd_weight<H1>(sT, L.ds, x2T, g + C_W1, g + C_B1, first);
     }
     // sum of squared errors of this CTA's tiles (threads 0..31 hold the partial sums)
     if (threadIdx.x < 32) {
@@ -493,12 +534,16 @@ __global__ void __launch_bounds__(NT) critic_grad_kernel(const CriticGradArgs A)
 struct ActorGradArgs {
     const float *theta, *phi, *obs;
     int64_t n;
-    float *work;             // [gridDim.x][A_N + 1]
+    float *work;             // [gridDim.x][a_n + 1]
+    int ds;                  // input width: 12 (reference) or 12 * frames
 };
 
 __global__ void __launch_bounds__(NT) actor_grad_kernel(const ActorGradArgs A) {
     extern __shared__ __align__(16) float smem[];
-    float *sT = smem, *h1T = sT + DS * PITCH, *h2T = h1T + H1 * PITCH, *aT = h2T + H2 * PITCH;
+    const Lay L = lay_of(A.ds);
+    const int A_W1 = 0, A_B1 = L.a_b1, A_W2 = L.a_w2, A_B2 = L.a_b2, A_W3 = L.a_w3, A_B3 = L.a_b3, A_N = L.a_n;
+    const int C_W1 = 0, C_B1 = L.c_b1, C_W2 = L.c_w2, C_B2 = L.c_b2, C_W3 = L.c_w3, C_B3 = L.c_b3;
+    float *sT = smem, *h1T = sT + L.ds * PITCH, *h2T = h1T + H1 * PITCH, *aT = h2T + H2 * PITCH;
     float *x2T = aT + DA * PITCH, *c2T = x2T + (H1 + DA) * PITCH, *dz3T = c2T + H2 * PITCH, *qv = dz3T + DA * PITCH;
     float *g = A.work + (int64_t)blockIdx.x * (A_N + 1);
     const int64_t tiles = (A.n + TB - 1) / TB;
@@ -507,12 +552,12 @@ __global__ void __launch_bounds__(NT) actor_grad_kernel(const ActorGradArgs A) {
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
         const int64_t base = tile * TB;
         __syncthreads();
-        load_tile_T<DS>(A.obs, base, A.n, sT);
+        load_tile_rt(A.obs, base, A.n, sT, L.ds);
         __syncthreads();
         // a = actor(s)
-        dense_fwd<H1, ACT_RELU>(A.theta + A_W1, A.theta + A_B1, sT, DS, h1T);
+        dense_fwd<H1, ACT_RELU>(A.theta + A_W1, A.theta + A_B1, sT, L.ds, h1T);
         // critic's first layer depends on s only (model called directly: Dropout off)
-        dense_fwd<H1, ACT_RELU>(A.phi + C_W1, A.phi + C_B1, sT, DS, x2T);
+        dense_fwd<H1, ACT_RELU>(A.phi + C_W1, A.phi + C_B1, sT, L.ds, x2T);
         __syncthreads();
         dense_fwd<H2, ACT_RELU>(A.theta + A_W2, A.theta + A_B2, h1T, H1, h2T);
         __syncthreads();
@@ -567,7 +612,7 @@ __global__ void __launch_bounds__(NT) actor_grad_kernel(const ActorGradArgs A) {
         __syncthreads();
         dense_bwd_input(A.theta + A_W2, c2T, h1T, 1.0f);
         __syncthreads();
-        dense_bwd_weight<H1>(sT, DS, h1T, g + A_W1, g + A_B1, first);
+        dense_bwd_weight<H1>(sT, L.ds, h1T, g + A_W1, g + A_B1, first);
     }
     if (threadIdx.x < 32) {
         for (int o = 16; o > 0; o >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
@@ -654,14 +699,15 @@ struct Ring {
     int64_t capacity;
 };
 
+// w4 = float4 per observation row: 3 (12 floats, the reference) or 3 * frames
 __global__ void replay_push_kernel(Ring R, int64_t pos, const float *s, const float *a, const float *r,
-                                   const float *s2, const uint8_t *done, int done_div, int64_t n) {
+                                   const float *s2, const uint8_t *done, int done_div, int64_t n, int w4) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 3 * n) return;
-    const int64_t row = e / 3, part = e - row * 3;
+    if (e >= w4 * n) return;
+    const int64_t row = e / w4, part = e - row * w4;
     const int64_t dst = (pos + row) % R.capacity;
-    reinterpret_cast<float4 *>(R.s)[dst * 3 + part] = reinterpret_cast<const float4 *>(s)[e];
-    reinterpret_cast<float4 *>(R.s2)[dst * 3 + part] = reinterpret_cast<const float4 *>(s2)[e];
+    reinterpret_cast<float4 *>(R.s)[dst * w4 + part] = reinterpret_cast<const float4 *>(s)[e];
+    if (s2) reinterpret_cast<float4 *>(R.s2)[dst * w4 + part] = reinterpret_cast<const float4 *>(s2)[e];
     if (part == 0) {
         reinterpret_cast<float2 *>(R.a)[dst] = reinterpret_cast<const float2 *>(a)[row];
         R.r[dst] = r[row];
@@ -671,10 +717,10 @@ __global__ void replay_push_kernel(Ring R, int64_t pos, const float *s, const fl
 
 __global__ void replay_sample_kernel(Ring R, int64_t size, const int64_t *indices, uint64_t seed, uint64_t counter,
                                      int64_t batch, float *s, float *a, float *r, float *s2, uint8_t *done,
-                                     int64_t *indices_out) {
+                                     int64_t *indices_out, int w4) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 3 * batch) return;
-    const int64_t b = e / 3, part = e - b * 3;
+    if (e >= w4 * batch) return;
+    const int64_t b = e / w4, part = e - b * w4;
     int64_t src;
     if (indices) {
         src = indices[b];
@@ -683,8 +729,8 @@ __global__ void replay_sample_kernel(Ring R, int64_t size, const int64_t *indice
         const uint32_t x = (b & 3) == 0 ? u.x : (b & 3) == 1 ? u.y : (b & 3) == 2 ? u.z : u.w;
         src = (int64_t)(((uint64_t)x * (uint64_t)size) >> 32);      // size < 2^32 rows
     }
-    reinterpret_cast<float4 *>(s)[e] = reinterpret_cast<const float4 *>(R.s)[src * 3 + part];
-    reinterpret_cast<float4 *>(s2)[e] = reinterpret_cast<const float4 *>(R.s2)[src * 3 + part];
+    reinterpret_cast<float4 *>(s)[e] = reinterpret_cast<const float4 *>(R.s)[src * w4 + part];
+    reinterpret_cast<float4 *>(s2)[e] = reinterpret_cast<const float4 *>(R.s2)[src * w4 + part];
     if (part == 0) {
         reinterpret_cast<float2 *>(a)[b] = reinterpret_cast<const float2 *>(R.a)[src];
         r[b] = R.r[src];
@@ -698,10 +744,10 @@ __global__ void replay_sample_kernel(Ring R, int64_t size, const int64_t *indice
 // ---------------------------------------------------------------------------
 constexpr size_t kSmemActorFwd = (size_t)(DS + H1 + H2 + DA) * PITCH * 4;
 constexpr size_t kSmemActorFwdNoisy = kSmemActorFwd + (size_t)((A_N + 3) / 4 * 4) * 4;
-constexpr size_t kSmemCriticFwd = (size_t)(DS + H1 + DA + H2) * PITCH * 4 + TB * 4;
-constexpr size_t kSmemCriticFwdActor = kSmemCriticFwd + (size_t)(H1 + H2) * PITCH * 4;
-constexpr size_t kSmemCriticGrad = (size_t)(DS + H1 + DA + H2) * PITCH * 4 + 2 * TB * 4;
-constexpr size_t kSmemActorGrad = (size_t)(DS + H1 + H2 + DA + H1 + DA + H2 + DA) * PITCH * 4 + TB * 4;
+inline size_t smem_critic_fwd(int ds) { return (size_t)(ds + H1 + DA + H2) * PITCH * 4 + TB * 4; }
+inline size_t smem_critic_fwd_actor(int ds) { return smem_critic_fwd(ds) + (size_t)(H1 + H2) * PITCH * 4; }
+inline size_t smem_critic_grad(int ds) { return (size_t)(ds + H1 + DA + H2) * PITCH * 4 + 2 * TB * 4; }
+inline size_t smem_actor_grad(int ds) { return (size_t)(ds + H1 + H2 + DA + H1 + DA + H2 + DA) * PITCH * 4 + TB * 4; }
 
 inline int check_launch() { return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA; }
 
@@ -764,63 +810,104 @@ int ss_param_noise(const float *params, float *out, int64_t n_params, float sd, 
     return check_launch();
 }
 
+// ---- critic forward / TD target / gradients with a first layer of 12 * frames inputs (frames = 1: the reference) ----
+int64_t ss_critic_frames_params(int frames) { return frames < 1 || frames > SS_MAX_FRAMES ? -1 : (int64_t)lay_of(DS * frames).c_n; }
+
+int64_t ss_learner_frames_workspace_bytes(int frames) {
+    if (frames < 1 || frames > SS_MAX_FRAMES) return -1;
+    const Lay L = lay_of(DS * frames);
+    return (int64_t)SS_LEARNER_MAX_PARTS * ((L.c_n > L.a_n ? L.c_n : L.a_n) + 1) * sizeof(float);
+}
+
+int ss_critic_forward_frames(const float *critic_params, int frames, const float *obs, const float *act, float *q_out,
+                             int64_t n, void *stream) {
+    if (!critic_params || !obs || !act || !q_out || n <= 0 || frames < 1 || frames > SS_MAX_FRAMES) return SS_ERR_INVALID_ARG;
+    const int ds = DS * frames;
+    CriticFwdArgs A{nullptr, critic_params, obs, act, nullptr, nullptr, 0.f, q_out, n, ds};
+    const int grid = grid_for(critic_fwd_kernel<false>, smem_critic_fwd(ds), (n + TB - 1) / TB, 0);
+    if (grid < 0) return SS_ERR_CUDA;
+    critic_fwd_kernel<false><<<grid, NT, smem_critic_fwd(ds), (cudaStream_t)stream>>>(A);
+    return check_launch();
+}
+
+int ss_ddpg_targets_frames(const float *target_actor_params, const float *target_critic_params, int frames,
+                           const float *reward, const float *next_obs, const uint8_t *done, float gamma, float *y_out,
+                           int64_t n, void *stream) {
+    if (!target_actor_params || !target_critic_params || !reward || !next_obs || !y_out || n <= 0 || frames < 1 ||
+        frames > SS_MAX_FRAMES)
+        return SS_ERR_INVALID_ARG;
+    const int ds = DS * frames;
+    CriticFwdArgs A{target_actor_params, target_critic_params, next_obs, nullptr, reward, done, gamma, y_out, n, ds};
+    const int grid = grid_for(critic_fwd_kernel<true>, smem_critic_fwd_actor(ds), (n + TB - 1) / TB, 0);
+    if (grid < 0) return SS_ERR_CUDA;
+    critic_fwd_kernel<true><<<grid, NT, smem_critic_fwd_actor(ds), (cudaStream_t)stream>>>(A);
+    return check_launch();
+}
+
+int ss_critic_grad_frames(const float *critic_params, int frames, const float *obs, const float *act, const float *target,
+                          const uint8_t *dropout_keep, float dropout_rate, uint64_t seed, uint64_t counter,
+                          int64_t n, int64_t n_global, int64_t row_offset, float *grad_out, float *sse_out,
+                          void *workspace, int64_t workspace_bytes, void *stream) {
+    if (!critic_params || !obs || !act || !target || !workspace || n <= 0 || frames < 1 || frames > SS_MAX_FRAMES)
+        return SS_ERR_INVALID_ARG;
+    if (dropout_rate < 0.f || dropout_rate >= 1.f) return SS_ERR_INVALID_ARG;
+    if ((uintptr_t)critic_params & 15) return SS_ERR_INVALID_ARG;
+    const Lay L = lay_of(DS * frames);
+    const int cap = (int)(workspace_bytes / ((int64_t)(L.c_n + 1) * 4));
+    if (cap < 1) return SS_ERR_INVALID_ARG;
+    const int grid = grid_for(critic_grad_kernel, smem_critic_grad(L.ds), (n + TB - 1) / TB,
+                              cap < SS_LEARNER_MAX_PARTS ? cap : SS_LEARNER_MAX_PARTS);
+    if (grid < 0) return SS_ERR_CUDA;
+    CriticGradArgs A{critic_params, obs, act, target, dropout_keep, dropout_rate, seed, counter,
+                     n, n_global > 0 ? n_global : n, row_offset, (float *)workspace, L.ds};
+    cudaStream_t st = (cudaStream_t)stream;
+    critic_grad_kernel<<<grid, NT, smem_critic_grad(L.ds), st>>>(A);
+    if (!grad_out) return check_launch() == SS_OK ? grid : SS_ERR_CUDA;      // slices only (ss_peer_reduce_push follows)
+    reduce_kernel<<<(L.c_n + 1 + 63) / 64, dim3(64, 4), 0, st>>>((const float *)workspace, grid, L.c_n, grad_out, sse_out);
+    return check_launch();
+}
+
+int ss_actor_grad_frames(const float *actor_params, const float *critic_params, int frames, const float *obs, int64_t n,
+                         float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, void *stream) {
+    if (!actor_params || !critic_params || !obs || !workspace || n <= 0 || frames < 1 || frames > SS_MAX_FRAMES)
+        return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)actor_params | (uintptr_t)critic_params) & 15) return SS_ERR_INVALID_ARG;
+    const Lay L = lay_of(DS * frames);
+    const int cap = (int)(workspace_bytes / ((int64_t)(L.a_n + 1) * 4));
+    if (cap < 1) return SS_ERR_INVALID_ARG;
+    const int grid = grid_for(actor_grad_kernel, smem_actor_grad(L.ds), (n + TB - 1) / TB,
+                              cap < SS_LEARNER_MAX_PARTS ? cap : SS_LEARNER_MAX_PARTS);
+    if (grid < 0) return SS_ERR_CUDA;
+    ActorGradArgs A{actor_params, critic_params, obs, n, (float *)workspace, L.ds};
+    cudaStream_t st = (cudaStream_t)stream;
+    actor_grad_kernel<<<grid, NT, smem_actor_grad(L.ds), st>>>(A);
+    if (!grad_out) return check_launch() == SS_OK ? grid : SS_ERR_CUDA;
+    reduce_kernel<<<(L.a_n + 1 + 63) / 64, dim3(64, 4), 0, st>>>((const float *)workspace, grid, L.a_n, grad_out, q_sum_out);
+    return check_launch();
+}
+
+// the reference's own width: 12 inputs
 int ss_critic_forward(const float *critic_params, const float *obs, const float *act, float *q_out, int64_t n,
                       void *stream) {
-    if (!critic_params || !obs || !act || !q_out || n <= 0) return SS_ERR_INVALID_ARG;
-    CriticFwdArgs A{nullptr, critic_params, obs, act, nullptr, nullptr, 0.f, q_out, n};
-    const int grid = grid_for(critic_fwd_kernel<false>, kSmemCriticFwd, (n + TB - 1) / TB, 0);
-    if (grid < 0) return SS_ERR_CUDA;
-    critic_fwd_kernel<false><<<grid, NT, kSmemCriticFwd, (cudaStream_t)stream>>>(A);
-    return check_launch();
+    return ss_critic_forward_frames(critic_params, 1, obs, act, q_out, n, stream);
 }
 
 int ss_ddpg_targets(const float *target_actor_params, const float *target_critic_params, const float *reward,
                     const float *next_obs, const uint8_t *done, float gamma, float *y_out, int64_t n, void *stream) {
-    if (!target_actor_params || !target_critic_params || !reward || !next_obs || !y_out || n <= 0)
-        return SS_ERR_INVALID_ARG;
-    CriticFwdArgs A{target_actor_params, target_critic_params, next_obs, nullptr, reward, done, gamma, y_out, n};
-    const int grid = grid_for(critic_fwd_kernel<true>, kSmemCriticFwdActor, (n + TB - 1) / TB, 0);
-    if (grid < 0) return SS_ERR_CUDA;
-    critic_fwd_kernel<true><<<grid, NT, kSmemCriticFwdActor, (cudaStream_t)stream>>>(A);
-    return check_launch();
+    return ss_ddpg_targets_frames(target_actor_params, target_critic_params, 1, reward, next_obs, done, gamma, y_out, n, stream);
 }
 
 int ss_critic_grad(const float *critic_params, const float *obs, const float *act, const float *target,
                    const uint8_t *dropout_keep, float dropout_rate, uint64_t seed, uint64_t counter,
                    int64_t n, int64_t n_global, int64_t row_offset, float *grad_out, float *sse_out,
                    void *workspace, int64_t workspace_bytes, void *stream) {
-    if (!critic_params || !obs || !act || !target || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
-    if (dropout_rate < 0.f || dropout_rate >= 1.f) return SS_ERR_INVALID_ARG;
-    if ((uintptr_t)critic_params & 15) return SS_ERR_INVALID_ARG;
-    const int cap = (int)(workspace_bytes / ((int64_t)(C_N + 1) * 4));
-    if (cap < 1) return SS_ERR_INVALID_ARG;
-    const int grid = grid_for(critic_grad_kernel, kSmemCriticGrad, (n + TB - 1) / TB,
-                              cap < SS_LEARNER_MAX_PARTS ? cap : SS_LEARNER_MAX_PARTS);
-    if (grid < 0) return SS_ERR_CUDA;
-    CriticGradArgs A{critic_params, obs, act, target, dropout_keep, dropout_rate, seed, counter,
-                     n, n_global > 0 ? n_global : n, row_offset, (float *)workspace};
-    cudaStream_t st = (cudaStream_t)stream;
-    critic_grad_kernel<<<grid, NT, kSmemCriticGrad, st>>>(A);
-    if (!grad_out) return check_launch() == SS_OK ? grid : SS_ERR_CUDA;      // slices only (ss_peer_reduce_push follows)
-    reduce_kernel<<<(C_N + 1 + 63) / 64, dim3(64, 4), 0, st>>>((const float *)workspace, grid, C_N, grad_out, sse_out);
-    return check_launch();
+    return ss_critic_grad_frames(critic_params, 1, obs, act, target, dropout_keep, dropout_rate, seed, counter, n, n_global,
+                                 row_offset, grad_out, sse_out, workspace, workspace_bytes, stream);
 }
 
 int ss_actor_grad(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
                   float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, void *stream) {
-    if (!actor_params || !critic_params || !obs || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
-    if (((uintptr_t)actor_params | (uintptr_t)critic_params) & 15) return SS_ERR_INVALID_ARG;
-    const int cap = (int)(workspace_bytes / ((int64_t)(A_N + 1) * 4));
-    if (cap < 1) return SS_ERR_INVALID_ARG;
-    const int grid = grid_for(actor_grad_kernel, kSmemActorGrad, (n + TB - 1) / TB,
-                              cap < SS_LEARNER_MAX_PARTS ? cap : SS_LEARNER_MAX_PARTS);
-    if (grid < 0) return SS_ERR_CUDA;
-    ActorGradArgs A{actor_params, critic_params, obs, n, (float *)workspace};
-    cudaStream_t st = (cudaStream_t)stream;
-    actor_grad_kernel<<<grid, NT, kSmemActorGrad, st>>>(A);
-    if (!grad_out) return check_launch() == SS_OK ? grid : SS_ERR_CUDA;
-    reduce_kernel<<<(A_N + 1 + 63) / 64, dim3(64, 4), 0, st>>>((const float *)workspace, grid, A_N, grad_out, q_sum_out);
-    return check_launch();
+    return ss_actor_grad_frames(actor_params, critic_params, 1, obs, n, grad_out, q_sum_out, workspace, workspace_bytes, stream);
 }
 
 int ss_adam_tf(float *params, const float *grads, float *m, float *v, float *target_params, int64_t n,
@@ -846,19 +933,47 @@ int ss_reduce_adam_tf(const void *workspace, int parts, int n_params, float *aux
     return check_launch();
 }
 
-int ss_replay_push(float *ring_obs, float *ring_act, float *ring_reward, float *ring_next_obs, uint8_t *ring_done,
-                   int64_t capacity, int64_t write_pos, const float *obs, const float *act, const float *reward,
-                   const float *next_obs, const uint8_t *done, int done_div, int64_t n, void *stream) {
+int ss_replay_push_frames(float *ring_obs, float *ring_act, float *ring_reward, float *ring_next_obs, uint8_t *ring_done,
+                          int64_t capacity, int64_t write_pos, int frames, const float *obs, const float *act,
+                          const float *reward, const float *next_obs, const uint8_t *done, int done_div, int64_t n,
+                          void *stream) {
     if (!ring_obs || !ring_act || !ring_reward || !ring_next_obs || !ring_done || !obs || !act || !reward || !next_obs)
         return SS_ERR_INVALID_ARG;
-    if (capacity <= 0 || n <= 0 || n > capacity || write_pos < 0 || write_pos >= capacity || done_div < 1)
+    if (capacity <= 0 || n <= 0 || n > capacity || write_pos < 0 || write_pos >= capacity || done_div < 1 || frames < 1 ||
+        frames > SS_MAX_FRAMES)
         return SS_ERR_INVALID_ARG;
     if (((uintptr_t)ring_obs | (uintptr_t)ring_next_obs | (uintptr_t)obs | (uintptr_t)next_obs) & 15)
         return SS_ERR_INVALID_ARG;
     Ring R{ring_obs, ring_act, ring_reward, ring_next_obs, ring_done, capacity};
-    replay_push_kernel<<<(unsigned)((3 * n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(R, write_pos, obs, act, reward,
-                                                                                         next_obs, done, done_div, n);
+    const int w4 = 3 * frames;
+    replay_push_kernel<<<(unsigned)((w4 * n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(R, write_pos, obs, act, reward,
+                                                                                          next_obs, done, done_div, n, w4);
     return check_launch();
+}
+
+int ss_replay_sample_frames(const float *ring_obs, const float *ring_act, const float *ring_reward,
+                            const float *ring_next_obs, const uint8_t *ring_done, int64_t capacity, int64_t size, int frames,
+                            const int64_t *indices, uint64_t seed, uint64_t counter, int64_t batch,
+                            float *obs, float *act, float *reward, float *next_obs, uint8_t *done, int64_t *indices_out,
+                            void *stream) {
+    if (!ring_obs || !ring_act || !ring_reward || !ring_next_obs || !ring_done || !obs || !act || !reward ||
+        !next_obs || !done)
+        return SS_ERR_INVALID_ARG;
+    if (capacity <= 0 || size <= 0 || size > capacity || batch <= 0 || frames < 1 || frames > SS_MAX_FRAMES)
+        return SS_ERR_INVALID_ARG;
+    Ring R{(float *)ring_obs, (float *)ring_act, (float *)ring_reward, (float *)ring_next_obs, (uint8_t *)ring_done,
+           capacity};
+    const int w4 = 3 * frames;
+    replay_sample_kernel<<<(unsigned)((w4 * batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        R, size, indices, seed, counter, batch, obs, act, reward, next_obs, done, indices_out, w4);
+    return check_launch();
+}
+
+int ss_replay_push(float *ring_obs, float *ring_act, float *ring_reward, float *ring_next_obs, uint8_t *ring_done,
+                   int64_t capacity, int64_t write_pos, const float *obs, const float *act, const float *reward,
+                   const float *next_obs, const uint8_t *done, int done_div, int64_t n, void *stream) {
+    return ss_replay_push_frames(ring_obs, ring_act, ring_reward, ring_next_obs, ring_done, capacity, write_pos, 1, obs, act,
+                                 reward, next_obs, done, done_div, n, stream);
 }
 
 int ss_replay_sample(const float *ring_obs, const float *ring_act, const float *ring_reward,
@@ -866,15 +981,8 @@ int ss_replay_sample(const float *ring_obs, const float *ring_act, const float *
                      const int64_t *indices, uint64_t seed, uint64_t counter, int64_t batch,
                      float *obs, float *act, float *reward, float *next_obs, uint8_t *done, int64_t *indices_out,
                      void *stream) {
-    if (!ring_obs || !ring_act || !ring_reward || !ring_next_obs || !ring_done || !obs || !act || !reward ||
-        !next_obs || !done)
-        return SS_ERR_INVALID_ARG;
-    if (capacity <= 0 || size <= 0 || size > capacity || batch <= 0) return SS_ERR_INVALID_ARG;
-    Ring R{(float *)ring_obs, (float *)ring_act, (float *)ring_reward, (float *)ring_next_obs, (uint8_t *)ring_done,
-           capacity};
-    replay_sample_kernel<<<(unsigned)((3 * batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        R, size, indices, seed, counter, batch, obs, act, reward, next_obs, done, indices_out);
-    return check_launch();
+    return ss_replay_sample_frames(ring_obs, ring_act, ring_reward, ring_next_obs, ring_done, capacity, size, 1, indices, seed,
+                                   counter, batch, obs, act, reward, next_obs, done, indices_out, stream);
 }
 
 int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_params, float *obs_a, float *obs_b,
@@ -962,6 +1070,14 @@ int ss_obs_stack_push(float *stack, int64_t n_rows, int frames, int64_t head, co
     if (((uintptr_t)stack | (uintptr_t)obs) & 15) return SS_ERR_INVALID_ARG;
     obs_stack_push_kernel<<<(unsigned)((3 * n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(stack, n_rows, frames, head, obs,
                                                                                                  done, done_div);
+    return check_launch();
+}
+
+int ss_obs_stack_ordered(const float *stack, int64_t n_rows, int frames, int64_t head, float *out, void *stream) {
+    if (!stack || !out || n_rows <= 0 || frames < 1 || frames > SS_MAX_FRAMES || head < 0) return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)stack | (uintptr_t)out) & 15) return SS_ERR_INVALID_ARG;
+    obs_stack_ordered_kernel<<<(unsigned)((3 * frames * n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(stack, n_rows, frames,
+                                                                                                          head, out);
     return check_launch();
 }
 

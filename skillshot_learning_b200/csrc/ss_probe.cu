@@ -2,8 +2,10 @@
 // fused step kernel.  That kernel plays K ticks per launch out of registers: its DRAM traffic is ~1/8 of the algorithmic
 // bytes and it is bound by the warp schedulers' issue rate and the float64 pipe (ncu: profiles/), so bench.py reports
 // it against these two measured ceilings next to the HBM figure.  Two register-only kernels, no memory traffic:
-//   issue  8 independent FFMA chains per thread, 16 warps per SM sub-partition: the scheduler issues one warp-instruction
-//          per cycle, so the rate is SMs x 4 x clock
+//   issue  8 independent integer chains per thread, alternating between the ALU pipe (LOP3) and the FMA pipe (IMAD), 16
+//          warps per SM sub-partition.  Each of those pipes alone takes one warp-instruction every 2 cycles
+//          (tools/op_probe.cu); fed in alternate cycles they reach the scheduler's one warp-instruction per cycle, so the
+//          rate is SMs x 4 x clock (measured 0.94-0.99 of it)
 //   fp64   8 independent DFMA chains per thread: the rate of the float64 pipe
 // Unlike every other entry point this one synchronises (it times its own launches with CUDA events) and returns HOST
 // numbers; it is a measurement aid, not part of the game / learner path.
@@ -17,21 +19,24 @@ namespace {
 constexpr int kChains = 8;
 constexpr int kInner = 64;          // unrolled instructions per chain per loop trip
 
-__global__ void __launch_bounds__(512) ffma_stream_kernel(float *sink, int trips, float a, float b) {
-    float x[kChains];
+__global__ void __launch_bounds__(512) issue_stream_kernel(int *sink, int trips, int a, int b) {
+    int x[kChains];
 #pragma unroll
-    for (int c = 0; c < kChains; ++c) x[c] = (float)(threadIdx.x + c);
+    for (int c = 0; c < kChains; ++c) x[c] = (int)threadIdx.x + c;
     for (int t = 0; t < trips; ++t) {
 #pragma unroll
         for (int i = 0; i < kInner; ++i) {
 #pragma unroll
-            for (int c = 0; c < kChains; ++c) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[c]) : "f"(a), "f"(b));
+            for (int c = 0; c < kChains; c += 2) {
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));          // ALU pipe
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x[c + 1]) : "r"(a), "r"(b));         // FMA pipe
+            }
         }
     }
-    float s = 0.f;
+    int s = 0;
 #pragma unroll
     for (int c = 0; c < kChains; ++c) s += x[c];
-    if (s == 12345.678f) sink[0] = s;        // never true: keeps the chains alive
+    if (s == 0x12345678 && trips < 0) sink[0] = s;        // never true: keeps the chains alive
 }
 
 __global__ void __launch_bounds__(512) dfma_stream_kernel(double *sink, int trips, double a, double b) {
@@ -84,10 +89,10 @@ extern "C" int ss_probe_rates(double *out_host, void *scratch, void *stream) {
     const int grid = sms * 4, block = 512;     // 2,048 threads = 64 warps per SM: 16 per sub-partition
     const double warps = (double)grid * (block / 32);
     const int trips_f = 64, trips_d = 16;
-    const double ms_f = time_ms([&] { ffma_stream_kernel<<<grid, block, 0, st>>>((float *)scratch, trips_f, 0.999f, 1e-3f); }, st);
+    const double ms_f = time_ms([&] { issue_stream_kernel<<<grid, block, 0, st>>>((int *)scratch, trips_f, 0x5bd1e995, 12345); }, st);
     const double ms_d = time_ms([&] { dfma_stream_kernel<<<grid, block, 0, st>>>((double *)scratch, trips_d, 0.999, 1e-3); }, st);
     if (cudaGetLastError() != cudaSuccess) return SS_ERR_CUDA;
-    out_host[0] = warps * trips_f * kInner * kChains / (ms_f * 1e-3);     // warp-instructions per second, FFMA stream
+    out_host[0] = warps * trips_f * kInner * kChains / (ms_f * 1e-3);     // warp-instructions per second, LOP3 / IMAD stream
     out_host[1] = warps * trips_d * kInner * kChains / (ms_d * 1e-3);     // warp-instructions per second, DFMA stream
     out_host[2] = (double)sms;
     out_host[3] = 0.0;

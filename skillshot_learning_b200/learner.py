@@ -86,7 +86,7 @@ class PeerExchange:
     rank's Adam kernel sums its inbox in rank order.  Replaces the NCCL all-reduce call between the
     gradient kernel and Adam (one node, up to 8 ranks)."""
 
-    def __init__(self, group, device, capacity: int = max(A_N, C_N)):
+    def __init__(self, group, device, capacity: int = max(A_N, C_N)):      # (ActorCritic passes its own sizes)
         import torch.distributed as dist
         g = None if group is True else group
         self.group, self.device, self.capacity = g, torch.device(device), int(capacity)
@@ -155,9 +155,20 @@ class ActorCritic:
 
     def __init__(self, device="cuda", seed: int = 0, lr_actor: float = 1e-3, lr_critic: float = 1e-3,
                  gamma: float = 0.0, tau: float = 1.0, dropout: float = 0.2, process_group=None,
-                 update_precision: str = "f32", collective: str = "nccl"):
+                 update_precision: str = "f32", collective: str = "nccl", frames: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("skillshot_learning_b200 needs a CUDA device (no CPU fallback)")
+        # frames > 1: the frame-stacked "planning" networks of readme.md:18-20 (no reference code): both first layers read
+        # 12 * frames inputs, oldest frame first.  frames = 1 is the reference.  Their update runs on the exact float32
+        # kernels (ss_*_frames); the tensor-core gradient kernels are built for the reference's 12 inputs.
+        self.frames = int(frames)
+        self.a_n, self.c_n = int(lib.ss_actor_frames_params(self.frames)), int(lib.ss_critic_frames_params(self.frames))
+        if self.a_n < 0 or self.c_n < 0:
+            raise ValueError("frames must be 1..20")
+        if self.frames > 1 and update_precision != "f32":
+            raise ValueError("the frame-stacked networks are updated by the float32 kernels: update_precision='f32'")
+        self.actor_shapes = [(12 * self.frames, 256)] + ACTOR_SHAPES[1:]
+        self.critic_shapes = [(12 * self.frames, 256)] + CRITIC_SHAPES[1:]
         self.device = torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -172,8 +183,10 @@ class ActorCritic:
         if collective not in ("nccl", "peer"):
             raise ValueError("collective must be 'nccl' (torch.distributed all-reduce) or 'peer' (fused NVLink exchange)")
         # the exchange step of a sharded update: an all-reduce call, or the fused peer-memory kernels
-        self.peer = PeerExchange(process_group, self.device) if (process_group is not None and collective == "peer") else None
+        self.peer = (PeerExchange(process_group, self.device, capacity=max(self.a_n, self.c_n))
+                     if (process_group is not None and collective == "peer") else None)
         dev = self.device
+        A_N, C_N = self.a_n, self.c_n
         # one allocation: [actor | pad | critic] so both vectors are 16-byte aligned
         self._a_off, self._c_off = 0, (A_N + 3) // 4 * 4
         total = self._c_off + C_N
@@ -183,7 +196,9 @@ class ActorCritic:
         self.adam_v = torch.zeros(total, dtype=torch.float32, device=dev)
         self.target = torch.zeros(total, dtype=torch.float32, device=dev)
         self.stats = torch.zeros(2, dtype=torch.float32, device=dev)        # [sum sq err, sum q] of the last steps
-        self._ws_base = int(lib.ss_learner_workspace_bytes())
+        # gradient slices: one per CTA of the gradient kernels (at most 160 of them run: 148 SMs, one CTA each for the wide nets)
+        self._ws_base = (int(lib.ss_learner_workspace_bytes()) if self.frames == 1
+                         else 160 * (max(A_N, C_N) + 1) * 4)
         self.workspace = torch.empty(self._ws_base, dtype=torch.uint8, device=dev)
         self.step_actor = 0
         self.step_critic = 0
@@ -195,22 +210,22 @@ class ActorCritic:
     # -- parameter views -----------------------------------------------------
     @property
     def actor(self):
-        return self.params[self._a_off:self._a_off + A_N]
+        return self.params[self._a_off:self._a_off + self.a_n]
 
     @property
     def critic(self):
-        return self.params[self._c_off:self._c_off + C_N]
+        return self.params[self._c_off:self._c_off + self.c_n]
 
     @property
     def target_actor(self):
-        return self.target[self._a_off:self._a_off + A_N]
+        return self.target[self._a_off:self._a_off + self.a_n]
 
     @property
     def target_critic(self):
-        return self.target[self._c_off:self._c_off + C_N]
+        return self.target[self._c_off:self._c_off + self.c_n]
 
     def _slice(self, buf, which):
-        return buf[self._a_off:self._a_off + A_N] if which == "actor" else buf[self._c_off:self._c_off + C_N]
+        return buf[self._a_off:self._a_off + self.a_n] if which == "actor" else buf[self._c_off:self._c_off + self.c_n]
 
     def init_weights(self, seed: int):
         """Keras initialisers of the reference's layers: actor kernels RandomNormal(0, 0.05)
@@ -218,9 +233,9 @@ class ActorCritic:
         critic output kernel "RandomNormal" = N(0, 0.05) (SkillshotLearner.py:113), biases 0."""
         g = torch.Generator(device="cpu")
         g.manual_seed(int(seed))
-        a = [torch.randn(s, generator=g) * 0.05 if len(s) == 2 else torch.zeros(s) for s in ACTOR_SHAPES]
+        a = [torch.randn(s, generator=g) * 0.05 if len(s) == 2 else torch.zeros(s) for s in self.actor_shapes]
         c = []
-        for i, s in enumerate(CRITIC_SHAPES):
+        for i, s in enumerate(self.critic_shapes):
             if len(s) == 1:
                 c.append(torch.zeros(s))
             elif i == 4:
@@ -233,9 +248,9 @@ class ActorCritic:
     def set_weights(self, actor=None, critic=None, reset_optimizer: bool = True):
         """Install flat parameter vectors (Keras get_weights() order); targets are set equal."""
         if actor is not None:
-            self.actor.copy_(_f32(actor, self.device, (A_N,)))
+            self.actor.copy_(_f32(actor, self.device, (self.a_n,)))
         if critic is not None:
-            self.critic.copy_(_f32(critic, self.device, (C_N,)))
+            self.critic.copy_(_f32(critic, self.device, (self.c_n,)))
         self.target.copy_(self.params)
         if reset_optimizer:
             self.adam_m.zero_()
@@ -245,18 +260,26 @@ class ActorCritic:
     def get_weights(self, which="actor"):
         """List of numpy arrays like keras Model.get_weights()."""
         flat = self._slice(self.params, which).detach().cpu().numpy()
-        return [w.copy() for w in split_params(flat, ACTOR_SHAPES if which == "actor" else CRITIC_SHAPES)]
+        return [w.copy() for w in split_params(flat, self.actor_shapes if which == "actor" else self.critic_shapes)]
 
     # -- forward ---------------------------------------------------------------
     def actor_forward(self, obs, param_noise_sd: float = 0.0, noise_group: int = 1, action_noise_sd: float = 0.0,
                       out: Optional[torch.Tensor] = None, target: bool = False, counter: Optional[int] = None,
                       precision: str = "f32"):
-        """actions [n,2] = actor(obs [n,12]) (model_act*, SkillshotLearner.py:215-281)."""
-        obs = _f32(obs, self.device).reshape(-1, 12)
+        """actions [n,2] = actor(obs [n,12]) (model_act*, SkillshotLearner.py:215-281).  frames > 1: obs [n, 12 * frames],
+        oldest frame first, float32 kernels, no noise (FrameStackActor is the acting path of the stacked networks)."""
+        obs = _f32(obs, self.device).reshape(-1, 12 * self.frames)
         n = obs.shape[0]
         if out is None:
             out = torch.empty((n, 2), dtype=torch.float32, device=self.device)
         theta = self.target_actor if target else self.actor
+        if self.frames > 1:
+            if param_noise_sd > 0 or action_noise_sd > 0 or precision != "f32":
+                raise ValueError("frame-stacked networks: plain float32 forward only (see FrameStackActor)")
+            with torch.cuda.device(self.device):      # dense ordered rows = a history ring read from slot 0
+                check(lib.ss_actor_forward_frames(theta.data_ptr(), 0, 0, obs.data_ptr(), self.frames, self.frames - 1,
+                                                  out.data_ptr(), n, _stream(self.device)), "ss_actor_forward_frames")
+            return out
         if counter is None:
             counter = self.counter
             if param_noise_sd > 0 or action_noise_sd > 0:
@@ -271,20 +294,26 @@ class ActorCritic:
 
     def noisy_actor_params(self, sd: float, group: int = 0, counter: Optional[int] = None):
         """The perturbed parameter vector actor_forward uses for one noise group."""
-        out = torch.empty(A_N, dtype=torch.float32, device=self.device)
+        out = torch.empty(self.a_n, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            check(lib.ss_param_noise(self.actor.data_ptr(), out.data_ptr(), A_N, float(sd), self.seed, int(group),
+            check(lib.ss_param_noise(self.actor.data_ptr(), out.data_ptr(), self.a_n, float(sd), self.seed, int(group),
                                      int(self.counter if counter is None else counter), _stream(self.device)),
                   "ss_param_noise")
         return out
 
     def critic_forward(self, obs, act, target: bool = False, precision: str = "f32", want_dq_da: bool = False):
         """q [n] = critic([obs, act]) with Dropout off; with want_dq_da (bf16 path) also -dQ/da [n,2]."""
-        obs, act = _f32(obs, self.device).reshape(-1, 12), _f32(act, self.device).reshape(-1, 2)
+        obs, act = _f32(obs, self.device).reshape(-1, 12 * self.frames), _f32(act, self.device).reshape(-1, 2)
         n = obs.shape[0]
         q = torch.empty(n, dtype=torch.float32, device=self.device)
         phi = self.target_critic if target else self.critic
         with torch.cuda.device(self.device):
+            if self.frames > 1:
+                if precision != "f32":
+                    raise ValueError("frame-stacked networks: float32 kernels only")
+                check(lib.ss_critic_forward_frames(phi.data_ptr(), self.frames, obs.data_ptr(), act.data_ptr(), q.data_ptr(), n,
+                                                   _stream(self.device)), "ss_critic_forward_frames")
+                return q
             if precision == "bf16":
                 up = torch.empty((n, 2), dtype=torch.float32, device=self.device) if want_dq_da else None
                 check(lib.ss_critic_forward_tc(phi.data_ptr(), obs.data_ptr(), act.data_ptr(), n, q.data_ptr(), _ptr(up),
@@ -300,7 +329,7 @@ class ActorCritic:
         reward = _f32(reward, self.device).reshape(-1)
         if self.gamma == 0.0:
             return reward
-        next_obs = _f32(next_obs, self.device).reshape(-1, 12)
+        next_obs = _f32(next_obs, self.device).reshape(-1, 12 * self.frames)
         y = torch.empty_like(reward)
         if done is not None:
             done = done.to(device=self.device, dtype=torch.uint8).contiguous()
@@ -313,9 +342,9 @@ class ActorCritic:
                                              y.data_ptr(), n, ws.data_ptr(), ws.numel(), _stream(self.device)),
                       "ss_ddpg_targets_tc")
             else:
-                check(lib.ss_ddpg_targets(self.target_actor.data_ptr(), self.target_critic.data_ptr(), reward.data_ptr(),
-                                          next_obs.data_ptr(), _ptr(done), self.gamma, y.data_ptr(), n,
-                                          _stream(self.device)), "ss_ddpg_targets")
+                check(lib.ss_ddpg_targets_frames(self.target_actor.data_ptr(), self.target_critic.data_ptr(), self.frames,
+                                                 reward.data_ptr(), next_obs.data_ptr(), _ptr(done), self.gamma, y.data_ptr(), n,
+                                                 _stream(self.device)), "ss_ddpg_targets")
         return y
 
     def _workspace_for(self, n: int) -> torch.Tensor:
@@ -333,19 +362,20 @@ class ActorCritic:
     def critic_grad(self, obs, act, y, keep=None, n_global: int = 0, row_offset: int = 0, slices_only: bool = False):
         """grads[critic] <- d/dphi mean (q - y)^2 of this (shard of a) batch; returns the gradient view.
         slices_only: leave the per-CTA slices in the workspace and return their number (peer exchange)."""
-        obs, act = _f32(obs, self.device).reshape(-1, 12), _f32(act, self.device).reshape(-1, 2)
+        obs, act = _f32(obs, self.device).reshape(-1, 12 * self.frames), _f32(act, self.device).reshape(-1, 2)
         y = _f32(y, self.device).reshape(-1)
         n = obs.shape[0]
         if keep is not None:
             keep = torch.as_tensor(keep).to(device=self.device, dtype=torch.uint8).contiguous()
         g = self._slice(self.grads, "critic")
-        fn = lib.ss_critic_grad_tc if self.update_precision == "bf16" else lib.ss_critic_grad
         ws = self._workspace_for(n)
+        tail = (_ptr(keep), self.dropout, self.seed, self.counter, n, int(n_global), int(row_offset),
+                None if slices_only else g.data_ptr(), self.stats[0:1].data_ptr(), ws.data_ptr(), ws.numel(), _stream(self.device))
         with torch.cuda.device(self.device):
-            rc = fn(self.critic.data_ptr(), obs.data_ptr(), act.data_ptr(), y.data_ptr(), _ptr(keep),
-                    self.dropout, self.seed, self.counter, n, int(n_global), int(row_offset),
-                    None if slices_only else g.data_ptr(), self.stats[0:1].data_ptr(), ws.data_ptr(), ws.numel(),
-                    _stream(self.device))
+            if self.update_precision == "bf16":
+                rc = lib.ss_critic_grad_tc(self.critic.data_ptr(), obs.data_ptr(), act.data_ptr(), y.data_ptr(), *tail)
+            else:
+                rc = lib.ss_critic_grad_frames(self.critic.data_ptr(), self.frames, obs.data_ptr(), act.data_ptr(), y.data_ptr(), *tail)
         self.counter += 1
         if slices_only and rc > 0:
             return rc
@@ -354,14 +384,16 @@ class ActorCritic:
 
     def actor_grad(self, obs, slices_only: bool = False):
         """grads[actor] <- -sum_batch dQ/da da/dtheta (model_actor_fit_step, SkillshotLearner.py:395-410)."""
-        obs = _f32(obs, self.device).reshape(-1, 12)
+        obs = _f32(obs, self.device).reshape(-1, 12 * self.frames)
         g = self._slice(self.grads, "actor")
-        fn = lib.ss_actor_grad_tc if self.update_precision == "bf16" else lib.ss_actor_grad
         ws = self._workspace_for(obs.shape[0])
+        tail = (obs.data_ptr(), obs.shape[0], None if slices_only else g.data_ptr(), self.stats[1:2].data_ptr(), ws.data_ptr(),
+                ws.numel(), _stream(self.device))
         with torch.cuda.device(self.device):
-            rc = fn(self.actor.data_ptr(), self.critic.data_ptr(), obs.data_ptr(), obs.shape[0],
-                    None if slices_only else g.data_ptr(), self.stats[1:2].data_ptr(), ws.data_ptr(), ws.numel(),
-                    _stream(self.device))
+            if self.update_precision == "bf16":
+                rc = lib.ss_actor_grad_tc(self.actor.data_ptr(), self.critic.data_ptr(), *tail)
+            else:
+                rc = lib.ss_actor_grad_frames(self.actor.data_ptr(), self.critic.data_ptr(), self.frames, *tail)
         if slices_only and rc > 0:
             return rc
         check(rc, "ss_actor_grad")
@@ -370,7 +402,7 @@ class ActorCritic:
     def apply_adam(self, which: str, grad_scale: float = 1.0, from_peers: bool = False):
         """tf.keras Adam.apply_gradients on one network (+ soft target update with self.tau).
         from_peers: the gradient is the rank-ordered sum of this rank's peer inbox (fused exchange)."""
-        n = A_N if which == "actor" else C_N
+        n = self.a_n if which == "actor" else self.c_n
         if which == "actor":
             self.step_actor += 1
             step, lr = self.step_actor, self.lr_actor
@@ -395,7 +427,7 @@ class ActorCritic:
 
     def reduce_adam(self, which: str, parts: int, aux: Optional[torch.Tensor], grad_scale: float = 1.0):
         """Single GPU: fixed-order sum of the `parts` gradient slices in the workspace + Adam + soft update, one kernel."""
-        n = A_N if which == "actor" else C_N
+        n = self.a_n if which == "actor" else self.c_n
         if which == "actor":
             self.step_actor += 1
             step, lr = self.step_actor, self.lr_actor
@@ -422,7 +454,7 @@ class ActorCritic:
         # rank's inbox for the peers' Adam kernel (fused exchange)
         parts = self.critic_grad(obs, act, y, keep, n_global=n_global, row_offset=row_offset, slices_only=True)
         if self.peer is not None:
-            self.peer.reduce_push(self.workspace, parts, C_N, self.stats[0:1])
+            self.peer.reduce_push(self.workspace, parts, self.c_n, self.stats[0:1])
             self.apply_adam("critic", from_peers=True)
         else:
             self.reduce_adam("critic", parts, self.stats[0:1])
@@ -437,7 +469,7 @@ class ActorCritic:
             return self.stats[1]
         parts = self.actor_grad(obs, slices_only=True)
         if self.peer is not None:
-            self.peer.reduce_push(self.workspace, parts, A_N, self.stats[1:2])
+            self.peer.reduce_push(self.workspace, parts, self.a_n, self.stats[1:2])
             self.apply_adam("actor", from_peers=True)
         else:
             self.reduce_adam("actor", parts, self.stats[1:2])
@@ -450,6 +482,8 @@ class ActorCritic:
         the host between the gradient and Adam: use the separate steps).  Returns the minibatch dict."""
         if self.group is not None and self.peer is None:
             raise ValueError("update_from_ring needs collective='peer' when the update is sharded")
+        if self.frames > 1:
+            raise ValueError("the single-call update is built for the reference's 12-input networks: use the separate steps")
         if ring.size == 0:
             raise ValueError("sampling from an empty ring")
         dev = self.device
@@ -524,20 +558,22 @@ class ReplayRing:
     Python lists and uses it once (SkillshotLearner.py:292-361); a ring sized to the episode and
     read back in order is that buffer."""
 
-    def __init__(self, capacity: int, device="cuda", seed: int = 0):
+    def __init__(self, capacity: int, device="cuda", seed: int = 0, frames: int = 1):
         self.capacity, self.device, self.seed = int(capacity), torch.device(device), int(seed)
+        self.frames = int(frames)          # observation rows of 12 * frames floats (the frame-stacked networks' inputs)
+        self.width = 12 * self.frames
         c, dev = self.capacity, self.device
-        self.obs = torch.zeros((c, 12), dtype=torch.float32, device=dev)
+        self.obs = torch.zeros((c, self.width), dtype=torch.float32, device=dev)
         self.act = torch.zeros((c, 2), dtype=torch.float32, device=dev)
         self.reward = torch.zeros(c, dtype=torch.float32, device=dev)
-        self.next_obs = torch.zeros((c, 12), dtype=torch.float32, device=dev)
+        self.next_obs = torch.zeros((c, self.width), dtype=torch.float32, device=dev)
         self.done = torch.zeros(c, dtype=torch.uint8, device=dev)
         self.pos = 0
         self.size = 0
         self.counter = 0
 
     def push(self, obs, act, reward, next_obs, done=None, done_div: int = 1):
-        obs, next_obs = _f32(obs, self.device).reshape(-1, 12), _f32(next_obs, self.device).reshape(-1, 12)
+        obs, next_obs = _f32(obs, self.device).reshape(-1, self.width), _f32(next_obs, self.device).reshape(-1, self.width)
         act, reward = _f32(act, self.device).reshape(-1, 2), _f32(reward, self.device).reshape(-1)
         n = obs.shape[0]
         if n > self.capacity:
@@ -545,15 +581,15 @@ class ReplayRing:
         if done is not None:
             done = done.to(device=self.device, dtype=torch.uint8).contiguous()
         with torch.cuda.device(self.device):
-            check(lib.ss_replay_push(self.obs.data_ptr(), self.act.data_ptr(), self.reward.data_ptr(),
-                                     self.next_obs.data_ptr(), self.done.data_ptr(), self.capacity, self.pos,
-                                     obs.data_ptr(), act.data_ptr(), reward.data_ptr(), next_obs.data_ptr(),
-                                     _ptr(done), int(done_div), n, _stream(self.device)), "ss_replay_push")
+            check(lib.ss_replay_push_frames(self.obs.data_ptr(), self.act.data_ptr(), self.reward.data_ptr(),
+                                            self.next_obs.data_ptr(), self.done.data_ptr(), self.capacity, self.pos, self.frames,
+                                            obs.data_ptr(), act.data_ptr(), reward.data_ptr(), next_obs.data_ptr(),
+                                            _ptr(done), int(done_div), n, _stream(self.device)), "ss_replay_push")
         self.pos = (self.pos + n) % self.capacity
         self.size = min(self.capacity, self.size + n)
 
     def state_dict(self):
-        return dict(capacity=self.capacity, seed=self.seed, pos=self.pos, size=self.size, counter=self.counter,
+        return dict(capacity=self.capacity, seed=self.seed, pos=self.pos, size=self.size, counter=self.counter, frames=self.frames,
                     **{k: getattr(self, k).cpu() for k in ("obs", "act", "reward", "next_obs", "done")})
 
     def load_state_dict(self, sd):
@@ -570,10 +606,10 @@ class ReplayRing:
             raise ValueError("sampling from an empty ring")
         dev = self.device
         if out is None or out["reward"].shape[0] != batch:
-            out = dict(obs=torch.empty((batch, 12), dtype=torch.float32, device=dev),
+            out = dict(obs=torch.empty((batch, self.width), dtype=torch.float32, device=dev),
                        act=torch.empty((batch, 2), dtype=torch.float32, device=dev),
                        reward=torch.empty(batch, dtype=torch.float32, device=dev),
-                       next_obs=torch.empty((batch, 12), dtype=torch.float32, device=dev),
+                       next_obs=torch.empty((batch, self.width), dtype=torch.float32, device=dev),
                        done=torch.empty(batch, dtype=torch.uint8, device=dev),
                        indices=torch.empty(batch, dtype=torch.int64, device=dev))
         if indices is not None:
@@ -581,8 +617,8 @@ class ReplayRing:
             if indices.numel() != batch:
                 raise ValueError("indices must have `batch` entries")
         with torch.cuda.device(dev):
-            check(lib.ss_replay_sample(self.obs.data_ptr(), self.act.data_ptr(), self.reward.data_ptr(),
-                                       self.next_obs.data_ptr(), self.done.data_ptr(), self.capacity, self.size,
+            check(lib.ss_replay_sample_frames(self.obs.data_ptr(), self.act.data_ptr(), self.reward.data_ptr(),
+                                       self.next_obs.data_ptr(), self.done.data_ptr(), self.capacity, self.size, self.frames,
                                        _ptr(indices), self.seed, self.counter, batch, out["obs"].data_ptr(),
                                        out["act"].data_ptr(), out["reward"].data_ptr(), out["next_obs"].data_ptr(),
                                        out["done"].data_ptr(), out["indices"].data_ptr(), _stream(dev)),
@@ -881,7 +917,11 @@ class FrameStackActor:
     perturbed parameter vector per noise group.
     """
 
-    def __init__(self, n_rows: int, frames: int = 20, device="cuda", seed: int = 0, precision: str = "f32"):
+    def __init__(self, n_rows: int, frames: int = 20, device="cuda", seed: int = 0, precision: str = "f32",
+                 params: Optional[torch.Tensor] = None, learner_stack: bool = False):
+        """params: the actor's flat parameter vector to act with (e.g. ActorCritic(frames=...).actor, so that the learner's
+        updates are what acts), default a fresh RandomNormal(0, 0.05) vector.  learner_stack: with the tensor-core path
+        (whose history is fp16 operand tiles) also keep the float32 history the learner's dense input rows are cut from."""
         if precision not in ("f32", "bf16"):
             raise ValueError("precision must be 'f32' (exact path) or 'bf16' (tensor cores)")
         self.precision = precision
@@ -897,7 +937,16 @@ class FrameStackActor:
         shapes = [(12 * self.frames, 256), (256,), (256, 128), (128,), (128, 2), (2,)]
         parts = [torch.randn(sh, generator=g) * 0.05 if len(sh) == 2 else torch.zeros(sh) for sh in shapes]   # RandomNormal(0, 0.05)
         self.shapes = shapes
-        self.params = torch.cat([p.reshape(-1) for p in parts]).to(self.device)
+        if params is not None:
+            if params.numel() != self.n_params or params.dtype != torch.float32 or not params.is_contiguous():
+                raise ValueError("params must be a contiguous float32 vector of %d values" % self.n_params)
+            self.params = params
+        else:
+            self.params = torch.cat([p.reshape(-1) for p in parts]).to(self.device)
+        self.stack32 = None
+        if precision == "bf16" and learner_stack:
+            self.stack32 = torch.zeros((self.n_rows, self.frames, 12), dtype=torch.float32, device=self.device)
+        self._ordered = None
         if precision == "bf16":
             # the tensor-core path keeps the history as fp16 tiles in the MMA operand layout (ss_obs_stack_push_tc)
             self.stack = torch.zeros(int(lib.ss_obs_stack_tc_bytes(self.n_rows, self.frames)), dtype=torch.uint8, device=self.device)
@@ -921,6 +970,22 @@ class FrameStackActor:
         with torch.cuda.device(self.device):
             check(fn(self.stack.data_ptr(), self.n_rows, self.frames, self.head, obs.data_ptr(), _ptr(done), int(done_div),
                      _stream(self.device)), "ss_obs_stack_push")
+            if self.stack32 is not None:
+                check(lib.ss_obs_stack_push(self.stack32.data_ptr(), self.n_rows, self.frames, self.head, obs.data_ptr(), _ptr(done),
+                                            int(done_div), _stream(self.device)), "ss_obs_stack_push")
+
+    def ordered_rows(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The network input of every row as dense float32 rows [n_rows, 12 * frames], oldest frame first: what the learner
+        of the stacked networks stores and trains on (ss_obs_stack_ordered)."""
+        src = self.stack if self.precision == "f32" else self.stack32
+        if src is None:
+            raise ValueError("tensor-core history only: construct with learner_stack=True")
+        if out is None:
+            out = torch.empty((self.n_rows, 12 * self.frames), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.ss_obs_stack_ordered(src.data_ptr(), self.n_rows, self.frames, self.head, out.data_ptr(), _stream(self.device)),
+                  "ss_obs_stack_ordered")
+        return out
 
     def forward(self, param_noise_sd: float = 0.0, noise_group: int = 0, out: Optional[torch.Tensor] = None):
         """actions [n_rows,2] from the current stack; param_noise_sd > 0: rows i share the perturbed parameters of
@@ -977,21 +1042,36 @@ class SelfPlayTrainer:
     def __init__(self, n_envs: int, device="cuda", seed: int = 0, replay_capacity: Optional[int] = None,
                  batch_size: int = 4096, gamma: float = 0.0, tau: float = 1.0, param_noise_sd: float = 0.5,
                  noise_group: int = 128, reward_mode: str = "looking", tick_limit: int = 2000,
-                 random_positions: bool = True, process_group=None, precision: str = "f32", collective: str = "nccl"):
+                 random_positions: bool = True, process_group=None, precision: str = "f32", collective: str = "nccl",
+                 frames: int = 1):
+        """frames > 1: the frame-stacked "planning" networks (readme.md:18-20, BASELINE.json configs[4]): both players act
+        from their last `frames` observations (FrameStackActor; `precision` selects its float32 or tensor-core kernels),
+        the replay ring stores the stacked observations, and the critic / actor update of SkillshotLearner.py:386-443 runs
+        on the 12 * frames-input networks (float32 kernels, separate steps)."""
         self.device = torch.device(device)
+        self.frames = int(frames)
         self.envs = SkillshotEnvs(n_envs, device=device, random_positions=random_positions, seed=seed,
                                   reward_mode=reward_mode, tick_limit=tick_limit, auto_reset=True)
         self.envs.collect_episode_stats = True     # the reference's per-episode ticks / winner log, reduced on the device
         self.networks = ActorCritic(device=device, seed=seed if process_group is None else 0, gamma=gamma, tau=tau,
-                                    process_group=process_group, update_precision=precision, collective=collective)
+                                    process_group=process_group, update_precision=precision if self.frames == 1 else "f32",
+                                    collective=collective, frames=self.frames)
         self.networks.seed = seed          # exploration / dropout streams differ per rank, weights do not
-        self.replay = ReplayRing(replay_capacity or 2 * n_envs * 8, device=device, seed=seed)
+        self.replay = ReplayRing(replay_capacity or 2 * n_envs * 8, device=device, seed=seed, frames=self.frames)
         self.batch_size, self.param_noise_sd, self.noise_group = int(batch_size), float(param_noise_sd), int(noise_group)
         self.precision = precision
         n = n_envs
         self.obs = self.envs.observe().contiguous()                       # [n,2,12] seen by the actor next
         self.prev_obs = torch.empty_like(self.obs)
         self.actions = torch.empty((n, 2, 2), dtype=torch.float32, device=self.device)
+        self.stack = None
+        if self.frames > 1:
+            # the acting network IS the learner's actor vector; the history lives in the FrameStackActor
+            self.stack = FrameStackActor(2 * n, frames=self.frames, device=device, seed=seed, precision=precision,
+                                         params=self.networks.actor, learner_stack=True)
+            self.stack.push(self.obs.reshape(-1, 12))
+            self.rows = self.stack.ordered_rows()                         # [2n, 12 frames]: the stacked observation now
+            self.prev_rows = torch.empty_like(self.rows)
         self._batch = None
         self.ticks = 0
         self.updates = 0
@@ -1000,6 +1080,8 @@ class SelfPlayTrainer:
     def rollout_tick(self, store: bool = True):
         """One tick of every env: actor forward on both players' observations (fresh parameter
         noise per noise group), env step, transition push."""
+        if self.frames > 1:
+            return self._rollout_tick_frames(store)
         self.prev_obs, self.obs = self.obs, self.prev_obs
         self.networks.actor_forward(self.prev_obs, param_noise_sd=self.param_noise_sd, noise_group=self.noise_group,
                                     out=self.actions.view(-1, 2), precision=self.precision)
@@ -1010,9 +1092,29 @@ class SelfPlayTrainer:
         self.ticks += 1
         return out
 
+    def _rollout_tick_frames(self, store: bool = True):
+        """The same tick for the frame-stacked networks: the actor reads each player's last `frames` observations; the stored
+        transition is (stacked obs, action, reward, stacked obs after the tick, hit flag).  A restarted game's history is
+        refilled with its first observation (FrameStackActor.push)."""
+        st = self.stack
+        st.forward(param_noise_sd=self.param_noise_sd, noise_group=self.noise_group if self.param_noise_sd > 0 else 0,
+                   out=self.actions.view(-1, 2))
+        out = self.envs.step(self.actions, obs_out=self.obs)
+        st.push(self.obs.reshape(-1, 12), out["done"], done_div=2)
+        self.prev_rows, self.rows = self.rows, self.prev_rows
+        st.ordered_rows(out=self.rows)
+        if store:
+            self.replay.push(self.prev_rows, self.actions, out["reward"], self.rows, out["winner"], done_div=2)
+        self.ticks += 1
+        return out
+
     def rollout(self, n_ticks: int, store: bool = True):
         """n_ticks rollout ticks enqueued by ONE library call (ss_selfplay_rollout): same kernels and Philox
         counters as n_ticks calls of rollout_tick, without the per-tick host work."""
+        if self.frames > 1:
+            for _ in range(int(n_ticks)):
+                out = self._rollout_tick_frames(store)
+            return dict(obs=self.obs, reward=out["reward"], done=out["done"], winner=out["winner"])
         envs, net, rp = self.envs, self.networks, self.replay
         if not envs.auto_reset:
             raise ValueError("the batched rollout needs auto_reset envs")
@@ -1047,9 +1149,14 @@ class SelfPlayTrainer:
     # -- checkpoint / resume (SkillshotLearner.py:123-162 keeps the two Keras models; a batched run also needs the
     #    optimiser moments, the targets, the games in flight, the replay ring and every Philox counter) ---------------
     def state_dict(self):
-        return dict(envs=self.envs.state_dict(), networks=self.networks.state_dict(), replay=self.replay.state_dict(),
-                    obs=self.obs.cpu(), actions=self.actions.cpu(), ticks=self.ticks, batch_size=self.batch_size,
-                    param_noise_sd=self.param_noise_sd, noise_group=self.noise_group, precision=self.precision)
+        sd = dict(envs=self.envs.state_dict(), networks=self.networks.state_dict(), replay=self.replay.state_dict(),
+                  obs=self.obs.cpu(), actions=self.actions.cpu(), ticks=self.ticks, batch_size=self.batch_size,
+                  param_noise_sd=self.param_noise_sd, noise_group=self.noise_group, precision=self.precision, frames=self.frames)
+        if self.stack is not None:      # the players' observation histories and the noise counter of the stacked actor
+            st = self.stack
+            sd["stack"] = dict(stack=st.stack.cpu(), stack32=None if st.stack32 is None else st.stack32.cpu(), head=st.head,
+                               counter=st.counter, rows=self.rows.cpu())
+        return sd
 
     def load_state_dict(self, sd):
         self.envs.load_state_dict(sd["envs"])
@@ -1059,6 +1166,13 @@ class SelfPlayTrainer:
         self.actions.copy_(sd["actions"].to(self.device))
         self.ticks, self.batch_size = int(sd["ticks"]), int(sd["batch_size"])
         self.param_noise_sd, self.noise_group = float(sd["param_noise_sd"]), int(sd["noise_group"])
+        if self.stack is not None:
+            st, ss = self.stack, sd["stack"]
+            st.stack.copy_(ss["stack"].to(self.device))
+            if st.stack32 is not None:
+                st.stack32.copy_(ss["stack32"].to(self.device))
+            st.head, st.counter = int(ss["head"]), int(ss["counter"])
+            self.rows.copy_(ss["rows"].to(self.device))
         self._batch = None
 
     def record_boards(self, env: int, n_ticks: int, path: Optional[str] = None, store: bool = True):
@@ -1104,7 +1218,7 @@ class SelfPlayTrainer:
         """One critic step and one actor step on a sampled minibatch: a single library call on one GPU or
         with the fused peer exchange, the separate steps (update_stepwise) around an NCCL all-reduce."""
         net = self.networks
-        if net.group is not None and net.peer is None:
+        if (net.group is not None and net.peer is None) or self.frames > 1:
             return self.update_stepwise()
         self._batch = net.update_from_ring(self.replay, self.batch_size, out=self._batch)
         self.updates += 1

@@ -112,7 +112,7 @@ def test_bench_report_assembles_without_a_gpu():
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     peaks = {"hbm_gbs": 6556.5, "bf16_tflops": 1631.0}
-    times = dict(zip(bench.LEG_KEYS, (0.08, 0.19, 0.044, 2.1, 0.79, 0.094, 0.188, 0.49, 0.17, 0.52)))
+    times = dict(zip(bench.LEG_KEYS, (0.08, 0.19, 0.044, 2.1, 0.79, 0.094, 0.188, 0.49, 0.17, 0.52, 4.4)))
     for world, collective in ((1, "peer"), (8, "peer"), (2, "nccl")):
         rep = bench.learner_report(times, world, peaks, "measured", collective, dict(times, roll=0.079, cfg5=0.09))
         json.dumps(rep)

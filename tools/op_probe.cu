@@ -67,6 +67,53 @@ int run(long long *d_cyc, double *d_sink) {
     return 0;
 }
 
+// ---- mixed streams: can two half-rate pipes be fed in alternate cycles? ----
+enum Mix { ALU_FMA, ALU_FP64, FMA_FP64, ALU_FMA_FP64, ALU_FP32, N_MIX };
+const char *kMixNames[N_MIX] = {"LOP3 + IMAD", "LOP3 + DFMA", "IMAD + DFMA", "LOP3 + IMAD + DFMA", "LOP3 + FFMA"};
+
+template <int MIX>
+__global__ void mix_probe(long long *cycles, double *sink, int trips, double a, double b) {
+    double x[4]; int xi[4], xj[4]; float xf[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { x[c] = 1.0 + threadIdx.x + c; xi[c] = threadIdx.x + c; xj[c] = threadIdx.x * 3 + c; xf[c] = 1.f + c; }
+    __syncthreads();
+    long long t0 = clock64();
+    for (int t = 0; t < trips; ++t) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (MIX == ALU_FMA || MIX == ALU_FP64 || MIX == ALU_FMA_FP64 || MIX == ALU_FP32)
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(xi[c]) : "r"(trips), "r"(i));
+                if (MIX == ALU_FMA || MIX == FMA_FP64 || MIX == ALU_FMA_FP64)
+                    asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(xj[c]) : "r"(trips), "r"(i));
+                if (MIX == ALU_FP64 || MIX == FMA_FP64 || MIX == ALU_FMA_FP64)
+                    asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x[c]) : "d"(a), "d"(b));
+                if (MIX == ALU_FP32)
+                    asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(xf[c]) : "f"((float)a), "f"((float)b));
+            }
+        }
+    }
+    long long t1 = clock64();
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s += x[c] + xi[c] + xj[c] + xf[c];
+    if (s == 12345.678) sink[0] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int MIX>
+int run_mix(long long *d_cyc, double *d_sink, int kinds) {
+    long long h[1];
+    const int trips = 64;
+    mix_probe<MIX><<<1, 1024>>>(d_cyc, d_sink, trips, 0.999, 1e-3);
+    CHK(cudaDeviceSynchronize());
+    CHK(cudaMemcpy(h, d_cyc, sizeof(long long), cudaMemcpyDeviceToHost));
+    const double per_smsp = (double)trips * 16 * 4 * kinds * 8 / (double)h[0];
+    printf("%-22s mixed stream, 8 warps per sub-partition: %.3f warp-instr/cycle/sub-partition in total\n", kMixNames[MIX], per_smsp);
+    return 0;
+}
+
 int main() {
     long long *d_cyc; double *d_sink;
     CHK(cudaMalloc(&d_cyc, 1024 * sizeof(long long)));
@@ -84,5 +131,10 @@ int main() {
     if (run<SHFL>(d_cyc, d_sink)) return 1;
     if (run<DSETP>(d_cyc, d_sink)) return 1;
     if (run<MAGIC_CVT>(d_cyc, d_sink)) return 1;
+    if (run_mix<ALU_FMA>(d_cyc, d_sink, 2)) return 1;
+    if (run_mix<ALU_FP64>(d_cyc, d_sink, 2)) return 1;
+    if (run_mix<FMA_FP64>(d_cyc, d_sink, 2)) return 1;
+    if (run_mix<ALU_FMA_FP64>(d_cyc, d_sink, 3)) return 1;
+    if (run_mix<ALU_FP32>(d_cyc, d_sink, 2)) return 1;
     return 0;
 }
