@@ -83,7 +83,7 @@ class all_host_cpus:
 
 ENVS_PER_GPU = 65536
 TICKS = 2048                # ticks per bench step (one full 2,000-tick episode plus the auto-reset)
-TICKS_PER_LAUNCH = 128      # fused ticks per ss_env_step launch (32: 4.8e10, 128: 5.1e10 env-steps/s)
+TICKS_PER_LAUNCH = 256      # fused ticks per ss_env_step launch (32: 6.9e10, 128: 7.7e10, 256: 7.9e10 env-steps/s)
 E2E_TICKS_PER_LAUNCH = 32   # the host-buffer leg pipelines copy in / kernel / copy out per chunk: finer chunks overlap better
 TICK_LIMIT = 2000           # SkillshotLearner.py:62
 ALGO_BYTES_PER_ENV_STEP = 202   # SURVEY.md 8(d), physics-only
@@ -706,7 +706,7 @@ def run_gpu_arm(args):
     barrier()
 
     # ---- end to end through the host-buffer API (e2e) ----
-    e2e_steps, e2e_s, e2e_solo_s, e2e_solo_steps = max(3, min(args.steps, 10)), float("nan"), 0.0, 3
+    e2e_steps, e2e_s, e2e_solo_s, e2e_solo_steps, e2e_flags_s = max(3, min(args.steps, 10)), float("nan"), 0.0, 3, float("nan")
     KE = E2E_TICKS_PER_LAUNCH if T % E2E_TICKS_PER_LAUNCH == 0 else KF
     if not args.no_e2e:
         host_actions = torch.empty((T, E, 2, 2), dtype=torch.float32, pin_memory=True)
@@ -720,6 +720,17 @@ def run_gpu_arm(args):
             envs.step_host(host_actions, host_out, ticks_per_launch=KE)   # synchronises before returning
         barrier()
         e2e_s = time.perf_counter() - t0
+        # the same with the packed one-byte-per-env-step output (ss_env_step_packed: done, winner and the tick of the hit, from
+        # which the terminal reward follows): 17 B per env-step cross the bus instead of 26
+        flags_out = envs.alloc_host_outputs(T, outputs="flags")
+        envs.step_host(host_actions, flags_out, ticks_per_launch=KE)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            envs.step_host(host_actions, flags_out, ticks_per_launch=KE)
+        barrier()
+        e2e_flags_s = time.perf_counter() - t0
+        del flags_out
         if world > 1:
             # in-run baseline of this leg's scaling: rank 0 alone on the host's memory and PCIe fabric, the others idle
             if rank == 0:
@@ -739,13 +750,13 @@ def run_gpu_arm(args):
 
     lt_min = None
     if world > 1:
-        t = torch.tensor([ms, e2e_s, e2e_solo_s] + [lt[k] for k in LEG_KEYS], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, e2e_s, e2e_solo_s, e2e_flags_s] + [lt[k] for k in LEG_KEYS], dtype=torch.float64, device=dev)
         tmin = t.clone()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
-        ms, e2e_s, e2e_solo_s = float(t[0]), float(t[1]), float(t[2])
-        lt = {k: float(x) for k, x in zip(LEG_KEYS, t[3:])}
-        lt_min = {k: float(x) for k, x in zip(LEG_KEYS, tmin[3:])}
+        ms, e2e_s, e2e_solo_s, e2e_flags_s = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        lt = {k: float(x) for k, x in zip(LEG_KEYS, t[4:])}
+        lt_min = {k: float(x) for k, x in zip(LEG_KEYS, tmin[4:])}
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -800,6 +811,11 @@ def run_gpu_arm(args):
             "gpu_launches": args.steps * launches_per_step,
             "clocks": clocks,
         }
+        if not args.no_e2e:
+            line["e2e"]["packed_flags_output"] = {
+                "value": world * E * T * e2e_steps / e2e_flags_s, "unit": UNIT, "d2h_bytes_per_step": T * E,
+                "note": "step_host(outputs='flags'): one byte per env-step back (done, winner, hit tick; the terminal reward "
+                        "follows from them) instead of 10"}
         if world > 1 and not args.no_e2e and e2e_solo_s > 0:
             solo = E * T * e2e_solo_steps / e2e_solo_s
             line["e2e"]["one_rank_alone_env_steps_per_sec"] = solo

@@ -132,6 +132,16 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
                      int reset_mode, uint64_t seed, uint64_t counter, const void *speeds,
                      uint32_t *status, int flags, void *stream);
 
+/* The physics-only step (reference speed constants, terminal +1 / -1 / 0 reward) with its three per-tick outputs packed
+ * into ONE byte per env: packed_out uint8 [n_ticks][n_envs] = done | winner_id << 1 | hit << 3, where `hit` says that the
+ * game ended by a hit on this very tick -- the tick on which the terminal reward is paid: reward of player p =
+ * hit ? (winner_id - 1 == p ? -1 : +1) : 0.  Same trajectory, bit for bit, as ss_env_step with SS_REWARD_TERMINAL; built for
+ * callers with HOST buffers, whose device-to-host traffic drops from 10 bytes per env-step to 1.
+ * Requires 2 n_envs (n_ticks + 2) < 2^31. */
+int ss_env_step_packed(void *state, int64_t n_envs, const float *actions, uint8_t *packed_out, int n_ticks,
+                       int64_t tick_limit, int auto_reset, int reset_mode, uint64_t seed, uint64_t counter,
+                       uint32_t *status, void *stream);
+
 /* SkillshotGame.get_state (SkillshotGame.py:136-166) + prepare_states
  * (SkillshotLearner.py:512-543) in float64, formulas evaluated as written.
  *   feat_out    float64 [n_envs][2][18] in the dict's key order, or NULL
@@ -220,6 +230,12 @@ int ss_critic_grad_tc(const float *critic_params, const float *obs, const float 
 int ss_actor_grad_tc(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
                      float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes,
                      void *stream);
+/* The same in two stages, for callers that have other work to put between them (ss_ddpg_update overlaps stage 1 with the
+ * critic's gradient exchange): stage 1 = a = actor(s) only, into the scratch area of `workspace`; stage 2 = the rest,
+ * reading those actions; stage 0 = ss_actor_grad_tc.  Same workspace and n in both stages. */
+int ss_actor_grad_tc_staged(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
+                            float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, int stage,
+                            void *stream);
 int ss_ddpg_targets_tc(const float *target_actor_params, const float *target_critic_params,
                        const float *reward, const float *next_obs, const uint8_t *done, float gamma,
                        float *y_out, int64_t n, void *workspace, int64_t workspace_bytes, void *stream);

@@ -60,6 +60,7 @@ SIGNATURES = {
                             _vp, _vp, _i32, _vp]),
     "ss_env_step_ring": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i32, _u64, _u64,
                                  _vp, _vp, _i32, _vp]),
+    "ss_env_step_packed": (_i32, [_vp, _i64, _vp, _vp, _i32, _i64, _i32, _i32, _u64, _u64, _vp, _vp]),
     "ss_env_features": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "ss_env_export": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ss_env_import": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
@@ -70,6 +71,7 @@ SIGNATURES = {
     "ss_critic_forward_tc": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp]),
     "ss_critic_grad_tc": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _u64, _u64, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
     "ss_actor_grad_tc": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "ss_actor_grad_tc_staged": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp]),
     "ss_ddpg_targets_tc": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _i64, _vp]),
     "ss_peer_bytes": (_i64, [_i32, _i64]),
     "ss_peer_alloc": (_i32, [_i32, _i64, _vp]),

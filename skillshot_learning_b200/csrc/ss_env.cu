@@ -87,6 +87,7 @@ struct StepArgs {
     const void *speeds;
     uint32_t *status;
     unsigned long long *stats;  // episode statistics (SS_STEP_EPISODE_STATS) or NULL
+    uint8_t *packed_out;        // ss_env_step_packed: one byte per env and tick instead of reward / done / winner
     TickParams P;
     int n_ticks, obs_every_tick;
 };
@@ -103,6 +104,10 @@ __global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
     const bool active = i < A.n;
     const StatePlanes S = planes_of(A.state, A.n);
 
+    // Programmatic dependent launch (one-tick physics launches, ss_env_step_ring): this grid may have been scheduled while
+    // the previous kernel of the stream was still running; nothing of global memory is touched before that kernel has
+    // completed.  A launch without the attribute passes straight through.
+    if (!OBS && !CARRY) asm volatile("griddepcontrol.wait;" ::: "memory");
     Env e;
     Speeds k = default_speeds();
     if (active) {
@@ -111,6 +116,7 @@ __global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
     } else {
         reset_env(e, 50, 50, 200, 200);
     }
+    if (!OBS && !CARRY) asm volatile("griddepcontrol.launch_dependents;");     // the next launch may start its own prologue
     uint32_t status = 0;
     const bool write_reward = A.reward_out && A.P.reward_mode != SS_REWARD_NONE;
     Trig tr;
@@ -247,9 +253,14 @@ __device__ __forceinline__ void turn_from(Turn &out, double rot_before, float lo
     else sincos_d_unchecked(out.rot, &out.s, &out.c);
 }
 
+// What a tick writes: OUT_FLAGS = done / winner bytes (+ zero rewards when asked), OUT_TERMINAL = those + the +1 / -1 / 0
+// reward (readme.md:10), OUT_PACKED = one byte per env {bit 0 done, bits 1-2 winner_id, bit 3 "the hit happened on this
+// tick"} from which the other three follow (ss_env_step_packed: the host-buffer path moves 1 byte per env-step, not 10).
+enum { OUT_FLAGS = 0, OUT_TERMINAL = 1, OUT_PACKED = 2 };
+
 // One tick of one player.  `now` = this tick's post-turn rotation with its sin / cos (computed during the previous tick),
 // `next` = the next tick's, computed here from `look_next`.  CHECKED: sin / cos with the |rot| < 1e5 range check.
-template <bool TERMINAL, bool CHECKED>
+template <int TERMINAL, bool CHECKED>
 __device__ __forceinline__ void lane_tick(Lane &L, double *qrot, const float move, const float look_next, const Turn &now, Turn &next,
                                           const StepArgs &A, LaneIo &io, int lane, int P, int64_t env, int tick, int limit,
                                           bool write_zero, bool &nan_seen) {
@@ -299,9 +310,13 @@ __device__ __forceinline__ void lane_tick(Lane &L, double *qrot, const float mov
         r = (L.winner - 1 == P) ? -1.f : 1.f;                         // readme.md:10: -1 for the hit player, +1 for the shooter
     }
     const bool done = !L.live || L.ticks >= limit;
-    if (TERMINAL) io.reward[io.idx] = r;
-    else if (write_zero) io.reward[io.idx] = 0.f;
-    io.flags[io.idx >> 1] = (uint8_t)(P ? L.winner : (int)done);
+    if (TERMINAL == OUT_PACKED) {
+        if (!P) io.flags[io.idx >> 1] = (uint8_t)((int)done | (L.winner << 1) | (pair ? 8 : 0));
+    } else {
+        if (TERMINAL == OUT_TERMINAL) io.reward[io.idx] = r;
+        else if (write_zero) io.reward[io.idx] = 0.f;
+        io.flags[io.idx >> 1] = (uint8_t)(P ? L.winner : (int)done);
+    }
     io.idx += io.n2;
     if (A.P.auto_reset && done) {                                     // game_reset (SkillshotGame.py:168-169)
         int x = P ? 200 : 50, y = x;
@@ -316,11 +331,11 @@ __device__ __forceinline__ void lane_tick(Lane &L, double *qrot, const float mov
     }
 }
 
-template <bool TERMINAL, bool CHECKED>
+template <int TERMINAL, bool CHECKED>
 __device__ __forceinline__ void lane_loop(Lane &L, double *qrot, const StepArgs &A, LaneIo &io, int lane, int P, int64_t env,
                                           bool &nan_seen) {
     const int limit = A.P.tick_limit > 0 ? (int)min((int64_t)0x7fffffff, A.P.tick_limit) : 0x7fffffff;
-    const bool write_zero = !TERMINAL && A.reward_out && A.P.reward_mode != SS_REWARD_NONE;
+    const bool write_zero = TERMINAL == OUT_FLAGS && A.reward_out && A.P.reward_mode != SS_REWARD_NONE;
     const int T = A.n_ticks;
     const float2 zero = make_float2(0.f, 0.f);
     // tick t needs move(t) and look(t + 1): the action of tick t + 1 is consumed during tick t (its look half now, its
@@ -332,6 +347,10 @@ __device__ __forceinline__ void lane_loop(Lane &L, double *qrot, const StepArgs 
     Turn ta, tb;
     turn_from<CHECKED>(ta, L.rot, a0.y);
     float move = a0.x;
+    // (The register loads run one tick ahead of their use, ~500 cycles of a warp's own time, less than a DRAM access under
+    //  load, and ncu attributes 36 % of the stall samples to the first use of a loaded action.  That is where a warp that
+    //  ran ahead parks, not what bounds the kernel: four loads in flight per lane, and an L2 prefetch eight ticks ahead,
+    //  were both measured and left the launch time unchanged -- 119 / 108.5 us -- while costing registers / issue slots.)
     for (int t = 0; t < T; t += 2) {
         lane_tick<TERMINAL, CHECKED>(L, qrot, move, qa.y, ta, tb, A, io, lane, P, env, t, limit, write_zero, nan_seen);
         move = qa.x;
@@ -344,8 +363,8 @@ __device__ __forceinline__ void lane_loop(Lane &L, double *qrot, const StepArgs 
     }
 }
 
-// TERMINAL: write the +1 / -1 / 0 reward (readme.md:10); otherwise rewards are not written (reward_mode none) or zero.
-template <bool TERMINAL>
+// TERMINAL: one of OUT_FLAGS / OUT_TERMINAL / OUT_PACKED.
+template <int TERMINAL>
 __global__ void __launch_bounds__(kBlockPP, 14) step_pp_kernel(const StepArgs A) {
     __shared__ double qrot_sh[kBlockPP];
     const int lane = threadIdx.x & 31, P = lane & 1;
@@ -376,7 +395,7 @@ __global__ void __launch_bounds__(kBlockPP, 14) step_pp_kernel(const StepArgs A)
     io.idx = (uint32_t)gl; io.n2 = (uint32_t)(2 * A.n);               // (the launch checks that 2n * (n_ticks + 2) fits 32 bits)
     io.actions = (const float2 *)A.actions;
     io.reward = (float *)A.reward_out;
-    io.flags = P ? A.winner_out : A.done_out;
+    io.flags = TERMINAL == OUT_PACKED ? A.packed_out : (P ? A.winner_out : A.done_out);
     // A rotation moves by at most 0.25 per tick and a reset zeroes it, so |rot| + 0.25 * n_ticks < 1e5 at the start keeps
     // every rotation of this launch inside the range of the fast sin / cos: the per-tick range check (and the basic-block
     // boundary it puts in the middle of the tick) then goes.  Otherwise (400,000 ticks of one-sided turning without a
@@ -530,6 +549,12 @@ inline bool getenv_pp() {
     if (v < 0) { const char *e = getenv("SS_STEP_PP"); v = (e && e[0] == '0') ? 0 : 1; }
     return v != 0;
 }
+// SS_STEP_PDL=0 launches the one-tick physics kernel without programmatic dependent launch (A/B measurements only)
+inline bool getenv_pdl() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SS_STEP_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
 inline int check_launch() { return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA; }
 inline unsigned blocks_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
@@ -566,7 +591,7 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
     A.state = state; A.n = n_envs; A.actions = (const float4 *)actions; A.obs_out = (float4 *)obs_out;
     A.reward_out = (float2 *)reward_out; A.done_out = done_out; A.winner_out = winner_out;
     A.obs_out2 = (float4 *)obs_out2; A.done_rows_out = (uint16_t *)done_rows_out;
-    A.speeds = speeds; A.status = status;
+    A.speeds = speeds; A.status = status; A.packed_out = nullptr;
     A.stats = (status && (flags & SS_STEP_EPISODE_STATS)) ? reinterpret_cast<unsigned long long *>(status) + 1 : nullptr;
     if (A.stats && ((uintptr_t)status & 7)) return SS_ERR_INVALID_ARG;
     A.P.seed = seed; A.P.counter = counter; A.P.tick_limit = tick_limit;
@@ -598,12 +623,12 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
             else step_kernel<true, true, false, 8><<<grid, block, 0, st>>>(A);
         }
     } else if (n_ticks > 1 && !A.stats && !speeds && !shaped && !done_rows_out && done_out && winner_out &&
-               2 * n_envs * ((int64_t)n_ticks + 2) < (int64_t)0x7fffffff && getenv_pp()) {
+               2 * n_envs * ((int64_t)n_ticks + 2) < (int64_t)0x7fffffff && getenv_pp()) {     // (32-bit running index)
         // physics-only fused ticks (bench.py's timed shape): one thread per player.  (A single tick per launch stays on
         // the one-thread-per-env kernel: a launch then pays 3 sincos per lane to set up what it carries, measured 4.1 vs 3.9 us.)
         const dim3 grid_pp(blocks_for(2 * n_envs, kBlockPP));
-        if (reward_out && reward_mode == SS_REWARD_TERMINAL) step_pp_kernel<true><<<grid_pp, kBlockPP, 0, st>>>(A);
-        else step_pp_kernel<false><<<grid_pp, kBlockPP, 0, st>>>(A);
+        if (reward_out && reward_mode == SS_REWARD_TERMINAL) step_pp_kernel<OUT_TERMINAL><<<grid_pp, kBlockPP, 0, st>>>(A);
+        else step_pp_kernel<OUT_FLAGS><<<grid_pp, kBlockPP, 0, st>>>(A);
     } else if (carry) {
         if (A.stats) {
             if (speeds) step_kernel<false, true, true, 1, true><<<grid, block, 0, st>>>(A);
@@ -613,13 +638,24 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
             else step_kernel<false, true, false><<<grid, block, 0, st>>>(A);
         }
     } else {
+        // One physics tick per launch: a ~2 us kernel behind ~2 us of launch latency.  Launched with programmatic stream
+        // serialization, the grid is scheduled while its predecessor drains and waits (griddepcontrol.wait) before its
+        // first global access: back-to-back one-tick launches overlap their launch latency with the previous tick's tail.
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = getenv_pdl() ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t err;
         if (A.stats) {
-            if (speeds) step_kernel<false, false, true, 1, true><<<grid, block, 0, st>>>(A);
-            else step_kernel<false, false, false, 1, true><<<grid, block, 0, st>>>(A);
+            if (speeds) err = cudaLaunchKernelEx(&cfg, step_kernel<false, false, true, 1, true>, A);
+            else err = cudaLaunchKernelEx(&cfg, step_kernel<false, false, false, 1, true>, A);
         } else {
-            if (speeds) step_kernel<false, false, true><<<grid, block, 0, st>>>(A);
-            else step_kernel<false, false, false><<<grid, block, 0, st>>>(A);
+            if (speeds) err = cudaLaunchKernelEx(&cfg, step_kernel<false, false, true>, A);
+            else err = cudaLaunchKernelEx(&cfg, step_kernel<false, false, false>, A);
         }
+        if (err != cudaSuccess) return SS_ERR_CUDA;
     }
     return check_launch();
 }
@@ -631,6 +667,21 @@ int ss_env_step(void *state, int64_t n_envs, const float *actions, float *obs_ou
                 uint32_t *status, int flags, void *stream) {
     return ss_env_step_ring(state, n_envs, actions, obs_out, nullptr, reward_out, done_out, nullptr, winner_out, n_ticks,
                             reward_mode, tick_limit, auto_reset, reset_mode, seed, counter, speeds, status, flags, stream);
+}
+
+int ss_env_step_packed(void *state, int64_t n_envs, const float *actions, uint8_t *packed_out, int n_ticks,
+                       int64_t tick_limit, int auto_reset, int reset_mode, uint64_t seed, uint64_t counter,
+                       uint32_t *status, void *stream) {
+    if (!state || !actions || !packed_out || n_envs <= 0 || n_ticks <= 0) return SS_ERR_INVALID_ARG;
+    if (auto_reset && reset_mode != SS_RESET_FIXED && reset_mode != SS_RESET_RANDOM) return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)state | (uintptr_t)actions) & 15) return SS_ERR_INVALID_ARG;
+    if (2 * n_envs * ((int64_t)n_ticks + 2) >= (int64_t)0x7fffffff) return SS_ERR_INVALID_ARG;
+    StepArgs A{};
+    A.state = state; A.n = n_envs; A.actions = (const float4 *)actions; A.packed_out = packed_out; A.status = status;
+    A.P.seed = seed; A.P.counter = counter; A.P.tick_limit = tick_limit; A.P.reward_mode = SS_REWARD_TERMINAL;
+    A.P.auto_reset = auto_reset ? 1 : 0; A.P.reset_mode = reset_mode; A.n_ticks = n_ticks;
+    step_pp_kernel<OUT_PACKED><<<blocks_for(2 * n_envs, kBlockPP), kBlockPP, 0, (cudaStream_t)stream>>>(A);
+    return check_launch();
 }
 
 int ss_env_features(const void *state, int64_t n_envs, double *feat_out, double *obs_out,

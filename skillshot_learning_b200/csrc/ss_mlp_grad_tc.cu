@@ -566,9 +566,12 @@ int ss_critic_grad_tc(const float *critic_params, const float *obs, const float 
     return launch_grad<NET_CRITIC>(A, grad_out, sse_out, workspace_bytes, stream);
 }
 
-int ss_actor_grad_tc(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
-                     float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, void *stream) {
-    if (!actor_params || !critic_params || !obs || !workspace || n <= 0) return SS_ERR_INVALID_ARG;
+// stage: 0 = the whole actor step; 1 = only a = actor(s) (it depends on neither network's pending update: a sharded update
+// runs it while the critic's gradient exchange is in flight); 2 = the rest, with stage 1's actions in the scratch area
+int ss_actor_grad_tc_staged(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
+                            float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, int stage,
+                            void *stream) {
+    if (!actor_params || !critic_params || !obs || !workspace || n <= 0 || stage < 0 || stage > 2) return SS_ERR_INVALID_ARG;
     if (((uintptr_t)actor_params | (uintptr_t)critic_params | (uintptr_t)obs | (uintptr_t)workspace) & 15)
         return SS_ERR_INVALID_ARG;
     // scratch behind the gradient slices: the actor's actions, -dQ/da and Q per row
@@ -579,8 +582,11 @@ int ss_actor_grad_tc(const float *actor_params, const float *critic_params, cons
     float *up = act + (n * 2 + 3) / 4 * 4;
     float *q = up + (n * 2 + 3) / 4 * 4;
     // a = actor(s);  q, -dq/da = critic([s, a]) with Dropout off;  then the actor's backward pass
-    int rc = ss_actor_forward_tc(actor_params, obs, act, n, 0.f, 0, 0.f, 0, 0, stream);
-    if (rc != SS_OK) return rc;
+    int rc;
+    if (stage != 2) {
+        rc = ss_actor_forward_tc(actor_params, obs, act, n, 0.f, 0, 0.f, 0, 0, stream);
+        if (rc != SS_OK || stage == 1) return rc;
+    }
     rc = ss_critic_forward_tc(critic_params, obs, act, n, q, up, nullptr, nullptr, 0.f, nullptr, stream);
     if (rc != SS_OK) return rc;
     GradArgs A{};
@@ -588,6 +594,11 @@ int ss_actor_grad_tc(const float *actor_params, const float *critic_params, cons
     // the rows' Q values are summed by the gradient kernel's row owners into the slices' extra slot: the fixed-order
     // reduction that follows (here or in ss_peer_reduce_push / ss_reduce_adam_tf) delivers sum Q without a kernel of its own
     return launch_grad<NET_ACTOR>(A, grad_out, q_sum_out, slice_bytes / 16 * 16, stream);
+}
+
+int ss_actor_grad_tc(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
+                     float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, void *stream) {
+    return ss_actor_grad_tc_staged(actor_params, critic_params, obs, n, grad_out, q_sum_out, workspace, workspace_bytes, 0, stream);
 }
 
 int ss_ddpg_targets_tc(const float *target_actor_params, const float *target_critic_params, const float *reward,

@@ -51,10 +51,21 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
     rc = critic_grad(a->critic, a->obs, a->act, y, nullptr, a->dropout_rate, a->seed, a->counter, n, a->n_global, a->row_offset,
                      nullptr, a->stats, a->workspace, a->workspace_bytes, stream);
     if (rc <= 0) return rc < 0 ? rc : SS_ERR_INVALID_ARG;
+    // The actor step begins with a = actor(s), which needs neither the critic's new weights nor anything the exchange
+    // delivers: on the tensor-core path of a sharded update it is enqueued BETWEEN the push of this rank's critic gradient and
+    // the Adam kernel that waits for the peers' pushes, so that the exchange's latency (rank skew + NVLink visibility,
+    // ~20 us on 8 GPUs) passes under 15 us of useful work instead of an idle spin.  (The gradient slices of the critic step
+    // have been consumed by the push kernel by then; the actions land in the scratch area behind the slices.)
+    const bool early_actor_forward = peers && tc;
     if (peers) {
         rc = ss_peer_reduce_push(a->workspace, rc, SS_CRITIC_PARAMS, a->stats, a->peer_bases, a->world, a->rank,
                                  a->peer_capacity, a->epoch, a->done_counter, stream);
         if (rc != SS_OK) return rc;
+        if (early_actor_forward) {
+            rc = ss_actor_grad_tc_staged(a->actor, a->critic, a->obs, n, nullptr, a->stats + 1, a->workspace, a->workspace_bytes, 1,
+                                         stream);
+            if (rc != SS_OK) return rc;
+        }
         rc = ss_peer_adam_tf(a->peer_bases[a->rank], a->world, a->peer_capacity, a->epoch, a->critic, a->m_critic, a->v_critic,
                              a->target_critic, a->grad_critic, SS_CRITIC_PARAMS, a->step_critic, a->lr_critic, a->beta1,
                              a->beta2, a->eps, a->tau, 1.0f, a->status, stream);
@@ -65,8 +76,11 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
     if (rc != SS_OK) return rc;
 
     // actor: model_actor_fit_step with the critic just updated (SkillshotLearner.py:440-443 follows 434)
-    auto actor_grad = tc ? ss_actor_grad_tc : ss_actor_grad;
-    rc = actor_grad(a->actor, a->critic, a->obs, n, nullptr, a->stats + 1, a->workspace, a->workspace_bytes, stream);
+    if (early_actor_forward)
+        rc = ss_actor_grad_tc_staged(a->actor, a->critic, a->obs, n, nullptr, a->stats + 1, a->workspace, a->workspace_bytes, 2, stream);
+    else
+        rc = (tc ? ss_actor_grad_tc : ss_actor_grad)(a->actor, a->critic, a->obs, n, nullptr, a->stats + 1, a->workspace,
+                                                     a->workspace_bytes, stream);
     if (rc <= 0) return rc < 0 ? rc : SS_ERR_INVALID_ARG;
     if (peers) {
         rc = ss_peer_reduce_push(a->workspace, rc, SS_ACTOR_PARAMS, a->stats + 1, a->peer_bases, a->world, a->rank,

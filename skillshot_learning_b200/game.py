@@ -202,9 +202,12 @@ class SkillshotEnvs:
         return dict(obs=obs, reward=buf["reward"], done=buf["done"], winner=buf["winner"])
 
     # -- host-buffer API (end-to-end path) -----------------------------------
-    def alloc_host_outputs(self, n_ticks: int):
-        """Pinned host buffers for step_host: reward [T,n,2] f32, done [T,n] u8, winner [T,n] u8."""
+    def alloc_host_outputs(self, n_ticks: int, outputs: str = "full"):
+        """Pinned host buffers for step_host: reward [T,n,2] f32, done [T,n] u8, winner [T,n] u8; outputs="flags": one packed
+        byte per env and tick, flags [T,n] u8 (unpack_flags)."""
         n = self.n_envs
+        if outputs == "flags":
+            return dict(flags=torch.empty((n_ticks, n), dtype=torch.uint8, pin_memory=True))
         return dict(reward=torch.empty((n_ticks, n, 2), dtype=torch.float32, pin_memory=True),
                     done=torch.empty((n_ticks, n), dtype=torch.uint8, pin_memory=True),
                     winner=torch.empty((n_ticks, n), dtype=torch.uint8, pin_memory=True))
@@ -219,6 +222,8 @@ class SkillshotEnvs:
         KF = min(ticks_per_launch, T)
         if T % KF:
             raise ValueError("T must be a multiple of ticks_per_launch")
+        if "flags" in host_out:
+            return self._step_host_flags(host_actions, host_out, KF, n_buffers)
         key = ("host", KF, n_buffers)
         ring = self._host_ring.get(key) if hasattr(self, "_host_ring") else None
         if ring is None:
@@ -247,6 +252,51 @@ class SkillshotEnvs:
             b["stream"].synchronize()
         cur.wait_event(prev)
         return host_out
+
+    def _step_host_flags(self, host_actions, host_out, KF, n_buffers):
+        """step_host with the packed one-byte-per-env-step output (ss_env_step_packed): terminal reward mode, reference speed
+        constants.  16 bytes per env-step go up the bus, 1 comes back."""
+        if self.reward_mode != "terminal" or self.speeds is not None or self.collect_episode_stats:
+            raise ValueError("packed flags: terminal reward mode, reference speeds, no episode statistics")
+        T, n = host_actions.shape[0], self.n_envs
+        key = ("flags", KF, n_buffers)
+        ring = self._host_ring.get(key) if hasattr(self, "_host_ring") else None
+        if ring is None:
+            ring = [dict(stream=torch.cuda.Stream(self.device),
+                         act=torch.empty((KF, n, 2, 2), dtype=torch.float32, device=self.device),
+                         flags=torch.zeros((KF, n), dtype=torch.uint8, device=self.device)) for _ in range(n_buffers)]
+            self._host_ring = {key: ring}
+        cur = torch.cuda.current_stream(self.device)
+        prev = cur.record_event()
+        mode = _lib.RESET_RANDOM if self.random_positions else _lib.RESET_FIXED
+        for c in range(T // KF):
+            b = ring[c % n_buffers]
+            sl = slice(c * KF, (c + 1) * KF)
+            with torch.cuda.stream(b["stream"]), torch.cuda.device(self.device):
+                b["act"].copy_(host_actions[sl], non_blocking=True)
+                b["stream"].wait_event(prev)                 # the state is carried from chunk to chunk
+                check(lib.ss_env_step_packed(self.state.data_ptr(), n, b["act"].data_ptr(), b["flags"].data_ptr(), KF,
+                                             self.tick_limit, int(self.auto_reset), mode, self.seed, self.counter,
+                                             self.status.data_ptr(), b["stream"].cuda_stream), "ss_env_step_packed")
+                self.counter += KF
+                prev = b["stream"].record_event()
+                host_out["flags"][sl].copy_(b["flags"], non_blocking=True)
+        for b in ring:
+            b["stream"].synchronize()
+        cur.wait_event(prev)
+        return host_out
+
+    @staticmethod
+    def unpack_flags(flags):
+        """Packed step outputs -> dict(done, winner, reward [...,2]) as numpy arrays (include/skillshot_b200.h,
+        ss_env_step_packed): done = bit 0, winner_id = bits 1-2, bit 3 = the hit happened on this tick, which is when the
+        terminal reward is paid: -1 to the player that was hit, +1 to the shooter."""
+        f = flags.numpy() if torch.is_tensor(flags) else np.asarray(flags)
+        done, winner, hit = f & 1, (f >> 1) & 3, (f >> 3) & 1
+        reward = np.zeros(f.shape + (2,), np.float32)
+        reward[..., 0] = np.where(hit == 1, np.where(winner == 1, -1.0, 1.0), 0.0)
+        reward[..., 1] = np.where(hit == 1, np.where(winner == 2, -1.0, 1.0), 0.0)
+        return dict(done=done.astype(np.uint8), winner=winner.astype(np.uint8), reward=reward)
 
     def observe(self) -> torch.Tensor:
         """float32 [n,2,12] observation of the current state (prepare_states of get_state)."""

@@ -121,6 +121,30 @@ def test_bench_shape_short_episodes():
     assert episodes > 8192 * 5
 
 
+def test_step_host_full_and_packed_outputs_agree():
+    """The host-buffer API: pinned host actions in, outputs to pinned host memory, chunks pipelined over streams.  The full
+    outputs (reward / done / winner) equal a device-resident run; the packed one-byte output (ss_env_step_packed) decodes to
+    the same three arrays and leaves the same state."""
+    import torch
+    from skillshot_learning_b200.game import SkillshotEnvs
+    n, T = 3000, 96
+    kw = dict(random_positions=True, seed=21, reward_mode="terminal", tick_limit=25, auto_reset=True)
+    ref, full, packed = (make(n, **kw) for _ in range(3))
+    g = torch.Generator().manual_seed(4)
+    actions = (torch.rand((T, n, 2, 2), generator=g) * 2.4 - 1.2).pin_memory()
+    want = ref.step(actions.cuda(), want_obs=False)
+    out_full = full.step_host(actions, full.alloc_host_outputs(T), ticks_per_launch=32)
+    out_flags = packed.step_host(actions, packed.alloc_host_outputs(T, outputs="flags"), ticks_per_launch=32)
+    dec = SkillshotEnvs.unpack_flags(out_flags["flags"])
+    for k in ("reward", "done", "winner"):
+        np.testing.assert_array_equal(out_full[k].numpy(), want[k].cpu().numpy(), err_msg=k)
+        np.testing.assert_array_equal(dec[k], want[k].cpu().numpy(), err_msg="packed " + k)
+    assert int(want["done"].sum()) > n and int((want["winner"] != 0).sum()) > 0
+    parity.assert_state_equal(full.export_state(), ref.export_state(), "step_host state")
+    parity.assert_state_equal(packed.export_state(), ref.export_state(), "packed state")
+    packed.check_status()
+
+
 def test_facade_matches_reference_surface():
     """The SkillshotGame / Player / Projectile object surface on one device env (KAT-A, KAT-D)."""
     from skillshot_learning_b200.game import SkillshotGame

@@ -7,6 +7,7 @@ and parameter counts printed by the reference's model.summary(), central-differe
 gradients in float64, a hand-computed tf.keras Adam step, and the gamma = 0 / tau = 1
 reduction to the reference's update."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import learner_oracle as lo
@@ -132,3 +133,32 @@ def test_sharded_gradient_sums_to_the_full_batch_gradient():
     fa, _ = lo.actor_grad(theta, phi, s)
     pa = [lo.actor_grad(theta, phi, s[i:i + 16])[0] for i in (0, 16)]
     np.testing.assert_allclose(pa[0] + pa[1], fa, rtol=2e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("frames", [1, 3])
+def test_two_independent_restatements_agree(frames):
+    """oracle/learner_oracle.py (torch autograd) against oracle/learner_oracle_np.py (numpy, hand-derived backward pass,
+    written separately): gradients of the critic's fit loss and of the actor step, and three Adam steps, in float64."""
+    import torch
+    from oracle import learner_oracle_np as ln
+    rng = np.random.default_rng(5)
+    theta, phi = lo.init_actor(rng, frames).astype(np.float64), lo.init_critic(rng, frames).astype(np.float64)
+    n = 37
+    s = rng.uniform(0, 1, (n, 12 * frames)); a = rng.uniform(-1, 1, (n, 2)); y = -rng.uniform(0, 1, n)
+    keep = (rng.uniform(size=(n, 256)) >= 0.2).astype(np.float64)
+    for k in (None, keep):
+        g1, sse1 = lo.critic_grad(phi, s, a, y, k, 0.2, n_global=50, dtype=torch.float64)
+        g2, sse2 = ln.critic_grad(phi, s, a, y, k, 0.2, n_global=50)
+        np.testing.assert_allclose(g2, g1, rtol=1e-9, atol=1e-13)
+        assert abs(sse1 - sse2) <= 1e-10 * abs(sse1)
+    g1, q1 = lo.actor_grad(theta, phi, s, dtype=torch.float64)
+    g2, q2 = ln.actor_grad(theta, phi, s)
+    np.testing.assert_allclose(g2, g1, rtol=1e-9, atol=1e-13)
+    assert abs(q1 - q2) <= 1e-10 * abs(q1)
+    opt = lo.AdamTF(len(phi), dtype=np.float64)
+    p1, p2, m, v = phi.copy(), phi.copy(), np.zeros_like(phi), np.zeros_like(phi)
+    for t in range(1, 4):
+        g = rng.normal(size=len(phi)) * 1e-3
+        p1 = opt.step(p1, g)
+        p2, m, v = ln.adam_step(p2, g, m, v, t)
+    np.testing.assert_allclose(p2, p1, rtol=1e-12, atol=1e-15)
