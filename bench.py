@@ -13,8 +13,10 @@ it from HBM ("inputs larger than L2"); the 4 MB game state is L2-resident by
 design.
 
   value     whole-job env-steps/s, actions resident in HBM, CUDA-event timed
-  e2e       the same through SkillshotEnvs.step_host: pinned HOST actions in,
-            reward/done/winner back to pinned HOST memory, copies inside the timing
+  e2e       the same through SkillshotEnvs.step_host: pinned HOST actions in, the
+            step's result back to pinned HOST memory as one packed byte per env-step
+            (done, winner, hit tick), copies inside the timing; the three-array form
+            (reward / done / winner, 10 B per env-step) is reported beside it
   roofline  HBM: algorithmic 202 B per env-step x env-steps per
             launch / average launch time, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the C oracle port (oracle/skillshot_oracle.c, OpenMP over envs)
@@ -730,16 +732,15 @@ def run_gpu_arm(args):
             envs.step_host(host_actions, flags_out, ticks_per_launch=KE)
         barrier()
         e2e_flags_s = time.perf_counter() - t0
-        del flags_out
         if world > 1:
             # in-run baseline of this leg's scaling: rank 0 alone on the host's memory and PCIe fabric, the others idle
             if rank == 0:
                 t0 = time.perf_counter()
                 for _ in range(e2e_solo_steps):
-                    envs.step_host(host_actions, host_out, ticks_per_launch=KE)
+                    envs.step_host(host_actions, flags_out, ticks_per_launch=KE)
                 e2e_solo_s = time.perf_counter() - t0
             barrier()
-        del host_actions, host_out
+        del host_actions, host_out, flags_out
 
     # ---- learner legs: rollout, DDPG update, tensor roofline of the actor forward ----
     lt, checks = {k: float("nan") for k in LEG_KEYS}, {}
@@ -802,20 +803,23 @@ def run_gpu_arm(args):
                                       "frac": None if fp64_inst is None else fp64_inst / launch_s / rates["fp64_warp_inst_per_sec"]},
                              "peak_source": "ss_probe_rates in this run: register-only LOP3+IMAD / DFMA streams (csrc/ss_probe.cu); "
                                             "instruction counts per launch from the committed ncu capture (profiles/traffic.json)"}},
-            "e2e": {"value": None if args.no_e2e else world * E * T * e2e_steps / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": T * E * 16, "d2h_bytes_per_step": T * E * 10,
+            # SkillshotEnvs.step_host with pinned HOST buffers, copies inside the timed region.  The step's result comes back as
+            # one packed byte per env-step (done, winner_id, hit tick: reward / done / winner follow from it without loss,
+            # SkillshotEnvs.unpack_flags); the same call returning the three arrays separately (10 B per env-step) is beside it.
+            "e2e": {"value": None if args.no_e2e else world * E * T * e2e_steps / e2e_flags_s, "unit": UNIT,
+                    "h2d_bytes_per_step": T * E * 16, "d2h_bytes_per_step": T * E,
                     "ticks_per_launch": KE,
-                    "note": "PCIe-bound: 26 B per env-step cross the bus (float32 actions in; reward, done, winner out); "
+                    "outputs": "step_host(outputs='flags'): uint8 [T, E] = done | winner_id << 1 | hit << 3",
+                    "note": "bus-bound: 17 B per env-step cross PCIe (16 of float32 actions up, 1 packed result byte down); "
                             "rank processes pinned to their GPU's NUMA node (%d CPUs) before the pinned buffers are allocated"
-                            % numa_cpus},
+                            % numa_cpus,
+                    "full_outputs": {"value": None if args.no_e2e else world * E * T * e2e_steps / e2e_s, "unit": UNIT,
+                                     "d2h_bytes_per_step": T * E * 10,
+                                     "note": "the same call returning reward float32 [T,E,2], done and winner uint8 [T,E]: 26 B per "
+                                             "env-step on the bus (round 1's e2e figure)"}},
             "gpu_launches": args.steps * launches_per_step,
             "clocks": clocks,
         }
-        if not args.no_e2e:
-            line["e2e"]["packed_flags_output"] = {
-                "value": world * E * T * e2e_steps / e2e_flags_s, "unit": UNIT, "d2h_bytes_per_step": T * E,
-                "note": "step_host(outputs='flags'): one byte per env-step back (done, winner, hit tick; the terminal reward "
-                        "follows from them) instead of 10"}
         if world > 1 and not args.no_e2e and e2e_solo_s > 0:
             solo = E * T * e2e_solo_steps / e2e_solo_s
             line["e2e"]["one_rank_alone_env_steps_per_sec"] = solo

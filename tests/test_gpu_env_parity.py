@@ -43,6 +43,14 @@ def test_oracle_lockstep_ragged_size():
     parity.check_oracle_lockstep(make, n=1000 + 37, T=32, seed=4)
 
 
+def test_oracle_lockstep_fused_ragged_sizes():
+    """Fused physics ticks (the one-thread-per-player kernel) on env counts that leave a warp / CTA partly filled: lanes past
+    the end replay the last env, and nothing may leak into its outputs."""
+    for n, seed in ((1, 21), (5, 22), (1000 + 37, 23)):
+        parity.check_oracle_lockstep(make, n=n, T=48, seed=seed, close=True, reward_mode="terminal", chunk=8)
+    parity.check_oracle_lockstep(make, n=333, T=33 * 3, seed=24, close=True, reward_mode="none", chunk=3)   # odd fused count
+
+
 def test_single_env():
     parity.check_oracle_lockstep(make, n=1, T=64, seed=6)
 
@@ -67,6 +75,24 @@ def test_nan_action_raises_like_reference():
     e.step(torch.from_numpy(a))
     with pytest.raises(ValueError):
         e.check_status()
+
+
+def test_nan_action_raises_like_reference_fused():
+    """The same through the fused physics-only kernel (one thread per player, rotations turned one tick ahead): a NaN move
+    raises on its own tick; a NaN look makes the rotation NaN and raises on the NEXT tick's move (int(round(nan)),
+    Player.py:63) -- so not at all when it arrives on the last tick of the run (no projectile is fired on tick 1: the
+    cooldown set on tick 0 is still running, so Projectile.move_forwards does not see the NaN either)."""
+    import torch
+    for component, n_ticks, raises in ((0, 4, True), (1, 4, True), (1, 2, False)):
+        e = make(6, reward_mode="terminal")
+        a = np.zeros((n_ticks, 6, 2, 2), np.float32)
+        a[1, 3, 1, component] = np.nan                  # tick 1, env 3, player 2: move (0) or look (1)
+        e.step(torch.from_numpy(a), want_obs=False)
+        if raises:
+            with pytest.raises(ValueError):
+                e.check_status()
+        else:
+            e.check_status()
 
 
 def test_tan_half_pi_matches_libm():
