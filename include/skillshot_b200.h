@@ -317,6 +317,20 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
                         uint64_t env_counter, uint64_t noise_seed, uint64_t noise_counter, const void *speeds,
                         uint32_t *status, int step_flags, void *stream);
 
+/* One rollout tick as ONE kernel (tensor-core path): ss_actor_forward_tc on the players' observations (n_rows = 2 x envs,
+ * row = 2 env + player) and, in its output stage, the env step of those players -- do_actions, game_tick, reward of the
+ * post-tick state, auto-reset, next observation (SkillshotLearner.py:304-315) -- by the lane that has just computed the
+ * player's action.  Same results, bit for bit, as ss_actor_forward_tc followed by ss_env_step_ring with auto_reset = 1:
+ * act_out [n_rows][2]; obs_next (and obs_next2 if not NULL) [n_rows][12]; reward_out [n_rows]; done_out / winner_out
+ * [n_rows / 2]; done_rows_out [n_rows] (the hit flag per row).  reward_mode none / looking / terminal, reference speeds.
+ * ss_selfplay_rollout uses it for its in-place ring form. */
+int ss_actor_forward_step_tc(const float *actor_params, const float *obs, float *act_out, int64_t n_rows,
+                             float param_noise_sd, int64_t noise_group, float action_noise_sd, uint64_t seed,
+                             uint64_t counter, void *env_state, float *obs_next, float *obs_next2, float *reward_out,
+                             uint8_t *done_out, uint8_t *done_rows_out, uint8_t *winner_out, int reward_mode,
+                             int64_t tick_limit, int reset_mode, uint64_t env_seed, uint64_t env_counter,
+                             uint32_t *status, int flags, void *stream);
+
 /* ---- frame-stacked ("planning") actor: readme.md:18-20, BASELINE.json configs[4]; no reference code ----
  * The actor reads the last `frames` observations of a player: first layer 12 * frames -> 256, the rest as
  * model_define_actor (SkillshotLearner.py:70-96); frames = 1 is the reference actor.  Parameters are one flat

@@ -26,7 +26,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = {
     "ss_env.cu": ["-fmad=false"],
     "ss_learner.cu": [],
-    "ss_mlp_tc.cu": [],
+    "ss_mlp_tc.cu": [],      # (NOT -fmad=false: it costs the noise staging's sqrtf / fast-math sequences 18 %; the per-player env tick
+                             #  it inlines, ss_env_pp.cuh, is written with explicit _rn intrinsics and needs no flag)
     "ss_mlp_grad_tc.cu": [],
     "ss_peer.cu": [],
     "ss_update.cu": [],

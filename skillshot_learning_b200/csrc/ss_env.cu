@@ -14,6 +14,7 @@
 
 #include "../../include/skillshot_b200.h"
 #include "ss_env_core.cuh"
+#include "ss_env_pp.cuh"
 
 namespace {
 
@@ -95,7 +96,7 @@ struct StepArgs {
 // OBS: write observations.  CARRY: keep sin/cos of the rotations in registers across
 // ticks (fused ticks, observations, shaped rewards); !CARRY is the lean one-tick
 // physics-only kernel.
-template <bool OBS, bool CARRY, bool SPEEDS, int MINB = 1, bool STATS = false>
+template <bool OBS, bool CARRY, bool SPEEDS, int MINB = 1, bool STATS = false, bool PDL = false>
 __global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
     __shared__ float4 tile[OBS ? kWarps : 1][OBS ? 32 * kRowF4 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
     // Programmatic dependent launch (one-tick physics launches, ss_env_step_ring): this grid may have been scheduled while
     // the previous kernel of the stream was still running; nothing of global memory is touched before that kernel has
     // completed.  A launch without the attribute passes straight through.
-    if (!OBS && !CARRY) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
     Env e;
     Speeds k = default_speeds();
     if (active) {
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
     } else {
         reset_env(e, 50, 50, 200, 200);
     }
-    if (!OBS && !CARRY) asm volatile("griddepcontrol.launch_dependents;");     // the next launch may start its own prologue
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;");     // the next launch may start its own prologue
     uint32_t status = 0;
     const bool write_reward = A.reward_out && A.P.reward_mode != SS_REWARD_NONE;
     Trig tr;
@@ -416,6 +417,56 @@ __global__ void __launch_bounds__(kBlockPP, 14) step_pp_kernel(const StepArgs A)
     if (nan_seen && A.status) atomicOr(A.status, kStatusNaN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// step_pp_obs_kernel -- ONE tick with observations, one thread per player (ss_env_pp.cuh): the rollout's env step.
+// Each lane loads its player's half of the state, plays the tick, and writes its reward, its 12-float observation (three
+// float4, staged through shared memory so that a warp's 1,536 bytes leave as three fully coalesced 512-byte requests,
+// to both copies when the replay ring wants two), its terminal byte; the env's done / winner bytes come from the two
+// lanes of the pair.  Bit-identical to step_kernel<OBS = true> (the golden lockstep tests run through this kernel).
+template <bool STATS>
+__global__ void __launch_bounds__(kBlockPP) step_pp_obs_kernel(const StepArgs A) {
+    __shared__ float4 tile[kBlockPP / 32][96];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, P = lane & 1;
+    const int64_t g0 = (int64_t)blockIdx.x * kBlockPP + threadIdx.x;
+    const int64_t last = 2 * A.n - 2 + P;
+    const bool active = g0 <= last;
+    const int64_t gl = active ? g0 : last;            // lanes past the end replay the last env and store nothing
+    const int64_t env = gl >> 1;
+    sspp::LaneState L;
+    sspp::lane_load((const char *)A.state, A.n, gl, L);
+    const float2 a = __ldg((const float2 *)A.actions + gl);
+    uint32_t status = 0;
+    sspp::LaneTrig T;
+    sspp::lane_trig(L, T);
+    sspp::LaneTickOut out;
+    sspp::lane_obs_tick(L, T, a.x, a.y, A.P, (uint64_t)env, A.P.counter, lane, P, status, out);
+    const int v_other = __shfl_xor_sync(0xffffffffu, L.valid, 1);
+    if (active) {
+        sspp::lane_store((char *)A.state, A.n, gl, L, v_other);
+        if (A.reward_out && A.P.reward_mode != SS_REWARD_NONE) ((float *)A.reward_out)[gl] = out.reward;
+        uint8_t *flag = P ? A.winner_out : A.done_out;
+        if (flag) flag[env] = (uint8_t)(P ? out.winner : out.done);
+        if (A.done_rows_out) ((uint8_t *)A.done_rows_out)[gl] = out.winner ? 1 : 0;
+        if (STATS && !P && out.episode_len >= 0) count_episode(A.stats, out.episode_len, out.winner, (int)A.P.tick_limit);
+    }
+    // observations: lane's three float4 -> tile -> three coalesced stores per warp and copy
+#pragma unroll
+    for (int j = 0; j < 3; ++j) tile[warp][lane * 3 + j] = out.obs[j];
+    __syncwarp();
+    const int64_t warp_base = (g0 - lane) * 3;                        // in float4
+    const int64_t total = 2 * A.n * 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int64_t idx = warp_base + j * 32 + lane;
+        if (idx < total) {
+            const float4 v = tile[warp][j * 32 + lane];
+            A.obs_out[idx] = v;
+            if (A.obs_out2) A.obs_out2[idx] = v;
+        }
+    }
+    if (status && A.status) atomicOr(A.status, status);
+}
+
 __global__ void reset_kernel(void *state, int64_t n, const uint8_t *mask, int reset_mode,
                              const int32_t *positions, uint64_t seed, uint64_t counter) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -612,7 +663,12 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
     }
     // (the statistics variants are separate instantiations: the bookkeeping costs the physics-only kernels a few
     //  registers and ~5 % when compiled in)
-    if (obs_out) {
+    if (obs_out && n_ticks == 1 && !speeds && reward_mode != SS_REWARD_SIMPLE && getenv_pp()) {
+        // the rollout's env step: one tick with observations, one thread per player
+        const dim3 grid_pp(blocks_for(2 * n_envs, kBlockPP));
+        if (A.stats) step_pp_obs_kernel<true><<<grid_pp, kBlockPP, 0, st>>>(A);
+        else step_pp_obs_kernel<false><<<grid_pp, kBlockPP, 0, st>>>(A);
+    } else if (obs_out) {
         // 8 CTAs (16 warps) per SM: capping the observation kernel at 128 registers measured
         // 83 us vs 100 us uncapped at 1M envs (profiles/README.md)
         if (A.stats) {
@@ -641,21 +697,21 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
         // One physics tick per launch: a ~2 us kernel behind ~2 us of launch latency.  Launched with programmatic stream
         // serialization, the grid is scheduled while its predecessor drains and waits (griddepcontrol.wait) before its
         // first global access: back-to-back one-tick launches overlap their launch latency with the previous tick's tail.
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = getenv_pdl() ? 1 : 0;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        cudaError_t err;
-        if (A.stats) {
-            if (speeds) err = cudaLaunchKernelEx(&cfg, step_kernel<false, false, true, 1, true>, A);
-            else err = cudaLaunchKernelEx(&cfg, step_kernel<false, false, false, 1, true>, A);
+        if (getenv_pdl() && !A.stats && !speeds) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            if (cudaLaunchKernelEx(&cfg, step_kernel<false, false, false, 1, false, true>, A) != cudaSuccess) return SS_ERR_CUDA;
+        } else if (A.stats) {
+            if (speeds) step_kernel<false, false, true, 1, true><<<grid, block, 0, st>>>(A);
+            else step_kernel<false, false, false, 1, true><<<grid, block, 0, st>>>(A);
         } else {
-            if (speeds) err = cudaLaunchKernelEx(&cfg, step_kernel<false, false, true>, A);
-            else err = cudaLaunchKernelEx(&cfg, step_kernel<false, false, false>, A);
+            if (speeds) step_kernel<false, false, true><<<grid, block, 0, st>>>(A);
+            else step_kernel<false, false, false><<<grid, block, 0, st>>>(A);
         }
-        if (err != cudaSuccess) return SS_ERR_CUDA;
     }
     return check_launch();
 }

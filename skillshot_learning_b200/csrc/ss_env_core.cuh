@@ -137,31 +137,35 @@ static __constant__ double kSinCosDev[17] = {SS_SINCOS_CONSTANTS};
 #endif
 #define SS_LIT(i) SS_C##i
 
+// Every multiply / add / subtract below goes through the explicit round-to-nearest wrappers (mul / add / sub): the
+// result is then the same whether or not the translation unit lets the compiler contract a * b + c (ss_env.cu is built
+// with -fmad=false, the tensor-core units that inline this for the fused rollout kernel are not), and the same as the
+// host build's.  The fma() calls are the algorithm's own.
 #define SS_SINCOS_BODY(C, CHECKED)                                                                          \
     {                                                                                                       \
         if (CHECKED && !(fabs(x) < 1.0e5)) { sincos_lib(x, sp, cp); return; }                               \
         const double kMagic = C(0);                                                                         \
         double q = fma(x, C(1), kMagic); /* x * 2/pi */                                                     \
         const int k = lo_word(q);                                                                           \
-        q -= kMagic;                                                                                        \
+        q = sub(q, kMagic);                                                                                 \
         double t = fma(q, C(2), x);                                                                         \
         t = fma(q, C(3), t);                                                                                \
         t = fma(q, C(4), t);                                                                                \
-        const double t2 = t * t;                                                                            \
+        const double t2 = mul(t, t);                                                                        \
         double ps = fma(C(5), t2, C(6));                                                                    \
         ps = fma(ps, t2, C(7));                                                                             \
         ps = fma(ps, t2, C(8));                                                                             \
         ps = fma(ps, t2, C(9));                                                                             \
         ps = fma(ps, t2, C(10));                                                                            \
-        const double sn = fma(t * t2, ps, t);                                                               \
+        const double sn = fma(mul(t, t2), ps, t);                                                           \
         double pc = fma(C(11), t2, C(12));                                                                  \
         pc = fma(pc, t2, C(13));                                                                            \
         pc = fma(pc, t2, C(14));                                                                            \
         pc = fma(pc, t2, C(15));                                                                            \
         pc = fma(pc, t2, C(16));                                                                            \
         /* 1 - t2/2 + t2^2*pc with the rounding error of (1 - t2/2) fed back (fdlibm/musl __cos form) */    \
-        const double hz = 0.5 * t2, w = 1.0 - hz;                                                           \
-        const double cs = w + (((1.0 - w) - hz) + (t2 * t2) * pc);                                          \
+        const double hz = mul(0.5, t2), w = sub(1.0, hz);                                                   \
+        const double cs = add(w, add(sub(sub(1.0, w), hz), mul(mul(t2, t2), pc)));                          \
         /* quadrant k mod 4: (s,c) = (sn,cs), (cs,-sn), (-sn,-cs), (-cs,sn) */                              \
         const int swap = k & 1;                                                                             \
         const double a = swap ? cs : sn, b = swap ? sn : cs;                                                \

@@ -34,6 +34,8 @@
 // draws.
 #include "ss_tc_common.cuh"
 
+#include "ss_env_pp.cuh"
+
 namespace {
 
 using namespace sstc;
@@ -55,6 +57,15 @@ struct FwdArgs {
     float gamma;
     long long *trace;        // development: event timestamps of CTA 0 (NULL in production)
     int dbg;                 // development ablations: 1 = output warps skip layer 3, 2 = producers skip the conversion
+    // fused env step (ss_actor_forward_step_tc): rows are players in env order (row = 2 env + player); the output-warp lane
+    // that has just computed a player's action plays that player's tick (ss_env_pp.cuh) and writes the transition
+    void *env_state;         // packed env state of n / 2 envs
+    ss::TickParams TP;
+    float4 *obs_next, *obs_next2;     // the next observation, [n][12] floats each (second copy may be NULL)
+    float *reward_out;       // [n]
+    uint8_t *done_out, *winner_out, *done_rows_out;     // [n / 2], [n / 2], [n]
+    uint32_t *env_status;
+    unsigned long long *env_stats;
 };
 
 // 32 accumulator columns (hidden-2 units) -> ReLU -> layer 3, four split accumulators per output.
@@ -118,7 +129,7 @@ constexpr uint32_t SMP_TMEM = SMP_BAR + B_COUNT * 8;
 constexpr uint32_t SMP_TOTAL = SMP_TMEM + 16;
 static_assert(SMP_TOTAL <= 227 * 1024, "shared memory budget");
 
-template <int NET>
+template <int NET, bool FUSED = false>
 __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -165,6 +176,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
 
     uint32_t tcount = 0;                                     // tiles done by this CTA: buffers = tcount & 1, parities from tcount
     uint32_t xph = 0;                                        // MMA warp: parity of the next X hand-off
+    uint32_t env_status = 0;                                 // FUSED: SS_STATUS_* bits of this thread's env ticks
 
     for (int64_t u = u0; u < u1;) {
         const int64_t g = u / upg;
@@ -234,6 +246,15 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                 const uint32_t tc = tcount + (uint32_t)i, slot = tc & 1;
                 const int64_t row = row0 + i * TM + r;
                 trace(1, 100 + (int)i);
+                // FUSED: this row's player.  Its state and the sin / cos of its two rotations do not depend on the action:
+                // they are fetched and evaluated here, in the time this warp would otherwise spend waiting for MMA2.
+                sspp::LaneState L;
+                sspp::LaneTrig T;
+                const int64_t gl = FUSED ? min(row, A.n - 2 + (int64_t)(lane & 1)) : 0;      // rows past the end replay the last env
+                if (FUSED) {
+                    sspp::lane_load((const char *)A.env_state, A.n >> 1, gl, L);
+                    sspp::lane_trig(L, T);
+                }
                 mbar_wait(bar(B_Y + slot), (tc >> 1) & 1);
                 tc_fence_after();
                 trace(1, 200 + (int)i);
@@ -258,6 +279,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                 const float out0 = (acc[0][0] + acc[0][1]) + (acc[0][2] + acc[0][3]);
                 const float out1 = (acc[1][0] + acc[1][1]) + (acc[1][2] + acc[1][3]);
                 const float out2 = (acc[2][0] + acc[2][1]) + (acc[2][2] + acc[2][3]);
+                float fa0 = 0.f, fa1 = 0.f;                   // FUSED: the action this lane hands to its player's tick
                 if (row < end) {
                     if (NET == NET_ACTOR) {
                         float a0 = tanhf(out0), a1 = tanhf(out1);
@@ -268,10 +290,33 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                             a1 += A.action_sd * zn[1];
                         }
                         reinterpret_cast<float2 *>(A.act_out)[row] = make_float2(a0, a1);
+                        if (FUSED) { fa0 = a0; fa1 = a1; }
                     } else {
                         if (A.q_out) A.q_out[row] = out0;
                         if (A.up_out) reinterpret_cast<float2 *>(A.up_out)[row] = make_float2(-out1, -out2);
                         if (A.y_out) A.y_out[row] = A.reward[row] + A.gamma * ((A.done && A.done[row]) ? 0.f : 1.f) * out0;
+                    }
+                }
+                if (FUSED) {
+                    // do_actions + game_tick + reward + auto-reset + next observation of this player, on the spot: all 32
+                    // lanes take part (the hit test is a shuffle and a ballot between the two lanes of an env)
+                    const int P = lane & 1;
+                    sspp::LaneTickOut o;
+                    sspp::lane_obs_tick(L, T, fa0, fa1, A.TP, (uint64_t)(gl >> 1), A.TP.counter, lane, P, env_status, o);
+                    const int v_other = __shfl_xor_sync(0xffffffffu, L.valid, 1);
+                    if (row < end) {
+                        sspp::lane_store((char *)A.env_state, A.n >> 1, row, L, v_other);
+                        if (A.reward_out) A.reward_out[row] = o.reward;
+                        uint8_t *flag = P ? A.winner_out : A.done_out;
+                        if (flag) flag[row >> 1] = (uint8_t)(P ? o.winner : o.done);
+                        if (A.done_rows_out) A.done_rows_out[row] = o.winner ? 1 : 0;
+                        if (A.env_stats && !P && o.episode_len >= 0)
+                            sspp::count_episode_pp(A.env_stats, o.episode_len, o.winner, (int)A.TP.tick_limit);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            A.obs_next[row * 3 + j] = o.obs[j];
+                            if (A.obs_next2) A.obs_next2[row * 3 + j] = o.obs[j];
+                        }
                     }
                 }
                 trace(1, 800 + (int)i);
@@ -352,11 +397,12 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
+    if (FUSED && env_status && A.env_status) atomicOr(A.env_status, env_status);
 }
 
 }  // namespace pipe
 
-template <int NET>
+template <int NET, bool FUSED = false>
 int launch_fwd(const FwdArgs &A, void *stream) {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return SS_ERR_CUDA;
@@ -367,10 +413,10 @@ int launch_fwd(const FwdArgs &A, void *stream) {
     // perturbed weights are staged once per noise group a CTA touches: when the groups fit the SMs, give every CTA
     // exactly one group (the kernel's even split of units is then group-aligned) instead of letting ranges straddle two
     if (A.group < A.n && n_groups <= sms) grid = (int)n_groups;
-    if (cudaFuncSetAttribute(pipe::mlp_fwd_pipe_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(pipe::mlp_fwd_pipe_kernel<NET, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)pipe::SMP_TOTAL) != cudaSuccess)
         return SS_ERR_CUDA;
-    pipe::mlp_fwd_pipe_kernel<NET><<<grid, pipe::NTH, pipe::SMP_TOTAL, (cudaStream_t)stream>>>(A);
+    pipe::mlp_fwd_pipe_kernel<NET, FUSED><<<grid, pipe::NTH, pipe::SMP_TOTAL, (cudaStream_t)stream>>>(A);
     return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
 }
 
@@ -388,6 +434,38 @@ extern "C" int ss_actor_forward_tc(const float *actor_params, const float *obs, 
     A.params = actor_params; A.obs = obs; A.n = n; A.group = noisy ? noise_group : n;
     A.act_out = act_out; A.param_sd = param_noise_sd; A.action_sd = action_noise_sd; A.seed = seed; A.counter = counter;
     return launch_fwd<NET_ACTOR>(A, stream);
+}
+
+// The rollout tick as ONE kernel: actor forward on the players' observations, and in its output stage the env step of
+// those very players (ss_env_pp.cuh) -- do_actions, game_tick, reward, auto-reset, next observation -- written straight
+// into the replay ring's rows.  Same results, bit for bit, as ss_actor_forward_tc followed by ss_env_step_ring.
+extern "C" int ss_actor_forward_step_tc(const float *actor_params, const float *obs, float *act_out, int64_t n_rows,
+                                        float param_noise_sd, int64_t noise_group, float action_noise_sd, uint64_t seed,
+                                        uint64_t counter, void *env_state, float *obs_next, float *obs_next2, float *reward_out,
+                                        uint8_t *done_out, uint8_t *done_rows_out, uint8_t *winner_out, int reward_mode,
+                                        int64_t tick_limit, int reset_mode, uint64_t env_seed, uint64_t env_counter,
+                                        uint32_t *status, int flags, void *stream) {
+    if (!actor_params || !obs || !act_out || n_rows <= 0 || (n_rows & 1) || param_noise_sd < 0.f || action_noise_sd < 0.f ||
+        !env_state || !obs_next)
+        return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)actor_params | (uintptr_t)obs | (uintptr_t)env_state | (uintptr_t)obs_next | (uintptr_t)obs_next2) & 15 ||
+        ((uintptr_t)act_out & 7) || ((uintptr_t)reward_out & 3))
+        return SS_ERR_INVALID_ARG;
+    if (reward_mode != SS_REWARD_NONE && reward_mode != SS_REWARD_LOOKING && reward_mode != SS_REWARD_TERMINAL) return SS_ERR_INVALID_ARG;
+    if (reset_mode != SS_RESET_FIXED && reset_mode != SS_RESET_RANDOM) return SS_ERR_INVALID_ARG;
+    const bool noisy = param_noise_sd > 0.f;
+    if (noisy && (noise_group <= 0 || noise_group % TM != 0)) return SS_ERR_INVALID_ARG;
+    FwdArgs A{};
+    A.params = actor_params; A.obs = obs; A.n = n_rows; A.group = noisy ? noise_group : n_rows;
+    A.act_out = act_out; A.param_sd = param_noise_sd; A.action_sd = action_noise_sd; A.seed = seed; A.counter = counter;
+    A.env_state = env_state; A.obs_next = (float4 *)obs_next; A.obs_next2 = (float4 *)obs_next2;
+    A.reward_out = reward_mode != SS_REWARD_NONE ? reward_out : nullptr;
+    A.done_out = done_out; A.winner_out = winner_out; A.done_rows_out = done_rows_out; A.env_status = status;
+    A.env_stats = (status && (flags & SS_STEP_EPISODE_STATS)) ? reinterpret_cast<unsigned long long *>(status) + 1 : nullptr;
+    if (A.env_stats && ((uintptr_t)status & 7)) return SS_ERR_INVALID_ARG;
+    A.TP.seed = env_seed; A.TP.counter = env_counter; A.TP.tick_limit = tick_limit; A.TP.reward_mode = reward_mode;
+    A.TP.auto_reset = 1; A.TP.reset_mode = reset_mode;
+    return launch_fwd<NET_ACTOR, true>(A, stream);
 }
 
 // development: the actor forward with an event trace of CTA 0 (3 roles x 256 events x {clock, code}); tools/tc_trace.py

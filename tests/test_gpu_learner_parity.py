@@ -477,6 +477,50 @@ def test_library_side_rollout_loop_equals_per_tick_calls(capacity):
         assert torch.equal(a.obs, b.obs) and a.replay.pos == b.replay.pos and a.replay.size == b.replay.size
 
 
+def test_fused_forward_and_env_step_kernel_equals_the_two_kernels():
+    """ss_actor_forward_step_tc (the rollout tick as ONE kernel: the env step of a row is played in the forward kernel's
+    output stage by the lane that computed its action; off by default in ss_selfplay_rollout because it is slower) against
+    ss_actor_forward_tc followed by the env step: actions, next observations, rewards, flags, episode statistics and the env
+    state must be bit-identical, tick after tick, through hits, tick-limit restarts and parameter noise."""
+    from skillshot_learning_b200 import ActorCritic, SkillshotEnvs, _lib
+    from skillshot_learning_b200._lib import lib, check
+    n = 1000                                                        # rows 2,000: a ragged last tile
+    ac = ActorCritic(device="cuda:0", seed=3)
+    a_envs, b_envs = (SkillshotEnvs(n, device="cuda:0", random_positions=True, seed=5, reward_mode="looking", tick_limit=12,
+                                    auto_reset=True) for _ in range(2))
+    for e in (a_envs, b_envs):
+        e.collect_episode_stats = True
+    obs_a = a_envs.observe().contiguous()
+    obs_b = obs_a.clone()
+    act_a, act_b = (torch.empty((n, 2, 2), device="cuda") for _ in range(2))
+    nxt = torch.empty((n, 2, 12), device="cuda"); nxt2 = torch.empty_like(nxt)
+    rew = torch.empty((n, 2), device="cuda"); done = torch.empty(n, dtype=torch.uint8, device="cuda")
+    win = torch.empty_like(done); rows = torch.empty((n, 2), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    restarts = 0
+    for t in range(40):
+        # two kernels
+        ac.actor_forward(obs_a.view(-1, 12), param_noise_sd=0.5, noise_group=256, out=act_a.view(-1, 2), counter=t, precision="bf16")
+        out = a_envs.step(act_a, obs_out=obs_a)
+        # one kernel
+        check(lib.ss_actor_forward_step_tc(ac.actor.data_ptr(), obs_b.data_ptr(), act_b.data_ptr(), 2 * n, 0.5, 256, 0.0, ac.seed, t,
+                                           b_envs.state.data_ptr(), nxt.data_ptr(), nxt2.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                           rows.data_ptr(), win.data_ptr(), _lib.REWARD_LOOKING, 12, _lib.RESET_RANDOM, b_envs.seed,
+                                           b_envs.counter, b_envs.status.data_ptr(), _lib.STEP_EPISODE_STATS, st), "fused")
+        b_envs.counter += 1
+        assert torch.equal(act_a, act_b), t
+        assert torch.equal(obs_a, nxt) and torch.equal(nxt, nxt2), t
+        assert torch.equal(out["reward"], rew) and torch.equal(out["done"], done) and torch.equal(out["winner"], win), t
+        assert torch.equal(rows, (win != 0).to(torch.uint8)[:, None].expand(n, 2)), t
+        assert torch.equal(a_envs.state, b_envs.state), t
+        restarts += int(done.sum())
+        obs_b.copy_(nxt)
+    assert restarts > 2 * n
+    sa, sb = a_envs.episode_summary(), b_envs.episode_summary()
+    assert sa["episodes"] == sb["episodes"] == restarts and np.array_equal(sa["histogram"], sb["histogram"])
+    b_envs.check_status()
+
+
 @pytest.mark.parametrize("precision,gamma,tau", [("f32", 0.0, 1.0), ("f32", 0.97, 0.01), ("bf16", 0.97, 0.01)])
 def test_single_call_update_equals_the_stepwise_update(precision, gamma, tau):
     """ss_ddpg_update (the whole update enqueued by one host call) against sample / target / critic step /
