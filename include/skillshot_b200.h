@@ -68,6 +68,7 @@ extern "C" {
 /* status bits OR-ed into *status by the kernels */
 #define SS_STATUS_NAN 1       /* where the reference raises ValueError: int(round(nan)), Player.py:63 */
 #define SS_STATUS_PEER_TIMEOUT 2   /* ss_peer_adam_tf gave up waiting for a peer's gradient */
+#define SS_STATUS_ROLLOUT_TIMEOUT 4   /* ss_env_step_tiles gave up waiting for the actor forward kernel's actions */
 
 /* ops of ss_env_apply: the single-object methods of the reference */
 #define SS_OP_MOVE_DIRECTION_FLOAT 0  /* Player.move_direction_float(value), Player.py:57-68 */
@@ -317,6 +318,22 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
                         uint64_t env_counter, uint64_t noise_seed, uint64_t noise_counter, const void *speeds,
                         uint32_t *status, int step_flags, void *stream);
 
+/* ss_selfplay_rollout with the env step OVERLAPPED with the actor forward (tensor-core path, in-place ring form, reference
+ * speeds, reward none / looking / terminal; anything else falls through to ss_selfplay_rollout): tile_ready = int32
+ * [2 n_envs / 128 + noise_group / 128 + 1] zeroed once by the caller and left zero by every call, stream2 = a second
+ * stream of the same device with HIGHER priority than `stream` (cudaStreamCreateWithPriority): per tick the forward kernel
+ * runs on stream2 and ss_env_step_tiles on `stream` beside it (the forward kernel's CTAs must be placed first: it needs
+ * whole SMs, the one-warp env CTAs fit in what it leaves); events order the two, and `stream` has caught up with stream2
+ * when the call returns.  Same results, bit for bit. */
+int ss_selfplay_rollout2(void *env_state, int64_t n_envs, const float *actor_params, float *obs_a, float *obs_b,
+                         float *actions, float *reward, uint8_t *done, uint8_t *winner,
+                         float *ring_obs, float *ring_act, float *ring_reward, float *ring_next_obs,
+                         uint8_t *ring_done, int64_t capacity, int64_t write_pos, int n_ticks,
+                         float param_noise_sd, int64_t noise_group, float action_noise_sd, int tensor_cores,
+                         int reward_mode, int64_t tick_limit, int reset_mode, uint64_t env_seed,
+                         uint64_t env_counter, uint64_t noise_seed, uint64_t noise_counter, const void *speeds,
+                         uint32_t *status, int step_flags, int *tile_ready, void *stream2, void *stream);
+
 /* One rollout tick as ONE kernel (tensor-core path): ss_actor_forward_tc on the players' observations (n_rows = 2 x envs,
  * row = 2 env + player) and, in its output stage, the env step of those players -- do_actions, game_tick, reward of the
  * post-tick state, auto-reset, next observation (SkillshotLearner.py:304-315) -- by the lane that has just computed the
@@ -330,6 +347,23 @@ int ss_actor_forward_step_tc(const float *actor_params, const float *obs, float 
                              uint8_t *done_out, uint8_t *done_rows_out, uint8_t *winner_out, int reward_mode,
                              int64_t tick_limit, int reset_mode, uint64_t env_seed, uint64_t env_counter,
                              uint32_t *status, int flags, void *stream);
+
+/* The two halves of the OVERLAPPED rollout tick (ss_selfplay_rollout with a second stream): ss_actor_forward_tc_signal is
+ * ss_actor_forward_tc that also increments tile_ready[row / 128] (int32, zero-initialised by the caller) once per output warp
+ * -- four times per 128-row tile -- when that tile's actions are in global memory, and reports its CTA count and tile count;
+ * ss_env_step_tiles, enqueued on ANOTHER stream, is the env step with observations of ss_env_step_ring (one tick,
+ * auto_reset = 1, reference speeds, reward none / looking / terminal) that walks the tiles in the order the forward
+ * kernel completes them, waits for each tile's four arrivals, plays its 128 players' tick and takes the arrivals away
+ * again.  It uses no shared memory and at most 64 registers, so it runs beside the forward kernel on the same SMs: the env
+ * step ends a few microseconds after the forward does.  A tile that never arrives raises SS_STATUS_ROLLOUT_TIMEOUT. */
+int ss_actor_forward_tc_signal(const float *actor_params, const float *obs, float *act_out, int64_t n,
+                               float param_noise_sd, int64_t noise_group, float action_noise_sd,
+                               uint64_t seed, uint64_t counter, int *tile_ready, int *grid_out, int64_t *units_out,
+                               void *stream);
+int ss_env_step_tiles(void *state, int64_t n_envs, const float *actions, float *obs_out, float *obs_out2,
+                      float *reward_out, uint8_t *done_out, uint8_t *done_rows_out, uint8_t *winner_out,
+                      int reward_mode, int64_t tick_limit, int reset_mode, uint64_t seed, uint64_t counter,
+                      uint32_t *status, int flags, int *tile_ready, int64_t units, int grid_fwd, void *stream);
 
 /* ---- frame-stacked ("planning") actor: readme.md:18-20, BASELINE.json configs[4]; no reference code ----
  * The actor reads the last `frames` observations of a player: first layer 12 * frames -> 256, the rest as

@@ -23,6 +23,7 @@ STEP_EPISODE_STATS = 2
 EPISODE_STATS = 72
 STATUS_NAN = 1
 STATUS_PEER_TIMEOUT = 2
+STATUS_ROLLOUT_TIMEOUT = 4
 (OP_MOVE_DIRECTION_FLOAT, OP_MOVE_LOOK_FLOAT, OP_SHOOT, OP_MOVE_FORWARDS, OP_MOVE_BACKWARDS,
  OP_LOOK_LEFT, OP_LOOK_RIGHT, OP_GAME_TICK) = range(8)
 
@@ -87,6 +88,12 @@ SIGNATURES = {
     "ss_selfplay_rollout": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32,
                                     _f32, _i64, _f32, _i32, _i32, _i64, _i32, _u64, _u64, _u64, _u64, _vp, _vp, _i32,
                                     _vp]),
+    "ss_selfplay_rollout2": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32,
+                                     _f32, _i64, _f32, _i32, _i32, _i64, _i32, _u64, _u64, _u64, _u64, _vp, _vp, _i32,
+                                     _vp, _vp, _vp]),
+    "ss_actor_forward_tc_signal": (_i32, [_vp, _vp, _vp, _i64, _f32, _i64, _f32, _u64, _u64, _vp, _vp, _vp, _vp]),
+    "ss_env_step_tiles": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _u64, _u64, _vp, _i32, _vp,
+                                  _i64, _i32, _vp]),
     "ss_actor_frames_params": (_i64, [_i32]),
     "ss_obs_stack_push": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _i32, _vp]),
     "ss_param_noise_groups": (_i32, [_vp, _vp, _i64, _i64, _i64, _f32, _u64, _u64, _vp]),

@@ -467,6 +467,83 @@ __global__ void __launch_bounds__(kBlockPP) step_pp_obs_kernel(const StepArgs A)
     if (status && A.status) atomicOr(A.status, status);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// step_pp_tiles_kernel -- the rollout's env step running BESIDE the actor forward kernel that produces its actions.
+// The forward kernel (ss_mlp_tc.cu) bumps tile_ready[tile] once per output warp when a 128-row tile's actions are in
+// memory; this kernel, launched on a second stream, walks the tiles in the order the forward kernel's CTAs complete them
+// (same even split of tiles over the same number of CTAs), waits for a tile's four arrivals and plays the tick of its 128
+// players -- so the env step costs no time of its own: it ends a few microseconds after the forward kernel does.
+// One WARP per CTA, at most 64 registers and NO shared memory, so that it fits beside the forward kernel's CTA on every SM.
+// That CTA owns 222 KB of shared memory and 9 warps of 168 registers, and registers are per SM SUB-PARTITION (4 x 16 K): the
+// partition that holds three of its warps has 256 registers left, the others 5.6 K each -- room for two 64-register warps
+// per partition, six per SM, but not for a multi-warp CTA that needs a slot in every partition (first attempt: 8-warp CTAs
+// never became resident beside the forward kernel and every tile timed out).
+// The wait is bounded: if a tile never arrives (the forward kernel failed) SS_STATUS_ROLLOUT_TIMEOUT is raised.
+struct TilesArgs {
+    StepArgs S;
+    int *tile_ready;
+    int64_t units;          // tiles of the forward launch
+    int grid_fwd;           // its CTA count
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(32, 16) step_pp_tiles_kernel(const TilesArgs T) {
+    const StepArgs &A = T.S;
+    const int lane = threadIdx.x, P = lane & 1;
+    // One warp per CTA, one quarter tile (32 rows) per CTA.  CTAs are numbered in the order the forward kernel completes its
+    // tiles: its CTA c walks tiles u0(c), u0(c) + 1, ..., so step j of every forward CTA comes before step j + 1 of any.
+    const int per_step = 4 * T.grid_fwd;
+    const int64_t j = blockIdx.x / per_step;
+    const int c = (int)(blockIdx.x % per_step) >> 2, quarter = blockIdx.x & 3;
+    const int64_t u0 = T.units * c / T.grid_fwd, u1 = T.units * (c + 1) / T.grid_fwd;
+    const int64_t tile = u0 + j;
+    if (tile >= u1) return;
+    const int64_t rows = 2 * A.n;
+    uint32_t status = 0;
+    // wait for the four output warps of the forward kernel
+    if (lane == 0) {
+        int seen = 0;
+        uint32_t spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(T.tile_ready + tile) : "memory");
+            if (seen >= 4) break;
+            if (++spins > (1u << 20)) { status |= SS_STATUS_ROLLOUT_TIMEOUT; break; }
+            __nanosleep(200);
+        }
+    }
+    __syncwarp();
+    const int64_t g0 = tile * 128 + quarter * 32 + lane;
+    const int64_t last = rows - 2 + P;
+    const bool active = g0 <= last;
+    const int64_t gl = active ? g0 : last;
+    const int64_t env = gl >> 1;
+    sspp::LaneState L;
+    sspp::lane_load((const char *)A.state, A.n, gl, L);
+    const float2 a = __ldcg((const float2 *)A.actions + gl);
+    sspp::LaneTrig Tr;
+    sspp::lane_trig(L, Tr);
+    sspp::LaneTickOut out;
+    sspp::lane_obs_tick(L, Tr, a.x, a.y, A.P, (uint64_t)env, A.P.counter, lane, P, status, out);
+    const int v_other = __shfl_xor_sync(0xffffffffu, L.valid, 1);
+    if (active) {
+        sspp::lane_store((char *)A.state, A.n, gl, L, v_other);
+        if (A.reward_out && A.P.reward_mode != SS_REWARD_NONE) ((float *)A.reward_out)[gl] = out.reward;
+        uint8_t *flag = P ? A.winner_out : A.done_out;
+        if (flag) flag[env] = (uint8_t)(P ? out.winner : out.done);
+        if (A.done_rows_out) ((uint8_t *)A.done_rows_out)[gl] = out.winner ? 1 : 0;
+        if (STATS && !P && out.episode_len >= 0) sspp::count_episode_pp(A.stats, out.episode_len, out.winner, (int)A.P.tick_limit);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            A.obs_out[gl * 3 + q] = out.obs[q];
+            if (A.obs_out2) A.obs_out2[gl * 3 + q] = out.obs[q];
+        }
+    }
+    // hand the counter back for the next tick (the four quarter-tile CTAs each take one arrival away)
+    __syncwarp();
+    if (lane == 0) atomicSub(T.tile_ready + tile, 1);
+    if (status && A.status) atomicOr(A.status, status);
+}
+
 __global__ void reset_kernel(void *state, int64_t n, const uint8_t *mask, int reset_mode,
                              const int32_t *positions, uint64_t seed, uint64_t counter) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -713,6 +790,41 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
             else step_kernel<false, false, false><<<grid, block, 0, st>>>(A);
         }
     }
+    return check_launch();
+}
+
+int ss_env_step_tiles(void *state, int64_t n_envs, const float *actions, float *obs_out, float *obs_out2,
+                      float *reward_out, uint8_t *done_out, uint8_t *done_rows_out, uint8_t *winner_out,
+                      int reward_mode, int64_t tick_limit, int reset_mode, uint64_t seed, uint64_t counter,
+                      uint32_t *status, int flags, int *tile_ready, int64_t units, int grid_fwd, void *stream) {
+    if (!state || !actions || !obs_out || n_envs <= 0 || !tile_ready || units <= 0 || grid_fwd <= 0) return SS_ERR_INVALID_ARG;
+    if (units < (2 * n_envs + 127) / 128) return SS_ERR_INVALID_ARG;      // (a noisy forward pads its last group with empty tiles)
+    if (reward_mode != SS_REWARD_NONE && reward_mode != SS_REWARD_LOOKING && reward_mode != SS_REWARD_TERMINAL) return SS_ERR_INVALID_ARG;
+    if (reset_mode != SS_RESET_FIXED && reset_mode != SS_RESET_RANDOM) return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)state | (uintptr_t)actions | (uintptr_t)obs_out | (uintptr_t)obs_out2) & 15) return SS_ERR_INVALID_ARG;
+    TilesArgs T{};
+    StepArgs &A = T.S;
+    A.state = state; A.n = n_envs; A.actions = (const float4 *)actions; A.obs_out = (float4 *)obs_out; A.obs_out2 = (float4 *)obs_out2;
+    A.reward_out = (float2 *)reward_out; A.done_out = done_out; A.winner_out = winner_out; A.done_rows_out = (uint16_t *)done_rows_out;
+    A.status = status;
+    A.stats = (status && (flags & SS_STEP_EPISODE_STATS)) ? reinterpret_cast<unsigned long long *>(status) + 1 : nullptr;
+    if (A.stats && ((uintptr_t)status & 7)) return SS_ERR_INVALID_ARG;
+    A.P.seed = seed; A.P.counter = counter; A.P.tick_limit = tick_limit; A.P.reward_mode = reward_mode; A.P.auto_reset = 1;
+    A.P.reset_mode = reset_mode; A.n_ticks = 1;
+    T.tile_ready = tile_ready; T.units = units; T.grid_fwd = grid_fwd;
+    // The forward kernel needs the SM's shared-memory carve-out at its maximum (222 KB per CTA), and an SM cannot change its
+    // carve-out while anything is resident on it: this kernel, which uses no shared memory at all, must ask for the same
+    // carve-out, or the first of the two to reach an SM locks the other out until it exits (measured: every tile timed out).
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(step_pp_tiles_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(step_pp_tiles_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    const int64_t steps = (units + grid_fwd - 1) / grid_fwd + 1;          // tiles per forward CTA, rounded up
+    const unsigned grid = (unsigned)(steps * 4 * grid_fwd);
+    if (A.stats) step_pp_tiles_kernel<true><<<grid, 32, 0, (cudaStream_t)stream>>>(T);
+    else step_pp_tiles_kernel<false><<<grid, 32, 0, (cudaStream_t)stream>>>(T);
     return check_launch();
 }
 

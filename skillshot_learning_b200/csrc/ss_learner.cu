@@ -996,6 +996,73 @@ int ss_replay_sample(const float *ring_obs, const float *ring_act, const float *
                                    counter, batch, obs, act, reward, next_obs, done, indices_out, stream);
 }
 
+// The in-place ring form with the env step running BESIDE the forward kernel (see ss_env_step_tiles).  The forward kernels go
+// to `st_hi`, a stream of HIGHER priority than the caller's: both kernels of a tick become eligible at the same moment (when
+// the previous tick's env step ends), and the forward kernel's CTAs, which need a whole SM's shared memory and three quarters
+// of its registers, must be placed first -- the one-warp env CTAs then fill what is left beside them; placed the other way
+// round they occupy every SM and the forward kernel starves while they wait for it (measured: every tile timed out).
+// env step(t) runs on the caller's stream; forward(t + 1) waits for it by an event, and reads its second observation copy.
+static int rollout_overlapped(void *env_state, int64_t n_envs, const float *actor_params, float *obs_a, float *actions, float *reward,
+                              uint8_t *done, uint8_t *winner, float *ring_obs, float *ring_act, float *ring_reward,
+                              float *ring_next_obs, uint8_t *ring_done, int64_t capacity, int64_t write_pos, int n_ticks,
+                              float param_noise_sd, int64_t noise_group, float action_noise_sd, int reward_mode, int64_t tick_limit,
+                              int reset_mode, uint64_t env_seed, uint64_t env_counter, uint64_t noise_seed, uint64_t noise_counter,
+                              uint32_t *status, int step_flags, int *tile_ready, cudaStream_t st, cudaStream_t st_hi) {
+    const int64_t rows = 2 * n_envs, segs = capacity / rows;
+    int64_t seg = write_pos / rows;
+    cudaEvent_t ev;                                            // one event, re-recorded: each wait is enqueued before the next record
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return SS_ERR_CUDA;
+    int rc = SS_OK;
+    auto fail = [&](int code) { cudaEventDestroy(ev); return code; };
+    if (cudaMemcpyAsync(ring_obs + seg * rows * 12, obs_a, (size_t)rows * 48, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return fail(SS_ERR_CUDA);
+    for (int t = 0; t < n_ticks; ++t, seg = (seg + 1) % segs) {
+        float *o = ring_obs + seg * rows * 12, *a = ring_act + seg * rows * 2;
+        float *o_next = (t + 1 < n_ticks) ? ring_obs + ((seg + 1) % segs) * rows * 12 : obs_a;
+        // the forward reads what the caller's stream has produced so far: the previous tick's env step (or, first, the copy above)
+        if (cudaEventRecord(ev, st) != cudaSuccess || cudaStreamWaitEvent(st_hi, ev, 0) != cudaSuccess) return fail(SS_ERR_CUDA);
+        int grid_fwd = 0;
+        int64_t units = 0;
+        rc = ss_actor_forward_tc_signal(actor_params, o, a, rows, param_noise_sd, noise_group, action_noise_sd, noise_seed,
+                                        noise_counter + (uint64_t)t, tile_ready, &grid_fwd, &units, st_hi);
+        if (rc != SS_OK) return fail(rc);
+        rc = ss_env_step_tiles(env_state, n_envs, a, ring_next_obs + seg * rows * 12, o_next, ring_reward + seg * rows, done,
+                               ring_done + seg * rows, winner, reward_mode, tick_limit, reset_mode, env_seed,
+                               env_counter + (uint64_t)t, status, step_flags, tile_ready, units, grid_fwd, st);
+        if (rc != SS_OK) return fail(rc);
+    }
+    // the caller's stream also waits for the last forward kernel itself (it has consumed all of its tiles, so this is immediate)
+    if (cudaEventRecord(ev, st_hi) != cudaSuccess || cudaStreamWaitEvent(st, ev, 0) != cudaSuccess) return fail(SS_ERR_CUDA);
+    seg = (seg + segs - 1) % segs;
+    if (cudaMemcpyAsync(actions, ring_act + seg * rows * 2, (size_t)rows * 8, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(reward, ring_reward + seg * rows, (size_t)rows * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return fail(SS_ERR_CUDA);
+    cudaEventDestroy(ev);
+    return SS_OK;
+}
+
+int ss_selfplay_rollout2(void *env_state, int64_t n_envs, const float *actor_params, float *obs_a, float *obs_b,
+                         float *actions, float *reward, uint8_t *done, uint8_t *winner,
+                         float *ring_obs, float *ring_act, float *ring_reward, float *ring_next_obs, uint8_t *ring_done,
+                         int64_t capacity, int64_t write_pos, int n_ticks, float param_noise_sd, int64_t noise_group,
+                         float action_noise_sd, int tensor_cores, int reward_mode, int64_t tick_limit, int reset_mode,
+                         uint64_t env_seed, uint64_t env_counter, uint64_t noise_seed, uint64_t noise_counter,
+                         const void *speeds, uint32_t *status, int step_flags, int *tile_ready, void *stream2, void *stream) {
+    const int64_t rows = 2 * n_envs;
+    const bool in_place = ring_obs && winner && n_envs > 0 && capacity % rows == 0 && write_pos % rows == 0 && write_pos >= 0 &&
+                          write_pos < capacity && (capacity / rows >= 2 || n_ticks == 1);
+    if (in_place && tile_ready && stream2 && stream2 != stream && tensor_cores && !speeds && reward_mode != SS_REWARD_SIMPLE &&
+        env_state && actor_params && obs_a && actions && reward && done && n_ticks > 0)
+        return rollout_overlapped(env_state, n_envs, actor_params, obs_a, actions, reward, done, winner, ring_obs, ring_act,
+                                  ring_reward, ring_next_obs, ring_done, capacity, write_pos, n_ticks, param_noise_sd, noise_group,
+                                  action_noise_sd, reward_mode, tick_limit, reset_mode, env_seed, env_counter, noise_seed,
+                                  noise_counter, status, step_flags, tile_ready, (cudaStream_t)stream, (cudaStream_t)stream2);
+    return ss_selfplay_rollout(env_state, n_envs, actor_params, obs_a, obs_b, actions, reward, done, winner, ring_obs, ring_act,
+                               ring_reward, ring_next_obs, ring_done, capacity, write_pos, n_ticks, param_noise_sd, noise_group,
+                               action_noise_sd, tensor_cores, reward_mode, tick_limit, reset_mode, env_seed, env_counter, noise_seed,
+                               noise_counter, speeds, status, step_flags, stream);
+}
+
 int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_params, float *obs_a, float *obs_b,
                         float *actions, float *reward, uint8_t *done, uint8_t *winner,
                         float *ring_obs, float *ring_act, float *ring_reward, float *ring_next_obs, uint8_t *ring_done,

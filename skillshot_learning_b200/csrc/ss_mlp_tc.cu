@@ -66,6 +66,9 @@ struct FwdArgs {
     uint8_t *done_out, *winner_out, *done_rows_out;     // [n / 2], [n / 2], [n]
     uint32_t *env_status;
     unsigned long long *env_stats;
+    // overlapped rollout (ss_selfplay_rollout): tile_ready[row / 128] is incremented once by each of the four output warps
+    // when its 32 actions of that tile are in global memory; the env step kernel running beside this one consumes them
+    int *tile_ready;
 };
 
 // 32 accumulator columns (hidden-2 units) -> ReLU -> layer 3, four split accumulators per output.
@@ -297,6 +300,11 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                         if (A.y_out) A.y_out[row] = A.reward[row] + A.gamma * ((A.done && A.done[row]) ? 0.f : 1.f) * out0;
                     }
                 }
+                if (NET == NET_ACTOR && A.tile_ready) {
+                    __threadfence();                                      // this lane's action store, device-wide
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(A.tile_ready + (row0 + i * TM) / TM, 1);
+                }
                 if (FUSED) {
                     // do_actions + game_tick + reward + auto-reset + next observation of this player, on the spot: all 32
                     // lanes take part (the hit test is a shuffle and a ballot between the two lanes of an env)
@@ -422,9 +430,12 @@ int launch_fwd(const FwdArgs &A, void *stream) {
 
 }  // namespace
 
-extern "C" int ss_actor_forward_tc(const float *actor_params, const float *obs, float *act_out, int64_t n,
-                                   float param_noise_sd, int64_t noise_group, float action_noise_sd,
-                                   uint64_t seed, uint64_t counter, void *stream) {
+// tile_ready (may be NULL): int32 [ceil(n / 128)], see FwdArgs; *grid_out / *units_out (may be NULL) receive the launch's
+// CTA count and tile count, which a consumer kernel needs to walk the tiles in the order this one completes them
+extern "C" int ss_actor_forward_tc_signal(const float *actor_params, const float *obs, float *act_out, int64_t n,
+                                          float param_noise_sd, int64_t noise_group, float action_noise_sd,
+                                          uint64_t seed, uint64_t counter, int *tile_ready, int *grid_out, int64_t *units_out,
+                                          void *stream) {
     if (!actor_params || !obs || !act_out || n <= 0 || param_noise_sd < 0.f || action_noise_sd < 0.f)
         return SS_ERR_INVALID_ARG;
     if (((uintptr_t)actor_params | (uintptr_t)obs) & 15 || ((uintptr_t)act_out & 7)) return SS_ERR_INVALID_ARG;
@@ -433,7 +444,25 @@ extern "C" int ss_actor_forward_tc(const float *actor_params, const float *obs, 
     FwdArgs A{};
     A.params = actor_params; A.obs = obs; A.n = n; A.group = noisy ? noise_group : n;
     A.act_out = act_out; A.param_sd = param_noise_sd; A.action_sd = action_noise_sd; A.seed = seed; A.counter = counter;
+    A.tile_ready = tile_ready;
+    if (grid_out || units_out) {                              // the launch geometry of launch_fwd, for the consumer
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            return SS_ERR_CUDA;
+        const int64_t n_groups = (A.n + A.group - 1) / A.group, units = n_groups * ((A.group + TM - 1) / TM);
+        int grid = (int)(units < sms ? units : sms);
+        if (A.group < A.n && n_groups <= sms) grid = (int)n_groups;
+        if (grid_out) *grid_out = grid;
+        if (units_out) *units_out = units;
+    }
     return launch_fwd<NET_ACTOR>(A, stream);
+}
+
+extern "C" int ss_actor_forward_tc(const float *actor_params, const float *obs, float *act_out, int64_t n,
+                                   float param_noise_sd, int64_t noise_group, float action_noise_sd,
+                                   uint64_t seed, uint64_t counter, void *stream) {
+    return ss_actor_forward_tc_signal(actor_params, obs, act_out, n, param_noise_sd, noise_group, action_noise_sd, seed, counter,
+                                      nullptr, nullptr, nullptr, stream);
 }
 
 // The rollout tick as ONE kernel: actor forward on the players' observations, and in its output stage the env step of

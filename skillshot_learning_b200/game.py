@@ -306,6 +306,9 @@ class SkillshotEnvs:
     def check_status(self):
         """Raises where the reference would have raised during the steps so far."""
         s = int(self.status.item())
+        if s & _lib.STATUS_ROLLOUT_TIMEOUT:
+            self.status.zero_()
+            raise RuntimeError("overlapped rollout: the env step never received a tile of actions from the forward kernel")
         if s & _lib.STATUS_NAN:
             self.status.zero_()
             raise ValueError("cannot convert float NaN to integer")   # int(round(nan)), Player.py:63

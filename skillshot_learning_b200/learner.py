@@ -1076,6 +1076,7 @@ class SelfPlayTrainer:
         self.ticks = 0
         self.updates = 0
         self.exchange_check_every = 256     # updates between looks at the peer exchange's status word
+        self._tile_ready, self._stream2 = None, None      # overlapped rollout (rollout()): allocated on first use
 
     def rollout_tick(self, store: bool = True):
         """One tick of every env: actor forward on both players' observations (fresh parameter
@@ -1123,16 +1124,26 @@ class SelfPlayTrainer:
         out = envs._buffers(1)
         # the current observation is in self.obs; it becomes buffer A of the call
         a, b = self.obs, self.prev_obs
+        # SS_ROLLOUT_OVERLAP=1 (experiment, off by default): the env step runs beside the forward kernel on a second stream
+        # (ss_selfplay_rollout2), consuming its actions tile by tile.  Bit-exact, and it works when both grids fit the GPU at
+        # once; at 262,144 envs the forward kernel's CTAs fill their SMs (223 KB shared memory, 3/4 of the registers), the env
+        # CTAs are not co-resident and their bounded waits expire (SS_STATUS_ROLLOUT_TIMEOUT) -- DESIGN.md section 6.5
+        overlap = self.precision == "bf16" and os.environ.get("SS_ROLLOUT_OVERLAP", "0") == "1"
+        if overlap and self._tile_ready is None:
+            tiles = (2 * envs.n_envs + 127) // 128 + max(self.noise_group, 128) // 128 + 1
+            self._tile_ready = torch.zeros(tiles, dtype=torch.int32, device=self.device)
+            self._stream2 = torch.cuda.Stream(self.device, priority=-1)      # HIGHER priority than the current stream: the forward kernels
         with torch.cuda.device(self.device):
-            check(lib.ss_selfplay_rollout(
+            check(lib.ss_selfplay_rollout2(
                 envs.state.data_ptr(), envs.n_envs, net.actor.data_ptr(), a.data_ptr(), b.data_ptr(), self.actions.data_ptr(),
                 out["reward"].data_ptr(), out["done"].data_ptr(), out["winner"].data_ptr(),
                 rp.obs.data_ptr() if store else None, rp.act.data_ptr(), rp.reward.data_ptr(), rp.next_obs.data_ptr(),
                 rp.done.data_ptr(), rp.capacity, rp.pos, int(n_ticks), self.param_noise_sd, self.noise_group, 0.0,
                 1 if self.precision == "bf16" else 0, REWARD_MODES[envs.reward_mode], envs.tick_limit,
                 _lib.RESET_RANDOM if envs.random_positions else _lib.RESET_FIXED, envs.seed, envs.counter, net.seed,
-                net.counter, _ptr(envs.speeds), envs.status.data_ptr(), _lib.STEP_EPISODE_STATS if envs.collect_episode_stats else 0, _stream(self.device)),
-                  "ss_selfplay_rollout")
+                net.counter, _ptr(envs.speeds), envs.status.data_ptr(), _lib.STEP_EPISODE_STATS if envs.collect_episode_stats else 0,
+                self._tile_ready.data_ptr() if overlap else None, self._stream2.cuda_stream if overlap else None,
+                _stream(self.device)), "ss_selfplay_rollout")
         envs.counter += n_ticks
         net.counter += n_ticks
         if store:

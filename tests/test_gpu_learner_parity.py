@@ -477,6 +477,27 @@ def test_library_side_rollout_loop_equals_per_tick_calls(capacity):
         assert torch.equal(a.obs, b.obs) and a.replay.pos == b.replay.pos and a.replay.size == b.replay.size
 
 
+def test_overlapped_rollout_equals_the_two_kernel_rollout(monkeypatch):
+    """SS_ROLLOUT_OVERLAP=1 (ss_selfplay_rollout2: the env step consumes the forward kernel's action tiles while that kernel
+    is still running, on a second stream) against the default back-to-back kernels at a size where both grids are resident
+    together: identical replay rows, observations, env state and counters; the tile counters are handed back zeroed."""
+    from skillshot_learning_b200 import SelfPlayTrainer
+    mk = lambda: SelfPlayTrainer(1024, device="cuda:0", seed=9, batch_size=256, noise_group=128, tick_limit=30, precision="bf16",
+                                 replay_capacity=2048 * 8)
+    a = mk()
+    a.rollout(4); a.rollout(3); a.rollout(12)
+    monkeypatch.setenv("SS_ROLLOUT_OVERLAP", "1")
+    b = mk()
+    b.rollout(4); b.rollout(3); b.rollout(12)
+    torch.cuda.synchronize()
+    assert b._tile_ready is not None and int(b._tile_ready.abs().sum()) == 0
+    b.envs.check_status()
+    for name in ("obs", "act", "reward", "next_obs", "done"):
+        assert torch.equal(getattr(a.replay, name), getattr(b.replay, name)), name
+    assert torch.equal(a.obs, b.obs) and torch.equal(a.envs.state, b.envs.state) and torch.equal(a.actions, b.actions)
+    assert a.replay.pos == b.replay.pos and a.envs.counter == b.envs.counter and a.networks.counter == b.networks.counter
+
+
 def test_fused_forward_and_env_step_kernel_equals_the_two_kernels():
     """ss_actor_forward_step_tc (the rollout tick as ONE kernel: the env step of a row is played in the forward kernel's
     output stage by the lane that computed its action; off by default in ss_selfplay_rollout because it is slower) against
