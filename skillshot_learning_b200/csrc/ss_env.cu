@@ -15,6 +15,7 @@
 #include "../../include/skillshot_b200.h"
 #include "ss_env_core.cuh"
 #include "ss_env_pp.cuh"
+#include "ss_launch.cuh"
 
 namespace {
 
@@ -432,6 +433,9 @@ __global__ void __launch_bounds__(kBlockPP) step_pp_obs_kernel(const StepArgs A)
     const bool active = g0 <= last;
     const int64_t gl = active ? g0 : last;            // lanes past the end replay the last env and store nothing
     const int64_t env = gl >> 1;
+    // ss_launch.cuh: in the rollout loop this grid is placed while the forward kernel's last CTAs finish, and waits here
+    sslaunch::griddep_wait();
+    sslaunch::griddep_launch();
     sspp::LaneState L;
     sspp::lane_load((const char *)A.state, A.n, gl, L);
     const float2 a = __ldg((const float2 *)A.actions + gl);
@@ -743,8 +747,9 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
     if (obs_out && n_ticks == 1 && !speeds && reward_mode != SS_REWARD_SIMPLE && getenv_pp()) {
         // the rollout's env step: one tick with observations, one thread per player
         const dim3 grid_pp(blocks_for(2 * n_envs, kBlockPP));
-        if (A.stats) step_pp_obs_kernel<true><<<grid_pp, kBlockPP, 0, st>>>(A);
-        else step_pp_obs_kernel<false><<<grid_pp, kBlockPP, 0, st>>>(A);
+        if ((A.stats ? sslaunch::launch(step_pp_obs_kernel<true>, grid_pp, dim3(kBlockPP), 0, st, A)
+                     : sslaunch::launch(step_pp_obs_kernel<false>, grid_pp, dim3(kBlockPP), 0, st, A)) != cudaSuccess)
+            return SS_ERR_CUDA;
     } else if (obs_out) {
         // 8 CTAs (16 warps) per SM: capping the observation kernel at 128 registers measured
         // 83 us vs 100 us uncapped at 1M envs (profiles/README.md)

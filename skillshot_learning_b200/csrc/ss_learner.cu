@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "../../include/skillshot_b200.h"
+#include "ss_launch.cuh"
 #include "ss_rng.cuh"
 
 namespace {
@@ -667,6 +668,8 @@ __global__ void reduce_adam_kernel(const float *work, int parts, int n_params, f
                                    float grad_scale) {
     __shared__ float red[4][64];
     const int p = blockIdx.x * 64 + threadIdx.x, q = threadIdx.y;
+    sslaunch::griddep_wait();            // ss_launch.cuh: placed beside the gradient kernel's last CTAs, held here until it is done
+    sslaunch::griddep_launch();
     float s = 0.f;
     if (p <= n_params) {
 #pragma unroll 4
@@ -720,6 +723,8 @@ __global__ void replay_sample_kernel(Ring R, int64_t size, const int64_t *indice
                                      int64_t batch, float *s, float *a, float *r, float *s2, uint8_t *done,
                                      int64_t *indices_out, int w4) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    sslaunch::griddep_wait();            // ss_launch.cuh (the minibatch buffers are still read by the previous update's kernels)
+    sslaunch::griddep_launch();
     if (e >= w4 * batch) return;
     const int64_t b = e / w4, part = e - b * w4;
     int64_t src;
@@ -938,9 +943,10 @@ int ss_reduce_adam_tf(const void *workspace, int parts, int n_params, float *aux
                       float grad_scale, void *stream) {
     if (!workspace || parts < 1 || n_params < 1 || !params || !m || !v || step < 1) return SS_ERR_INVALID_ARG;
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
-    reduce_adam_kernel<<<(n_params + 1 + 63) / 64, dim3(64, 4), 0, (cudaStream_t)stream>>>(
-        (const float *)workspace, parts, n_params, aux_out, grad_out, params, m, v, target_params, (float)lr_t, beta1, beta2, eps,
-        tau, grad_scale);
+    if (sslaunch::launch(reduce_adam_kernel, dim3((n_params + 1 + 63) / 64), dim3(64, 4), 0, (cudaStream_t)stream,
+                         (const float *)workspace, parts, n_params, aux_out, grad_out, params, m, v, target_params, (float)lr_t,
+                         beta1, beta2, eps, tau, grad_scale) != cudaSuccess)
+        return SS_ERR_CUDA;
     return check_launch();
 }
 
@@ -975,8 +981,9 @@ int ss_replay_sample_frames(const float *ring_obs, const float *ring_act, const 
     Ring R{(float *)ring_obs, (float *)ring_act, (float *)ring_reward, (float *)ring_next_obs, (uint8_t *)ring_done,
            capacity};
     const int w4 = 3 * frames;
-    replay_sample_kernel<<<(unsigned)((w4 * batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        R, size, indices, seed, counter, batch, obs, act, reward, next_obs, done, indices_out, w4);
+    if (sslaunch::launch(replay_sample_kernel, dim3((unsigned)((w4 * batch + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, R,
+                         size, indices, seed, counter, batch, obs, act, reward, next_obs, done, indices_out, w4) != cudaSuccess)
+        return SS_ERR_CUDA;
     return check_launch();
 }
 
@@ -1085,10 +1092,18 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
         int64_t seg = write_pos / rows;
         if (cudaMemcpyAsync(ring_obs + seg * rows * 12, obs_a, (size_t)rows * 48, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
             return SS_ERR_CUDA;
+        // The two kernels of a tick form a dependent-launch chain (ss_launch.cuh): each grid is placed while its predecessor
+        // drains and holds at griddepcontrol.wait.  From the second tick on the forward kernel also stages (and perturbs) the
+        // actor's parameters ahead of that wait -- its predecessor, the env step, does not write them; the first tick's
+        // forward may follow an update's Adam kernel and waits first.  SS_ROLLOUT_PDL=0: ordinary launches (A/B).
+        static const bool pdl_env = [] { const char *e = getenv("SS_ROLLOUT_PDL"); return !(e && e[0] == '0'); }();
+        const int kOn = (tensor_cores && pdl_env) ? sslaunch::kPdlOn : sslaunch::kPdlOff;
+        sslaunch::PdlScope scope(kOn);
         for (int t = 0; t < n_ticks; ++t, seg = (seg + 1) % segs) {
             float *o = ring_obs + seg * rows * 12, *a = ring_act + seg * rows * 2;
             // the last tick's observation goes to the caller's buffer, the others to the next segment's rows
             float *o_next = (t + 1 < n_ticks) ? ring_obs + ((seg + 1) % segs) * rows * 12 : obs_a;
+            sslaunch::pdl_mode() = (kOn && t > 0) ? (sslaunch::kPdlOn | sslaunch::kPdlEarlyWeights) : kOn;
             if (tensor_cores && !speeds && reward_mode != SS_REWARD_SIMPLE && rollout_fused()) {
                 // the whole tick as ONE kernel: the forward kernel's output stage plays the env step of the rows it has
                 // just computed the actions of, and writes the transition straight into the ring (ss_mlp_tc.cu)
@@ -1106,6 +1121,7 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
                          : ss_actor_forward(actor_params, o, a, rows, param_noise_sd, noise_group, action_noise_sd, noise_seed,
                                             noise_counter + (uint64_t)t, stream);
             if (rc != SS_OK) return rc;
+            sslaunch::pdl_mode() = kOn;
             rc = ss_env_step_ring(env_state, n_envs, a, ring_next_obs + seg * rows * 12, o_next, ring_reward + seg * rows, done,
                                   ring_done + seg * rows, winner, 1, reward_mode, tick_limit, 1, reset_mode, env_seed,
                                   env_counter + (uint64_t)t, speeds, status, step_flags, stream);

@@ -24,6 +24,8 @@
 // Gradients are therefore computed from bf16 operands (products exact, fp32 accumulation):
 // relative error ~1e-3 against the float32 path of ss_learner.cu, which remains the exact one.
 // Per-CTA partial gradients go to the same workspace layout and fixed-order reduction as there.
+#include <stdlib.h>
+
 #include "ss_tc_common.cuh"
 
 namespace {
@@ -68,6 +70,7 @@ struct GradArgs {
     int64_t n, n_global, row_offset;
     float *work;                     // [gridDim.x][params + 1]
     long long *trace;                // development: event timestamps of CTA 0 (NULL in production)
+    int early_weights;               // ss_launch.cuh: the parameters may be staged ahead of griddepcontrol.wait (set by launch_grad)
 };
 
 // inverted-dropout keep bits of 8 consecutive hidden-1 units of one row: one Philox draw, 16 bits per unit
@@ -136,8 +139,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
     __syncthreads();
     if (warp < 4 && NET == NET_ACTOR)
         *reinterpret_cast<uint4 *>(smem + SM_X2 + (H1 / 8) * CHUNK_A + threadIdx.x * 16) = tail_chunk_actor();
+    // dependent launch (ss_launch.cuh): the set-up above ran beside the previous grid's tail; the weights are staged ahead of
+    // the wait too when the caller knows that grid does not write them
+    if (!A.early_weights) { sslaunch::griddep_wait(); sslaunch::griddep_launch(); }
     stage_weights<NET, NTHREADS>(Stager{A.params, smem + SM_B1, smem + SM_B2, reinterpret_cast<float4 *>(smem + SM_W3),
                                         reinterpret_cast<float *>(smem + SM_B3), false, 0.f, 0, 0, 0});
+    if (A.early_weights) { sslaunch::griddep_wait(); sslaunch::griddep_launch(); }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -161,22 +168,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
         const uint32_t thresh16 = (uint32_t)(A.rate * 65536.0f);
         uint32_t ph = 0;
         float stat = 0.f, dsum0 = 0.f, dsum1 = 0.f;      // sum of squared errors; db3 partials
-        int ev = 0;
-        auto to_mma = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(bar_mma); trace(0, 100 + ev); };
-        auto from_mma = [&]() { mbar_wait(bar_epi, ph); ph ^= 1; tc_fence_after(); trace(0, 200 + ev); ++ev; };
+        // development trace codes: kind * 1000 + 8 * (tile of this CTA) + phase (0 L1a, 1 L1b, 2 L2, 3 G2|BXa|G3, 4 BXb, 5 G1)
+        int tl_i = 0;
+        auto to_mma = [&](int phase) { fence_proxy_async(); tc_fence_before(); mbar_arrive(bar_mma); trace(0, 1000 + tl_i * 8 + phase); };
+        auto from_mma = [&](int phase) { mbar_wait(bar_epi, ph); ph ^= 1; tc_fence_after(); trace(0, 2000 + tl_i * 8 + phase); };
 
         // hidden layer 1, one 128-unit half: WORK -> ReLU (+ dropout) -> bf16 -> X2 chunks 16 * half ..
         // Inverted-dropout keep bits of this thread's row for the columns its warp handles: 2 halves x 4 steps x 16
-        // units = 128 bits.  They are generated one tile AHEAD, while the warp would otherwise idle in the wait for the
-        // two long MMA phases (32 Philox draws per row and tile cost ~5 k cycles when computed inside hidden1).
+        // units = 128 bits.  They are generated one tile AHEAD, in four parts, while the warp would otherwise idle in the waits
+        // for the three long MMA phases (32 Philox draws per row and tile cost ~5 k cycles when computed inside hidden1).
         uint32_t kb_cur[4] = {~0u, ~0u, ~0u, ~0u}, kb_next[4] = {~0u, ~0u, ~0u, ~0u};
-        auto make_keep = [&](int64_t tile, int half) {
+        // part = 0, 1: the first / second pair of this warp's four 16-unit steps of the half (4 of the row's 16 draws)
+        auto make_keep = [&](int64_t tile, int half, int part) {
             if (!(NET == NET_CRITIC && A.rate > 0.f) || tile >= tiles) return;
             const int64_t row = tile * TM + r;
-            kb_next[half * 2] = kb_next[half * 2 + 1] = 0u;
+            kb_next[half * 2 + part] = 0u;
             {
 #pragma unroll
-                for (int k = 0; k < 8 / NSLICE; ++k) {
+                for (int k = 2 * part; k < 2 * part + 2; ++k) {
                     const int c0 = half * 16 + (cs + k * NSLICE) * 2;          // first of the step's two 8-unit chunks
                     uint32_t kb = 0;
                     if (A.keep) {
@@ -244,8 +253,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
             }
         };
         fetch(blockIdx.x);
-        make_keep(blockIdx.x, 0);
-        make_keep(blockIdx.x, 1);
+        for (int q = 0; q < 4; ++q) make_keep(blockIdx.x, q >> 1, q & 1);
         for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int64_t row = tile * TM + r;
             const bool valid = row < A.n;
@@ -256,18 +264,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
             const float2 side = side_next;
             const float tgt = tgt_next;
             fetch(tile + gridDim.x);
-            store_obs_half(xin, dz2row, cs);
+            store_obs_half(xin, h2row, cs);               // (G1 of the previous tile may still be reading its X0 in the DZ2 buffer)
             if (NET == NET_CRITIC && cs == 0)
                 *reinterpret_cast<uint4 *>(x2row + (H1 / 8) * CHUNK_A) = tail_chunk_critic(side.x, side.y);
-            to_mma();                                     // -> L1a
-            from_mma();
+            // every warp has arrived for the previous tile's G1 before any arrives for this tile's L1a (no wait lies between
+            // the two arrivals, and a warp that arrived twice in one phase would complete it without the slowest one)
+            if (tl_i > 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+            to_mma(0);                                    // -> L1a
+            from_mma(0);                                  // (the commit behind L1a also retires the previous tile's G1)
             hidden1(0);
-            to_mma();                                     // -> L1b
-            from_mma();
+            to_mma(1);                                    // -> L1b
+            from_mma(1);
             hidden1(1);
-            to_mma();                                     // -> L2
-            make_keep(tile + gridDim.x, 0);               // in the shadow of the 17-step layer-2 chain
-            from_mma();
+            to_mma(2);                                    // -> L2
+            make_keep(tile + gridDim.x, 0, 0);            // in the shadow of the 17-step layer-2 chain
+            make_keep(tile + gridDim.x, 0, 1);
+            from_mma(2);
             // ---- output layer, loss / upstream gradient (fp32) ----
             float z0 = 0.f, z1 = 0.f;
             sweep_work(tl + T_WORK, cs, [&](const uint32_t (&v)[16], int j) {
@@ -335,17 +347,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                         make_uint4(pack_bf16(gz[0], gz[1]), pack_bf16(gz[2], gz[3]), pack_bf16(gz[4], gz[5]), pack_bf16(gz[6], gz[7]));
                 }
             });
-            to_mma();                                     // -> G3, G2, BXa
-            make_keep(tile + gridDim.x, 1);               // ... and of the weight-gradient chains
-            from_mma();
-            back1(0);
-            to_mma();                                     // -> BXb
-            from_mma();
+            to_mma(3);                                    // -> G2 (first half), BXa | G2 (second half), G3
+            make_keep(tile + gridDim.x, 1, 0);            // ... of G2's first half and BXa
+            from_mma(3);                                  // dx2[:, :128] is there and h1[:, :128] has been consumed
+            back1(0);                                     // (beside the rest of G2 and G3)
+            to_mma(4);                                    // -> BXb
+            make_keep(tile + gridDim.x, 1, 1);            // ... and of the rest of the weight-gradient group and BXb
+            from_mma(4);                                  // ... which also retires G2 / G3: h1[:, 128:], h2, dz2 are free
             back1(1);
-            store_obs_half(xin, dz2row, cs);              // X0 again (the DZ2 buffer is free: BXb has retired)
-            to_mma();                                     // -> G1
-            from_mma();                                   // tiles free for the next round
+            store_obs_half(xin, dz2row, cs);              // X0 for G1 (the DZ2 buffer is free: BXb has retired)
+            to_mma(5);                                    // -> G1, not waited for: it retires with the next tile's L1a
+            ++tl_i;
         }
+        from_mma(5);                                      // the last tile's G1
 
         trace(0, 902);
         // ======================= write this CTA's partial gradient =======================
@@ -419,24 +433,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
         const uint32_t h2 = sbase + SM_H2, dz3 = sbase + SM_DZ3;
         constexpr uint32_t kFwd = umma_idesc(TM, 128);                // K-major x K-major
         constexpr uint32_t kBx = umma_idesc(TM, 128, 0, 1);           // dz2 (K-major) x W2 image (MN-major)
-        constexpr uint32_t kG256 = umma_idesc(TM, 256, 1, 1), kG16 = umma_idesc(TM, 16, 1, 1), kG32 = umma_idesc(TM, 32, 1, 1);
-        int ev = 0;
-        auto wait_epi = [&]() { mbar_wait(bar_mma, ph); ph ^= 1; tc_fence_after(); trace(1, 300 + ev); ++ev; };
+        constexpr uint32_t kG128 = umma_idesc(TM, 128, 1, 1), kG16 = umma_idesc(TM, 16, 1, 1), kG32 = umma_idesc(TM, 32, 1, 1);
+        int tl_i = 0;
+        auto wait_epi = [&](int phase) { mbar_wait(bar_mma, ph); ph ^= 1; tc_fence_after(); trace(1, 3000 + tl_i * 8 + phase); };
+        auto issued = [&](int phase) { trace(1, 4000 + tl_i * 8 + phase); };
         uint32_t acc = 0;                                             // 0 on the CTA's first tile: accumulators start fresh
         for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, acc = 1) {
-            for (int half = 0; half < 2; ++half) {                    // L1a, L1b
-                wait_epi();
+            for (int half = 0; half < 2; ++half) {                    // L1a, L1b (X0 sits in the head of the H2 buffer)
+                wait_epi(half);
                 if (lane == 0) {
-                    const uint64_t ad = desc_kmajor(dz2, CHUNK_A), bd = desc_kmajor(b1 + half * 128 * 16, CHUNK_B1);
+                    const uint64_t ad = desc_kmajor(h2, CHUNK_A), bd = desc_kmajor(b1 + half * 128 * 16, CHUNK_B1);
 #pragma unroll
                     for (int ks = 0; ks < K1 / 16; ++ks)
                         umma_bf16(work, desc_advance(ad, 2 * CHUNK_A * ks), desc_advance(bd, 2 * CHUNK_B1 * ks), kFwd, ks > 0);
                     umma_commit(bar_epi);
                 }
                 __syncwarp();
-                trace(1, 400 + ev);
+                issued(half);
             }
-            wait_epi();                                               // L2
+            wait_epi(2);                                              // L2
             if (lane == 0) {
                 const uint64_t ad = desc_kmajor(x2, CHUNK_A), bd = desc_kmajor(b2, CHUNK_B2);
 #pragma unroll
@@ -445,26 +460,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                 umma_commit(bar_epi);
             }
             __syncwarp();
-            wait_epi();                                               // G3, G2, BXa
+            issued(2);
+            // The epilogue warps wait for nothing but dx2: what they need first goes first.  The first half of G2 consumes
+            // h1[:, :128] (the chunks back1(0) overwrites with dz1), BXa delivers dx2[:, :128]; the commit behind those two
+            // releases back1(0), which then runs beside the second half of G2, its bias / action columns and G3.
+            wait_epi(3);                                              // G2, BXa, G3
             if (lane == 0) {
                 const uint64_t h2t = desc_mnmajor(h2, CHUNK_A), dz3t = desc_mnmajor(dz3, CHUNK_A);
                 const uint64_t dz2t = desc_mnmajor(dz2, CHUNK_A), x2t = desc_mnmajor(x2, CHUNK_A);
+                const uint64_t x2hi = desc_mnmajor(x2 + 16 * CHUNK_A, CHUNK_A);
                 const uint64_t x2tail = desc_mnmajor(x2 + (H1 / 8) * CHUNK_A, CHUNK_A);
 #pragma unroll
                 for (int ks = 0; ks < TM / 16; ++ks) {                // reduction over the 128 rows, 16 per step
-                    const uint32_t off = 2 * CORE * ks, a = acc | (ks > 0);
-                    umma_bf16(tmem + T_W3T, desc_advance(h2t, off), desc_advance(dz3t, off), kG16, a);
-                    umma_bf16(tmem + T_W2T, desc_advance(dz2t, off), desc_advance(x2t, off), kG256, a);
-                    umma_bf16(tmem + T_W2T + H1, desc_advance(dz2t, off), desc_advance(x2tail, off), kG16, a);
+                    const uint32_t off = 2 * CORE * ks;
+                    umma_bf16(tmem + T_W2T, desc_advance(dz2t, off), desc_advance(x2t, off), kG128, acc | (ks > 0));
                 }
                 const uint64_t ad = desc_kmajor(dz2, CHUNK_A), bd = desc_mnmajor(b2, CHUNK_B2);
 #pragma unroll
                 for (int ks = 0; ks < H2 / 16; ++ks)
                     umma_bf16(work, desc_advance(ad, 2 * CHUNK_A * ks), desc_advance(bd, 2 * CORE * ks), kBx, ks > 0);
                 umma_commit(bar_epi);
+#pragma unroll
+                for (int ks = 0; ks < TM / 16; ++ks) {
+                    const uint32_t off = 2 * CORE * ks, a = acc | (ks > 0);
+                    umma_bf16(tmem + T_W2T + 128, desc_advance(dz2t, off), desc_advance(x2hi, off), kG128, a);
+                    umma_bf16(tmem + T_W2T + H1, desc_advance(dz2t, off), desc_advance(x2tail, off), kG16, a);
+                    umma_bf16(tmem + T_W3T, desc_advance(h2t, off), desc_advance(dz3t, off), kG16, a);
+                }
             }
             __syncwarp();
-            wait_epi();                                               // BXb
+            issued(3);
+            wait_epi(4);                                              // BXb; its commit also retires the G group above
             if (lane == 0) {
                 const uint64_t ad = desc_kmajor(dz2, CHUNK_A), bd = desc_mnmajor(b2 + 16 * CHUNK_B2, CHUNK_B2);
 #pragma unroll
@@ -473,7 +499,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                 umma_commit(bar_epi);
             }
             __syncwarp();
-            wait_epi();                                               // G1
+            issued(4);
+            wait_epi(5);                                              // G1: no commit of its own, the next L1a's covers it
             if (lane == 0) {
                 const uint64_t x0t = desc_mnmajor(dz2, CHUNK_A);
 #pragma unroll
@@ -484,10 +511,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
                         umma_bf16(tmem + T_W1T + half * 32, desc_advance(dz1t, 2 * CORE * ks), desc_advance(x0t, 2 * CORE * ks),
                                   kG32, acc | (ks > 0));
                 }
-                umma_commit(bar_epi);
             }
             __syncwarp();
+            issued(5);
+            ++tl_i;
         }
+        if (lane == 0) umma_commit(bar_epi);                          // the last tile's G1
+        __syncwarp();
     }
 
     __syncthreads();
@@ -531,7 +561,9 @@ int launch_grad(const GradArgs &A0, float *grad_out, float *aux_out, int64_t wor
     if (cap < 1) return SS_ERR_INVALID_ARG;
     const int grid = (int)(tiles < cap ? tiles : cap);
     cudaStream_t st = (cudaStream_t)stream;
-    mlp_grad_tc_kernel<NET><<<grid, NTHREADS, SM_TOTAL, st>>>(A0);
+    GradArgs A1 = A0;
+    A1.early_weights = (sslaunch::pdl_mode() & sslaunch::kPdlEarlyWeights) ? 1 : 0;
+    if (sslaunch::launch(mlp_grad_tc_kernel<NET>, dim3(grid), dim3(NTHREADS), SM_TOTAL, st, A1) != cudaSuccess) return SS_ERR_CUDA;
     if (!grad_out) return cudaGetLastError() == cudaSuccess ? grid : SS_ERR_CUDA;   // slices only (ss_peer_reduce_push follows)
     reduce_parts_kernel<<<(PN + 1 + 63) / 64, dim3(64, 4), 0, st>>>(A0.work, grid, PN, grad_out, aux_out);
     return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
@@ -547,6 +579,7 @@ int ss_debug_critic_grad_trace(const float *critic_params, const float *obs, con
                                void *stream) {
     GradArgs A{};
     A.params = critic_params; A.obs = obs; A.act = act; A.target = target; A.rate = 0.2f; A.n = n; A.n_global = n;
+    if (const char *e = getenv("SS_TRACE_RATE")) A.rate = (float)atof(e);      // 0: no dropout, the actor kernel's schedule
     A.work = (float *)workspace; A.trace = trace;
     return launch_grad<NET_CRITIC>(A, grad_out, nullptr, workspace_bytes, stream);
 }

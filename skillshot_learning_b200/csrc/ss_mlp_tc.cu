@@ -69,6 +69,7 @@ struct FwdArgs {
     // overlapped rollout (ss_selfplay_rollout): tile_ready[row / 128] is incremented once by each of the four output warps
     // when its 32 actions of that tile are in global memory; the env step kernel running beside this one consumes them
     int *tile_ready;
+    int early_weights;       // ss_launch.cuh: the parameters may be staged ahead of griddepcontrol.wait (set by launch_fwd)
 };
 
 // 32 accumulator columns (hidden-2 units) -> ReLU -> layer 3, four split accumulators per output.
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
     uint32_t tcount = 0;                                     // tiles done by this CTA: buffers = tcount & 1, parities from tcount
     uint32_t xph = 0;                                        // MMA warp: parity of the next X hand-off
     uint32_t env_status = 0;                                 // FUSED: SS_STATUS_* bits of this thread's env ticks
+    bool waited = false;                                     // griddepcontrol.wait executed (ss_launch.cuh)
 
     for (int64_t u = u0; u < u1;) {
         const int64_t g = u / upg;
@@ -190,10 +192,19 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
         const int r = (warp & 3) * 32 + lane;                     // row of the tile = tensor-memory lane
 
         float4 xin[3];
-        if (warp < P_WARPS) load_obs(A.obs, row0 + r, end, xin);
+        // first segment of a dependent launch (ss_launch.cuh): everything above ran beside the previous grid's tail; the
+        // weights are staged ahead of the wait too when the caller knows that grid does not write them
+        if (!waited && !A.early_weights) { sslaunch::griddep_wait(); sslaunch::griddep_launch(); waited = true; }
+        if (waited && warp < P_WARPS) load_obs(A.obs, row0 + r, end, xin);
         stage_weights<NET, NTH, true>(Stager{A.params, smem + SMP_B1, smem + SMP_B2, reinterpret_cast<float4 *>(smem + SMP_W3),
                                              reinterpret_cast<float *>(smem + SMP_B3), noisy, A.param_sd, A.seed, A.counter,
                                              (uint32_t)g});
+        if (!waited) {
+            sslaunch::griddep_wait();
+            sslaunch::griddep_launch();
+            waited = true;
+            if (warp < P_WARPS) load_obs(A.obs, row0 + r, end, xin);
+        }
         fence_proxy_async();
         __syncthreads();
         trace(0, 902);
@@ -399,6 +410,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
         trace(0, 903);
     }
 
+    if (!waited) { sslaunch::griddep_wait(); sslaunch::griddep_launch(); }      // a CTA without a tile still waits
     tc_fence_before();
     __syncthreads();
     if (warp == MMA_W) {
@@ -424,7 +436,11 @@ int launch_fwd(const FwdArgs &A, void *stream) {
     if (cudaFuncSetAttribute(pipe::mlp_fwd_pipe_kernel<NET, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)pipe::SMP_TOTAL) != cudaSuccess)
         return SS_ERR_CUDA;
-    pipe::mlp_fwd_pipe_kernel<NET, FUSED><<<grid, pipe::NTH, pipe::SMP_TOTAL, (cudaStream_t)stream>>>(A);
+    FwdArgs B = A;
+    B.early_weights = (sslaunch::pdl_mode() & sslaunch::kPdlEarlyWeights) ? 1 : 0;
+    if (sslaunch::launch(pipe::mlp_fwd_pipe_kernel<NET, FUSED>, dim3(grid), dim3(pipe::NTH), pipe::SMP_TOTAL, (cudaStream_t)stream, B) !=
+        cudaSuccess)
+        return SS_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
 }
 

@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "../../include/skillshot_b200.h"
+#include "ss_launch.cuh"
 #include "ss_rng.cuh"
 
 namespace sstc {

@@ -10,8 +10,15 @@
 // arguments, from C.  Nothing here touches the device directly.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/skillshot_b200.h"
+#include "ss_launch.cuh"
+
+int &sslaunch::pdl_mode() {
+    static thread_local int mode = sslaunch::kPdlOff;
+    return mode;
+}
 
 extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
     if (!a || !a->ring_obs || !a->ring_act || !a->ring_reward || !a->ring_next_obs || !a->ring_done || a->batch < 1 ||
@@ -27,6 +34,19 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
     const int64_t n = a->batch;
     const bool tc = a->tensor_cores != 0;
     int rc;
+    // Single GPU: the launches of this call form one dependent chain (ss_launch.cuh): each grid's CTAs are placed while its
+    // predecessor drains and hold at griddepcontrol.wait.  kEarly additionally lets a tensor-core kernel stage its network's
+    // parameters ahead of that wait; it is given to exactly the launches whose immediate predecessor does not write those
+    // parameters (the one before that is complete by then, see the header):
+    //   sample -> [actor'(s2) -> critic'(s2, a2)] -> critic gradient     none of the predecessors writes parameters
+    //   reduce + Adam (critic, critic') -> actor(s)                        reads the actor
+    //   actor(s) -> critic(s, a)                                           Adam is two launches back
+    //   critic(s, a) -> actor gradient -> reduce + Adam (actor, actor')
+    // SS_UPDATE_PDL=0 switches the chain off (A/B measurements).  The peer exchange path launches the ordinary way.
+    static const bool pdl_env = [] { const char *e = getenv("SS_UPDATE_PDL"); return !(e && e[0] == '0'); }();
+    const int kOn = (!peers && pdl_env) ? sslaunch::kPdlOn : sslaunch::kPdlOff;
+    const int kEarly = kOn ? (sslaunch::kPdlOn | sslaunch::kPdlEarlyWeights) : sslaunch::kPdlOff;
+    sslaunch::PdlScope scope(kOn);
 
     // minibatch (uniform with replacement from the filled part of the ring)
     rc = ss_replay_sample(a->ring_obs, a->ring_act, a->ring_reward, a->ring_next_obs, a->ring_done, a->capacity, a->size,
@@ -36,6 +56,7 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
 
     // critic target: the reference regresses on the reward itself (gamma = 0, SkillshotLearner.py:434)
     const float *y = a->reward;
+    sslaunch::pdl_mode() = kEarly;
     if (a->gamma != 0.f) {
         rc = tc ? ss_ddpg_targets_tc(a->target_actor, a->target_critic, a->reward, a->next_obs, a->done, a->gamma, a->y, n,
                                      a->workspace, a->workspace_bytes, stream)
@@ -51,6 +72,7 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
     rc = critic_grad(a->critic, a->obs, a->act, y, nullptr, a->dropout_rate, a->seed, a->counter, n, a->n_global, a->row_offset,
                      nullptr, a->stats, a->workspace, a->workspace_bytes, stream);
     if (rc <= 0) return rc < 0 ? rc : SS_ERR_INVALID_ARG;
+    sslaunch::pdl_mode() = kOn;
     // The actor step begins with a = actor(s), which needs neither the critic's new weights nor anything the exchange
     // delivers: on the tensor-core path of a sharded update it is enqueued BETWEEN the push of this rank's critic gradient and
     // the Adam kernel that waits for the peers' pushes, so that the exchange's latency (rank skew + NVLink visibility,
@@ -76,12 +98,14 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
     if (rc != SS_OK) return rc;
 
     // actor: model_actor_fit_step with the critic just updated (SkillshotLearner.py:440-443 follows 434)
+    sslaunch::pdl_mode() = kEarly;
     if (early_actor_forward)
         rc = ss_actor_grad_tc_staged(a->actor, a->critic, a->obs, n, nullptr, a->stats + 1, a->workspace, a->workspace_bytes, 2, stream);
     else
         rc = (tc ? ss_actor_grad_tc : ss_actor_grad)(a->actor, a->critic, a->obs, n, nullptr, a->stats + 1, a->workspace,
                                                      a->workspace_bytes, stream);
     if (rc <= 0) return rc < 0 ? rc : SS_ERR_INVALID_ARG;
+    sslaunch::pdl_mode() = kOn;
     if (peers) {
         rc = ss_peer_reduce_push(a->workspace, rc, SS_ACTOR_PARAMS, a->stats + 1, a->peer_bases, a->world, a->rank,
                                  a->peer_capacity, a->epoch + 1, a->done_counter, stream);

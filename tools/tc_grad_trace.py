@@ -18,19 +18,19 @@ for _ in range(3):
 torch.cuda.synchronize()
 t = tr.cpu().numpy()
 t0 = min(t[r, 0, 0] for r in range(2) if t[r, 0, 0] > 0)
-step = ["L1a", "L1b", "L2", "G3+G2+BXa", "BXb", "G1"]
+step = ["L1a", "L1b", "L2", "G2a+BXa|G2b+G3", "BXb", "G1"]
 ev = []
 for r in range(2):
     for k in range(256):
         if t[r, k, 0] > 0:
-            code = int(t[r, k, 1]); kind, e = code // 100, code % 100
-            if kind == 9:
-                ev.append((int(t[r, k, 0] - t0), "K " + ["entry", "set up + weights staged", "tiles done", "gradient slice written"][e]))
+            code = int(t[r, k, 1]); kind, e = code // 1000, code % 1000
+            if kind == 0:
+                ev.append((int(t[r, k, 0] - t0), "K " + ["entry", "set up + weights staged", "tiles done", "gradient slice written"][code - 900]))
                 continue
             what = {1: "E handed over ->", 2: "E resumed after", 3: "M woke for", 4: "M issued"}[kind]
-            ev.append((int(t[r, k, 0] - t0), "%s %s (tile %d)" % (what, step[(e if kind in (1, 3) else e - 1) % 6], (e if kind in (1, 3) else e - 1) // 6)))
+            ev.append((int(t[r, k, 0] - t0), "%s %s (tile %d)" % (what, step[e % 8], e // 8)))
 ev.sort()
 prev = 0
-show = ev[:110] if len(sys.argv) <= 2 else [x for x in ev if x[1].startswith("K")]
+show = ev[:140] if len(sys.argv) <= 2 else [x for x in ev if x[1].startswith("K")]
 for c, what in show:
     print("%7d  (+%5d)  %s" % (c, c - prev, what)); prev = c
