@@ -529,8 +529,30 @@ typedef struct ss_ddpg_update_args {
     int64_t peer_capacity;
     uint32_t epoch;
     uint32_t *done_counter, *status;
+    void *pair_mail;                           /* ss_actor_critic_forward_tc's mailbox for `batch` rows, or NULL: the
+                                                  actor -> critic forward pairs then run as two launches each */
 } ss_ddpg_update_args;
 int ss_ddpg_update(const ss_ddpg_update_args *args, void *stream);
+
+/* a = actor(s) -> act_out [n][2], then critic([s, a]) -> any of q_out [n] / neg_dq_da_out [n][2] / y_out [n] (the TD target
+ * reward + gamma (1 - done) q, as ss_critic_forward_tc), in ONE launch: half of the CTAs play the actor, the other half the
+ * critic, which takes each row's actions as soon as the actor half has written them.  The two steps of
+ * model_actor_fit_step's forward pass (SkillshotLearner.py:395-400) and of the TD target.  Bit-identical to
+ * ss_actor_forward_tc (no noise) followed by ss_critic_forward_tc.
+ * pair_mail: 8 bytes per row (8-byte aligned), every 32-bit word SS_PAIR_MAIL_EMPTY before the first call; every call
+ * leaves it so.  The actor half writes a row's two actions there, the critic half polls the row until neither word is the
+ * empty mark (the data is its own flag), takes them and puts the mark back. */
+#define SS_PAIR_MAIL_EMPTY 0x7fc0dead          /* a NaN payload no arithmetic produces */
+int ss_actor_critic_forward_tc(const float *actor_params, const float *critic_params, const float *obs, float *act_out,
+                               int64_t n, float *q_out, float *neg_dq_da_out, const float *reward, const uint8_t *done,
+                               float gamma, float *y_out, void *pair_mail, void *stream);
+/* ss_actor_grad_tc_staged / ss_ddpg_targets_tc with the forward pair as one launch when pair_mail != NULL (stage 0 only) */
+int ss_actor_grad_tc_paired(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
+                            float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, int stage,
+                            void *pair_mail, void *stream);
+int ss_ddpg_targets_tc_paired(const float *target_actor_params, const float *target_critic_params, const float *reward,
+                              const float *next_obs, const uint8_t *done, float gamma, float *y_out, int64_t n,
+                              void *workspace, int64_t workspace_bytes, void *pair_mail, void *stream);
 
 /* Measurement aid (no reference counterpart): instruction-rate ceilings of this GPU for the roofline record of the fused
  * step kernel, which is bound by the warp schedulers and the float64 pipe rather than by HBM once K ticks are played per

@@ -38,6 +38,9 @@ PEER_MAX_WORLD, PEER_HANDLE_BYTES = 8, 64
 _u32 = ctypes.c_uint32
 
 
+PAIR_MAIL_EMPTY = 0x7fc0dead      # SS_PAIR_MAIL_EMPTY
+
+
 class DdpgUpdateArgs(ctypes.Structure):
     """struct ss_ddpg_update_args of include/skillshot_b200.h (same field order)."""
     _fields_ = ([(k, _vp) for k in ("ring_obs", "ring_act", "ring_reward", "ring_next_obs", "ring_done")] +
@@ -49,7 +52,7 @@ class DdpgUpdateArgs(ctypes.Structure):
                 [("seed", _u64), ("counter", _u64), ("step_critic", _i64), ("step_actor", _i64), ("n_global", _i64),
                  ("row_offset", _i64), ("workspace", _vp), ("workspace_bytes", _i64), ("tensor_cores", _i32),
                  ("world", _i32), ("rank", _i32), ("peer_bases", _vp), ("peer_capacity", _i64), ("epoch", _u32),
-                 ("done_counter", _vp), ("status", _vp)])
+                 ("done_counter", _vp), ("status", _vp), ("pair_mail", _vp)])
 
 
 # name -> (restype, argtypes); every symbol the header declares
@@ -76,6 +79,9 @@ SIGNATURES = {
     "ss_actor_grad_tc": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "ss_actor_grad_tc_staged": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp]),
     "ss_ddpg_targets_tc": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _i64, _vp]),
+    "ss_actor_critic_forward_tc": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp]),
+    "ss_actor_grad_tc_paired": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "ss_ddpg_targets_tc_paired": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _i64, _vp, _vp]),
     "ss_peer_bytes": (_i64, [_i32, _i64]),
     "ss_peer_alloc": (_i32, [_i32, _i64, _vp]),
     "ss_peer_free": (_i32, [_vp]),

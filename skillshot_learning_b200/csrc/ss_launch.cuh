@@ -21,7 +21,10 @@
 
 namespace sslaunch {
 
-enum : int { kPdlOff = 0, kPdlOn = 1, kPdlEarlyWeights = 2 };
+// kPdlEarlyAfterFirst: the next tensor-core launch stages its parameters behind the wait (its predecessor writes them), the
+// ones after it ahead of it
+// kPdlPairCriticLate: in an actor -> critic pair launch only the actor role stages ahead of the wait
+enum : int { kPdlOff = 0, kPdlOn = 1, kPdlEarlyWeights = 2, kPdlEarlyAfterFirst = 4, kPdlPairCriticLate = 8 };
 
 // the launch mode of the calling host thread; set by ss_ddpg_update around each entry point it calls
 int &pdl_mode();
@@ -31,6 +34,14 @@ struct PdlScope {                     // sets the mode for the lifetime of the o
     explicit PdlScope(int mode) : saved(pdl_mode()) { pdl_mode() = mode; }
     ~PdlScope() { pdl_mode() = saved; }
 };
+
+// whether the tensor-core launch about to be made may stage its parameters ahead of griddepcontrol.wait
+inline int take_early_weights() {
+    int &m = pdl_mode();
+    if (!(m & kPdlOn)) return 0;
+    if (m & kPdlEarlyAfterFirst) { m = (m & ~kPdlEarlyAfterFirst) | kPdlEarlyWeights; return 0; }
+    return (m & kPdlEarlyWeights) ? 1 : 0;
+}
 
 template <class... KArgs, class... Args>
 inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {

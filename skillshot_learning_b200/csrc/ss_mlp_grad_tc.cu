@@ -562,7 +562,7 @@ int launch_grad(const GradArgs &A0, float *grad_out, float *aux_out, int64_t wor
     const int grid = (int)(tiles < cap ? tiles : cap);
     cudaStream_t st = (cudaStream_t)stream;
     GradArgs A1 = A0;
-    A1.early_weights = (sslaunch::pdl_mode() & sslaunch::kPdlEarlyWeights) ? 1 : 0;
+    A1.early_weights = sslaunch::take_early_weights();
     if (sslaunch::launch(mlp_grad_tc_kernel<NET>, dim3(grid), dim3(NTHREADS), SM_TOTAL, st, A1) != cudaSuccess) return SS_ERR_CUDA;
     if (!grad_out) return cudaGetLastError() == cudaSuccess ? grid : SS_ERR_CUDA;   // slices only (ss_peer_reduce_push follows)
     reduce_parts_kernel<<<(PN + 1 + 63) / 64, dim3(64, 4), 0, st>>>(A0.work, grid, PN, grad_out, aux_out);
@@ -604,6 +604,14 @@ int ss_critic_grad_tc(const float *critic_params, const float *obs, const float 
 int ss_actor_grad_tc_staged(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
                             float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, int stage,
                             void *stream) {
+    return ss_actor_grad_tc_paired(actor_params, critic_params, obs, n, grad_out, q_sum_out, workspace, workspace_bytes, stage,
+                                   nullptr, stream);
+}
+
+// pair_mail != NULL (stage 0 only): a = actor(s) and critic([s, a]) run as one launch (ss_actor_critic_forward_tc)
+int ss_actor_grad_tc_paired(const float *actor_params, const float *critic_params, const float *obs, int64_t n,
+                            float *grad_out, float *q_sum_out, void *workspace, int64_t workspace_bytes, int stage,
+                            void *pair_mail, void *stream) {
     if (!actor_params || !critic_params || !obs || !workspace || n <= 0 || stage < 0 || stage > 2) return SS_ERR_INVALID_ARG;
     if (((uintptr_t)actor_params | (uintptr_t)critic_params | (uintptr_t)obs | (uintptr_t)workspace) & 15)
         return SS_ERR_INVALID_ARG;
@@ -616,12 +624,18 @@ int ss_actor_grad_tc_staged(const float *actor_params, const float *critic_param
     float *q = up + (n * 2 + 3) / 4 * 4;
     // a = actor(s);  q, -dq/da = critic([s, a]) with Dropout off;  then the actor's backward pass
     int rc;
-    if (stage != 2) {
-        rc = ss_actor_forward_tc(actor_params, obs, act, n, 0.f, 0, 0.f, 0, 0, stream);
-        if (rc != SS_OK || stage == 1) return rc;
+    if (stage == 0 && pair_mail) {
+        rc = ss_actor_critic_forward_tc(actor_params, critic_params, obs, act, n, q, up, nullptr, nullptr, 0.f, nullptr, pair_mail,
+                                        stream);
+        if (rc != SS_OK) return rc;
+    } else {
+        if (stage != 2) {
+            rc = ss_actor_forward_tc(actor_params, obs, act, n, 0.f, 0, 0.f, 0, 0, stream);
+            if (rc != SS_OK || stage == 1) return rc;
+        }
+        rc = ss_critic_forward_tc(critic_params, obs, act, n, q, up, nullptr, nullptr, 0.f, nullptr, stream);
+        if (rc != SS_OK) return rc;
     }
-    rc = ss_critic_forward_tc(critic_params, obs, act, n, q, up, nullptr, nullptr, 0.f, nullptr, stream);
-    if (rc != SS_OK) return rc;
     GradArgs A{};
     A.params = actor_params; A.obs = obs; A.up = up; A.q = q; A.n = n; A.n_global = n; A.work = (float *)workspace;
     // the rows' Q values are summed by the gradient kernel's row owners into the slices' extra slot: the fixed-order
@@ -637,10 +651,21 @@ int ss_actor_grad_tc(const float *actor_params, const float *critic_params, cons
 int ss_ddpg_targets_tc(const float *target_actor_params, const float *target_critic_params, const float *reward,
                        const float *next_obs, const uint8_t *done, float gamma, float *y_out, int64_t n,
                        void *workspace, int64_t workspace_bytes, void *stream) {
+    return ss_ddpg_targets_tc_paired(target_actor_params, target_critic_params, reward, next_obs, done, gamma, y_out, n, workspace,
+                                     workspace_bytes, nullptr, stream);
+}
+
+// pair_mail != NULL: actor'(s2) and critic'(s2, a2) run as one launch (ss_actor_critic_forward_tc)
+int ss_ddpg_targets_tc_paired(const float *target_actor_params, const float *target_critic_params, const float *reward,
+                              const float *next_obs, const uint8_t *done, float gamma, float *y_out, int64_t n,
+                              void *workspace, int64_t workspace_bytes, void *pair_mail, void *stream) {
     if (!target_actor_params || !target_critic_params || !reward || !next_obs || !y_out || !workspace || n <= 0)
         return SS_ERR_INVALID_ARG;
     if (workspace_bytes < n * 8 || ((uintptr_t)workspace & 15)) return SS_ERR_INVALID_ARG;
     float *act = (float *)workspace;
+    if (pair_mail)
+        return ss_actor_critic_forward_tc(target_actor_params, target_critic_params, next_obs, act, n, nullptr, nullptr, reward, done,
+                                          gamma, y_out, pair_mail, stream);
     int rc = ss_actor_forward_tc(target_actor_params, next_obs, act, n, 0.f, 0, 0.f, 0, 0, stream);
     if (rc != SS_OK) return rc;
     return ss_critic_forward_tc(target_critic_params, next_obs, act, n, nullptr, nullptr, reward, done, gamma, y_out, stream);

@@ -32,6 +32,8 @@
 // them, w + w * (sd * eps), eps from the same Philox stream as the float32 path (ss_rng.cuh),
 // one draw per noise group; groups are multiples of the 128-row tile so a tile never mixes two
 // draws.
+#include <stdlib.h>
+
 #include "ss_tc_common.cuh"
 
 #include "ss_env_pp.cuh"
@@ -70,6 +72,11 @@ struct FwdArgs {
     // when its 32 actions of that tile are in global memory; the env step kernel running beside this one consumes them
     int *tile_ready;
     int early_weights;       // ss_launch.cuh: the parameters may be staged ahead of griddepcontrol.wait (set by launch_fwd)
+    // actor -> critic pair in ONE launch (mlp_fwd_pair_kernel): the actor role's output lane of a row also writes the row's
+    // two actions into pair_mail[row]; the critic role's producer lane of that row polls those 8 bytes until neither word is
+    // the empty mark, takes them and puts the mark back.  The data is its own flag: no fence, no separate flag traffic
+    // (a release store per tile cost the output warps ~700 cycles each, measured).
+    int2 *pair_mail;
 };
 
 // 32 accumulator columns (hidden-2 units) -> ReLU -> layer 3, four split accumulators per output.
@@ -116,6 +123,9 @@ __device__ __forceinline__ void layer3(const uint32_t (&v)[32], const float4 *w3
 // version (tools/tc_trace.py) shows the MMA warp as the pacing role.
 namespace pipe {
 
+// the "empty" word of the pair mailbox: a NaN payload no arithmetic produces (tanhf of a NaN gives the canonical 0x7fffffff)
+constexpr int kMailEmpty = SS_PAIR_MAIL_EMPTY;
+
 constexpr int P_WARPS = 4, Q_WARPS = 4, MMA_W = 8, NTH = 32 * 9;
 
 constexpr uint32_t SMP_B1 = 0;                              // [K1F/8][256][8] fp16
@@ -133,8 +143,9 @@ constexpr uint32_t SMP_TMEM = SMP_BAR + B_COUNT * 8;
 constexpr uint32_t SMP_TOTAL = SMP_TMEM + 16;
 static_assert(SMP_TOTAL <= 227 * 1024, "shared memory budget");
 
-template <int NET, bool FUSED = false>
-__global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
+// cta / ncta: this CTA's index among the CTAs that share the work of A (the whole grid, or one role's part of a pair launch)
+template <int NET, bool FUSED>
+__device__ __forceinline__ void fwd_body(const FwdArgs &A, const int cta, const int ncta) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
     // development trace (A.trace != NULL): role 0 = producer warp 0, 1 = output warp 4, 2 = MMA warp
     int tr_n = 0;
     auto trace = [&](int role, int code) {
-        if (A.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == P_WARPS || warp == MMA_W) && tr_n < 256) {
+        if (A.trace && cta == 0 && lane == 0 && (warp == 0 || warp == P_WARPS || warp == MMA_W) && tr_n < 256) {
             A.trace[(role * 256 + tr_n) * 2] = clock64();
             A.trace[(role * 256 + tr_n) * 2 + 1] = code;
             ++tr_n;
@@ -176,7 +187,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
     const int64_t upg = (group + TM - 1) / TM;
     const int64_t n_groups = (A.n + group - 1) / group;
     const int64_t units = n_groups * upg;
-    const int64_t u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+    const int64_t u0 = units * cta / ncta, u1 = units * (cta + 1) / ncta;
 
     uint32_t tcount = 0;                                     // tiles done by this CTA: buffers = tcount & 1, parities from tcount
     uint32_t xph = 0;                                        // MMA warp: parity of the next X hand-off
@@ -216,6 +227,8 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                 store_obs_row_f16(xin, smem + SMP_X0 + ((tcount + (uint32_t)i) & 1) * X0_BYTES + r * 16);
                 load_obs(A.obs, row0 + (i + 1) * TM + r, (i + 1 < ntiles) ? end : 0, xin);   // prefetch the next tile's row
             };
+            int2 pair_v = make_int2(0, 0);                        // pair launch, critic role: this lane's row of the mailbox ...
+            bool pair_have = false;                               // ... holds the coming tile's actions already
             stage_x0(0);
             fence_proxy_async();
             mbar_arrive(bar(B_X));                                // -> MMA1(tile 0)
@@ -224,7 +237,29 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                 const uint32_t tc = tcount + (uint32_t)i;
                 uint8_t *arow = smem + SMP_A1 + (tc & 1) * X2_BYTES + r * 16;
                 float2 act = make_float2(0.f, 0.f);
-                if (NET == NET_CRITIC && row0 + i * TM + r < end) act = __ldg(reinterpret_cast<const float2 *>(A.act_in) + row0 + i * TM + r);
+                if (NET == NET_CRITIC && A.pair_mail) {
+                    // pair launch: this row's action comes from the actor role.  Usually it was taken during the previous
+                    // tile (below); otherwise poll for it here.
+                    const int64_t prow = row0 + i * TM + r;
+                    if (!pair_have) {
+                        uint32_t spins = 0;
+                        for (;;) {
+                            if (prow < end)
+                                asm volatile("ld.volatile.global.v2.s32 {%0, %1}, [%2];" : "=r"(pair_v.x), "=r"(pair_v.y) : "l"(A.pair_mail + prow));
+                            if (__all_sync(0xffffffffu, prow >= end || (pair_v.x != kMailEmpty && pair_v.y != kMailEmpty))) break;
+                            if (++spins > (1u << 24)) __trap();       // the actor role never ran: a protocol bug, not a hang
+                            __nanosleep(20);
+                        }
+                        if (prow < end) A.pair_mail[prow] = make_int2(kMailEmpty, kMailEmpty);      // left empty for the next launch
+                    }
+                    if (prow < end) act = make_float2(__int_as_float(pair_v.x), __int_as_float(pair_v.y));
+                    pair_have = false;
+                    // one look at the next tile's row, issued now and examined at the end of this iteration
+                    if (i + 1 < ntiles && prow + TM < end)
+                        asm volatile("ld.volatile.global.v2.s32 {%0, %1}, [%2];" : "=r"(pair_v.x), "=r"(pair_v.y) : "l"(A.pair_mail + prow + TM));
+                } else if (NET == NET_CRITIC && row0 + i * TM + r < end) {
+                    act = __ldg(reinterpret_cast<const float2 *>(A.act_in) + row0 + i * TM + r);
+                }
                 trace(0, 100 + (int)i);
                 // MMA1(tile) retired: D1 holds layer 1 and X0[tc & 1] is dead.  The tensor pipe retires one thread's MMAs
                 // in issue order and MMA2(tile - 2) was issued before MMA1(tile), so A1[tc & 1] is free as well.
@@ -250,6 +285,12 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                 mbar_arrive(bar(B_X));                            // A1[tile] full, D1 free, X0(tile + 1) staged
                 trace(0, 500 + (int)i);
                 if (i + 2 < ntiles) stage_x0(i + 2);              // into X0[tc & 1]
+                if (NET == NET_CRITIC && A.pair_mail && i + 1 < ntiles) {
+                    // the next tile's actions, if the actor role has delivered all 32 by now
+                    const int64_t nrow = row0 + (i + 1) * TM + r;
+                    pair_have = __all_sync(0xffffffffu, nrow >= end || (pair_v.x != kMailEmpty && pair_v.y != kMailEmpty));
+                    if (pair_have && nrow < end) A.pair_mail[nrow] = make_int2(kMailEmpty, kMailEmpty);
+                }
             }
         } else if (warp < P_WARPS + Q_WARPS) {
             // ============ output warps: layer 3 on D2 ============
@@ -304,6 +345,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
                             a1 += A.action_sd * zn[1];
                         }
                         reinterpret_cast<float2 *>(A.act_out)[row] = make_float2(a0, a1);
+                        if (A.pair_mail) A.pair_mail[row] = make_int2(__float_as_int(a0), __float_as_int(a1));
                         if (FUSED) { fa0 = a0; fa1 = a1; }
                     } else {
                         if (A.q_out) A.q_out[row] = out0;
@@ -420,6 +462,21 @@ __global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
     if (FUSED && env_status && A.env_status) atomicOr(A.env_status, env_status);
 }
 
+template <int NET, bool FUSED = false>
+__global__ void __launch_bounds__(NTH, 1) mlp_fwd_pipe_kernel(const FwdArgs A) {
+    fwd_body<NET, FUSED>(A, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// a = actor(s) and critic(s, a) in ONE launch: the first `ga` CTAs play the actor role, the others the critic role, each
+// over all the tiles; a critic CTA walks the same tiles in the same order as the actor CTA of the same index and takes
+// each row's actions as soon as they are out (pair_mail).  At a 65,536-row minibatch a forward launch is mostly set-up
+// and pipeline fill (3.5 tiles per CTA); two launches back to back pay that twice, the pair once, on half the SMs each.
+// All CTAs are resident together (grid <= SMs, one CTA per SM), and a producer never waits for a consumer.
+__global__ void __launch_bounds__(NTH, 1) mlp_fwd_pair_kernel(const FwdArgs Aa, const FwdArgs Ac, const int ga) {
+    if ((int)blockIdx.x < ga) fwd_body<NET_ACTOR, false>(Aa, (int)blockIdx.x, ga);
+    else fwd_body<NET_CRITIC, false>(Ac, (int)blockIdx.x - ga, (int)gridDim.x - ga);
+}
+
 }  // namespace pipe
 
 template <int NET, bool FUSED = false>
@@ -437,7 +494,7 @@ int launch_fwd(const FwdArgs &A, void *stream) {
                              (int)pipe::SMP_TOTAL) != cudaSuccess)
         return SS_ERR_CUDA;
     FwdArgs B = A;
-    B.early_weights = (sslaunch::pdl_mode() & sslaunch::kPdlEarlyWeights) ? 1 : 0;
+    B.early_weights = sslaunch::take_early_weights();
     if (sslaunch::launch(pipe::mlp_fwd_pipe_kernel<NET, FUSED>, dim3(grid), dim3(pipe::NTH), pipe::SMP_TOTAL, (cudaStream_t)stream, B) !=
         cudaSuccess)
         return SS_ERR_CUDA;
@@ -533,4 +590,39 @@ extern "C" int ss_critic_forward_tc(const float *critic_params, const float *obs
     A.act_in = act; A.q_out = q_out; A.up_out = neg_dq_da_out; A.y_out = y_out; A.reward = reward; A.done = done;
     A.gamma = gamma;
     return launch_fwd<NET_CRITIC>(A, stream);
+}
+
+// a = actor(s) -> act_out, then critic(s, a) -> any of q_out / neg_dq_da_out / y_out, as ONE launch (mlp_fwd_pair_kernel).
+// Same results, bit for bit, as ss_actor_forward_tc (no noise) followed by ss_critic_forward_tc.
+extern "C" int ss_actor_critic_forward_tc(const float *actor_params, const float *critic_params, const float *obs, float *act_out,
+                                          int64_t n, float *q_out, float *neg_dq_da_out, const float *reward, const uint8_t *done,
+                                          float gamma, float *y_out, void *pair_mail, void *stream) {
+    if (!actor_params || !critic_params || !obs || !act_out || !pair_mail || n <= 0 || (!q_out && !neg_dq_da_out && !y_out))
+        return SS_ERR_INVALID_ARG;
+    if (y_out && !reward) return SS_ERR_INVALID_ARG;
+    if (((uintptr_t)actor_params | (uintptr_t)critic_params | (uintptr_t)obs) & 15 ||
+        (((uintptr_t)act_out | (uintptr_t)neg_dq_da_out | (uintptr_t)pair_mail) & 7))
+        return SS_ERR_INVALID_ARG;
+    FwdArgs Aa{}, Ac{};
+    Aa.params = actor_params; Aa.obs = obs; Aa.n = n; Aa.group = n; Aa.act_out = act_out; Aa.pair_mail = (int2 *)pair_mail;
+    Ac.params = critic_params; Ac.obs = obs; Ac.n = n; Ac.group = n; Ac.act_in = act_out; Ac.pair_mail = (int2 *)pair_mail;
+    Ac.q_out = q_out; Ac.up_out = neg_dq_da_out; Ac.y_out = y_out; Ac.reward = reward; Ac.done = done; Ac.gamma = gamma;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return SS_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SS_ERR_CUDA;
+    const int64_t units = (n + TM - 1) / TM;
+    const int half = sms / 2;
+    if (half < 1) return SS_ERR_CUDA;
+    const int ga = (int)(units < half ? units : half);          // the two roles split the tiles identically: same count
+    if (cudaFuncSetAttribute(pipe::mlp_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe::SMP_TOTAL) !=
+        cudaSuccess)
+        return SS_ERR_CUDA;
+    // (the critic role stages behind the wait when the launch directly follows the kernel that writes the critic)
+    const int critic_late = sslaunch::pdl_mode() & sslaunch::kPdlPairCriticLate;
+    Aa.early_weights = sslaunch::take_early_weights();
+    Ac.early_weights = critic_late ? 0 : Aa.early_weights;
+    if (sslaunch::launch(pipe::mlp_fwd_pair_kernel, dim3(2 * ga), dim3(pipe::NTH), pipe::SMP_TOTAL, (cudaStream_t)stream, Aa, Ac, ga) !=
+        cudaSuccess)
+        return SS_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
 }

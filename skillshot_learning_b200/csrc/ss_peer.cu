@@ -27,6 +27,7 @@
 #include <stdint.h>
 
 #include "../../include/skillshot_b200.h"
+#include "ss_launch.cuh"
 
 namespace {
 
@@ -52,6 +53,8 @@ __global__ void reduce_push_kernel(const float *work, int parts, int n_params, f
     __shared__ bool last;
     const int p = blockIdx.x * 64 + threadIdx.x, q = threadIdx.y;
     const int parity = (int)(epoch & 1u);
+    sslaunch::griddep_wait();            // ss_launch.cuh: placed beside the gradient kernel's last CTAs, held here until it is done
+    sslaunch::griddep_launch();
     float s = 0.f;
     if (p <= n_params) {
 #pragma unroll 4
@@ -89,6 +92,8 @@ __global__ void peer_adam_kernel(void *base, int world, int64_t capacity, uint32
                                  float tau, float grad_scale, uint32_t *status) {
     const int parity = (int)(epoch & 1u);
     __shared__ int timed_out;
+    sslaunch::griddep_wait();            // ss_launch.cuh
+    sslaunch::griddep_launch();
     // A timeout is sticky: once a rank's gradient has failed to arrive, no later step is applied either (the ranks would no
     // longer hold the same weights) until the host has seen the status word and decided what to do (PeerExchange.check_status).
     if (threadIdx.x == 0) timed_out = (status && (*(volatile uint32_t *)status & SS_STATUS_PEER_TIMEOUT)) ? 1 : 0;
@@ -168,8 +173,10 @@ int ss_peer_reduce_push(const void *workspace, int parts, int n_params, float *a
         if (!peer_bases_host[d]) return SS_ERR_INVALID_ARG;
         T.base[d] = peer_bases_host[d];
     }
-    reduce_push_kernel<<<(n_params + 1 + 63) / 64, dim3(64, 4), 0, (cudaStream_t)stream>>>(
-        (const float *)workspace, parts, n_params, aux_out, T, world, rank, capacity, epoch, done_counter);
+    if (sslaunch::launch(reduce_push_kernel, dim3((n_params + 1 + 63) / 64), dim3(64, 4), 0, (cudaStream_t)stream,
+                         (const float *)workspace, parts, n_params, aux_out, T, world, rank, capacity, epoch,
+                         (unsigned int *)done_counter) != cudaSuccess)
+        return SS_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
 }
 
@@ -179,9 +186,10 @@ int ss_peer_adam_tf(void *own_base, int world, int64_t capacity, uint32_t epoch,
     if (!own_base || world < 1 || world > kMaxWorld || capacity < n || epoch == 0 || !params || !m || !v || n <= 0 || step < 1)
         return SS_ERR_INVALID_ARG;
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
-    peer_adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        own_base, world, capacity, epoch, params, m, v, target_params, grad_out, n, (float)lr_t, beta1, beta2, eps, tau,
-        grad_scale, status);
+    if (sslaunch::launch(peer_adam_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, own_base, world,
+                         capacity, epoch, params, m, v, target_params, grad_out, n, (float)lr_t, beta1, beta2, eps, tau, grad_scale,
+                         status) != cudaSuccess)
+        return SS_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
 }
 

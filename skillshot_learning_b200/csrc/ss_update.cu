@@ -41,10 +41,13 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
     //   sample -> [actor'(s2) -> critic'(s2, a2)] -> critic gradient     none of the predecessors writes parameters
     //   reduce + Adam (critic, critic') -> actor(s)                        reads the actor
     //   actor(s) -> critic(s, a)                                           Adam is two launches back
+    //     (as ONE pair launch the critic role directly follows Adam and stages behind its wait: kPdlPairCriticLate)
     //   critic(s, a) -> actor gradient -> reduce + Adam (actor, actor')
-    // SS_UPDATE_PDL=0 switches the chain off (A/B measurements).  The peer exchange path launches the ordinary way.
+    // With the peer exchange the order is ... critic gradient -> push -> actor(s) -> peers' Adam (critic) -> critic(s, a) -> ...:
+    // critic(s, a) then directly follows the kernel that writes the critic and stages behind its wait (kPdlEarlyAfterFirst).
+    // SS_UPDATE_PDL=0 switches the chain off (A/B measurements).
     static const bool pdl_env = [] { const char *e = getenv("SS_UPDATE_PDL"); return !(e && e[0] == '0'); }();
-    const int kOn = (!peers && pdl_env) ? sslaunch::kPdlOn : sslaunch::kPdlOff;
+    const int kOn = pdl_env ? sslaunch::kPdlOn : sslaunch::kPdlOff;
     const int kEarly = kOn ? (sslaunch::kPdlOn | sslaunch::kPdlEarlyWeights) : sslaunch::kPdlOff;
     sslaunch::PdlScope scope(kOn);
 
@@ -58,8 +61,8 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
     const float *y = a->reward;
     sslaunch::pdl_mode() = kEarly;
     if (a->gamma != 0.f) {
-        rc = tc ? ss_ddpg_targets_tc(a->target_actor, a->target_critic, a->reward, a->next_obs, a->done, a->gamma, a->y, n,
-                                     a->workspace, a->workspace_bytes, stream)
+        rc = tc ? ss_ddpg_targets_tc_paired(a->target_actor, a->target_critic, a->reward, a->next_obs, a->done, a->gamma, a->y, n,
+                                            a->workspace, a->workspace_bytes, a->pair_mail, stream)
                 : ss_ddpg_targets(a->target_actor, a->target_critic, a->reward, a->next_obs, a->done, a->gamma, a->y, n, stream);
         if (rc != SS_OK) return rc;
         y = a->y;
@@ -84,9 +87,11 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
                                  a->peer_capacity, a->epoch, a->done_counter, stream);
         if (rc != SS_OK) return rc;
         if (early_actor_forward) {
+            sslaunch::pdl_mode() = kEarly;
             rc = ss_actor_grad_tc_staged(a->actor, a->critic, a->obs, n, nullptr, a->stats + 1, a->workspace, a->workspace_bytes, 1,
                                          stream);
             if (rc != SS_OK) return rc;
+            sslaunch::pdl_mode() = kOn;
         }
         rc = ss_peer_adam_tf(a->peer_bases[a->rank], a->world, a->peer_capacity, a->epoch, a->critic, a->m_critic, a->v_critic,
                              a->target_critic, a->grad_critic, SS_CRITIC_PARAMS, a->step_critic, a->lr_critic, a->beta1,
@@ -99,11 +104,15 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
 
     // actor: model_actor_fit_step with the critic just updated (SkillshotLearner.py:440-443 follows 434)
     sslaunch::pdl_mode() = kEarly;
+    if (early_actor_forward && kOn) sslaunch::pdl_mode() = kOn | sslaunch::kPdlEarlyAfterFirst;
+    else if (kOn && tc && a->pair_mail) sslaunch::pdl_mode() = kEarly | sslaunch::kPdlPairCriticLate;   // the pair follows Adam(critic)
     if (early_actor_forward)
         rc = ss_actor_grad_tc_staged(a->actor, a->critic, a->obs, n, nullptr, a->stats + 1, a->workspace, a->workspace_bytes, 2, stream);
+    else if (tc)
+        rc = ss_actor_grad_tc_paired(a->actor, a->critic, a->obs, n, nullptr, a->stats + 1, a->workspace, a->workspace_bytes, 0,
+                                     a->pair_mail, stream);
     else
-        rc = (tc ? ss_actor_grad_tc : ss_actor_grad)(a->actor, a->critic, a->obs, n, nullptr, a->stats + 1, a->workspace,
-                                                     a->workspace_bytes, stream);
+        rc = ss_actor_grad(a->actor, a->critic, a->obs, n, nullptr, a->stats + 1, a->workspace, a->workspace_bytes, stream);
     if (rc <= 0) return rc < 0 ? rc : SS_ERR_INVALID_ARG;
     sslaunch::pdl_mode() = kOn;
     if (peers) {

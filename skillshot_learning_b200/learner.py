@@ -516,6 +516,14 @@ class ActorCritic:
                 setattr(a, "grad_" + k, self._slice(self.grads, k).data_ptr())
             a.stats = self.stats.data_ptr()
             a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+            # the actor -> critic forward pairs (TD target, actor step) as one launch each (ss_actor_critic_forward_tc), for
+            # minibatches small enough that a forward launch is mostly set-up and pipeline fill; the mailbox is filled with its
+            # empty mark here once and left so by every call (SS_UPDATE_PAIR=0: two launches each, for A/B measurements)
+            self._pair_mail = None
+            # (measured, profiles/r2_update_pair_ab.txt: 162.5 -> 158.9 us at 65,536 rows, 236 -> 252 us at 131,072)
+            if batch <= 65536 and os.environ.get("SS_UPDATE_PAIR", "1") != "0":
+                self._pair_mail = torch.full((batch, 2), _lib.PAIR_MAIL_EMPTY, dtype=torch.int32, device=dev)
+                a.pair_mail = self._pair_mail.data_ptr()
             if self.peer is not None:
                 px = self.peer
                 a.world, a.rank, a.peer_capacity = px.world, px.rank, px.capacity

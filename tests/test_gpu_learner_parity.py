@@ -373,6 +373,35 @@ def test_tensor_core_critic_forward_and_dq_da(net, n):
     assert np.abs(up - want).mean() <= 1e-2 * scale + 5e-4
 
 
+@pytest.mark.parametrize("n", [1, 128, 333, 20000, 65536 + 77])
+def test_actor_and_critic_forward_as_one_launch_equals_the_two_launches(net, n):
+    """ss_actor_critic_forward_tc (half of the CTAs play a = actor(s), the other half critic([s, a]), handing each quarter
+    tile's actions over through flags) against ss_actor_forward_tc followed by ss_critic_forward_tc: actions, Q, -dQ/da and
+    the TD target must be bit-identical; the mailbox comes back empty, so a second call on it works as well."""
+    from skillshot_learning_b200._lib import lib, check
+    ac = _tc_net(net)
+    s, _, r = _batch(n, 7000 + n)
+    s = torch.tensor(s, device="cuda"); r = torch.tensor(r, device="cuda")
+    done = (torch.arange(n, device="cuda") % 3 == 0).to(torch.uint8)
+    a_ref = ac.actor_forward(s, precision="bf16")
+    q_ref, up_ref = ac.critic_forward(s, a_ref, precision="bf16", want_dq_da=True)
+    y_ref = torch.empty(n, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib.ss_critic_forward_tc(ac.critic.data_ptr(), s.data_ptr(), a_ref.data_ptr(), n, None, None, r.data_ptr(), done.data_ptr(),
+                                   0.9, y_ref.data_ptr(), st), "critic")
+    from skillshot_learning_b200 import _lib
+    mail = torch.full((n, 2), _lib.PAIR_MAIL_EMPTY, dtype=torch.int32, device="cuda")
+    for rep in range(2):
+        a = torch.full((n, 2), 7.0, device="cuda"); q = torch.empty(n, device="cuda"); up = torch.empty((n, 2), device="cuda")
+        y = torch.empty(n, device="cuda")
+        check(lib.ss_actor_critic_forward_tc(ac.actor.data_ptr(), ac.critic.data_ptr(), s.data_ptr(), a.data_ptr(), n, q.data_ptr(),
+                                             up.data_ptr(), r.data_ptr(), done.data_ptr(), 0.9, y.data_ptr(), mail.data_ptr(), st),
+              "pair")
+        torch.cuda.synchronize()
+        assert torch.equal(a, a_ref) and torch.equal(q, q_ref) and torch.equal(up, up_ref) and torch.equal(y, y_ref), rep
+        assert bool((mail == _lib.PAIR_MAIL_EMPTY).all())
+
+
 @pytest.mark.parametrize("n", [128, 77, 1000, 20000])
 def test_tensor_core_critic_gradient(net, n):
     ac = _tc_net(net)
