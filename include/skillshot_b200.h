@@ -534,6 +534,12 @@ typedef struct ss_ddpg_update_args {
 } ss_ddpg_update_args;
 int ss_ddpg_update(const ss_ddpg_update_args *args, void *stream);
 
+/* ss_ddpg_update and ss_selfplay_rollout launch their kernels as a programmatic-dependent-launch chain (each grid is placed
+ * while its predecessor drains and waits, griddepcontrol.wait, before its first dependent access; csrc/ss_launch.cuh).
+ * enabled = 0: ordinary launches; 1: chained; -1: back to the default (chained unless the environment says SS_UPDATE_PDL=0 /
+ * SS_ROLLOUT_PDL=0).  Returns the previous setting (-1 / 0 / 1).  Results are bit-identical either way. */
+int ss_set_dependent_launch(int enabled);
+
 /* a = actor(s) -> act_out [n][2], then critic([s, a]) -> any of q_out [n] / neg_dq_da_out [n][2] / y_out [n] (the TD target
  * reward + gamma (1 - done) q, as ss_critic_forward_tc), in ONE launch: half of the CTAs play the actor, the other half the
  * critic, which takes each row's actions as soon as the actor half has written them.  The two steps of

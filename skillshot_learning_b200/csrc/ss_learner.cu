@@ -1095,9 +1095,8 @@ int ss_selfplay_rollout(void *env_state, int64_t n_envs, const float *actor_para
         // The two kernels of a tick form a dependent-launch chain (ss_launch.cuh): each grid is placed while its predecessor
         // drains and holds at griddepcontrol.wait.  From the second tick on the forward kernel also stages (and perturbs) the
         // actor's parameters ahead of that wait -- its predecessor, the env step, does not write them; the first tick's
-        // forward may follow an update's Adam kernel and waits first.  SS_ROLLOUT_PDL=0: ordinary launches (A/B).
-        static const bool pdl_env = [] { const char *e = getenv("SS_ROLLOUT_PDL"); return !(e && e[0] == '0'); }();
-        const int kOn = (tensor_cores && pdl_env) ? sslaunch::kPdlOn : sslaunch::kPdlOff;
+        // forward may follow an update's Adam kernel and waits first.  SS_ROLLOUT_PDL=0 / ss_set_dependent_launch(0): ordinary launches.
+        const int kOn = (tensor_cores && sslaunch::chain_enabled("SS_ROLLOUT_PDL")) ? sslaunch::kPdlOn : sslaunch::kPdlOff;
         sslaunch::PdlScope scope(kOn);
         for (int t = 0; t < n_ticks; ++t, seg = (seg + 1) % segs) {
             float *o = ring_obs + seg * rows * 12, *a = ring_act + seg * rows * 2;

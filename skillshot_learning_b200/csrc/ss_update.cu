@@ -15,9 +15,25 @@
 #include "../../include/skillshot_b200.h"
 #include "ss_launch.cuh"
 
+#include <atomic>
+#include <string.h>
+
 int &sslaunch::pdl_mode() {
     static thread_local int mode = sslaunch::kPdlOff;
     return mode;
+}
+
+static std::atomic<int> g_chain_override{-1};       // -1: the environment decides
+
+bool sslaunch::chain_enabled(const char *env_name) {
+    const int o = g_chain_override.load(std::memory_order_relaxed);
+    if (o >= 0) return o != 0;
+    const char *e = getenv(env_name);
+    return !(e && e[0] == '0');
+}
+
+extern "C" int ss_set_dependent_launch(int enabled) {
+    return g_chain_override.exchange(enabled < 0 ? -1 : (enabled ? 1 : 0), std::memory_order_relaxed);
 }
 
 extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
@@ -45,9 +61,8 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
     //   critic(s, a) -> actor gradient -> reduce + Adam (actor, actor')
     // With the peer exchange the order is ... critic gradient -> push -> actor(s) -> peers' Adam (critic) -> critic(s, a) -> ...:
     // critic(s, a) then directly follows the kernel that writes the critic and stages behind its wait (kPdlEarlyAfterFirst).
-    // SS_UPDATE_PDL=0 switches the chain off (A/B measurements).
-    static const bool pdl_env = [] { const char *e = getenv("SS_UPDATE_PDL"); return !(e && e[0] == '0'); }();
-    const int kOn = pdl_env ? sslaunch::kPdlOn : sslaunch::kPdlOff;
+    // SS_UPDATE_PDL=0 or ss_set_dependent_launch(0) switches the chain off (A/B measurements, the equality test).
+    const int kOn = sslaunch::chain_enabled("SS_UPDATE_PDL") ? sslaunch::kPdlOn : sslaunch::kPdlOff;
     const int kEarly = kOn ? (sslaunch::kPdlOn | sslaunch::kPdlEarlyWeights) : sslaunch::kPdlOff;
     sslaunch::PdlScope scope(kOn);
 

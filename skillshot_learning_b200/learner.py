@@ -204,6 +204,7 @@ class ActorCritic:
         self.step_critic = 0
         self.counter = 0            # Philox counter: advances with every noisy call
         self._update_args = None    # cached ss_ddpg_update argument block (pointers change rarely)
+        self._pair_mail = None      # ss_actor_critic_forward_tc's mailbox, allocated with the argument block
         self._update_args_key = None
         self.init_weights(seed)
 

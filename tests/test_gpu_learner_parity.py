@@ -527,6 +527,43 @@ def test_overlapped_rollout_equals_the_two_kernel_rollout(monkeypatch):
     assert a.replay.pos == b.replay.pos and a.envs.counter == b.envs.counter and a.networks.counter == b.networks.counter
 
 
+def test_chained_launches_and_forward_pairs_change_no_bit(monkeypatch):
+    """The rollout and the update as dependent-launch chains with the actor -> critic forward pairs as one launch each (the
+    default) against ordinary launches and separate forward kernels: after interleaved rollouts and updates every
+    parameter, Adam moment, target, replay row and env state must be bit-identical."""
+    from skillshot_learning_b200 import SelfPlayTrainer
+    from skillshot_learning_b200._lib import lib
+    mk = lambda: SelfPlayTrainer(4096, device="cuda:0", seed=21, batch_size=8192 + 77, noise_group=256, tick_limit=40, precision="bf16",
+                                 replay_capacity=8192 * 6, gamma=0.97, tau=0.01)
+    def run(tr):
+        for _ in range(6):
+            tr.rollout(3)
+            tr.update(); tr.update()
+        torch.cuda.synchronize()
+        return tr
+    a = run(mk())                                                   # default: chained, paired
+    assert a.networks._pair_mail is not None
+    prev = lib.ss_set_dependent_launch(0)
+    monkeypatch.setenv("SS_UPDATE_PAIR", "0")
+    try:
+        b = run(mk())
+    finally:
+        lib.ss_set_dependent_launch(prev)
+    assert b.networks._pair_mail is None
+    for name in ("params", "target", "adam_m", "adam_v"):
+        assert torch.equal(getattr(a.networks, name), getattr(b.networks, name)), name
+    for name in ("obs", "act", "reward", "next_obs", "done"):
+        assert torch.equal(getattr(a.replay, name), getattr(b.replay, name)), name
+    assert torch.equal(a.envs.state, b.envs.state) and torch.equal(a.obs, b.obs)
+    assert bool((a.networks._pair_mail == _pair_empty()).all())
+    a.envs.check_status()
+
+
+def _pair_empty():
+    from skillshot_learning_b200 import _lib
+    return _lib.PAIR_MAIL_EMPTY
+
+
 def test_fused_forward_and_env_step_kernel_equals_the_two_kernels():
     """ss_actor_forward_step_tc (the rollout tick as ONE kernel: the env step of a row is played in the forward kernel's
     output stage by the lane that computed its action; off by default in ss_selfplay_rollout because it is slower) against
