@@ -469,6 +469,14 @@ int ss_peer_adam_tf(void *own_base, int world, int64_t capacity, uint32_t epoch,
                     float *v, float *target_params, float *grad_out, int64_t n, int64_t step, float lr,
                     float beta1, float beta2, float eps, float tau, float grad_scale, uint32_t *status,
                     void *stream);
+/* ss_peer_reduce_push + ss_peer_adam_tf as ONE kernel: each 64-parameter CTA sums the slices, pushes its sums to every
+ * rank's inbox, raises its own flag there, waits for the same CTA's flag of every rank, and applies Adam to the sum taken
+ * in rank order.  Same results as the two calls, bit for bit; one launch and no grid-wide completion counter per exchange.
+ * (The allocation of ss_peer_alloc holds these per-CTA flags behind the inboxes.) */
+int ss_peer_reduce_adam_tf(const void *workspace, int parts, int n_params, float *aux_out, void *const *peer_bases_host,
+                           int world, int rank, int64_t capacity, uint32_t epoch, float *params, float *m, float *v,
+                           float *target_params, float *grad_out, int64_t step, float lr, float beta1, float beta2, float eps,
+                           float tau, float grad_scale, uint32_t *status, void *stream);
 
 /* Device-resident replay ring, structure of arrays with `capacity` rows:
  * obs [cap][12], act [cap][2], reward [cap], next_obs [cap][12], done [cap] u8.

@@ -92,6 +92,8 @@ SIGNATURES = {
     "ss_peer_reduce_push": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _i64, ctypes.c_uint32, _vp, _vp]),
     "ss_peer_adam_tf": (_i32, [_vp, _i32, _i64, ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
                                 _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
+    "ss_peer_reduce_adam_tf": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _i64, ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp, _i64,
+                                       _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
     "ss_selfplay_rollout": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32,
                                     _f32, _i64, _f32, _i32, _i32, _i64, _i32, _u64, _u64, _u64, _u64, _vp, _vp, _i32,
                                     _vp]),

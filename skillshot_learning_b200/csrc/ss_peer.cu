@@ -44,6 +44,13 @@ __device__ inline uint32_t *flag_ptr(void *base, int world, int parity, int src)
 __device__ inline float *inbox_ptr(void *base, int world, int64_t capacity, int parity, int src) {
     return reinterpret_cast<float *>(reinterpret_cast<char *>(base) + flags_bytes(world)) + ((int64_t)parity * world + src) * capacity;
 }
+// the one-kernel form's flags, one per (parity, source rank, 64-parameter CTA), behind the inboxes
+__host__ __device__ inline int64_t cta_count(int64_t capacity) { return (capacity + 1 + 63) / 64; }
+__device__ inline uint32_t *cta_flag_ptr(void *base, int world, int64_t capacity, int parity, int src, int cta) {
+    uint32_t *f = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(base) + flags_bytes(world) +
+                                               (int64_t)2 * world * capacity * (int64_t)sizeof(float));
+    return f + ((int64_t)parity * world + src) * cta_count(capacity) + cta;
+}
 
 // grad[p] = sum of the CTA slices (fixed order), written into slot `rank` of every rank's inbox; aux[0] = extra slot.
 // The last CTA to finish raises this rank's flag for `epoch` in every inbox.
@@ -130,13 +137,84 @@ __global__ void peer_adam_kernel(void *base, int world, int64_t capacity, uint32
     if (target) target[p] = tau * w + (1.0f - tau) * target[p];
 }
 
+// push + wait + Adam as ONE kernel.  A CTA owns 64 parameters from the slice reduction to the parameter update: it sums the
+// gradient slices (fixed order), stores the sums into slot `rank` of every rank's inbox, raises ITS flag of this epoch in
+// every inbox (release at system scope, after a system-scope fence over the CTA's stores), waits for the same CTA's flag
+// of every rank (acquire), sums the inbox slots in rank order -- the same order on every rank -- and applies Adam and the
+// soft target update.  Against the two-kernel form: no kernel boundary between push and reduce, no grid-wide completion
+// counter, and a CTA proceeds as soon as ITS 64 values have arrived from everybody instead of after everybody's last CTA.
+// Every CTA pushes before it waits, so the ranks cannot wait for each other in a cycle.  The inbox parity argument of the
+// header comment holds unchanged: epoch e + 2 is pushed only by the kernel after the one that waited for every rank's
+// epoch e + 1 flags of EVERY CTA, and a rank publishes those only in the kernel after its own epoch-e reads.
+// A timeout is sticky and applies nothing in the CTA that saw it (a rank that never launched times out every CTA alike).
+__global__ void peer_reduce_adam_kernel(const float *work, int parts, int n_params, float *aux, PeerTable T, int world, int rank,
+                                        int64_t capacity, uint32_t epoch, float *params, float *m, float *v, float *target,
+                                        float *grad_out, float lr_t, float beta1, float beta2, float eps, float tau,
+                                        float grad_scale, uint32_t *status) {
+    __shared__ float red[4][64];
+    __shared__ int timed_out;
+    const int p = blockIdx.x * 64 + threadIdx.x, q = threadIdx.y;
+    const int parity = (int)(epoch & 1u);
+    sslaunch::griddep_wait();            // ss_launch.cuh
+    sslaunch::griddep_launch();
+    if (threadIdx.x == 0 && q == 0) timed_out = (status && (*(volatile uint32_t *)status & SS_STATUS_PEER_TIMEOUT)) ? 1 : 0;
+    float s = 0.f;
+    if (p <= n_params) {
+#pragma unroll 4
+        for (int c = q; c < parts; c += 4) s += __ldcg(work + (int64_t)c * (n_params + 1) + p);
+    }
+    red[q][threadIdx.x] = s;
+    __syncthreads();
+    if (timed_out) return;
+    if (q == 0 && p <= n_params) {
+        const float t = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
+        if (p < n_params) {
+            for (int d = 0; d < world; ++d) inbox_ptr(T.base[d], world, capacity, parity, rank)[p] = t;
+        } else if (aux) {
+            aux[0] = t;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (q == 0 && threadIdx.x < world) {
+        uint32_t *mine = cta_flag_ptr(T.base[threadIdx.x], world, capacity, parity, rank, blockIdx.x);
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(mine), "r"(epoch) : "memory");
+        const uint32_t *f = cta_flag_ptr(T.base[rank], world, capacity, parity, threadIdx.x, blockIdx.x);
+        uint32_t seen = 0, spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+            if (seen == epoch) break;
+            if (++spins > (1u << 26)) {                        // a peer never arrived: report instead of hanging
+                if (status) atomicOr(status, SS_STATUS_PEER_TIMEOUT);
+                *(volatile int *)&timed_out = 1;
+                break;
+            }
+            __nanosleep(32);
+        }
+    }
+    __syncthreads();
+    if (timed_out || q != 0 || p >= n_params) return;
+    float g = 0.f;
+    for (int r = 0; r < world; ++r) g += __ldcg(inbox_ptr(T.base[rank], world, capacity, parity, r) + p);
+    if (grad_out) grad_out[p] = g;
+    const float gr = g * grad_scale;
+    const float mm = beta1 * m[p] + (1.0f - beta1) * gr;
+    const float vv = beta2 * v[p] + (1.0f - beta2) * gr * gr;
+    m[p] = mm;
+    v[p] = vv;
+    const float w = params[p] - lr_t * mm / (sqrtf(vv) + eps);
+    params[p] = w;
+    if (target) target[p] = tau * w + (1.0f - tau) * target[p];
+}
+
 }  // namespace
 
 extern "C" {
 
 int64_t ss_peer_bytes(int world, int64_t capacity) {
     if (world < 1 || world > kMaxWorld || capacity < 1) return -1;
-    return flags_bytes(world) + (int64_t)2 * world * capacity * (int64_t)sizeof(float);
+    return flags_bytes(world) + (int64_t)2 * world * capacity * (int64_t)sizeof(float) +
+           (int64_t)2 * world * cta_count(capacity) * (int64_t)sizeof(uint32_t);
 }
 
 int ss_peer_alloc(int world, int64_t capacity, void **base_out) {
@@ -176,6 +254,26 @@ int ss_peer_reduce_push(const void *workspace, int parts, int n_params, float *a
     if (sslaunch::launch(reduce_push_kernel, dim3((n_params + 1 + 63) / 64), dim3(64, 4), 0, (cudaStream_t)stream,
                          (const float *)workspace, parts, n_params, aux_out, T, world, rank, capacity, epoch,
                          (unsigned int *)done_counter) != cudaSuccess)
+        return SS_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
+}
+
+int ss_peer_reduce_adam_tf(const void *workspace, int parts, int n_params, float *aux_out, void *const *peer_bases_host,
+                           int world, int rank, int64_t capacity, uint32_t epoch, float *params, float *m, float *v,
+                           float *target_params, float *grad_out, int64_t step, float lr, float beta1, float beta2, float eps,
+                           float tau, float grad_scale, uint32_t *status, void *stream) {
+    if (!workspace || parts < 1 || n_params < 1 || !peer_bases_host || world < 1 || world > kMaxWorld || rank < 0 ||
+        rank >= world || capacity < n_params || epoch == 0 || !params || !m || !v || step < 1)
+        return SS_ERR_INVALID_ARG;
+    PeerTable T{};
+    for (int d = 0; d < world; ++d) {
+        if (!peer_bases_host[d]) return SS_ERR_INVALID_ARG;
+        T.base[d] = peer_bases_host[d];
+    }
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+    if (sslaunch::launch(peer_reduce_adam_kernel, dim3((n_params + 1 + 63) / 64), dim3(64, 4), 0, (cudaStream_t)stream,
+                         (const float *)workspace, parts, n_params, aux_out, T, world, rank, capacity, epoch, params, m, v,
+                         target_params, grad_out, (float)lr_t, beta1, beta2, eps, tau, grad_scale, status) != cudaSuccess)
         return SS_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA;
 }

@@ -96,8 +96,19 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
     // the Adam kernel that waits for the peers' pushes, so that the exchange's latency (rank skew + NVLink visibility,
     // ~20 us on 8 GPUs) passes under 15 us of useful work instead of an idle spin.  (The gradient slices of the critic step
     // have been consumed by the push kernel by then; the actions land in the scratch area behind the slices.)
-    const bool early_actor_forward = peers && tc;
-    if (peers) {
+    // SS_PEER_FUSED=1 (experiment, off by default) makes push, wait and Adam ONE kernel per exchange (ss_peer_reduce_adam_tf:
+    // each 64-parameter CTA goes on as soon as its own values have arrived from every rank) and runs the actor step as on a
+    // single GPU.  Bit-identical (peer_check ok) and SLOWER: 0.203 vs 0.189 ms per update on 2 GPUs
+    // (profiles/r2_peer_fused_ab_n2.txt) -- 573 CTAs each fencing and polling at system scope cost more than the kernel
+    // boundary they remove, and nothing runs under the wait any more.
+    static const bool fused_env = [] { const char *e = getenv("SS_PEER_FUSED"); return e && e[0] == '1'; }();
+    const bool fused_exchange = peers && fused_env;
+    const bool early_actor_forward = peers && tc && !fused_exchange;
+    if (fused_exchange) {
+        rc = ss_peer_reduce_adam_tf(a->workspace, rc, SS_CRITIC_PARAMS, a->stats, a->peer_bases, a->world, a->rank, a->peer_capacity,
+                                    a->epoch, a->critic, a->m_critic, a->v_critic, a->target_critic, a->grad_critic, a->step_critic,
+                                    a->lr_critic, a->beta1, a->beta2, a->eps, a->tau, 1.0f, a->status, stream);
+    } else if (peers) {
         rc = ss_peer_reduce_push(a->workspace, rc, SS_CRITIC_PARAMS, a->stats, a->peer_bases, a->world, a->rank,
                                  a->peer_capacity, a->epoch, a->done_counter, stream);
         if (rc != SS_OK) return rc;
@@ -130,7 +141,11 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
         rc = ss_actor_grad(a->actor, a->critic, a->obs, n, nullptr, a->stats + 1, a->workspace, a->workspace_bytes, stream);
     if (rc <= 0) return rc < 0 ? rc : SS_ERR_INVALID_ARG;
     sslaunch::pdl_mode() = kOn;
-    if (peers) {
+    if (fused_exchange) {
+        rc = ss_peer_reduce_adam_tf(a->workspace, rc, SS_ACTOR_PARAMS, a->stats + 1, a->peer_bases, a->world, a->rank, a->peer_capacity,
+                                    a->epoch + 1, a->actor, a->m_actor, a->v_actor, a->target_actor, a->grad_actor, a->step_actor,
+                                    a->lr_actor, a->beta1, a->beta2, a->eps, a->tau, 1.0f, a->status, stream);
+    } else if (peers) {
         rc = ss_peer_reduce_push(a->workspace, rc, SS_ACTOR_PARAMS, a->stats + 1, a->peer_bases, a->world, a->rank,
                                  a->peer_capacity, a->epoch + 1, a->done_counter, stream);
         if (rc != SS_OK) return rc;
