@@ -19,7 +19,8 @@
 // reduced epoch e+1, which needed every peer's epoch-e+1 flag, which each peer publishes only
 // after its own epoch-e reduction kernel has finished (stream order).  No other barrier exists.
 //
-// Memory: one allocation per rank {flags[2][world] | inbox[2][world][capacity]}, created here
+// Memory: one allocation per rank {flags[2][world] | inbox[2][world][capacity] | per-CTA flags[2][world][ctas] of the
+// one-kernel form}, created here
 // with cudaMalloc and shared between the processes of one node through CUDA IPC handles
 // (ss_peer_alloc / ss_peer_export / ss_peer_import), because the library's other entry points
 // never allocate: these are the explicit exception.

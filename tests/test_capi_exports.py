@@ -46,7 +46,12 @@ def test_learner_entry_points_reject_invalid_arguments_without_a_gpu():
     assert L.ss_actor_grad_tc(None, None, None, 16, None, None, None, 0, None) == -1
     assert L.ss_adam_tf(None, None, None, None, None, 10, 1, 1e-3, 0.9, 0.999, 1e-7, 1.0, 1.0, None) == -1
     assert L.ss_replay_push(None, None, None, None, None, 10, 0, None, None, None, None, None, 1, 4, None) == -1
-    assert L.ss_peer_bytes(9, 100) == -1 and L.ss_peer_bytes(2, 100) == 256 + 2 * 2 * 100 * 4
+    # flags | inbox[2][world][capacity] | the one-kernel exchange's flags [2][world][ceil((capacity + 1) / 64)]
+    assert L.ss_peer_bytes(9, 100) == -1 and L.ss_peer_bytes(2, 100) == 256 + 2 * 2 * 100 * 4 + 2 * 2 * 2 * 4
+    assert L.ss_peer_reduce_adam_tf(None, 1, 10, None, None, 2, 0, 100, 1, None, None, None, None, None, 1, 1e-3, 0.9, 0.999, 1e-7,
+                                    1.0, 1.0, None, None) == -1
+    assert L.ss_actor_critic_forward_tc(None, None, None, None, 16, None, None, None, None, 0.0, None, None, None) == -1
+    assert L.ss_set_dependent_launch(-1) == -1
     assert L.ss_peer_reduce_push(None, 1, 10, None, None, 2, 0, 100, 1, None, None) == -1
     assert L.ss_ddpg_update(None, None) == -1
     assert L.ss_actor_frames_params(20) == 240 * 256 + 256 + 256 * 128 + 128 + 128 * 2 + 2 and L.ss_actor_frames_params(0) == -1
