@@ -633,7 +633,7 @@ __global__ void reduce_kernel(const float *work, int parts, int n_params, float 
     const int p = blockIdx.x * 64 + threadIdx.x, q = threadIdx.y;
     float s = 0.f;
     if (p <= n_params) {
-#pragma unroll 4
+#pragma unroll 10        // ten independent loads in flight per thread; the additions keep their order
         for (int c = q; c < parts; c += 4) s += __ldcg(work + (int64_t)c * (n_params + 1) + p);
     }
     red[q][threadIdx.x] = s;
@@ -672,7 +672,7 @@ __global__ void reduce_adam_kernel(const float *work, int parts, int n_params, f
     sslaunch::griddep_launch();
     float s = 0.f;
     if (p <= n_params) {
-#pragma unroll 4
+#pragma unroll 10        // ten independent loads in flight per thread; the additions keep their order
         for (int c = q; c < parts; c += 4) s += __ldcg(work + (int64_t)c * (n_params + 1) + p);
     }
     red[q][threadIdx.x] = s;

@@ -130,8 +130,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_grad_tc_kernel(const GradArgs
         mbar_fence_init();
     }
     if (warp == MMA_WARP) tmem_alloc(sbase + SM_TMEM, 512);
-    // zero everything that is only partly rewritten: weight images (padding rows), DZ3 (chunk 1), X2 tail chunks
-    for (uint32_t o = threadIdx.x * 16; o < SM_X2; o += NTHREADS * 16) *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
+    // zero what is only partly rewritten: the padding chunk of the layer-2 weight image (stage_weights writes every other
+    // byte of both images), DZ3 (chunk 1), X2 tail chunks
+    for (uint32_t o = threadIdx.x * 16; o < CHUNK_B2; o += NTHREADS * 16)
+        *reinterpret_cast<uint4 *>(smem + SM_B2 + (K2 / 8 - 1) * CHUNK_B2 + o) = make_uint4(0, 0, 0, 0);
     for (uint32_t o = threadIdx.x * 16; o < 2 * CHUNK_A; o += NTHREADS * 16) {
         *reinterpret_cast<uint4 *>(smem + SM_DZ3 + o) = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4 *>(smem + SM_X2 + (H1 / 8) * CHUNK_A + o) = make_uint4(0, 0, 0, 0);
@@ -535,7 +537,7 @@ __global__ void reduce_parts_kernel(const float *work, int parts, int n_params, 
     const int p = blockIdx.x * 64 + threadIdx.x, q = threadIdx.y;
     float s = 0.f;
     if (p <= n_params) {
-#pragma unroll 4
+#pragma unroll 10        // ten independent loads in flight per thread; the additions keep their order
         for (int c = q; c < parts; c += 4) s += __ldcg(work + (int64_t)c * (n_params + 1) + p);
     }
     red[q][threadIdx.x] = s;

@@ -168,7 +168,9 @@ __device__ __forceinline__ void fwd_body(const FwdArgs &A, const int cta, const 
         mbar_fence_init();
     }
     if (warp == MMA_W) tmem_alloc(sbase + SMP_TMEM, 512);
-    for (uint32_t o = threadIdx.x * 16; o < SMP_A1; o += NTH * 16) *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
+    // (stage_weights writes every byte of both weight images except the layer-2 image's padding chunk)
+    for (uint32_t o = threadIdx.x * 16; o < CHUNK_B2; o += NTH * 16)
+        *reinterpret_cast<uint4 *>(smem + SMP_B2 + (K2 / 8 - 1) * CHUNK_B2 + o) = make_uint4(0, 0, 0, 0);
     if (warp < P_WARPS) {                                    // tail chunks of both activation tiles: actor {1 1 0 ..} | 0
         for (int t = 0; t < 2; ++t) {
             uint8_t *arow = smem + SMP_A1 + t * X2_BYTES + threadIdx.x * 16;

@@ -65,7 +65,7 @@ __global__ void reduce_push_kernel(const float *work, int parts, int n_params, f
     sslaunch::griddep_launch();
     float s = 0.f;
     if (p <= n_params) {
-#pragma unroll 4
+#pragma unroll 10        // ten independent loads in flight per thread; the additions keep their order
         for (int c = q; c < parts; c += 4) s += __ldcg(work + (int64_t)c * (n_params + 1) + p);
     }
     red[q][threadIdx.x] = s;
@@ -161,7 +161,7 @@ __global__ void peer_reduce_adam_kernel(const float *work, int parts, int n_para
     if (threadIdx.x == 0 && q == 0) timed_out = (status && (*(volatile uint32_t *)status & SS_STATUS_PEER_TIMEOUT)) ? 1 : 0;
     float s = 0.f;
     if (p <= n_params) {
-#pragma unroll 4
+#pragma unroll 10        // ten independent loads in flight per thread; the additions keep their order
         for (int c = q; c < parts; c += 4) s += __ldcg(work + (int64_t)c * (n_params + 1) + p);
     }
     red[q][threadIdx.x] = s;
