@@ -103,7 +103,9 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
     // boundary they remove, and nothing runs under the wait any more.
     static const bool fused_env = [] { const char *e = getenv("SS_PEER_FUSED"); return e && e[0] == '1'; }();
     const bool fused_exchange = peers && fused_env;
-    const bool early_actor_forward = peers && tc && !fused_exchange;
+    // SS_PEER_STAGED=0 (A/B): no early actor forward; the actor step's forward pair then runs as one launch after Adam
+    static const bool staged_env = [] { const char *e = getenv("SS_PEER_STAGED"); return !(e && e[0] == '0'); }();
+    const bool early_actor_forward = peers && tc && !fused_exchange && staged_env;
     if (fused_exchange) {
         rc = ss_peer_reduce_adam_tf(a->workspace, rc, SS_CRITIC_PARAMS, a->stats, a->peer_bases, a->world, a->rank, a->peer_capacity,
                                     a->epoch, a->critic, a->m_critic, a->v_critic, a->target_critic, a->grad_critic, a->step_critic,
