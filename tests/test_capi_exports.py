@@ -149,3 +149,15 @@ def test_cpu_legs_ignore_omp_num_threads(monkeypatch):
         from oracle.oracle import lib as olib
         dt, envs, actions = bench.cpu_port_run(4096, 4, bench.host_cores())
         assert olib().ss_oracle_max_threads() == bench.host_cores()      # omp_set_num_threads took effect
+
+
+def test_header_constants_match_the_python_mirror():
+    """SS_PAIR_MAIL_EMPTY (the empty mark of ss_actor_critic_forward_tc's mailbox) and the status bits are written twice, in
+    include/skillshot_b200.h and in _lib.py: they must agree."""
+    import re
+    from skillshot_learning_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "skillshot_b200.h")).read()
+    m = re.search(r"#define\s+SS_PAIR_MAIL_EMPTY\s+(0x[0-9a-fA-F]+)", text)
+    assert m and int(m.group(1), 16) == _lib.PAIR_MAIL_EMPTY
+    m = re.search(r"#define\s+SS_STATUS_ROLLOUT_TIMEOUT\s+(\d+)", text)
+    assert m and int(m.group(1)) == 4
