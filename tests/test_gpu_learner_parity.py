@@ -931,3 +931,47 @@ def test_single_call_update_at_ragged_batch_sizes(precision, batch):
     for name in ("params", "target", "adam_m", "adam_v", "grads", "stats"):
         assert torch.equal(getattr(a.networks, name), getattr(b.networks, name)), name
     assert torch.isfinite(a.networks.params).all()
+
+
+def test_peer_exchange_kernels_with_a_world_of_one_equal_the_local_reduction():
+    """The exchange kernels on a single GPU (world = 1: the rank pushes into its own inbox and waits for its own flag):
+    ss_peer_reduce_push + ss_peer_adam_tf, and the one-kernel form ss_peer_reduce_adam_tf, must leave exactly the parameters,
+    Adam moments, target, summed gradient and extra-slot sum that ss_reduce_adam_tf leaves, over several epochs (both inbox
+    parities).  (The multi-GPU behaviour is covered by tests/test_gpu_multi.py and bench.py's peer_check.)"""
+    import ctypes
+    from skillshot_learning_b200._lib import lib, check
+    n, parts = 36609, 37
+    st = torch.cuda.current_stream().cuda_stream
+    own = ctypes.c_void_p()
+    check(lib.ss_peer_alloc(1, n, ctypes.byref(own)), "alloc")
+    try:
+        bases = (ctypes.c_void_p * 1)(own.value)
+        g = torch.Generator(device="cuda"); g.manual_seed(3)
+        mk = lambda: dict(p=torch.randn(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)),
+                          m=torch.zeros(n, device="cuda"), v=torch.zeros(n, device="cuda"),
+                          t=torch.randn(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2)),
+                          grad=torch.empty(n, device="cuda"), aux=torch.zeros(1, device="cuda"))
+        a, b, c = mk(), mk(), mk()
+        counter = torch.zeros(1, dtype=torch.int32, device="cuda"); status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        epoch = 1
+        for step in range(1, 5):
+            work = torch.randn((parts, n + 1), device="cuda", generator=g) * 1e-2
+            args = (step, 1e-3, 0.9, 0.999, 1e-7, 0.25, 1.0)
+            check(lib.ss_reduce_adam_tf(work.data_ptr(), parts, n, a["aux"].data_ptr(), a["grad"].data_ptr(), a["p"].data_ptr(),
+                                        a["m"].data_ptr(), a["v"].data_ptr(), a["t"].data_ptr(), *args, st), "local")
+            check(lib.ss_peer_reduce_push(work.data_ptr(), parts, n, b["aux"].data_ptr(), bases, 1, 0, n, epoch, counter.data_ptr(), st),
+                  "push")
+            check(lib.ss_peer_adam_tf(own, 1, n, epoch, b["p"].data_ptr(), b["m"].data_ptr(), b["v"].data_ptr(), b["t"].data_ptr(),
+                                      b["grad"].data_ptr(), n, *args, status.data_ptr(), st), "adam")
+            epoch += 1
+            check(lib.ss_peer_reduce_adam_tf(work.data_ptr(), parts, n, c["aux"].data_ptr(), bases, 1, 0, n, epoch, c["p"].data_ptr(),
+                                             c["m"].data_ptr(), c["v"].data_ptr(), c["t"].data_ptr(), c["grad"].data_ptr(), *args,
+                                             status.data_ptr(), st), "fused")
+            epoch += 1
+            torch.cuda.synchronize()
+            for k in a:
+                assert torch.equal(a[k], b[k]), (step, "two kernels", k)
+                assert torch.equal(a[k], c[k]), (step, "one kernel", k)
+        assert int(status) == 0
+    finally:
+        lib.ss_peer_free(own)
