@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
 // Physics-only: reward modes none / terminal, reference speed constants, no observations, no episode statistics; the
 // other combinations stay on step_kernel.  Same HBM layout, same outputs, bit-identical results (tests: every fused
 // physics test of tests/test_gpu_env_parity.py runs through it, bench shape included).
-constexpr int kBlockPP = 64;        // 32 envs per CTA: a 65,536-env launch is 2,048 CTAs, 13.8 per SM, all resident at once
+constexpr int kBlockPP = 64;        // the per-player observation kernel's CTA, and the smallest of step_pp_kernel's (pp_block_for)
 constexpr double kRound = 6755399441055744.0;      // 1.5 * 2^52
 
 // A position coordinate x (0 ... 250) is carried as the double kRound + x: its low word IS the integer (hit test, bounds,
@@ -366,8 +366,16 @@ __device__ __forceinline__ void lane_loop(Lane &L, double *qrot, const StepArgs 
 }
 
 // TERMINAL: one of OUT_FLAGS / OUT_TERMINAL / OUT_PACKED.
-template <int TERMINAL>
-__global__ void __launch_bounds__(kBlockPP, 14) step_pp_kernel(const StepArgs A) {
+// BLK: threads per CTA, 896 / BLK CTAs per SM (always 28 warps of 72 registers: the whole register file).  The work is the
+// same whatever BLK; what changes is how the SM's 28 warps are made up.  As ONE CTA (BLK = 896) they are dealt to the four
+// schedulers seven each; as 14 CTAs of two warps the launch measured 7.6 % slower at 65,536 envs (200.4 vs 215.7 us for 256
+// ticks, profiles/r2_step_blk_sweep.txt; CTAs of 32 / 128 / 224 threads were like 64, 448 in between), with ncu showing
+// 22.8 active warps per SM on average out of 28 -- warps finishing at different times.  (Neither start-up phase offsets
+// between the warps nor a CTA barrier every 16 / 64 ticks helped: profiles/r2_step_stagger_experiment.txt.)
+// pp_block_for() picks BLK from the env count.
+template <int TERMINAL, int BLK = kBlockPP>
+__global__ void __launch_bounds__(BLK, 896 / BLK) step_pp_kernel(const StepArgs A) {
+    constexpr int kBlockPP = BLK;
     __shared__ double qrot_sh[kBlockPP];
     const int lane = threadIdx.x & 31, P = lane & 1;
     // global lane = 2 * env + player.  Lanes past the end replay the last env (same inputs, same values stored twice):
@@ -689,6 +697,35 @@ inline bool getenv_pdl() {
 }
 inline int check_launch() { return cudaGetLastError() == cudaSuccess ? SS_OK : SS_ERR_CUDA; }
 inline unsigned blocks_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+// CTA size of step_pp_kernel for n_envs (see the kernel): 896 when that still makes at least ~one CTA per SM (65,536 envs
+// are 147 CTAs on 148 SMs), else 448, else 64.  SS_STEP_BLK = 64 / 448 / 896 forces one (A/B measurements, the equality test).
+inline int pp_block_for(int64_t n_envs) {
+    if (const char *e = getenv("SS_STEP_BLK")) {
+        const int v = atoi(e);
+        if (v == 64 || v == 448 || v == 896) return v;
+    }
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = 148;
+        sms = v;
+    }
+    // Measured on one box (profiles/r2_step_blk_sweep.txt, 256 ticks per launch, 896 against 64 threads): 65,536 envs
+    // +7.6 %, 131,072 +6.7 %, 262,144 +1.8 % (-1.2 % at 32 ticks), 1,048,576 -1.6 % (-5.3 % at 32 ticks): with many waves
+    // the small CTAs refill an SM two warps at a time and win.  Hence: one big CTA per SM up to three waves.
+    const int64_t lanes = 2 * n_envs, c896 = (lanes + 895) / 896, c448 = (lanes + 447) / 448;
+    if (c896 * 20 >= (int64_t)sms * 19) return c896 <= 3 * (int64_t)sms ? 896 : 64;
+    if (c448 * 20 >= (int64_t)sms * 19) return 448;
+    return 64;
+}
+template <int OUT>
+inline void launch_step_pp(const StepArgs &A, int64_t n_envs, cudaStream_t st) {
+    switch (pp_block_for(n_envs)) {
+        case 896: step_pp_kernel<OUT, 896><<<blocks_for(2 * n_envs, 896), 896, 0, st>>>(A); break;
+        case 448: step_pp_kernel<OUT, 448><<<blocks_for(2 * n_envs, 448), 448, 0, st>>>(A); break;
+        default: step_pp_kernel<OUT, 64><<<blocks_for(2 * n_envs, 64), 64, 0, st>>>(A); break;
+    }
+}
 
 }  // namespace
 
@@ -764,9 +801,8 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
                2 * n_envs * ((int64_t)n_ticks + 2) < (int64_t)0x7fffffff && getenv_pp()) {     // (32-bit running index)
         // physics-only fused ticks (bench.py's timed shape): one thread per player.  (A single tick per launch stays on
         // the one-thread-per-env kernel: a launch then pays 3 sincos per lane to set up what it carries, measured 4.1 vs 3.9 us.)
-        const dim3 grid_pp(blocks_for(2 * n_envs, kBlockPP));
-        if (reward_out && reward_mode == SS_REWARD_TERMINAL) step_pp_kernel<OUT_TERMINAL><<<grid_pp, kBlockPP, 0, st>>>(A);
-        else step_pp_kernel<OUT_FLAGS><<<grid_pp, kBlockPP, 0, st>>>(A);
+        if (reward_out && reward_mode == SS_REWARD_TERMINAL) launch_step_pp<OUT_TERMINAL>(A, n_envs, st);
+        else launch_step_pp<OUT_FLAGS>(A, n_envs, st);
     } else if (carry) {
         if (A.stats) {
             if (speeds) step_kernel<false, true, true, 1, true><<<grid, block, 0, st>>>(A);
@@ -853,7 +889,7 @@ int ss_env_step_packed(void *state, int64_t n_envs, const float *actions, uint8_
     A.state = state; A.n = n_envs; A.actions = (const float4 *)actions; A.packed_out = packed_out; A.status = status;
     A.P.seed = seed; A.P.counter = counter; A.P.tick_limit = tick_limit; A.P.reward_mode = SS_REWARD_TERMINAL;
     A.P.auto_reset = auto_reset ? 1 : 0; A.P.reset_mode = reset_mode; A.n_ticks = n_ticks;
-    step_pp_kernel<OUT_PACKED><<<blocks_for(2 * n_envs, kBlockPP), kBlockPP, 0, (cudaStream_t)stream>>>(A);
+    launch_step_pp<OUT_PACKED>(A, n_envs, (cudaStream_t)stream);
     return check_launch();
 }
 

@@ -147,6 +147,36 @@ def test_bench_shape_short_episodes():
     assert episodes > 8192 * 5
 
 
+def test_fused_physics_kernel_is_identical_for_every_cta_size(monkeypatch):
+    """step_pp_kernel picks its CTA size from the env count (896 threads = one CTA of 28 warps per SM when that still fills
+    the GPU, else 448, else 64; SS_STEP_BLK forces one).  The three sizes must produce the same rewards, flags, packed bytes
+    and state on a ragged env count with short episodes (restarts inside the fused launch), and the 64-thread form is the
+    one every small oracle test above runs through."""
+    import torch
+    n, K = 70001, 48
+    kw = dict(random_positions=True, seed=31, reward_mode="terminal", tick_limit=19, auto_reset=True)
+    g = torch.Generator(device="cuda").manual_seed(8)
+    actions = (torch.rand((K, n, 2, 2), device="cuda", generator=g) * 2.4 - 1.2).contiguous()
+    host_actions = actions.cpu().pin_memory()
+    got = {}
+    for blk in ("64", "448", "896"):
+        monkeypatch.setenv("SS_STEP_BLK", blk)
+        e = make(n, **kw)
+        out = e.step(actions, want_obs=False)
+        p = make(n, **kw)
+        flags = p.step_host(host_actions, p.alloc_host_outputs(K, outputs="flags"), ticks_per_launch=K)["flags"].clone()
+        got[blk] = (out["reward"].clone(), out["done"].clone(), out["winner"].clone(), e.export_state(), flags, p.export_state())
+        e.check_status()
+    assert int(got["64"][1].sum()) > n
+    for blk in ("448", "896"):
+        for a, b in zip(got["64"][:3], got[blk][:3]):
+            assert torch.equal(a, b), blk
+        parity.assert_state_equal(got[blk][3], got["64"][3], "state, CTA size " + blk)
+        assert torch.equal(got[blk][4], got["64"][4]), blk
+        parity.assert_state_equal(got[blk][5], got["64"][5], "packed state, CTA size " + blk)
+    parity.assert_state_equal(got["64"][5], got["64"][3], "packed vs three arrays")
+
+
 def test_step_host_full_and_packed_outputs_agree():
     """The host-buffer API: pinned host actions in, outputs to pinned host memory, chunks pipelined over streams.  The full
     outputs (reward / done / winner) equal a device-resident run; the packed one-byte output (ss_env_step_packed) decodes to
