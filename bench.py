@@ -85,7 +85,7 @@ class all_host_cpus:
 
 ENVS_PER_GPU = 65536
 TICKS = 2048                # ticks per bench step (one full 2,000-tick episode plus the auto-reset)
-TICKS_PER_LAUNCH = 256      # fused ticks per ss_env_step launch (32: 6.9e10, 128: 7.7e10, 256: 7.9e10 env-steps/s)
+TICKS_PER_LAUNCH = 256      # fused ticks per ss_env_step launch (32: 7.4e10, 256: 8.4e10 env-steps/s, graph-replayed; tools/explore_step.py)
 E2E_TICKS_PER_LAUNCH = 32   # the host-buffer leg pipelines copy in / kernel / copy out per chunk: finer chunks overlap better
 TICK_LIMIT = 2000           # SkillshotLearner.py:62
 ALGO_BYTES_PER_ENV_STEP = 202   # SURVEY.md 8(d), physics-only
