@@ -97,11 +97,11 @@ struct StepArgs {
 // OBS: write observations.  CARRY: keep sin/cos of the rotations in registers across
 // ticks (fused ticks, observations, shaped rewards); !CARRY is the lean one-tick
 // physics-only kernel.
-template <bool OBS, bool CARRY, bool SPEEDS, int MINB = 1, bool STATS = false, bool PDL = false>
-__global__ void __launch_bounds__(kBlock, MINB) step_kernel(const StepArgs A) {
-    __shared__ float4 tile[OBS ? kWarps : 1][OBS ? 32 * kRowF4 : 1];
+template <bool OBS, bool CARRY, bool SPEEDS, int MINB = 1, bool STATS = false, bool PDL = false, int BLK = kBlock>
+__global__ void __launch_bounds__(BLK, MINB) step_kernel(const StepArgs A) {
+    __shared__ float4 tile[OBS ? BLK / 32 : 1][OBS ? 32 * kRowF4 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * BLK + threadIdx.x;
     const int64_t warp_base = i - lane;
     const bool active = i < A.n;
     const StatePlanes S = planes_of(A.state, A.n);
@@ -822,6 +822,25 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
+            // CTA size: when the whole batch is ONE wave of one 448-thread CTA per SM (65,536 envs on 148 SMs: 147 CTAs) the
+            // launch measured 3.53 us against 4.11 us with two-warp CTAs (0.57 against 0.49 of the HBM roofline of the
+            // 202-byte model, profiles/r2_step1_blk_sweep.txt); with more than one wave the small CTAs win (9.7 against
+            // 12.2 us at 262,144 envs).  SS_STEP1_BLK = 64 / 448 forces one.
+            int blk1 = 64;
+            {
+                const char *xe = getenv("SS_STEP1_BLK");
+                const int xb = xe ? atoi(xe) : 0;
+                int dev = 0, sms = 148;
+                if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+                    sms = 148;
+                const int64_t c448 = (n_envs + 447) / 448;
+                if (xb == 64 || xb == 448) blk1 = xb;
+                else if (c448 <= sms && c448 * 20 >= (int64_t)sms * 19) blk1 = 448;
+            }
+            if (blk1 == 448) {
+                cfg.gridDim = dim3(blocks_for(n_envs, 448)); cfg.blockDim = dim3(448);
+                if (cudaLaunchKernelEx(&cfg, step_kernel<false, false, false, 1, false, true, 448>, A) != cudaSuccess) return SS_ERR_CUDA;
+            } else
             if (cudaLaunchKernelEx(&cfg, step_kernel<false, false, false, 1, false, true>, A) != cudaSuccess) return SS_ERR_CUDA;
         } else if (A.stats) {
             if (speeds) step_kernel<false, false, true, 1, true><<<grid, block, 0, st>>>(A);

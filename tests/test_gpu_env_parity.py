@@ -175,6 +175,23 @@ def test_fused_physics_kernel_is_identical_for_every_cta_size(monkeypatch):
         assert torch.equal(got[blk][4], got["64"][4]), blk
         parity.assert_state_equal(got[blk][5], got["64"][5], "packed state, CTA size " + blk)
     parity.assert_state_equal(got["64"][5], got["64"][3], "packed vs three arrays")
+    # the one-tick physics kernel has two CTA sizes as well (448 threads when the batch is exactly one wave of one CTA per SM)
+    monkeypatch.delenv("SS_STEP_BLK")
+    one = {}
+    for blk in ("64", "448"):
+        monkeypatch.setenv("SS_STEP1_BLK", blk)
+        e = make(n, **kw)
+        outs = []
+        for t in range(40):
+            o = e.step(actions[t], want_obs=False)
+            outs.append((o["reward"].clone(), o["done"].clone(), o["winner"].clone()))
+        one[blk] = (outs, e.export_state())
+        e.check_status()
+    for (ra, da, wa), (rb, db, wb) in zip(one["64"][0], one["448"][0]):
+        assert torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(wa, wb)
+    parity.assert_state_equal(one["448"][1], one["64"][1], "one-tick kernel, CTA size 448")
+    for t in range(40):                                       # ... and the one-tick launches equal the fused launch's first ticks
+        assert torch.equal(one["64"][0][t][2], got["64"][2][t]) and torch.equal(one["64"][0][t][0], got["64"][0][t])
 
 
 def test_step_host_full_and_packed_outputs_agree():
