@@ -561,7 +561,10 @@ int launch_grad(const GradArgs &A0, float *grad_out, float *aux_out, int64_t wor
     int64_t cap = workspace_bytes / ((int64_t)(PN + 1) * 4);
     if (cap > sms) cap = sms;
     if (cap < 1) return SS_ERR_INVALID_ARG;
-    const int grid = (int)(tiles < cap ? tiles : cap);
+    // No more CTAs than the rounds need: 512 tiles on 148 SMs are four rounds whichever way, and 128 CTAs of four tiles stage
+    // the weights 128 times instead of 148 (the staging is L2-bandwidth bound) and leave 128 gradient slices to reduce.
+    const int64_t rounds = (tiles + cap - 1) / cap;
+    const int grid = (int)((tiles + rounds - 1) / rounds);
     cudaStream_t st = (cudaStream_t)stream;
     GradArgs A1 = A0;
     A1.early_weights = sslaunch::take_early_weights();

@@ -488,7 +488,9 @@ int launch_fwd(const FwdArgs &A, void *stream) {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SS_ERR_CUDA;
     const int64_t n_groups = (A.n + A.group - 1) / A.group;
     const int64_t units = n_groups * ((A.group + TM - 1) / TM);
-    int grid = (int)(units < sms ? units : sms);
+    // no more CTAs than the rounds need (512 tiles on 148 SMs: 128 CTAs of four tiles each; fewer CTAs stage the weights)
+    const int64_t rounds = (units + sms - 1) / sms;
+    int grid = (int)((units + rounds - 1) / rounds);
     // perturbed weights are staged once per noise group a CTA touches: when the groups fit the SMs, give every CTA
     // exactly one group (the kernel's even split of units is then group-aligned) instead of letting ranges straddle two
     if (A.group < A.n && n_groups <= sms) grid = (int)n_groups;
@@ -525,7 +527,8 @@ extern "C" int ss_actor_forward_tc_signal(const float *actor_params, const float
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
             return SS_ERR_CUDA;
         const int64_t n_groups = (A.n + A.group - 1) / A.group, units = n_groups * ((A.group + TM - 1) / TM);
-        int grid = (int)(units < sms ? units : sms);
+        const int64_t rounds = (units + sms - 1) / sms;
+        int grid = (int)((units + rounds - 1) / rounds);
         if (A.group < A.n && n_groups <= sms) grid = (int)n_groups;
         if (grid_out) *grid_out = grid;
         if (units_out) *units_out = units;
@@ -615,7 +618,8 @@ extern "C" int ss_actor_critic_forward_tc(const float *actor_params, const float
     const int64_t units = (n + TM - 1) / TM;
     const int half = sms / 2;
     if (half < 1) return SS_ERR_CUDA;
-    const int ga = (int)(units < half ? units : half);          // the two roles split the tiles identically: same count
+    const int64_t prounds = (units + half - 1) / half;
+    const int ga = (int)((units + prounds - 1) / prounds);      // the two roles split the tiles identically: same count
     if (cudaFuncSetAttribute(pipe::mlp_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe::SMP_TOTAL) !=
         cudaSuccess)
         return SS_ERR_CUDA;
