@@ -539,6 +539,11 @@ typedef struct ss_ddpg_update_args {
     uint32_t *done_counter, *status;
     void *pair_mail;                           /* ss_actor_critic_forward_tc's mailbox for `batch` rows, or NULL: the
                                                   actor -> critic forward pairs then run as two launches each */
+    int sample_early;                          /* 1: the caller guarantees that the launch preceding this call on the stream
+                                                  neither writes the replay ring nor touches THIS call's minibatch buffers
+                                                  (obs .. y, indices) -- e.g. the previous ss_ddpg_update used another set of
+                                                  buffers and no rollout came between: the minibatch is then gathered while
+                                                  that launch still runs.  0: the gather waits for it */
 } ss_ddpg_update_args;
 int ss_ddpg_update(const ss_ddpg_update_args *args, void *stream);
 

@@ -52,7 +52,7 @@ class DdpgUpdateArgs(ctypes.Structure):
                 [("seed", _u64), ("counter", _u64), ("step_critic", _i64), ("step_actor", _i64), ("n_global", _i64),
                  ("row_offset", _i64), ("workspace", _vp), ("workspace_bytes", _i64), ("tensor_cores", _i32),
                  ("world", _i32), ("rank", _i32), ("peer_bases", _vp), ("peer_capacity", _i64), ("epoch", _u32),
-                 ("done_counter", _vp), ("status", _vp), ("pair_mail", _vp)])
+                 ("done_counter", _vp), ("status", _vp), ("pair_mail", _vp), ("sample_early", _i32)])
 
 
 # name -> (restype, argtypes); every symbol the header declares

@@ -24,7 +24,10 @@ namespace sslaunch {
 // kPdlEarlyAfterFirst: the next tensor-core launch stages its parameters behind the wait (its predecessor writes them), the
 // ones after it ahead of it
 // kPdlPairCriticLate: in an actor -> critic pair launch only the actor role stages ahead of the wait
-enum : int { kPdlOff = 0, kPdlOn = 1, kPdlEarlyWeights = 2, kPdlEarlyAfterFirst = 4, kPdlPairCriticLate = 8 };
+// kPdlSampleEarly: replay_sample_kernel gathers BEFORE its wait (and waits before it exits, so that its completion still
+// implies its predecessor's): the caller guarantees that its predecessor on the stream neither writes the ring nor reads
+// or writes the minibatch buffers of this call
+enum : int { kPdlOff = 0, kPdlOn = 1, kPdlEarlyWeights = 2, kPdlEarlyAfterFirst = 4, kPdlPairCriticLate = 8, kPdlSampleEarly = 16 };
 
 // the launch mode of the calling host thread; set by ss_ddpg_update around each entry point it calls
 int &pdl_mode();

@@ -719,13 +719,9 @@ __global__ void replay_push_kernel(Ring R, int64_t pos, const float *s, const fl
     }
 }
 
-__global__ void replay_sample_kernel(Ring R, int64_t size, const int64_t *indices, uint64_t seed, uint64_t counter,
-                                     int64_t batch, float *s, float *a, float *r, float *s2, uint8_t *done,
-                                     int64_t *indices_out, int w4) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    sslaunch::griddep_wait();            // ss_launch.cuh (the minibatch buffers are still read by the previous update's kernels)
-    sslaunch::griddep_launch();
-    if (e >= w4 * batch) return;
+__device__ __forceinline__ void replay_sample_row(const Ring &R, int64_t size, const int64_t *indices, uint64_t seed,
+                                                  uint64_t counter, float *s, float *a, float *r, float *s2, uint8_t *done,
+                                                  int64_t *indices_out, int w4, int64_t e) {
     const int64_t b = e / w4, part = e - b * w4;
     int64_t src;
     if (indices) {
@@ -742,6 +738,23 @@ __global__ void replay_sample_kernel(Ring R, int64_t size, const int64_t *indice
         r[b] = R.r[src];
         done[b] = R.done[src];
         if (indices_out) indices_out[b] = src;
+    }
+}
+
+// early (ss_launch.cuh, kPdlSampleEarly): gather first, wait afterwards -- the rows are then drawn while the previous
+// update's last kernel still runs
+__global__ void replay_sample_kernel(Ring R, int64_t size, const int64_t *indices, uint64_t seed, uint64_t counter,
+                                     int64_t batch, float *s, float *a, float *r, float *s2, uint8_t *done,
+                                     int64_t *indices_out, int w4, int early) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (!early) {                        // (the minibatch buffers may still be read by the previous update's kernels)
+        sslaunch::griddep_wait();
+        sslaunch::griddep_launch();
+    }
+    if (e < w4 * batch) replay_sample_row(R, size, indices, seed, counter, s, a, r, s2, done, indices_out, w4, e);
+    if (early) {
+        sslaunch::griddep_wait();
+        sslaunch::griddep_launch();
     }
 }
 
@@ -981,8 +994,9 @@ int ss_replay_sample_frames(const float *ring_obs, const float *ring_act, const 
     Ring R{(float *)ring_obs, (float *)ring_act, (float *)ring_reward, (float *)ring_next_obs, (uint8_t *)ring_done,
            capacity};
     const int w4 = 3 * frames;
+    const int early = (sslaunch::pdl_mode() & sslaunch::kPdlOn) && (sslaunch::pdl_mode() & sslaunch::kPdlSampleEarly) ? 1 : 0;
     if (sslaunch::launch(replay_sample_kernel, dim3((unsigned)((w4 * batch + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, R,
-                         size, indices, seed, counter, batch, obs, act, reward, next_obs, done, indices_out, w4) != cudaSuccess)
+                         size, indices, seed, counter, batch, obs, act, reward, next_obs, done, indices_out, w4, early) != cudaSuccess)
         return SS_ERR_CUDA;
     return check_launch();
 }

@@ -66,7 +66,9 @@ extern "C" int ss_ddpg_update(const ss_ddpg_update_args *a, void *stream) {
     const int kEarly = kOn ? (sslaunch::kPdlOn | sslaunch::kPdlEarlyWeights) : sslaunch::kPdlOff;
     sslaunch::PdlScope scope(kOn);
 
-    // minibatch (uniform with replacement from the filled part of the ring)
+    // minibatch (uniform with replacement from the filled part of the ring); drawn beside the previous launch's tail when the
+    // caller vouches for it (args.sample_early)
+    if (kOn && a->sample_early) sslaunch::pdl_mode() = kOn | sslaunch::kPdlSampleEarly;
     rc = ss_replay_sample(a->ring_obs, a->ring_act, a->ring_reward, a->ring_next_obs, a->ring_done, a->capacity, a->size,
                           nullptr, a->replay_seed, a->replay_counter, n, a->obs, a->act, a->reward, a->next_obs, a->done,
                           a->indices, stream);

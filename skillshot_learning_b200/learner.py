@@ -205,7 +205,6 @@ class ActorCritic:
         self.counter = 0            # Philox counter: advances with every noisy call
         self._update_args = None    # cached ss_ddpg_update argument block (pointers change rarely)
         self._pair_mail = None      # ss_actor_critic_forward_tc's mailbox, allocated with the argument block
-        self._update_args_key = None
         self.init_weights(seed)
 
     # -- parameter views -----------------------------------------------------
@@ -476,11 +475,13 @@ class ActorCritic:
             self.reduce_adam("actor", parts, self.stats[1:2])
         return self.stats[1]
 
-    def update_from_ring(self, ring: "ReplayRing", batch: int, out: Optional[dict] = None):
+    def update_from_ring(self, ring: "ReplayRing", batch: int, out: Optional[dict] = None, sample_early: bool = False):
         """One whole update step from ONE library call (ss_ddpg_update): sample `batch` rows of `ring`,
         TD target, critic step, actor step -- the launches critic_step / actor_step make, without the
         interpreter time between them.  Single GPU or the fused peer exchange (an NCCL all-reduce needs
-        the host between the gradient and Adam: use the separate steps).  Returns the minibatch dict."""
+        the host between the gradient and Adam: use the separate steps).  Returns the minibatch dict.
+        sample_early: the caller guarantees that the previous launch on the stream neither writes the ring nor touches
+        `out` (ss_ddpg_update_args.sample_early): the minibatch is gathered while that launch still runs."""
         if self.group is not None and self.peer is None:
             raise ValueError("update_from_ring needs collective='peer' when the update is sharded")
         if self.frames > 1:
@@ -498,12 +499,15 @@ class ActorCritic:
                        y=torch.empty(batch, dtype=torch.float32, device=dev))
         _, n_global, row_offset = shard_info(batch, self.group)
         ws = self._workspace_for(batch)
-        a = self._update_args
         key = (ring.obs.data_ptr(), ring.next_obs.data_ptr(), ring.capacity, out["obs"].data_ptr(), out["y"].data_ptr(), ws.data_ptr(),
                ws.numel(), batch, id(self.peer))
-        if a is None or self._update_args_key != key:
-            a = self._update_args = _lib.DdpgUpdateArgs()
-            self._update_args_key = key
+        if self._update_args is None:
+            self._update_args = {}
+        a = self._update_args.get(key)      # one cached argument block per set of minibatch buffers (callers alternate two)
+        if a is None:
+            if len(self._update_args) >= 4:
+                self._update_args.clear()
+            a = self._update_args[key] = _lib.DdpgUpdateArgs()
             a.ring_obs, a.ring_act, a.ring_reward = ring.obs.data_ptr(), ring.act.data_ptr(), ring.reward.data_ptr()
             a.ring_next_obs, a.ring_done, a.capacity = ring.next_obs.data_ptr(), ring.done.data_ptr(), ring.capacity
             a.batch = batch
@@ -520,11 +524,13 @@ class ActorCritic:
             # the actor -> critic forward pairs (TD target, actor step) as one launch each (ss_actor_critic_forward_tc), for
             # minibatches small enough that a forward launch is mostly set-up and pipeline fill; the mailbox is filled with its
             # empty mark here once and left so by every call (SS_UPDATE_PAIR=0: two launches each, for A/B measurements)
-            self._pair_mail = None
             # (measured, profiles/r2_update_pair_ab.txt: 162.5 -> 158.9 us at 65,536 rows, 236 -> 252 us at 131,072)
             if batch <= 65536 and os.environ.get("SS_UPDATE_PAIR", "1") != "0":
-                self._pair_mail = torch.full((batch, 2), _lib.PAIR_MAIL_EMPTY, dtype=torch.int32, device=dev)
+                if self._pair_mail is None or self._pair_mail.shape[0] != batch:
+                    self._pair_mail = torch.full((batch, 2), _lib.PAIR_MAIL_EMPTY, dtype=torch.int32, device=dev)
                 a.pair_mail = self._pair_mail.data_ptr()
+            else:
+                self._pair_mail = None
             if self.peer is not None:
                 px = self.peer
                 a.world, a.rank, a.peer_capacity = px.world, px.rank, px.capacity
@@ -537,6 +543,7 @@ class ActorCritic:
         a.step_critic, a.step_actor = self.step_critic + 1, self.step_actor + 1
         a.n_global, a.row_offset = n_global, row_offset
         a.tensor_cores = 1 if self.update_precision == "bf16" else 0
+        a.sample_early = 1 if sample_early else 0
         if self.peer is not None:
             a.epoch = self.peer.epoch + 1
         with torch.cuda.device(dev):
@@ -1082,6 +1089,8 @@ class SelfPlayTrainer:
             self.rows = self.stack.ordered_rows()                         # [2n, 12 frames]: the stacked observation now
             self.prev_rows = torch.empty_like(self.rows)
         self._batch = None
+        self._batches = [None, None]        # update(): two sets of minibatch buffers used in turn
+        self._ring_clean = False            # no rollout (nothing of this object's that writes the ring) since the last update
         self.ticks = 0
         self.updates = 0
         self.exchange_check_every = 256     # updates between looks at the peer exchange's status word
@@ -1090,6 +1099,7 @@ class SelfPlayTrainer:
     def rollout_tick(self, store: bool = True):
         """One tick of every env: actor forward on both players' observations (fresh parameter
         noise per noise group), env step, transition push."""
+        self._ring_clean = False
         if self.frames > 1:
             return self._rollout_tick_frames(store)
         self.prev_obs, self.obs = self.obs, self.prev_obs
@@ -1121,6 +1131,7 @@ class SelfPlayTrainer:
     def rollout(self, n_ticks: int, store: bool = True):
         """n_ticks rollout ticks enqueued by ONE library call (ss_selfplay_rollout): same kernels and Philox
         counters as n_ticks calls of rollout_tick, without the per-tick host work."""
+        self._ring_clean = False
         if self.frames > 1:
             for _ in range(int(n_ticks)):
                 out = self._rollout_tick_frames(store)
@@ -1194,6 +1205,8 @@ class SelfPlayTrainer:
             st.head, st.counter = int(ss["head"]), int(ss["counter"])
             self.rows.copy_(ss["rows"].to(self.device))
         self._batch = None
+        self._batches = [None, None]
+        self._ring_clean = False
 
     def record_boards(self, env: int, n_ticks: int, path: Optional[str] = None, store: bool = True):
         """Play n_ticks rollout ticks and return the 250 x 250 rasters of game `env` after each of them
@@ -1240,7 +1253,15 @@ class SelfPlayTrainer:
         net = self.networks
         if (net.group is not None and net.peer is None) or self.frames > 1:
             return self.update_stepwise()
-        self._batch = net.update_from_ring(self.replay, self.batch_size, out=self._batch)
+        # two sets of minibatch buffers in turn: when no rollout has touched the ring since the previous update, this
+        # update's rows are drawn while that update's last kernels still run (ss_ddpg_update_args.sample_early)
+        k = self.updates & 1
+        # (measured, profiles/r2_update_sample_early_ab.txt: 158.1 -> 152.1 us at 65,536 rows; at 524,288 rows the gather
+        #  competes with what it runs beside, 759 -> 764 us: small minibatches only)
+        early = (self._ring_clean and self._batches[k] is not None and self.batch_size <= 131072 and
+                 os.environ.get("SS_UPDATE_SAMPLE_EARLY", "1") != "0")
+        self._batch = self._batches[k] = net.update_from_ring(self.replay, self.batch_size, out=self._batches[k], sample_early=early)
+        self._ring_clean = True
         self.updates += 1
         if net.peer is not None and self.updates % self.exchange_check_every == 0:
             net.peer.check_status()         # one device-to-host read every few hundred updates
@@ -1248,6 +1269,7 @@ class SelfPlayTrainer:
 
     def update_stepwise(self):
         """The same update as one library call per step (sample, target, critic step, actor step)."""
+        self._ring_clean = False
         self._batch = b = self.replay.sample(self.batch_size, out=self._batch)
         net = self.networks
         y = net.td_targets(b["reward"], b["next_obs"], b["done"])

@@ -2,5 +2,4 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_learner_parity.py tests/test_gpu_frames_learner.py -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest_gpu.log
 tail -5 gpurun_out/r2_pytest_gpu.log
-timeout 300 python tools/update_time.py 65536 75776 524288 2>&1 | grep SS_UPDATE | tee gpurun_out/r2_update_time.txt
-timeout 300 python tools/update_time.py 65536 2>&1 | grep SS_UPDATE | tee -a gpurun_out/r2_update_time.txt
+for f in 0 1 0 1; do SS_UPDATE_SAMPLE_EARLY=$f timeout 300 python tools/update_time.py 65536 524288 2>&1 | grep SS_UPDATE | sed "s/^/SAMPLE_EARLY=$f /"; done | tee gpurun_out/r2_update_sample_early.txt
