@@ -17,9 +17,18 @@
 // CTA processes: nothing but the final sums ever leaves the SM.  Because the bias rows are part of
 // W1' / W2' (constant-one columns in X0 / X2), db1 and db2 fall out of G1 / G2 for free, as do the
 // gradients of the critic's two action rows.  The element-wise steps between the GEMMs (ReLU,
-// inverted dropout, the 128 -> 1|2 output layer, loss / upstream gradient, ReLU masks) run on four
-// epilogue warps, one thread per row, between tcgen05.ld and the shared-memory tile stores.
-// One tile is in flight per CTA (the accumulators take 352 of the 512 columns), 148 CTAs.
+// inverted dropout, the 128 -> 1|2 output layer, loss / upstream gradient, ReLU masks) run on eight
+// epilogue warps (two per tensor-memory lane quadrant, splitting the columns of every sweep), one
+// thread per row and column slice, between tcgen05.ld and the shared-memory tile stores.
+// One tile is in flight per CTA (its activations take 136 KB of shared memory beside 86 KB of
+// weight images; the accumulators take 352 of the 512 tensor-memory columns).
+//
+// Order of issue within a tile (round 2): L1a, L1b, L2 one by one (each output is consumed before
+// the next can overwrite the work columns); then G2's first half and BXa behind ONE commit -- the
+// epilogue warps wait for dx2 only, and its first half may overwrite h1[:, :128] as soon as G2 has
+// consumed it -- with the rest of G2, its bias / action columns and G3 running beside back1(0) and
+// retiring with BXb's commit; G1 has no commit of its own and retires with the next tile's L1a
+// (X0 of the next tile is staged into the head of the H2 buffer meanwhile).
 //
 // Gradients are therefore computed from bf16 operands (products exact, fp32 accumulation):
 // relative error ~1e-3 against the float32 path of ss_learner.cu, which remains the exact one.
