@@ -85,7 +85,8 @@ class all_host_cpus:
 
 ENVS_PER_GPU = 65536
 TICKS = 2048                # ticks per bench step (one full 2,000-tick episode plus the auto-reset)
-TICKS_PER_LAUNCH = 256      # fused ticks per ss_env_step launch (32: 7.4e10, 256: 8.4e10 env-steps/s, graph-replayed; tools/explore_step.py)
+TICKS_PER_LAUNCH = 1024     # fused ticks per ss_env_step launch (65,536 envs, graph-replayed, tools/explore_step.py: 32: 7.4e10, 128: 8.15e10,
+                            # 256: 8.36e10, 512: 8.47e10, 1024: 8.53e10 env-steps/s; a step of 2,048 ticks is two launches)
 E2E_TICKS_PER_LAUNCH = 32   # the host-buffer leg pipelines copy in / kernel / copy out per chunk: finer chunks overlap better
 TICK_LIMIT = 2000           # SkillshotLearner.py:62
 ALGO_BYTES_PER_ENV_STEP = 202   # SURVEY.md 8(d), physics-only

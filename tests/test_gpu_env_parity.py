@@ -128,16 +128,17 @@ def test_full_size_physics_matches_oracle_256_ticks():
 
 
 def test_bench_shape_full_size_matches_oracle():
-    """bench.py's timed configuration as it is timed: 65,536 envs x 2,048 ticks in launches of 128 fused ticks, Philox
-    random starts and auto-reset at the 2,000-tick limit, terminal reward.  Every winner, done flag and reward of all
-    1.3e8 env-steps and the state after every launch are compared with the oracle for equality."""
+    """bench.py's timed configuration as it is timed: 65,536 envs x 2,048 ticks in launches of 1,024 fused ticks (one
+    896-thread CTA per SM), Philox random starts and auto-reset at the 2,000-tick limit, terminal reward.  Every winner,
+    done flag and reward of all 1.3e8 env-steps and the state after every launch are compared with the oracle for equality."""
     import torch
     g = torch.Generator(device="cuda").manual_seed(99)
 
     def actions(K):
         return (torch.rand((K, 65536, 2, 2), device="cuda", generator=g) * 2.4 - 1.2).contiguous()
 
-    episodes, hits = parity.check_bench_shape(make, n=65536, T=2048, K=128, action_source=actions)
+    import bench
+    episodes, hits = parity.check_bench_shape(make, n=65536, T=2048, K=bench.TICKS_PER_LAUNCH, action_source=actions)
     assert episodes >= 65536 and hits > 1000          # every env restarts at least once (the 2,000-tick limit), many by a hit
 
 

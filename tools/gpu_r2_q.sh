@@ -10,7 +10,7 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-learne
 $CMD > gpurun_out/r2_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_bench_physics.csv $CMD > gpurun_out/r2_ncu_list.log 2>&1
 $CMD > gpurun_out/r2_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:step_pp -s 25 -c 1 -o gpurun_out/r2_prof_step_pp -f $CMD > gpurun_out/r2_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:step_pp -s 6 -c 1 -o gpurun_out/r2_prof_step_pp -f $CMD > gpurun_out/r2_ncu_full.log 2>&1
 timeout 300 python tools/prof_all.py > /dev/null 2>&1 && timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_tick_and_update.csv python tools/prof_all.py > gpurun_out/ncu.log 2>&1
 python tools/prof_grad_tc.py > gpurun_out/r2_prof_grad_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:mlp_grad_tc -s 4 -c 2 -o gpurun_out/r2_prof_grad_tc -f python tools/prof_grad_tc.py > gpurun_out/r2_ncu_grad_full.log 2>&1
