@@ -699,17 +699,22 @@ inline int check_launch() { return cudaGetLastError() == cudaSuccess ? SS_OK : S
 inline unsigned blocks_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 // CTA size of step_pp_kernel for n_envs (see the kernel): 896 when that still makes at least ~one CTA per SM (65,536 envs
 // are 147 CTAs on 148 SMs), else 448, else 64.  SS_STEP_BLK = 64 / 448 / 896 forces one (A/B measurements, the equality test).
-inline int pp_block_for(int64_t n_envs) {
-    if (const char *e = getenv("SS_STEP_BLK")) {
-        const int v = atoi(e);
-        if (v == 64 || v == 448 || v == 896) return v;
-    }
+// SM count of the current device (asked once: the GPUs of a box are alike)
+inline int sm_count() {
     static int sms = 0;
     if (sms == 0) {
         int dev = 0, v = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = 148;
         sms = v;
     }
+    return sms;
+}
+inline int pp_block_for(int64_t n_envs) {
+    if (const char *e = getenv("SS_STEP_BLK")) {
+        const int v = atoi(e);
+        if (v == 64 || v == 448 || v == 896) return v;
+    }
+    const int sms = sm_count();
     // Measured on one box (profiles/r2_step_blk_sweep.txt, 256 ticks per launch, 896 against 64 threads): 65,536 envs
     // +7.6 %, 131,072 +6.7 %, 262,144 +1.8 % (-1.2 % at 32 ticks), 1,048,576 -1.6 % (-5.3 % at 32 ticks): with many waves
     // the small CTAs refill an SM two warps at a time and win.  Hence: one big CTA per SM up to three waves.
@@ -830,9 +835,7 @@ int ss_env_step_ring(void *state, int64_t n_envs, const float *actions, float *o
             {
                 const char *xe = getenv("SS_STEP1_BLK");
                 const int xb = xe ? atoi(xe) : 0;
-                int dev = 0, sms = 148;
-                if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-                    sms = 148;
+                const int sms = sm_count();
                 const int64_t c448 = (n_envs + 447) / 448;
                 if (xb == 64 || xb == 448) blk1 = xb;
                 else if (c448 <= sms && c448 * 20 >= (int64_t)sms * 19) blk1 = 448;
