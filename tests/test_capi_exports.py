@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -161,3 +163,18 @@ def test_header_constants_match_the_python_mirror():
     assert m and int(m.group(1), 16) == _lib.PAIR_MAIL_EMPTY
     m = re.search(r"#define\s+SS_STATUS_ROLLOUT_TIMEOUT\s+(\d+)", text)
     assert m and int(m.group(1)) == 4
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/skillshot_b200.h is the drop-in boundary: it must compile as C99 on its own (no C++ or CUDA types in the
+    signatures), with every struct complete."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "skillshot_b200.h"\n'
+                   'int main(void) { ss_ddpg_update_args a; (void)a; return SS_PAIR_MAIL_EMPTY == 0x7fc0dead ? 0 : 1; }\n')
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                    "-o", str(tmp_path / "hdr.o")], check=True)
