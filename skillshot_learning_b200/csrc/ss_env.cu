@@ -22,7 +22,6 @@ namespace {
 using namespace ss;
 
 constexpr int kBlock = 64;             // 2 warps: fine-grained CTAs balance small grids over 148 SMs
-constexpr int kWarps = kBlock / 32;
 constexpr int kRowF4 = 7;              // 6 float4 of observation + 1 pad: conflict-free float4 smem rows
 
 struct StatePlanes {
@@ -61,9 +60,6 @@ __device__ __forceinline__ Speeds load_speeds(const void *speeds, int64_t n, int
 struct SmemSink {
     float4 *row;
     __device__ __forceinline__ void put(int j, float a, float b, float c, float d) { row[j] = make_float4(a, b, c, d); }
-};
-struct NoSink {
-    __device__ __forceinline__ void put(int, float, float, float, float) {}
 };
 
 // One finished game into the episode statistics (SS_STEP_EPISODE_STATS).  Kept out of line: it runs once per game,

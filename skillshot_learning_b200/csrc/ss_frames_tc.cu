@@ -55,11 +55,6 @@ struct FramesArgs {
 
 __host__ __device__ constexpr int frames_k1(int frames) { return (DS * frames + 2 + 15) / 16 * 16; }
 
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
 // L2 policies.  The hidden tiles written by the layer-1 kernel are read back by the layer-2/3 kernel moments later: at
 // 131,072 rows they are 67 MB and fit the 126 MB L2 if the 67 MB of history that streams through beside them does not
 // push them out, which saves their round trip to HBM (two thirds of the traffic of the pair of kernels).
