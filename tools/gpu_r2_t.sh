@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_env_parity.py -m gpu -x -q -k "not bench_shape_full" 2>&1 | tail -2
-timeout 200 python __graft_entry__.py smoke 2>&1 | tail -4
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest_gpu.log
+tail -4 gpurun_out/r2_pytest_gpu.log
